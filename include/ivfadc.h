@@ -1,0 +1,221 @@
+/*
+ * libivfadc_cuda -- C ABI of the B200-native IVFADC search / encoding engine.
+ *
+ * This header is the drop-in boundary for the hot path of JuliaNeighbors/IVFADC.jl.  The
+ * reference has no FFI of its own (it is pure Julia); each entry point below replaces the body
+ * of the Julia method cited next to it (paths relative to the reference tree) and is what the
+ * Julia glue package binds with `ccall`.
+ *
+ * Conventions
+ *   - every function returns an int status (IVFADC_OK == 0, negative on error) and never aborts
+ *     the process; ivfadc_last_error() returns the message of the last failure on a handle;
+ *   - host buffers are caller-owned: the library copies in / out and never retains a pointer;
+ *   - matrices are passed exactly as Julia lays them out: a D x n column-major Matrix{T} is n
+ *     contiguous vectors of D elements, so `pointer(data)` crosses the boundary zero-copy;
+ *   - T is f32 or f64 (fixed at create), PQ codes are uint8 (k <= 256), vector ids are 0-based
+ *     unsigned (reference src/index.jl:189) and cross the boundary as uint64;
+ *   - cell (Voronoi cell / inverted list) numbers are 0-based int32 on output; the one input
+ *     that carries cells (`assign`) has an explicit base so Julia's 1-based
+ *     `KmeansResult.assignments` can be passed untouched;
+ *   - a handle is bound to ONE CUDA device and is not thread-safe; host-buffer calls are
+ *     synchronous, `_device` calls are asynchronous on the stream given;
+ *   - there is no CPU fallback: every entry point fails with IVFADC_ERR_CUDA when no device
+ *     is present.
+ */
+#ifndef IVFADC_H
+#define IVFADC_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IVFADC_ABI_VERSION 1
+
+/* status codes */
+#define IVFADC_OK               0
+#define IVFADC_ERR_BAD_ARG     -1   /* null pointer, wrong dimension, k < 1, w < 1 ...            */
+#define IVFADC_ERR_CAPACITY    -2   /* id type cannot index one more vector (src/utils.jl:134)   */
+#define IVFADC_ERR_CUDA        -3   /* CUDA runtime failure (message in ivfadc_last_error)       */
+#define IVFADC_ERR_OOM         -4
+#define IVFADC_ERR_UNSUPPORTED -5   /* metric / code width outside the hot-path scope            */
+#define IVFADC_ERR_EMPTY       -6   /* pop from an empty index (src/utils.jl:44)                 */
+
+/* element type T of data, centroids, codebooks and returned distances */
+#define IVFADC_F32 0
+#define IVFADC_F64 1
+
+/* Distances.PreMetric of the coarse / residual quantizer (src/defaults.jl:6,8) */
+#define IVFADC_SQEUCLIDEAN 0
+
+/* position argument of push!/pushfirst! and pop!/popfirst! (src/utils.jl:29,37,114,123) */
+#define IVFADC_LAST  0
+#define IVFADC_FIRST 1
+
+typedef struct ivfadc_index ivfadc_index;   /* opaque, owns all device memory */
+
+typedef struct ivfadc_config {
+    int32_t dim;            /* D: rows of the data matrix                                         */
+    int32_t kc;             /* number of coarse centroids / inverted lists                        */
+    int32_t m;              /* number of PQ codebooks; sub-dimension = floor(D / m)               */
+    int32_t ksub;           /* codewords per codebook (<= 256, codes are uint8)                   */
+    int32_t dtype;          /* IVFADC_F32 | IVFADC_F64                                            */
+    int32_t id_bytes;       /* sizeof(I) of the Julia index type: 1, 2, 4 or 8                    */
+    int32_t metric_coarse;  /* IVFADC_SQEUCLIDEAN                                                 */
+    int32_t metric_resid;   /* IVFADC_SQEUCLIDEAN                                                 */
+    int32_t device;         /* CUDA device ordinal                                                */
+    int32_t shard_rank;     /* this handle keeps only cells with cell % shard_world == shard_rank */
+    int32_t shard_world;    /* 1 = unsharded                                                      */
+    int32_t reserved;
+} ivfadc_config;
+
+typedef struct ivfadc_stats {
+    uint64_t searches;          /* number of search calls since reset                             */
+    uint64_t queries;           /* queries processed                                              */
+    uint64_t scanned_vectors;   /* sum over (query, probed list) of list length                   */
+    uint64_t scan_code_bytes;   /* scanned_vectors * m : the algorithmic bytes of the list scan   */
+    uint64_t gpu_launches;      /* kernels launched by this library since reset                   */
+    double   coarse_ms;         /* accumulated device time, CUDA events on the launch stream      */
+    double   plan_ms;
+    double   scan_ms;
+    double   merge_ms;
+    double   encode_ms;
+    uint64_t scan_launches;
+    uint64_t reserved[4];
+} ivfadc_stats;
+
+int ivfadc_abi_version(void);
+
+/* Number of CUDA devices visible, or a negative status. */
+int ivfadc_device_count(void);
+
+/*
+ * Build an empty index around trained quantizers.
+ *   centroids        : T[kc][D]            (Julia: cq.vectors, D x kc)
+ *   codebook_vectors : T[m][ksub][dsub]    (Julia: codebooks[i].vectors, dsub x ksub, i = 1..m)
+ *   codebook_codes   : uint8[m][ksub]      (Julia: codebooks[i].codes)
+ * Replaces the struct construction at src/index.jl:155-164 and src/persistency.jl:95-117.
+ */
+int ivfadc_create(ivfadc_index** out, const ivfadc_config* cfg, const void* centroids,
+                  const void* codebook_vectors, const uint8_t* codebook_codes);
+
+int ivfadc_destroy(ivfadc_index* h);
+
+const char* ivfadc_last_error(const ivfadc_index* h);
+
+/*
+ * Add n vectors X[n][D].
+ *   position = IVFADC_LAST : vector j gets id N + j                  (n x push!,      src/utils.jl:114)
+ *   position = IVFADC_FIRST: every stored id += n, vector j gets id n-1-j
+ *                            (what n successive pushfirst! calls do, src/utils.jl:123,140-141)
+ *   assign == NULL : cell = coarse_search(x, 1)                      (_encode_point, src/utils.jl:148-161)
+ *   assign != NULL : cell = assign[j] - assign_base                  (index build from k-means
+ *                            assignments, _build_residuals + _build_inverted_index,
+ *                            src/index.jl:168-194)
+ * Codes are the PQ encoding of x - centroid[cell]; entries are appended at the list tail in
+ * batch order (src/utils.jl:142-143).  cells_out (optional, int32[n]) receives the cells.
+ * Fails with IVFADC_ERR_CAPACITY, leaving the index untouched, when N + n > 2^(8*id_bytes).
+ */
+int ivfadc_add(ivfadc_index* h, const void* X, int64_t n, int32_t position,
+               const int64_t* assign, int32_t assign_base, int32_t* cells_out);
+
+/*
+ * Encode without mutating: cells int32[n] (0-based), codes uint8[n][m].  If assign != NULL
+ * the cells are taken from it as in ivfadc_add.  Parity hook for _encode_point
+ * (src/utils.jl:148-161) and QuantizedArrays.quantize_data (src/index.jl:187).
+ */
+int ivfadc_encode(ivfadc_index* h, const void* X, int64_t n, const int64_t* assign,
+                  int32_t assign_base, int32_t* cells_out, uint8_t* codes_out);
+
+/*
+ * coarse_search for a batch (src/coarsequantizers.jl:33-37): the w nearest centroids of every
+ * query in ascending (distance, cell) order.  cells int32[nq][w] 0-based, dc T[nq][w].
+ * w is clamped to kc by the caller (src/index.jl:216).
+ */
+int ivfadc_coarse_search(ivfadc_index* h, const void* Q, int64_t nq, int32_t w,
+                         int32_t* cells_out, void* dc_out);
+
+/*
+ * Batched knn_search (src/index.jl:204-273).  Q[nq][D]; k >= 1; w >= 1 (clamped to kc).
+ * Outputs, row i for query i, first counts[i] (<= k) entries valid, ascending in
+ * (distance, probe rank, position in list) (src/index.jl:247-257):
+ *   ids   uint64[nq][k]  0-based vector ids
+ *   dists T[nq][k]       dc + sum of lookup-table entries (src/index.jl:242-246)
+ *   counts int32[nq]
+ * Unused slots are filled with id = UINT64_MAX, dist = +inf.
+ */
+int ivfadc_search(ivfadc_index* h, const void* Q, int64_t nq, int32_t k, int32_t w,
+                  uint64_t* ids_out, void* dists_out, int32_t* counts_out);
+
+/*
+ * Same, with every pointer a DEVICE pointer on the handle's device and the work enqueued on
+ * `stream` (a cudaStream_t; NULL = the legacy default stream).  Returns without synchronising.
+ */
+int ivfadc_search_device(ivfadc_index* h, const void* dQ, int64_t nq, int32_t k, int32_t w,
+                         uint64_t* d_ids, void* d_dists, int32_t* d_counts, void* stream);
+
+/*
+ * Sharded search, step 1 (device pointers): scan only the probed cells this shard owns and
+ * return, per query, its k best local candidates with their merge keys
+ *   key = (probe rank << 32) | position in list
+ * so that ranks can be merged in the reference's order.  d_keys uint64[nq][k].
+ */
+int ivfadc_search_local_device(ivfadc_index* h, const void* dQ, int64_t nq, int32_t k, int32_t w,
+                               uint64_t* d_ids, void* d_dists, uint64_t* d_keys,
+                               int32_t* d_counts, void* stream);
+
+/*
+ * Sharded search, step 2 (device pointers): merge `parts` candidate sets laid out
+ * [parts][nq][k] (as gathered from the ranks) into the final [nq][k] by (dist, key).
+ */
+int ivfadc_merge_device(ivfadc_index* h, int32_t parts, int64_t nq, int32_t k,
+                        const uint64_t* d_ids_in, const void* d_dists_in,
+                        const uint64_t* d_keys_in, uint64_t* d_ids, void* d_dists,
+                        int32_t* d_counts, void* stream);
+
+/*
+ * delete_from_index! (src/utils.jl:90-105): ids are the STORED 0-based ids (the Julia glue
+ * performs the `I.(points .- 1)` conversion and its InexactError).  Duplicates and unknown
+ * ids are ignored; survivors keep their in-list order and are renumbered
+ * new_id = old_id - |{deleted ids < old_id}|.  When sharded, `ids` must be the full global list.
+ */
+int ivfadc_delete(ivfadc_index* h, const uint64_t* ids, int64_t n);
+
+/*
+ * pop! / popfirst! (src/utils.jl:29-81): remove id N-1 (LAST) or id 0 (FIRST; all other ids
+ * -= 1) and return centroid + decoded residual in vec_out T[D].
+ * found_out (optional) is 1 when this shard owned the vector (always 1 unsharded).
+ */
+int ivfadc_pop(ivfadc_index* h, int32_t position, void* vec_out, int32_t* found_out);
+
+/* length(ivfadc) (src/index.jl:56): total over ALL shards as tracked by this handle. */
+int ivfadc_length(const ivfadc_index* h, int64_t* n_out);
+
+/* Per-list lengths of the cells stored in this handle, int64[kc] (0 for cells of other shards). */
+int ivfadc_list_sizes(ivfadc_index* h, int64_t* sizes_out);
+
+/*
+ * Copy one inverted list out / in (persistency, src/persistency.jl:68-78,119-131):
+ * ids uint64[len], codes uint8[len][m] in list order.  Import replaces the list and adjusts
+ * the length of the index.
+ */
+int ivfadc_export_list(ivfadc_index* h, int32_t cell, uint64_t* ids_out, uint8_t* codes_out);
+int ivfadc_import_list(ivfadc_index* h, int32_t cell, const uint64_t* ids, const uint8_t* codes,
+                       int64_t len);
+
+/* Copy the quantizers back out (same layouts as ivfadc_create). */
+int ivfadc_export_quantizers(ivfadc_index* h, void* centroids_out, void* codebook_vectors_out,
+                             uint8_t* codebook_codes_out);
+
+/* Override the global vector count (used by load and by sharded handles). */
+int ivfadc_set_length(ivfadc_index* h, int64_t n_total);
+
+int ivfadc_get_stats(ivfadc_index* h, ivfadc_stats* out);
+int ivfadc_reset_stats(ivfadc_index* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IVFADC_H */

@@ -1,0 +1,583 @@
+// The C ABI of include/ivfadc.h: argument checking, host<->device staging, chunking, statistics.
+// All numerics live in coarse.cu / scan*.cu / encode.cu / lists.cu.
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "common.cuh"
+
+using namespace ivf;
+
+namespace {
+
+constexpr int kEventSets = 32;   // ring of per-search event sets (coarse a/b, scan a/b, end)
+constexpr int kEventsPerSet = 6;
+
+struct Timing {
+    cudaEvent_t ev[kEventSets][kEventsPerSet];
+    int pending[kEventSets];  // 0 = free, 1 = recorded
+    int next = 0;
+    bool ok = false;
+};
+
+// handle-private extras kept out of common.cuh
+struct Extra {
+    Timing tm;
+    uint64_t* d_scanned = nullptr;  // device counter of scanned vectors
+    uint64_t scanned_flushed = 0;
+};
+
+Extra* extra(ivfadc_index* h) { return reinterpret_cast<Extra*>(h->stats.reserved[3]); }
+
+int fail(ivfadc_index* h, int code, const char* msg, cudaError_t e = cudaSuccess) {
+    if (h) {
+        h->err = msg;
+        if (e != cudaSuccess) {
+            h->err += ": ";
+            h->err += cudaGetErrorString(e);
+        }
+    }
+    return code;
+}
+
+#define CUDA_OR_FAIL(h, call, what)                                   \
+    do {                                                              \
+        cudaError_t _e = (call);                                      \
+        if (_e != cudaSuccess) {                                      \
+            cudaGetLastError();                                       \
+            return fail(h, _e == cudaErrorMemoryAllocation ? IVFADC_ERR_OOM : IVFADC_ERR_CUDA, what, _e); \
+        }                                                             \
+    } while (0)
+
+void flush_set(ivfadc_index* h, int i) {
+    Timing& tm = extra(h)->tm;
+    if (!tm.pending[i]) return;
+    cudaEventSynchronize(tm.ev[i][5]);
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, tm.ev[i][0], tm.ev[i][1]) == cudaSuccess) h->stats.coarse_ms += ms;
+    if (cudaEventElapsedTime(&ms, tm.ev[i][1], tm.ev[i][2]) == cudaSuccess) h->stats.plan_ms += ms;
+    if (cudaEventElapsedTime(&ms, tm.ev[i][2], tm.ev[i][3]) == cudaSuccess) {
+        h->stats.scan_ms += ms;
+        h->stats.scan_launches += 1;
+    }
+    if (cudaEventElapsedTime(&ms, tm.ev[i][3], tm.ev[i][5]) == cudaSuccess) h->stats.merge_ms += ms;
+    tm.pending[i] = 0;
+}
+
+void flush_all(ivfadc_index* h) {
+    for (int i = 0; i < kEventSets; ++i) flush_set(h, i);
+    cudaGetLastError();
+}
+
+int check_handle(const ivfadc_index* h) { return h ? IVFADC_OK : IVFADC_ERR_BAD_ARG; }
+
+// One chunk of queries, everything on the device, asynchronous on `s`.
+int search_chunk(ivfadc_index* h, const void* dQ, int64_t nq, int k, int w, uint64_t* d_ids, void* d_dists,
+                 uint64_t* d_keys, int32_t* d_counts, cudaStream_t s) {
+    const ScanPlanSizes z = scan_plan_sizes(h, nq, w, k);
+    CUDA_OR_FAIL(h, h->ws_cells.reserve(sizeof(int32_t) * (size_t)nq * w), "workspace");
+    CUDA_OR_FAIL(h, h->ws_dc.reserve(h->tsize * (size_t)nq * w), "workspace");
+    CUDA_OR_FAIL(h, h->ws_bucket.reserve(z.bucket_bytes), "workspace");
+    CUDA_OR_FAIL(h, h->ws_sorted.reserve(z.sorted_bytes), "workspace");
+    CUDA_OR_FAIL(h, h->ws_pair_d.reserve(z.pair_d_bytes), "workspace");
+    CUDA_OR_FAIL(h, h->ws_pair_pos.reserve(z.pair_pos_bytes), "workspace");
+    CUDA_OR_FAIL(h, h->ws_pair_cnt.reserve(z.pair_cnt_bytes), "workspace");
+    CUDA_OR_FAIL(h, h->ws_thr.reserve(z.thr_bytes), "workspace");
+
+    Timing& tm = extra(h)->tm;
+    int set = -1;
+    if (h->stats_timing && tm.ok) {
+        set = tm.next;
+        tm.next = (tm.next + 1) % kEventSets;
+        flush_set(h, set);
+        h->ev[2] = tm.ev[set][2];
+        h->ev[3] = tm.ev[set][3];
+        cudaEventRecord(tm.ev[set][0], s);
+    }
+    int launches = 0;
+    int32_t* d_cells = h->ws_cells.as<int32_t>();
+    CUDA_OR_FAIL(h, launch_coarse(h, dQ, nq, w, d_cells, h->ws_dc.p, s, &launches), "coarse kernel");
+    if (set >= 0) cudaEventRecord(tm.ev[set][1], s);
+    const bool timing = h->stats_timing;
+    h->stats_timing = set >= 0;
+    cudaError_t e = launch_search(h, dQ, nq, k, w, d_cells, h->ws_dc.p, d_ids, d_dists, d_keys, d_counts,
+                                  extra(h)->d_scanned, s, &launches);
+    h->stats_timing = timing;
+    CUDA_OR_FAIL(h, e, "scan kernels");
+    if (set >= 0) {
+        cudaEventRecord(tm.ev[set][5], s);
+        tm.pending[set] = 1;
+    }
+    h->stats.gpu_launches += launches;
+    h->stats.queries += nq;
+    return IVFADC_OK;
+}
+
+int search_core(ivfadc_index* h, const void* dQ, int64_t nq, int k, int w, uint64_t* d_ids, void* d_dists,
+                uint64_t* d_keys, int32_t* d_counts, cudaStream_t s) {
+    if (!dQ || !d_ids || !d_dists || !d_counts) return fail(h, IVFADC_ERR_BAD_ARG, "null pointer");
+    if (nq < 0) return fail(h, IVFADC_ERR_BAD_ARG, "nq < 0");
+    if (k < 1) return fail(h, IVFADC_ERR_BAD_ARG, "Number of neighbors must be k >= 1");
+    if (w < 1) return fail(h, IVFADC_ERR_BAD_ARG, "Number of clusters to search in must be w >= 1");
+    w = std::min(w, h->cfg.kc);  // reference src/index.jl:216
+    if (k > scan_max_k()) return fail(h, IVFADC_ERR_UNSUPPORTED, "k > 128 is not supported by the scan kernel yet");
+    if (w > coarse_max_w()) return fail(h, IVFADC_ERR_UNSUPPORTED, "w > 128 is not supported by the coarse kernel yet");
+    if (nq == 0) return IVFADC_OK;
+    h->stats.searches += 1;
+    // bound the per-pair candidate workspace (~512 MB)
+    const size_t per_query = (size_t)w * k * (h->tsize + 4) + 64;
+    int64_t chunk = (int64_t)std::max<size_t>(1, ((size_t)512 << 20) / per_query);
+    chunk = std::min<int64_t>(chunk, (int64_t)1 << 20);
+    for (int64_t q0 = 0; q0 < nq; q0 += chunk) {
+        const int64_t n = std::min(chunk, nq - q0);
+        int rc = search_chunk(h, static_cast<const char*>(dQ) + (size_t)q0 * h->cfg.dim * h->tsize, n, k, w,
+                              d_ids + q0 * k, static_cast<char*>(d_dists) + (size_t)q0 * k * h->tsize,
+                              d_keys ? d_keys + q0 * k : nullptr, d_counts + q0, s);
+        if (rc != IVFADC_OK) return rc;
+    }
+    return IVFADC_OK;
+}
+
+// cells (+ optional codes) of a device-resident batch
+int cells_and_codes(ivfadc_index* h, const void* dX, int64_t n, const int64_t* d_assign, int base,
+                    int32_t* d_cells, uint8_t* d_codes, int* launches) {
+    cudaStream_t s = h->stream;
+    if (d_assign) {
+        CUDA_OR_FAIL(h, launch_assign_to_cells(d_assign, n, base, d_cells, s, launches), "assign kernel");
+    } else {
+        CUDA_OR_FAIL(h, h->ws_dc.reserve(h->tsize * (size_t)n), "workspace");
+        CUDA_OR_FAIL(h, launch_coarse(h, dX, n, 1, d_cells, h->ws_dc.p, s, launches), "coarse kernel");
+    }
+    if (d_codes) CUDA_OR_FAIL(h, launch_encode(h, dX, n, d_cells, d_codes, s, launches), "encode kernel");
+    return IVFADC_OK;
+}
+
+constexpr int64_t kAddChunk = 1 << 20;
+
+}  // namespace
+
+extern "C" {
+
+int ivfadc_abi_version(void) { return IVFADC_ABI_VERSION; }
+
+int ivfadc_device_count(void) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return IVFADC_ERR_CUDA;
+    }
+    return n;
+}
+
+int ivfadc_create(ivfadc_index** out, const ivfadc_config* cfg, const void* centroids,
+                  const void* codebook_vectors, const uint8_t* codebook_codes) {
+    if (!out || !cfg || !centroids || !codebook_vectors || !codebook_codes) return IVFADC_ERR_BAD_ARG;
+    *out = nullptr;
+    if (cfg->dim < 1 || cfg->kc < 1 || cfg->m < 1 || cfg->m > cfg->dim || cfg->ksub < 1) return IVFADC_ERR_BAD_ARG;
+    if (cfg->dtype != IVFADC_F32 && cfg->dtype != IVFADC_F64) return IVFADC_ERR_BAD_ARG;
+    if (cfg->id_bytes != 1 && cfg->id_bytes != 2 && cfg->id_bytes != 4 && cfg->id_bytes != 8)
+        return IVFADC_ERR_UNSUPPORTED;
+    if (cfg->metric_coarse != IVFADC_SQEUCLIDEAN || cfg->metric_resid != IVFADC_SQEUCLIDEAN)
+        return IVFADC_ERR_UNSUPPORTED;
+    if (cfg->ksub > 256) return IVFADC_ERR_UNSUPPORTED;
+    if (cfg->shard_world < 1 || cfg->shard_rank < 0 || cfg->shard_rank >= cfg->shard_world)
+        return IVFADC_ERR_BAD_ARG;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1 || cfg->device < 0 || cfg->device >= ndev) {
+        cudaGetLastError();
+        return IVFADC_ERR_CUDA;  // no CPU fallback
+    }
+    if (cudaSetDevice(cfg->device) != cudaSuccess) return IVFADC_ERR_CUDA;
+
+    ivfadc_index* h = new (std::nothrow) ivfadc_index();
+    if (!h) return IVFADC_ERR_OOM;
+    Extra* x = new (std::nothrow) Extra();
+    if (!x) {
+        delete h;
+        return IVFADC_ERR_OOM;
+    }
+    h->cfg = *cfg;
+    h->dsub = cfg->dim / cfg->m;  // QuantizedArrays.rowrange: floor(D / m)
+    h->tsize = cfg->dtype == IVFADC_F32 ? 4 : 8;
+    h->id_dev_bytes = cfg->id_bytes <= 4 ? 4 : 8;
+    h->stats.reserved[3] = reinterpret_cast<uint64_t>(x);
+
+    const size_t cbytes = (size_t)cfg->kc * cfg->dim * h->tsize;
+    const size_t vbytes = (size_t)cfg->m * cfg->ksub * h->dsub * h->tsize;
+    const size_t kbytes = (size_t)cfg->m * cfg->ksub;
+    bool ok = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) == cudaSuccess;
+    ok = ok && cudaMalloc(&h->d_centroids, cbytes) == cudaSuccess;
+    ok = ok && cudaMalloc(&h->d_cb, vbytes + 16) == cudaSuccess;
+    ok = ok && cudaMalloc(&h->d_cb_codes, kbytes) == cudaSuccess;
+    ok = ok && cudaMalloc(&h->d_cb_norms, kbytes * h->tsize) == cudaSuccess;
+    ok = ok && cudaMalloc(&x->d_scanned, sizeof(uint64_t)) == cudaSuccess;
+    ok = ok && cudaMemset(x->d_scanned, 0, sizeof(uint64_t)) == cudaSuccess;
+    ok = ok && cudaMemcpy(h->d_centroids, centroids, cbytes, cudaMemcpyHostToDevice) == cudaSuccess;
+    ok = ok && cudaMemcpy(h->d_cb, codebook_vectors, vbytes, cudaMemcpyHostToDevice) == cudaSuccess;
+    ok = ok && cudaMemcpy(h->d_cb_codes, codebook_codes, kbytes, cudaMemcpyHostToDevice) == cudaSuccess;
+    ok = ok && lists_init(h) == cudaSuccess;
+    if (ok) {
+        x->tm.ok = true;
+        for (int i = 0; i < kEventSets && x->tm.ok; ++i) {
+            x->tm.pending[i] = 0;
+            for (int j = 0; j < kEventsPerSet; ++j)
+                if (cudaEventCreate(&x->tm.ev[i][j]) != cudaSuccess) x->tm.ok = false;
+        }
+        ok = x->tm.ok;
+    }
+    h->cb_identity = 1;
+    for (int i = 0; i < cfg->m && h->cb_identity; ++i)
+        for (int c = 0; c < cfg->ksub; ++c)
+            if (codebook_codes[(size_t)i * cfg->ksub + c] != (uint8_t)c) {
+                h->cb_identity = 0;
+                break;
+            }
+    int launches = 0;
+    ok = ok && launch_codebook_norms(h, h->stream, &launches) == cudaSuccess;
+    ok = ok && cudaStreamSynchronize(h->stream) == cudaSuccess;
+    std::string why;
+    if (ok && !scan_supported(h, &why)) {
+        ivfadc_destroy(h);
+        return IVFADC_ERR_UNSUPPORTED;
+    }
+    if (!ok) {
+        cudaGetLastError();
+        ivfadc_destroy(h);
+        return IVFADC_ERR_CUDA;
+    }
+    h->stats.gpu_launches += launches;
+    *out = h;
+    return IVFADC_OK;
+}
+
+int ivfadc_destroy(ivfadc_index* h) {
+    if (!h) return IVFADC_OK;
+    cudaSetDevice(h->cfg.device);
+    cudaDeviceSynchronize();
+    Extra* x = extra(h);
+    if (x) {
+        if (x->tm.ok)
+            for (int i = 0; i < kEventSets; ++i)
+                for (int j = 0; j < kEventsPerSet; ++j) cudaEventDestroy(x->tm.ev[i][j]);
+        if (x->d_scanned) cudaFree(x->d_scanned);
+        delete x;
+    }
+    lists_free(h);
+    if (h->d_centroids) cudaFree(h->d_centroids);
+    if (h->d_cb) cudaFree(h->d_cb);
+    if (h->d_cb_codes) cudaFree(h->d_cb_codes);
+    if (h->d_cb_norms) cudaFree(h->d_cb_norms);
+    DevBuf* bufs[] = {&h->ws_q, &h->ws_cells, &h->ws_dc, &h->ws_bucket, &h->ws_sorted, &h->ws_pair_d,
+                      &h->ws_pair_pos, &h->ws_pair_cnt, &h->ws_thr, &h->ws_out_ids, &h->ws_out_d,
+                      &h->ws_out_cnt, &h->ws_out_keys, &h->ws_misc, &h->ws_x, &h->ws_codes, &h->ws_assign,
+                      &h->ws_sort_tmp, &h->ws_sort_keys, &h->ws_sort_vals, &h->ws_del};
+    for (DevBuf* b : bufs) b->release();
+    if (h->stream) cudaStreamDestroy(h->stream);
+    cudaGetLastError();
+    delete h;
+    return IVFADC_OK;
+}
+
+const char* ivfadc_last_error(const ivfadc_index* h) { return h ? h->err.c_str() : "null handle"; }
+
+int ivfadc_add(ivfadc_index* h, const void* X, int64_t n, int32_t position, const int64_t* assign,
+               int32_t assign_base, int32_t* cells_out) {
+    if (check_handle(h)) return IVFADC_ERR_BAD_ARG;
+    if (n < 0 || (n > 0 && !X)) return fail(h, IVFADC_ERR_BAD_ARG, "null data");
+    if (position != IVFADC_LAST && position != IVFADC_FIRST) return fail(h, IVFADC_ERR_BAD_ARG, "bad position");
+    if (n == 0) return IVFADC_OK;
+    cudaSetDevice(h->cfg.device);
+    // reference src/utils.jl:134-135: bits(I) >= log2(N + 1) for every single push
+    if (h->cfg.id_bytes < 8) {
+        const uint64_t capacity = 1ull << (8 * h->cfg.id_bytes);
+        if ((uint64_t)h->n_total + (uint64_t)n > capacity)
+            return fail(h, IVFADC_ERR_CAPACITY, "Cannot index, exceeding index capacity");
+    }
+    const int D = h->cfg.dim, m = h->cfg.m;
+    int launches = 0;
+    if (position == IVFADC_FIRST)
+        CUDA_OR_FAIL(h, lists_shift_ids(h, n, &launches), "shift ids");  // _shift_up_inverse_index!
+    for (int64_t j0 = 0; j0 < n; j0 += kAddChunk) {
+        const int64_t nb = std::min(kAddChunk, n - j0);
+        CUDA_OR_FAIL(h, h->ws_x.reserve((size_t)nb * D * h->tsize), "workspace");
+        CUDA_OR_FAIL(h, h->ws_cells.reserve(sizeof(int32_t) * (size_t)nb), "workspace");
+        CUDA_OR_FAIL(h, h->ws_codes.reserve((size_t)nb * m), "workspace");
+        CUDA_OR_FAIL(h, cudaMemcpyAsync(h->ws_x.p, static_cast<const char*>(X) + (size_t)j0 * D * h->tsize,
+                                        (size_t)nb * D * h->tsize, cudaMemcpyHostToDevice, h->stream), "H2D");
+        const int64_t* d_assign = nullptr;
+        if (assign) {
+            CUDA_OR_FAIL(h, h->ws_assign.reserve(sizeof(int64_t) * (size_t)nb), "workspace");
+            CUDA_OR_FAIL(h, cudaMemcpyAsync(h->ws_assign.p, assign + j0, sizeof(int64_t) * nb,
+                                            cudaMemcpyHostToDevice, h->stream), "H2D");
+            d_assign = h->ws_assign.as<int64_t>();
+        }
+        int32_t* d_cells = h->ws_cells.as<int32_t>();
+        int rc = cells_and_codes(h, h->ws_x.p, nb, d_assign, assign_base, d_cells, h->ws_codes.as<uint8_t>(),
+                                 &launches);
+        if (rc != IVFADC_OK) return rc;
+        if (cells_out)
+            CUDA_OR_FAIL(h, cudaMemcpyAsync(cells_out + j0, d_cells, sizeof(int32_t) * nb, cudaMemcpyDeviceToHost,
+                                            h->stream), "D2H");
+        const uint64_t first_id = position == IVFADC_LAST ? (uint64_t)h->n_total + (uint64_t)j0
+                                                          : (uint64_t)(n - 1 - j0);
+        CUDA_OR_FAIL(h, lists_append(h, d_cells, h->ws_codes.as<uint8_t>(), nb, first_id,
+                                     position == IVFADC_LAST ? 1 : -1, &launches), "append");
+    }
+    h->n_total += n;
+    h->stats.gpu_launches += launches;
+    return IVFADC_OK;
+}
+
+int ivfadc_encode(ivfadc_index* h, const void* X, int64_t n, const int64_t* assign, int32_t assign_base,
+                  int32_t* cells_out, uint8_t* codes_out) {
+    if (check_handle(h)) return IVFADC_ERR_BAD_ARG;
+    if (n < 0 || (n > 0 && (!X || !cells_out || !codes_out))) return fail(h, IVFADC_ERR_BAD_ARG, "null pointer");
+    cudaSetDevice(h->cfg.device);
+    const int D = h->cfg.dim, m = h->cfg.m;
+    int launches = 0;
+    for (int64_t j0 = 0; j0 < n; j0 += kAddChunk) {
+        const int64_t nb = std::min(kAddChunk, n - j0);
+        CUDA_OR_FAIL(h, h->ws_x.reserve((size_t)nb * D * h->tsize), "workspace");
+        CUDA_OR_FAIL(h, h->ws_cells.reserve(sizeof(int32_t) * (size_t)nb), "workspace");
+        CUDA_OR_FAIL(h, h->ws_codes.reserve((size_t)nb * m), "workspace");
+        CUDA_OR_FAIL(h, cudaMemcpyAsync(h->ws_x.p, static_cast<const char*>(X) + (size_t)j0 * D * h->tsize,
+                                        (size_t)nb * D * h->tsize, cudaMemcpyHostToDevice, h->stream), "H2D");
+        const int64_t* d_assign = nullptr;
+        if (assign) {
+            CUDA_OR_FAIL(h, h->ws_assign.reserve(sizeof(int64_t) * (size_t)nb), "workspace");
+            CUDA_OR_FAIL(h, cudaMemcpyAsync(h->ws_assign.p, assign + j0, sizeof(int64_t) * nb,
+                                            cudaMemcpyHostToDevice, h->stream), "H2D");
+            d_assign = h->ws_assign.as<int64_t>();
+        }
+        int rc = cells_and_codes(h, h->ws_x.p, nb, d_assign, assign_base, h->ws_cells.as<int32_t>(),
+                                 h->ws_codes.as<uint8_t>(), &launches);
+        if (rc != IVFADC_OK) return rc;
+        CUDA_OR_FAIL(h, cudaMemcpyAsync(cells_out + j0, h->ws_cells.p, sizeof(int32_t) * nb,
+                                        cudaMemcpyDeviceToHost, h->stream), "D2H");
+        CUDA_OR_FAIL(h, cudaMemcpyAsync(codes_out + (size_t)j0 * m, h->ws_codes.p, (size_t)nb * m,
+                                        cudaMemcpyDeviceToHost, h->stream), "D2H");
+        CUDA_OR_FAIL(h, cudaStreamSynchronize(h->stream), "sync");
+    }
+    h->stats.gpu_launches += launches;
+    return IVFADC_OK;
+}
+
+int ivfadc_coarse_search(ivfadc_index* h, const void* Q, int64_t nq, int32_t w, int32_t* cells_out,
+                         void* dc_out) {
+    if (check_handle(h)) return IVFADC_ERR_BAD_ARG;
+    if (nq < 0 || (nq > 0 && (!Q || !cells_out || !dc_out))) return fail(h, IVFADC_ERR_BAD_ARG, "null pointer");
+    if (w < 1) return fail(h, IVFADC_ERR_BAD_ARG, "w < 1");
+    if (w > h->cfg.kc) return fail(h, IVFADC_ERR_BAD_ARG, "w > kc (clamp before calling)");
+    if (w > coarse_max_w()) return fail(h, IVFADC_ERR_UNSUPPORTED, "w > 128");
+    if (nq == 0) return IVFADC_OK;
+    cudaSetDevice(h->cfg.device);
+    int launches = 0;
+    CUDA_OR_FAIL(h, h->ws_q.reserve((size_t)nq * h->cfg.dim * h->tsize), "workspace");
+    CUDA_OR_FAIL(h, h->ws_cells.reserve(sizeof(int32_t) * (size_t)nq * w), "workspace");
+    CUDA_OR_FAIL(h, h->ws_dc.reserve(h->tsize * (size_t)nq * w), "workspace");
+    CUDA_OR_FAIL(h, cudaMemcpyAsync(h->ws_q.p, Q, (size_t)nq * h->cfg.dim * h->tsize, cudaMemcpyHostToDevice,
+                                    h->stream), "H2D");
+    CUDA_OR_FAIL(h, launch_coarse(h, h->ws_q.p, nq, w, h->ws_cells.as<int32_t>(), h->ws_dc.p, h->stream,
+                                  &launches), "coarse kernel");
+    CUDA_OR_FAIL(h, cudaMemcpyAsync(cells_out, h->ws_cells.p, sizeof(int32_t) * (size_t)nq * w,
+                                    cudaMemcpyDeviceToHost, h->stream), "D2H");
+    CUDA_OR_FAIL(h, cudaMemcpyAsync(dc_out, h->ws_dc.p, h->tsize * (size_t)nq * w, cudaMemcpyDeviceToHost,
+                                    h->stream), "D2H");
+    CUDA_OR_FAIL(h, cudaStreamSynchronize(h->stream), "sync");
+    h->stats.gpu_launches += launches;
+    return IVFADC_OK;
+}
+
+int ivfadc_search(ivfadc_index* h, const void* Q, int64_t nq, int32_t k, int32_t w, uint64_t* ids_out,
+                  void* dists_out, int32_t* counts_out) {
+    if (check_handle(h)) return IVFADC_ERR_BAD_ARG;
+    if (nq > 0 && (!Q || !ids_out || !dists_out || !counts_out)) return fail(h, IVFADC_ERR_BAD_ARG, "null pointer");
+    if (k < 1) return fail(h, IVFADC_ERR_BAD_ARG, "Number of neighbors must be k >= 1");
+    if (w < 1) return fail(h, IVFADC_ERR_BAD_ARG, "Number of clusters to search in must be w >= 1");
+    if (nq <= 0) return nq == 0 ? IVFADC_OK : fail(h, IVFADC_ERR_BAD_ARG, "nq < 0");
+    cudaSetDevice(h->cfg.device);
+    const size_t qbytes = (size_t)nq * h->cfg.dim * h->tsize;
+    CUDA_OR_FAIL(h, h->ws_q.reserve(qbytes), "workspace");
+    CUDA_OR_FAIL(h, h->ws_out_ids.reserve(sizeof(uint64_t) * (size_t)nq * k), "workspace");
+    CUDA_OR_FAIL(h, h->ws_out_d.reserve(h->tsize * (size_t)nq * k), "workspace");
+    CUDA_OR_FAIL(h, h->ws_out_cnt.reserve(sizeof(int32_t) * (size_t)nq), "workspace");
+    CUDA_OR_FAIL(h, cudaMemcpyAsync(h->ws_q.p, Q, qbytes, cudaMemcpyHostToDevice, h->stream), "H2D");
+    int rc = search_core(h, h->ws_q.p, nq, k, w, h->ws_out_ids.as<uint64_t>(), h->ws_out_d.p, nullptr,
+                         h->ws_out_cnt.as<int32_t>(), h->stream);
+    if (rc != IVFADC_OK) return rc;
+    CUDA_OR_FAIL(h, cudaMemcpyAsync(ids_out, h->ws_out_ids.p, sizeof(uint64_t) * (size_t)nq * k,
+                                    cudaMemcpyDeviceToHost, h->stream), "D2H");
+    CUDA_OR_FAIL(h, cudaMemcpyAsync(dists_out, h->ws_out_d.p, h->tsize * (size_t)nq * k, cudaMemcpyDeviceToHost,
+                                    h->stream), "D2H");
+    CUDA_OR_FAIL(h, cudaMemcpyAsync(counts_out, h->ws_out_cnt.p, sizeof(int32_t) * (size_t)nq,
+                                    cudaMemcpyDeviceToHost, h->stream), "D2H");
+    CUDA_OR_FAIL(h, cudaStreamSynchronize(h->stream), "search");
+    return IVFADC_OK;
+}
+
+int ivfadc_search_device(ivfadc_index* h, const void* dQ, int64_t nq, int32_t k, int32_t w, uint64_t* d_ids,
+                         void* d_dists, int32_t* d_counts, void* stream) {
+    if (check_handle(h)) return IVFADC_ERR_BAD_ARG;
+    cudaSetDevice(h->cfg.device);
+    return search_core(h, dQ, nq, k, w, d_ids, d_dists, nullptr, d_counts, static_cast<cudaStream_t>(stream));
+}
+
+int ivfadc_search_local_device(ivfadc_index* h, const void* dQ, int64_t nq, int32_t k, int32_t w,
+                               uint64_t* d_ids, void* d_dists, uint64_t* d_keys, int32_t* d_counts,
+                               void* stream) {
+    if (check_handle(h)) return IVFADC_ERR_BAD_ARG;
+    if (!d_keys) return fail(h, IVFADC_ERR_BAD_ARG, "null keys");
+    cudaSetDevice(h->cfg.device);
+    return search_core(h, dQ, nq, k, w, d_ids, d_dists, d_keys, d_counts, static_cast<cudaStream_t>(stream));
+}
+
+int ivfadc_merge_device(ivfadc_index* h, int32_t parts, int64_t nq, int32_t k, const uint64_t* d_ids_in,
+                        const void* d_dists_in, const uint64_t* d_keys_in, uint64_t* d_ids, void* d_dists,
+                        int32_t* d_counts, void* stream) {
+    if (check_handle(h)) return IVFADC_ERR_BAD_ARG;
+    if (parts < 1 || parts > 128 || k < 1 || nq < 0) return fail(h, IVFADC_ERR_BAD_ARG, "bad merge shape");
+    if (!d_ids_in || !d_dists_in || !d_keys_in || !d_ids || !d_dists || !d_counts)
+        return fail(h, IVFADC_ERR_BAD_ARG, "null pointer");
+    if (nq == 0) return IVFADC_OK;
+    cudaSetDevice(h->cfg.device);
+    int launches = 0;
+    CUDA_OR_FAIL(h, launch_merge_parts(h, parts, nq, k, d_ids_in, d_dists_in, d_keys_in, d_ids, d_dists, d_counts,
+                                       static_cast<cudaStream_t>(stream), &launches), "merge kernel");
+    h->stats.gpu_launches += launches;
+    return IVFADC_OK;
+}
+
+int ivfadc_delete(ivfadc_index* h, const uint64_t* ids, int64_t n) {
+    if (check_handle(h)) return IVFADC_ERR_BAD_ARG;
+    if (n < 0 || (n > 0 && !ids)) return fail(h, IVFADC_ERR_BAD_ARG, "null ids");
+    if (n == 0) return IVFADC_OK;
+    cudaSetDevice(h->cfg.device);
+    // sort(unique(points)) -- reference src/utils.jl:94; ids >= N are unknown and ignored
+    std::vector<uint64_t> v(ids, ids + n);
+    std::sort(v.begin(), v.end());
+    v.erase(std::unique(v.begin(), v.end()), v.end());
+    while (!v.empty() && v.back() >= (uint64_t)h->n_total) v.pop_back();
+    if (v.empty()) return IVFADC_OK;
+    CUDA_OR_FAIL(h, h->ws_del.reserve(sizeof(uint64_t) * v.size()), "workspace");
+    CUDA_OR_FAIL(h, cudaMemcpyAsync(h->ws_del.p, v.data(), sizeof(uint64_t) * v.size(), cudaMemcpyHostToDevice,
+                                    h->stream), "H2D");
+    int launches = 0;
+    int64_t removed = 0;
+    CUDA_OR_FAIL(h, lists_delete(h, h->ws_del.as<uint64_t>(), (int64_t)v.size(), &removed, &launches), "delete");
+    CUDA_OR_FAIL(h, cudaStreamSynchronize(h->stream), "sync");
+    h->n_total -= (int64_t)v.size();  // every id in [0, N) exists exactly once across the shards
+    h->stats.gpu_launches += launches;
+    if (h->cfg.shard_world == 1 && removed != (int64_t)v.size())
+        return fail(h, IVFADC_ERR_CUDA, "internal: id set of the index is not dense");
+    return IVFADC_OK;
+}
+
+int ivfadc_pop(ivfadc_index* h, int32_t position, void* vec_out, int32_t* found_out) {
+    if (check_handle(h)) return IVFADC_ERR_BAD_ARG;
+    if (!vec_out) return fail(h, IVFADC_ERR_BAD_ARG, "null output");
+    if (position != IVFADC_LAST && position != IVFADC_FIRST) return fail(h, IVFADC_ERR_BAD_ARG, "bad position");
+    if (h->n_total <= 0) return fail(h, IVFADC_ERR_EMPTY, "Cannot pop element from empty index");
+    cudaSetDevice(h->cfg.device);
+    const uint64_t vecid = position == IVFADC_LAST ? (uint64_t)h->n_total - 1 : 0;  // src/utils.jl:47
+    int launches = 0;
+    int32_t cell = -1;
+    int64_t pos = -1;
+    CUDA_OR_FAIL(h, lists_find(h, vecid, &cell, &pos, &launches), "find");
+    if (found_out) *found_out = cell >= 0;
+    if (cell >= 0) {
+        CUDA_OR_FAIL(h, h->ws_x.reserve((size_t)h->cfg.dim * h->tsize), "workspace");
+        CUDA_OR_FAIL(h, lists_decode(h, cell, pos, h->ws_x.p, &launches), "decode");
+        CUDA_OR_FAIL(h, cudaMemcpyAsync(vec_out, h->ws_x.p, (size_t)h->cfg.dim * h->tsize, cudaMemcpyDeviceToHost,
+                                        h->stream), "D2H");
+        CUDA_OR_FAIL(h, cudaStreamSynchronize(h->stream), "sync");
+    } else if (h->cfg.shard_world == 1) {
+        return fail(h, IVFADC_ERR_CUDA, "internal: id not found");
+    }
+    h->stats.gpu_launches += launches;
+    return ivfadc_delete(h, &vecid, 1);  // deleteat! + _shift_down_inverse_index! (src/utils.jl:62-66)
+}
+
+int ivfadc_length(const ivfadc_index* h, int64_t* n_out) {
+    if (!h || !n_out) return IVFADC_ERR_BAD_ARG;
+    *n_out = h->n_total;
+    return IVFADC_OK;
+}
+
+int ivfadc_list_sizes(ivfadc_index* h, int64_t* sizes_out) {
+    if (check_handle(h) || !sizes_out) return IVFADC_ERR_BAD_ARG;
+    std::copy(h->h_len.begin(), h->h_len.end(), sizes_out);
+    return IVFADC_OK;
+}
+
+int ivfadc_export_list(ivfadc_index* h, int32_t cell, uint64_t* ids_out, uint8_t* codes_out) {
+    if (check_handle(h)) return IVFADC_ERR_BAD_ARG;
+    if (cell < 0 || cell >= h->cfg.kc) return fail(h, IVFADC_ERR_BAD_ARG, "bad cell");
+    if (h->h_len[cell] > 0 && (!ids_out || !codes_out)) return fail(h, IVFADC_ERR_BAD_ARG, "null pointer");
+    cudaSetDevice(h->cfg.device);
+    CUDA_OR_FAIL(h, lists_export(h, cell, ids_out, codes_out), "export");
+    return IVFADC_OK;
+}
+
+int ivfadc_import_list(ivfadc_index* h, int32_t cell, const uint64_t* ids, const uint8_t* codes, int64_t len) {
+    if (check_handle(h)) return IVFADC_ERR_BAD_ARG;
+    if (cell < 0 || cell >= h->cfg.kc || len < 0) return fail(h, IVFADC_ERR_BAD_ARG, "bad cell / length");
+    if (len > 0 && (!ids || !codes)) return fail(h, IVFADC_ERR_BAD_ARG, "null pointer");
+    cudaSetDevice(h->cfg.device);
+    int launches = 0;
+    CUDA_OR_FAIL(h, lists_import(h, cell, ids, codes, len, &launches), "import");
+    h->stats.gpu_launches += launches;
+    return IVFADC_OK;
+}
+
+int ivfadc_export_quantizers(ivfadc_index* h, void* centroids_out, void* codebook_vectors_out,
+                             uint8_t* codebook_codes_out) {
+    if (check_handle(h)) return IVFADC_ERR_BAD_ARG;
+    cudaSetDevice(h->cfg.device);
+    const ivfadc_config& c = h->cfg;
+    if (centroids_out)
+        CUDA_OR_FAIL(h, cudaMemcpy(centroids_out, h->d_centroids, (size_t)c.kc * c.dim * h->tsize,
+                                   cudaMemcpyDeviceToHost), "D2H");
+    if (codebook_vectors_out)
+        CUDA_OR_FAIL(h, cudaMemcpy(codebook_vectors_out, h->d_cb, (size_t)c.m * c.ksub * h->dsub * h->tsize,
+                                   cudaMemcpyDeviceToHost), "D2H");
+    if (codebook_codes_out)
+        CUDA_OR_FAIL(h, cudaMemcpy(codebook_codes_out, h->d_cb_codes, (size_t)c.m * c.ksub,
+                                   cudaMemcpyDeviceToHost), "D2H");
+    return IVFADC_OK;
+}
+
+int ivfadc_set_length(ivfadc_index* h, int64_t n_total) {
+    if (check_handle(h) || n_total < 0) return IVFADC_ERR_BAD_ARG;
+    h->n_total = n_total;
+    return IVFADC_OK;
+}
+
+int ivfadc_get_stats(ivfadc_index* h, ivfadc_stats* out) {
+    if (check_handle(h) || !out) return IVFADC_ERR_BAD_ARG;
+    cudaSetDevice(h->cfg.device);
+    flush_all(h);
+    Extra* x = extra(h);
+    uint64_t scanned = 0;
+    if (cudaMemcpy(&scanned, x->d_scanned, sizeof(uint64_t), cudaMemcpyDeviceToHost) == cudaSuccess) {
+        h->stats.scanned_vectors = scanned;
+        h->stats.scan_code_bytes = scanned * (uint64_t)h->cfg.m;
+    }
+    *out = h->stats;
+    out->reserved[3] = 0;
+    return IVFADC_OK;
+}
+
+int ivfadc_reset_stats(ivfadc_index* h) {
+    if (check_handle(h)) return IVFADC_ERR_BAD_ARG;
+    cudaSetDevice(h->cfg.device);
+    flush_all(h);
+    const uint64_t keep = h->stats.reserved[3];
+    h->stats = ivfadc_stats{};
+    h->stats.reserved[3] = keep;
+    cudaMemset(extra(h)->d_scanned, 0, sizeof(uint64_t));
+    return IVFADC_OK;
+}
+
+}  // extern "C"

