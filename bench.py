@@ -1,0 +1,354 @@
+#!/usr/bin/env python
+"""Benchmark of the IVFADC hot path: batched knn_search QPS (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload B]
+
+A "step" is one batched knn_search of the whole query batch (10 000 queries, k = 10, nprobe = 16)
+over the SIFT1M-shaped synthetic index (128-d, 1M vectors, kc = 1024, m = 16, 256 codewords).
+  value  queries/s with the query batch already resident in HBM (CUDA events on the launch stream,
+         L2 flushed between steps, max over ranks);
+  e2e    queries/s through the public host API (ivfadc_search on pinned host buffers: H2D of the
+         queries and D2H of ids/distances/counts inside the timed region);
+  roofline  list-scan kernel: algorithmic PQ-code bytes per launch / its CUDA-event time, against
+         the measured HBM copy bandwidth (MEASURED_PEAKS.json);
+  cpu_baseline  the C restatement of the reference's CPU path (oracle/, Julia is not available in
+         this image) on the box's host cores over a bounded sample of the same queries.
+N > 1 (torchrun, one rank per GPU): inverted lists sharded by cell, one NCCL all-gather of the
+per-rank top-k candidates per step, merge kernel; total work is fixed -> "strong" scaling.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: D, N, kc, m, ksub, nq, k, w
+    "B": dict(name="SIFT1M-shaped synthetic: 128-d, 1M vectors, kc=1024, m=16, k=256, 10k-query batch, nprobe=16, k=10",
+              D=128, N=1_000_000, kc=1024, m=16, ksub=256, nq=10_000, k=10, w=16),
+    "C": dict(name="Deep10M-shaped synthetic: 96-d, 10M vectors, kc=4096, m=12, SqEuclidean",
+              D=96, N=10_000_000, kc=4096, m=12, ksub=256, nq=10_000, k=10, w=16),
+    "S": dict(name="small smoke workload (not a bench line)",
+              D=64, N=100_000, kc=128, m=16, ksub=256, nq=2_000, k=10, w=8),
+}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index=0):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self.reasons = set()
+        self._halt = threading.Event()
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self._halt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
+                f = [x.strip() for x in out.strip().split(",")]
+                self.samples.append((float(f[0]), float(f[1])))
+                for n, v in zip(names, f[2:]):
+                    if v.lower().startswith("active"):
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            self._halt.wait(0.2)
+
+    def stop(self):
+        self._halt.set()
+        self.join(timeout=6)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        sm = sorted(s[0] for s in self.samples)
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.samples[0][1], "reasons": sorted(self.reasons),
+                "samples": len(sm)}
+
+
+def make_inputs(wl, seed=1002):
+    from ivfadc_jl_b200 import synth
+    X = synth.blobs(wl["N"], wl["D"], wl["kc"], seed=seed)
+    Q = synth.blobs(wl["nq"], wl["D"], wl["kc"], seed=2001)
+    return X, Q
+
+
+def cpu_reference_qps(qz, offsets, codes, ids, Q, k, w, nthreads, budget_s=12.0):
+    """Time the oracle (C restatement of the reference's CPU path) on a bounded sample."""
+    from oracle import oracle as orc
+    n0 = min(len(Q), 64 * nthreads)
+    t = time.perf_counter()
+    orc.search_csr(qz, offsets, codes, ids, Q[:n0], k, w, nthreads=nthreads)
+    dt = time.perf_counter() - t
+    n1 = int(min(len(Q), max(n0, n0 * budget_s / max(dt, 1e-6))))
+    t = time.perf_counter()
+    orc.search_csr(qz, offsets, codes, ids, Q[:n1], k, w, nthreads=nthreads)
+    dt = time.perf_counter() - t
+    return n1 / dt, n1, dt
+
+
+def export_csr(engine):
+    sizes = engine.list_sizes()
+    offsets = np.zeros(len(sizes) + 1, dtype=np.int64)
+    np.cumsum(sizes, out=offsets[1:])
+    ids = np.empty(int(offsets[-1]), dtype=np.uint64)
+    codes = np.empty((int(offsets[-1]), engine.m), dtype=np.uint8)
+    for c in range(len(sizes)):
+        if sizes[c]:
+            i, cd = engine.export_list(c)
+            ids[offsets[c]:offsets[c + 1]] = i
+            codes[offsets[c]:offsets[c + 1]] = cd
+    return offsets, codes, ids
+
+
+def run_reference(args, wl):
+    """--impl reference: the reference's CPU algorithm (oracle port; Julia unavailable) on the host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import oracle as orc
+    from ivfadc_jl_b200 import synth
+    nthreads = os.cpu_count() or 1
+    # a bounded index: the oracle's CPU cost per query depends on list length, so keep the full
+    # list length (N / kc) but only as many cells as a ~minute-long build allows
+    X, Q = make_inputs(wl)
+    cent, cb, codes = synth.random_quantizers(wl["kc"], wl["D"], wl["m"], wl["ksub"], seed=5, data=X)
+    qz = orc.Quantizers(cent, cb, codes)
+    # Index contents for the timing harness: cells by a BLAS nearest-centroid pass, PQ codes uniform
+    # random -- the cost of the timed search depends on list lengths, not on code values.
+    t0 = time.perf_counter()
+    cells = np.empty(wl["N"], dtype=np.int64)
+    cn = (cent.astype(np.float64) ** 2).sum(1)
+    for s0 in range(0, wl["N"], 1 << 16):
+        xb = X[s0:s0 + (1 << 16)]
+        cells[s0:s0 + (1 << 16)] = (cn[None, :] - 2.0 * (xb @ cent.T)).argmin(1)
+    ocodes = np.random.default_rng(7).integers(0, wl["ksub"], size=(wl["N"], wl["m"]), dtype=np.uint8)
+    enc_s = time.perf_counter() - t0
+    order = np.argsort(cells, kind="stable")
+    offsets = np.zeros(wl["kc"] + 1, dtype=np.int64)
+    np.cumsum(np.bincount(cells, minlength=wl["kc"]), out=offsets[1:])
+    codes_csr, ids_csr = ocodes[order], order.astype(np.uint64)
+    per_step = max(64, min(wl["nq"], 2000))
+    vals = []
+    for s in range(args.warmup + args.steps):
+        t = time.perf_counter()
+        orc.search_csr(qz, offsets, codes_csr, ids_csr, Q[:per_step], wl["k"], wl["w"], nthreads=nthreads)
+        dt = time.perf_counter() - t
+        if s >= args.warmup:
+            vals.append(dt)
+    ms = 1e3 * sum(vals) / len(vals)
+    qps = per_step / (ms / 1e3)
+    sample = f"{per_step} of {wl['nq']} queries per step on the full index; index fill (BLAS assignment, random codes) {enc_s:.1f}s untimed"
+    line = {"impl": "reference", "metric": "knn_search QPS (batch 10k, k=10, nprobe=16)", "value": qps,
+            "unit": "queries/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": wl["name"], "note": "C restatement of IVFADC.jl's CPU path (Julia is not "
+                       "installed in this image); real Julia would be slower (LittleDict / SortedMultiDict)"},
+            "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": nthreads, "kind": "port", "sample": sample},
+            "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="B", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--check", type=int, default=256, help="queries verified against the oracle")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    wl = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        return run_reference(args, wl)
+
+    import torch
+    import ivfadc_jl_b200 as iv
+    from ivfadc_jl_b200 import sharded, synth
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the engine has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    t0 = time.perf_counter()
+    X, Q = make_inputs(wl)
+    # rank 0 trains (torch on the GPU: plumbing, outside the hot path) and broadcasts
+    if rank == 0:
+        cent, cb = synth.train_on_device(X, wl["kc"], wl["m"], wl["ksub"])
+        tc, tb = torch.from_numpy(cent).to(dev), torch.from_numpy(cb).to(dev)
+    else:
+        tc = torch.empty((wl["kc"], wl["D"]), dtype=torch.float32, device=dev)
+        tb = torch.empty((wl["m"], wl["ksub"], wl["D"] // wl["m"]), dtype=torch.float32, device=dev)
+    if world > 1:
+        dist.broadcast(tc, 0)
+        dist.broadcast(tb, 0)
+    cent, cb = tc.cpu().numpy(), tb.cpu().numpy()
+    prep_s = time.perf_counter() - t0
+
+    engine = iv.IVFADCIndex.from_quantizers(cent, cb, None, index_type=np.uint32, device=local_rank,
+                                            shard=(rank, world))
+    t0 = time.perf_counter()
+    iv.push_batch(engine, X)
+    build_s = time.perf_counter() - t0
+    nq, k, w, D = wl["nq"], wl["k"], wl["w"], wl["D"]
+
+    dQ = torch.from_numpy(Q).to(dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    searcher = sharded.ShardedSearcher(sharded.CudaShardEngine(engine)) if world > 1 else None
+
+    def step_device():
+        if world > 1:
+            return searcher.search(dQ, k, w)
+        return sharded.search_device(engine, dQ, k, w)
+
+    # ---- device-resident timing -------------------------------------------------------------
+    for _ in range(args.warmup):
+        flush.zero_()
+        out = step_device()
+    torch.cuda.synchronize()
+    engine.stats(reset=True)
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    torch.cuda.synchronize()
+    for a, b in evs:
+        flush.zero_()
+        a.record()
+        out = step_device()
+        b.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    dev_ms = sum(a.elapsed_time(b) for a, b in evs) / args.steps
+    st = engine.stats()
+    clocks = sampler.stop()
+    if world > 1:
+        t = torch.tensor([dev_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_ms = float(t.item())
+
+    # ---- end to end through the host API (pinned host buffers) -------------------------------
+    e2e = None
+    if world == 1:
+        hQ = torch.from_numpy(Q).pin_memory()
+        h_ids = torch.empty((nq, k), dtype=torch.int64).pin_memory()
+        h_d = torch.empty((nq, k), dtype=torch.float32).pin_memory()
+        h_c = torch.empty((nq,), dtype=torch.int32).pin_memory()
+        lib, h = engine._lib, engine._h
+        import ctypes
+
+        def step_host():
+            rc = lib.ivfadc_search(h, ctypes.c_void_p(hQ.data_ptr()), nq, k, w, ctypes.c_void_p(h_ids.data_ptr()),
+                                   ctypes.c_void_p(h_d.data_ptr()), ctypes.c_void_p(h_c.data_ptr()))
+            assert rc == 0
+        for _ in range(args.warmup):
+            step_host()
+        ts = []
+        for _ in range(args.steps):
+            flush.zero_()
+            torch.cuda.synchronize()
+            t = time.perf_counter()
+            step_host()  # synchronous: H2D + kernels + D2H
+            ts.append(time.perf_counter() - t)
+        e2e_ms = 1e3 * sum(ts) / len(ts)
+        e2e = {"value": nq / (e2e_ms / 1e3), "unit": "queries/s", "ms_per_step": e2e_ms,
+               "h2d_bytes_per_step": int(nq * D * 4), "d2h_bytes_per_step": int(nq * k * 12 + nq * 4)}
+
+    # ---- parity spot check + CPU baseline (rank 0, N = 1) -------------------------------------
+    cpu = None
+    parity = None
+    if rank == 0 and world == 1:
+        from oracle import oracle as orc
+        qz = orc.Quantizers(cent, cb, None)
+        offsets, codes_csr, ids_csr = export_csr(engine)
+        nchk = min(args.check, nq)
+        if nchk:
+            oi, od, oc, _ = orc.search_csr(qz, offsets, codes_csr, ids_csr, Q[:nchk], k, w, nthreads=os.cpu_count())
+            gi = out[0][:nchk].cpu().numpy().view(np.uint64)
+            gd = out[1][:nchk].cpu().numpy()
+            parity = {"queries": nchk, "ids_equal": bool(np.array_equal(gi, oi)),
+                      "dists_bit_equal": bool(np.array_equal(gd.view(np.uint8), od.view(np.uint8)))}
+        if not args.no_cpu_baseline:
+            nth = os.cpu_count() or 1
+            qps1, n1, dt1 = cpu_reference_qps(qz, offsets, codes_csr, ids_csr, Q, k, w, 1, budget_s=8.0)
+            qpsN, nN, dtN = cpu_reference_qps(qz, offsets, codes_csr, ids_csr, Q, k, w, nth, budget_s=12.0)
+            cpu = {"value": qpsN, "unit": "queries/s", "cores": nth, "kind": "port",
+                   "sample": f"{nN} of {nq} queries, full index, {dtN:.1f}s; single thread: {qps1:.0f} q/s on {n1} queries",
+                   "single_thread_value": qps1}
+
+    if rank == 0:
+        peak, peak_src = measured_peaks()
+        scan_ms = st["scan_ms"] / max(1, st["scan_launches"])
+        bytes_per_launch = st["scan_code_bytes"] / max(1, st["scan_launches"])
+        achieved = bytes_per_launch / (scan_ms * 1e-3) / 1e9 if scan_ms > 0 else 0.0
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "scan_dram_traffic.json")
+        if os.path.exists(tp):
+            traffic = json.load(open(tp)).get(args.workload)
+        qps = nq / (dev_ms / 1e3)
+        line = {
+            "metric": "knn_search QPS (batch 10k, k=10, nprobe=16)", "value": qps, "unit": "queries/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": wl["name"], "nq": nq, "k": k, "nprobe": w, "lists": "cell-sharded" if world > 1 else "one GPU",
+                       "l2": "flushed between steps (256 MiB write); the 16 MB code array is L2-resident within a step",
+                       "timing": "CUDA events on the launch stream, per step, mean"},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": traffic, "kernel": "scan_kernel (K2+K3)",
+                         "algorithmic_bytes_per_launch": bytes_per_launch, "kernel_ms": scan_ms,
+                         "peak_source": peak_src,
+                         "per_rank": world > 1},
+            "cpu_baseline": cpu,
+            "e2e": e2e,
+            "gpu_launches": int(st["gpu_launches"]),
+            "clocks": clocks,
+            "breakdown_ms": {"coarse": st["coarse_ms"] / args.steps, "plan": st["plan_ms"] / args.steps,
+                             "scan": st["scan_ms"] / args.steps, "merge": st["merge_ms"] / args.steps},
+            "build": {"vectors": wl["N"], "seconds": build_s, "vectors_per_s": wl["N"] / build_s, "prep_s": prep_s},
+            "parity": parity,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    engine.close()
+
+
+if __name__ == "__main__":
+    main()

@@ -123,10 +123,13 @@ class ShardedSearcher:
         ids, dists, keys = self.engine.search_local(Q, k, w)
         if self.world == 1:
             return self.engine.merge(ids[None], dists[None], keys[None], k)
-        ids_all = torch.empty((self.world,) + tuple(ids.shape), dtype=ids.dtype, device=ids.device)
-        dists_all = torch.empty((self.world,) + tuple(dists.shape), dtype=dists.dtype, device=ids.device)
-        keys_all = torch.empty((self.world,) + tuple(keys.shape), dtype=keys.dtype, device=ids.device)
+        nq = ids.shape[0]
+        # rank-major concatenation along dim 0 == [world, nq, k] (the layout ivfadc_merge_device takes)
+        ids_all = torch.empty((self.world * nq, k), dtype=ids.dtype, device=ids.device)
+        dists_all = torch.empty((self.world * nq, k), dtype=dists.dtype, device=ids.device)
+        keys_all = torch.empty((self.world * nq, k), dtype=keys.dtype, device=ids.device)
         self.dist.all_gather_into_tensor(ids_all, ids.contiguous(), group=self.group)
         self.dist.all_gather_into_tensor(dists_all, dists.contiguous(), group=self.group)
         self.dist.all_gather_into_tensor(keys_all, keys.contiguous(), group=self.group)
-        return self.engine.merge(ids_all, dists_all, keys_all, k)
+        shape = (self.world, nq, k)
+        return self.engine.merge(ids_all.view(shape), dists_all.view(shape), keys_all.view(shape), k)
