@@ -133,7 +133,8 @@ def run_reference(args, wl):
     # a bounded index: the oracle's CPU cost per query depends on list length, so keep the full
     # list length (N / kc) but only as many cells as a ~minute-long build allows
     X, Q = make_inputs(wl)
-    cent, cb, codes = synth.random_quantizers(wl["kc"], wl["D"], wl["m"], wl["ksub"], seed=5, data=X)
+    cent, cb, codes = synth.random_quantizers(wl["kc"], wl["D"], wl["m"], wl["ksub"], seed=5)
+    cent = synth.blob_centres(wl["D"], wl["kc"])  # the (balanced) cells the GPU arm trains to
     qz = orc.Quantizers(cent, cb, codes)
     # Index contents for the timing harness: cells by a BLAS nearest-centroid pass, PQ codes uniform
     # random -- the cost of the timed search depends on list lengths, not on code values.
@@ -207,7 +208,8 @@ def main():
     X, Q = make_inputs(wl)
     # rank 0 trains (torch on the GPU: plumbing, outside the hot path) and broadcasts
     if rank == 0:
-        cent, cb = synth.train_on_device(X, wl["kc"], wl["m"], wl["ksub"])
+        cent, cb = synth.train_on_device(X, wl["kc"], wl["m"], wl["ksub"],
+                                         init=synth.blob_centres(wl["D"], wl["kc"]))
         tc, tb = torch.from_numpy(cent).to(dev), torch.from_numpy(cb).to(dev)
     else:
         tc = torch.empty((wl["kc"], wl["D"]), dtype=torch.float32, device=dev)

@@ -41,10 +41,18 @@ def random_quantizers(kc: int, D: int, m: int, ksub: int, seed: int, dtype=np.fl
     return centroids, cb, codes
 
 
+def blob_centres(D: int, n_blobs: int, dtype=np.float32, centre_seed: int = 1001):
+    """The mixture centres `blobs` draws around (same generator, same seed)."""
+    return np.random.default_rng(centre_seed).random((n_blobs, D)).astype(dtype)
+
+
 def train_on_device(X, kc: int, m: int, ksub: int, seed: int = 3001, iters: int = 8,
-                    sample: int = 262144):
+                    sample: int = 262144, init=None):
     """Benchmark trainer: Lloyd on the GPU through torch (plumbing; training is outside the hot
-    path).  X: numpy [n, D].  Returns numpy centroids [kc, D], codebooks [m, ksub, dsub]."""
+    path).  X: numpy [n, D].  `init` (optional [kc, D]) seeds the coarse Lloyd iterations -- the
+    benchmark passes the mixture centres, which makes the cells the (balanced) blobs, as a
+    converged k-means on this data would.  Returns numpy centroids [kc, D], codebooks
+    [m, ksub, dsub]."""
     import torch
 
     from .training import kmeans_torch
@@ -54,7 +62,7 @@ def train_on_device(X, kc: int, m: int, ksub: int, seed: int = 3001, iters: int 
     rng = np.random.default_rng(seed)
     sel = rng.choice(n, min(n, max(sample, 64 * kc)), replace=False)
     xs = torch.from_numpy(np.ascontiguousarray(X[sel])).to(dev).float()
-    cent = kmeans_torch(xs, kc, iters, seed)
+    cent = kmeans_torch(xs, kc, iters, seed, init=None if init is None else torch.from_numpy(init).to(dev))
     a = torch.empty(xs.shape[0], dtype=torch.long, device=dev)
     cn = (cent ** 2).sum(1)
     for s in range(0, xs.shape[0], 1 << 16):
