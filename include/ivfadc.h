@@ -54,6 +54,15 @@ extern "C" {
 #define IVFADC_LAST  0
 #define IVFADC_FIRST 1
 
+/*
+ * ivfadc_config.flags.  The list scan has two kernels with identical results: the
+ * query-per-lane kernel (32 queries of one list per CTA; large batches, fp32, k <= 16) and the
+ * general vector-per-lane kernel (any T, k <= 128, any batch).  By default the engine picks per
+ * batch; the flags pin the choice (parity tests exercise both).
+ */
+#define IVFADC_FLAG_SCAN_LEGACY 1   /* always the vector-per-lane kernel                          */
+#define IVFADC_FLAG_SCAN_QLANE  2   /* the query-per-lane kernel whenever the shape allows it     */
+
 typedef struct ivfadc_index ivfadc_index;   /* opaque, owns all device memory */
 
 typedef struct ivfadc_config {
@@ -68,7 +77,7 @@ typedef struct ivfadc_config {
     int32_t device;         /* CUDA device ordinal                                                */
     int32_t shard_rank;     /* this handle keeps only cells with cell % shard_world == shard_rank */
     int32_t shard_world;    /* 1 = unsharded                                                      */
-    int32_t reserved;
+    int32_t flags;          /* 0 = defaults; IVFADC_FLAG_* tuning / test switches                 */
 } ivfadc_config;
 
 typedef struct ivfadc_stats {

@@ -18,6 +18,7 @@ ERR_BAD_ARG, ERR_CAPACITY, ERR_CUDA, ERR_OOM, ERR_UNSUPPORTED, ERR_EMPTY = -1, -
 F32, F64 = 0, 1
 SQEUCLIDEAN = 0
 LAST, FIRST = 0, 1
+FLAG_SCAN_LEGACY, FLAG_SCAN_QLANE = 1, 2
 
 # every symbol include/ivfadc.h declares (tests check that the library exports all of them)
 SYMBOLS = [
@@ -32,7 +33,7 @@ SYMBOLS = [
 class Config(ctypes.Structure):
     _fields_ = [(n, c_int32) for n in (
         "dim", "kc", "m", "ksub", "dtype", "id_bytes", "metric_coarse", "metric_resid", "device",
-        "shard_rank", "shard_world", "reserved")]
+        "shard_rank", "shard_world", "flags")]
 
 
 class Stats(ctypes.Structure):

@@ -1,5 +1,6 @@
 // Search planning, the scan launcher, and the final merges.  See scan_impl.cuh for K2/K3.
 #include "scan_impl.cuh"
+#include "scanq_impl.cuh"
 
 namespace ivf {
 
@@ -12,7 +13,7 @@ namespace {
 // ---------------------------------------------------------------------------------------------
 template <typename BitsT>
 __global__ void plan_count_kernel(const int32_t* __restrict__ cells, int64_t npairs, int64_t nq, int w,
-                                  int kc, const int64_t* __restrict__ list_len, int* bucket_cnt,
+                                  int kc, int split, const int64_t* __restrict__ list_len, int* bucket_cnt,
                                   BitsT* thr, BitsT inf_bits, unsigned long long* scanned) {
     const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     unsigned long long mylen = 0;
@@ -22,7 +23,7 @@ __global__ void plan_count_kernel(const int32_t* __restrict__ cells, int64_t npa
         const int64_t len = (cell >= 0 && cell < kc) ? list_len[cell] : 0;
         if (len > 0) {
             const int rank = (int)(p % w);
-            atomicAdd(&bucket_cnt[(rank ? kc : 0) + cell], 1);
+            atomicAdd(&bucket_cnt[((split && rank) ? kc : 0) + cell], 1);
             mylen = (unsigned long long)len;
         }
     }
@@ -71,14 +72,14 @@ plan_scan_kernel(const int* __restrict__ bucket_cnt, int nb, int qn, int* bucket
 }
 
 __global__ void plan_scatter_kernel(const int32_t* __restrict__ cells, int64_t npairs, int w, int kc,
-                                    const int64_t* __restrict__ list_len,
+                                    int split, const int64_t* __restrict__ list_len,
                                     const int* __restrict__ bucket_off, int* cursor,
                                     int32_t* sorted_pairs) {
     const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= npairs) return;
     const int cell = cells[p];
     if (cell < 0 || cell >= kc || list_len[cell] <= 0) return;
-    const int b = ((p % w) ? kc : 0) + cell;
+    const int b = ((split && (p % w)) ? kc : 0) + cell;
     const int slot = bucket_off[b] + atomicAdd(&cursor[b], 1);
     sorted_pairs[slot] = (int32_t)p;
 }
@@ -302,28 +303,68 @@ int choose_qn_h(const ivfadc_index* h, int k) {
                                       : choose_qn<double>(h->cfg.m, h->dsub, k);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Query-per-lane path (scanq_impl.cuh): fp32, k <= 16, m in {4, 8, 12, 16}
+// ---------------------------------------------------------------------------------------------
+constexpr int kQLdw = 32;
+
+bool scanq_shape_ok(const ivfadc_index* h, int k) {
+    const int m = h->cfg.m;
+    if (h->cfg.dtype != IVFADC_F32 || k > QMAXK || m % QCS != 0 || m > 16 || h->cfg.ksub > 256) return false;
+    return scanq_smem_layout(m, h->dsub, kQLdw).total <= kSmemMax;
+}
+
+// Which kernel serves this batch.  flags (ivfadc_config.flags): IVFADC_FLAG_SCAN_LEGACY forces the
+// vector-per-lane kernel, IVFADC_FLAG_SCAN_QLANE forces the query-per-lane kernel whenever the
+// shape allows it; otherwise the query-per-lane kernel is used when its 32-query groups are
+// reasonably full (>= 8 probes per list on average).
+bool use_scanq(const ivfadc_index* h, int64_t npairs, int k) {
+    if (h->cfg.flags & IVFADC_FLAG_SCAN_LEGACY) return false;
+    if (!scanq_shape_ok(h, k)) return false;
+    if (h->cfg.flags & IVFADC_FLAG_SCAN_QLANE) return true;
+    return npairs >= (int64_t)8 * h->cfg.kc;
+}
+
+template <typename T, int MC>
+cudaError_t launch_redo_r(const ScanArgs<T>& a, const int32_t* redo_pairs, const int* redo_cnt, int grid,
+                          size_t smem, cudaStream_t s) {
+    auto kern = scan_redo_kernel<T, MC, 1>;
+    static size_t configured = 0;
+    if (smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured = smem;
+    }
+    kern<<<grid, STHREADS, smem, s>>>(a, redo_pairs, redo_cnt);
+    return cudaGetLastError();
+}
+
 template <typename T>
 cudaError_t search_t(ivfadc_index* h, const void* dQ, int64_t nq, int k, int w, const int32_t* d_cells,
                      const void* d_dc, uint64_t* d_ids, void* d_dists, uint64_t* d_keys,
                      int32_t* d_counts, uint64_t* d_scanned, cudaStream_t s, int* launches) {
     typedef typename Limits<T>::bits_t bits_t;
-    const int kc = h->cfg.kc, nb = 2 * kc;
+    const int kc = h->cfg.kc;
     const int64_t npairs = nq * w;
-    const int qn = choose_qn<T>(h->cfg.m, h->dsub, k);
+    const bool qlane = use_scanq(h, npairs, k);
+    const int nb = qlane ? kc : 2 * kc;
+    const int qn = qlane ? QG : choose_qn<T>(h->cfg.m, h->dsub, k);
     cudaError_t e;
 
     // workspaces (sizes validated / reserved by the caller through scan_plan_sizes)
-    int* bucket_cnt = h->ws_bucket.as<int>();  // [nb] counts | [nb] cursor | [nb+1] off | [nb+1] groups
-    int* cursor = bucket_cnt + nb;
-    int* bucket_off = cursor + nb;
-    int* group_off = bucket_off + nb + 1;
+    int* bucket_cnt = h->ws_bucket.as<int>();  // [2kc] counts | [2kc] cursor | [2kc+1] off | [2kc+1] groups | redo_cnt
+    int* cursor = bucket_cnt + 2 * kc;
+    int* bucket_off = cursor + 2 * kc;
+    int* group_off = bucket_off + 2 * kc + 1;
+    int* redo_cnt = group_off + 2 * kc + 1;
     int32_t* sorted_pairs = h->ws_sorted.as<int32_t>();
+    int32_t* redo_pairs = sorted_pairs + npairs;
     T* pair_d = h->ws_pair_d.as<T>();
     uint32_t* pair_pos = h->ws_pair_pos.as<uint32_t>();
     int32_t* pair_cnt = h->ws_pair_cnt.as<int32_t>();
     bits_t* thr = h->ws_thr.as<bits_t>();
 
-    if ((e = cudaMemsetAsync(bucket_cnt, 0, sizeof(int) * 2 * nb, s)) != cudaSuccess) return e;
+    if ((e = cudaMemsetAsync(bucket_cnt, 0, sizeof(int) * (size_t)(8 * kc + 3), s)) != cudaSuccess) return e;
     if ((e = cudaMemsetAsync(pair_cnt, 0, sizeof(int32_t) * npairs, s)) != cudaSuccess) return e;
 
     const int pthreads = 256;
@@ -331,10 +372,11 @@ cudaError_t search_t(ivfadc_index* h, const void* dQ, int64_t nq, int k, int w, 
     T inf = Limits<T>::inf();
     bits_t inf_bits;
     memcpy(&inf_bits, &inf, sizeof(T));
-    plan_count_kernel<bits_t><<<pgrid, pthreads, 0, s>>>(d_cells, npairs, nq, w, kc, h->d_len, bucket_cnt, thr,
-                                                         inf_bits, (unsigned long long*)d_scanned);
+    const int split = qlane ? 0 : 1;
+    plan_count_kernel<bits_t><<<pgrid, pthreads, 0, s>>>(d_cells, npairs, nq, w, kc, split, h->d_len, bucket_cnt,
+                                                         thr, inf_bits, (unsigned long long*)d_scanned);
     plan_scan_kernel<<<1, 1024, 0, s>>>(bucket_cnt, nb, qn, bucket_off, group_off);
-    plan_scatter_kernel<<<pgrid, pthreads, 0, s>>>(d_cells, npairs, w, kc, h->d_len, bucket_off, cursor,
+    plan_scatter_kernel<<<pgrid, pthreads, 0, s>>>(d_cells, npairs, w, kc, split, h->d_len, bucket_off, cursor,
                                                    sorted_pairs);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     *launches += 3;
@@ -348,20 +390,53 @@ cudaError_t search_t(ivfadc_index* h, const void* dQ, int64_t nq, int k, int w, 
     a.D = h->cfg.dim; a.m = h->cfg.m; a.dsub = h->dsub; a.ksub = h->cfg.ksub; a.kc = kc; a.w = w; a.k = k;
     a.list_off = h->d_off; a.list_len = h->d_len; a.codes = h->d_codes;
     a.cells = d_cells; a.dc = static_cast<const T*>(d_dc);
-    a.bucket_off = bucket_off; a.group_off = group_off; a.sorted_pairs = sorted_pairs;
+    a.bucket_off = bucket_off; a.group_off = group_off; a.nb = nb; a.sorted_pairs = sorted_pairs;
     a.pair_d = pair_d; a.pair_pos = pair_pos; a.pair_cnt = pair_cnt; a.thr = thr;
 
     // upper bound on the number of work items: every bucket adds at most one partial group
     int64_t max_items = std::min<int64_t>(npairs, npairs / qn + nb);
     if (max_items < 1) max_items = 1;
-    const size_t smem = smem_for<T>(qn, h->cfg.m, h->dsub, k);
     if (h->stats_timing) cudaEventRecord(h->ev[2], s);
-    if (qn == 4) e = launch_scan_m<T, 4>(a, (int)max_items, smem, s);
-    else if (qn == 2) e = launch_scan_m<T, 2>(a, (int)max_items, smem, s);
-    else e = launch_scan_m<T, 1>(a, (int)max_items, smem, s);
-    if (e != cudaSuccess) return e;
+    if (qlane) {
+        if constexpr (sizeof(T) == 4) {
+            ScanQArgs qa;
+            qa.Q = a.Q; qa.C = a.C; qa.cb = a.cb; qa.cb_codes = a.cb_codes; qa.cb_identity = a.cb_identity;
+            qa.D = a.D; qa.m = a.m; qa.dsub = a.dsub; qa.ksub = a.ksub; qa.kc = kc; qa.w = w; qa.k = k;
+            qa.list_off = a.list_off; qa.list_len = a.list_len; qa.codes = a.codes; qa.dc = a.dc;
+            qa.bucket_off = bucket_off; qa.group_off = group_off; qa.sorted_pairs = sorted_pairs;
+            qa.pair_d = pair_d; qa.pair_pos = pair_pos; qa.pair_cnt = pair_cnt;
+            qa.redo_pairs = redo_pairs; qa.redo_cnt = redo_cnt;
+            const size_t qsmem = scanq_smem_layout(a.m, a.dsub, kQLdw).total;
+            auto kern = scanq_kernel<kQLdw>;
+            static size_t configured = 0;
+            if (qsmem > configured) {
+                e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)qsmem);
+                if (e != cudaSuccess) return e;
+                configured = qsmem;
+            }
+            kern<<<(unsigned)max_items, QTHREADS, qsmem, s>>>(qa);
+            if ((e = cudaGetLastError()) != cudaSuccess) return e;
+            // pairs whose candidate list overflowed (heavy ties): general kernel, one pair per item
+            const size_t rsmem = smem_for<T>(1, h->cfg.m, h->dsub, k);
+            const int rgrid = 2 * 148;
+            switch (a.m) {
+                case 8: e = launch_redo_r<T, 8>(a, redo_pairs, redo_cnt, rgrid, rsmem, s); break;
+                case 12: e = launch_redo_r<T, 12>(a, redo_pairs, redo_cnt, rgrid, rsmem, s); break;
+                case 16: e = launch_redo_r<T, 16>(a, redo_pairs, redo_cnt, rgrid, rsmem, s); break;
+                default: e = launch_redo_r<T, 0>(a, redo_pairs, redo_cnt, rgrid, rsmem, s); break;
+            }
+            if (e != cudaSuccess) return e;
+            *launches += 2;
+        }
+    } else {
+        const size_t smem = smem_for<T>(qn, h->cfg.m, h->dsub, k);
+        if (qn == 4) e = launch_scan_m<T, 4>(a, (int)max_items, smem, s);
+        else if (qn == 2) e = launch_scan_m<T, 2>(a, (int)max_items, smem, s);
+        else e = launch_scan_m<T, 1>(a, (int)max_items, smem, s);
+        if (e != cudaSuccess) return e;
+        *launches += 1;
+    }
     if (h->stats_timing) cudaEventRecord(h->ev[3], s);
-    *launches += 1;
 
     const unsigned mgrid = (unsigned)((nq + 3) / 4);
     if (h->id_dev_bytes == 4)
@@ -396,8 +471,8 @@ ScanPlanSizes scan_plan_sizes(const ivfadc_index* h, int64_t nq, int w, int k) {
     ScanPlanSizes z;
     const int64_t npairs = nq * w;
     const int nb = 2 * h->cfg.kc;
-    z.bucket_bytes = sizeof(int) * (size_t)(4 * nb + 2);
-    z.sorted_bytes = sizeof(int32_t) * (size_t)npairs;
+    z.bucket_bytes = sizeof(int) * (size_t)(4 * nb + 3);
+    z.sorted_bytes = sizeof(int32_t) * (size_t)npairs * 2;  // sorted pairs | redo queue
     z.pair_d_bytes = h->tsize * (size_t)npairs * k;
     z.pair_pos_bytes = sizeof(uint32_t) * (size_t)npairs * k;
     z.pair_cnt_bytes = sizeof(int32_t) * (size_t)npairs;

@@ -40,6 +40,7 @@ template <typename T> struct ScanArgs {
     const T* dc;                // [nq][w]
     const int* bucket_off;      // [2kc+1] pairs
     const int* group_off;       // [2kc+1] work items
+    int nb;                     // number of buckets (2kc: probe rank 0 / ranks >= 1 per list)
     const int32_t* sorted_pairs;
     // outputs per pair
     T* pair_d;                  // [npairs][k]
@@ -215,32 +216,16 @@ template <typename T, int QN, int MC> struct CodeScan {
     }
 };
 
+// One work item: list `cell` x the nj (<= QN) pairs pairs[0..nj).  Called by every thread of the CTA.
 template <typename T, int QN, int MC, int R>
-__global__ void __launch_bounds__(STHREADS)
-scan_kernel(const ScanArgs<T> a) {
+__device__ __forceinline__ void scan_item(const ScanArgs<T>& a, const int cell, const int32_t* pairs,
+                                          const int nj, unsigned char* smem_raw) {
     typedef typename Limits<T>::bits_t bits_t;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const int wid = tid >> 5;
-    const int nb = 2 * a.kc;
     const int m = MC > 0 ? MC : a.m;
     const int k = a.k;
-
-    // ---- work item -> (bucket, group) : last bucket with group_off[b] <= item ----
-    const int item = blockIdx.x;
-    if (item >= a.group_off[nb]) return;
-    int lo = 0, hi = nb;  // invariant: group_off[lo] <= item < group_off[hi]
-    while (hi - lo > 1) {
-        const int mid = (lo + hi) >> 1;
-        if (a.group_off[mid] <= item) lo = mid; else hi = mid;
-    }
-    const int b = lo;
-    const int cell = b >= a.kc ? b - a.kc : b;
-    const int g = item - a.group_off[b];
-    const int first = a.bucket_off[b] + g * QN;
-    const int nj = min(QN, a.bucket_off[b + 1] - first);
 
     const int Dp = m * a.dsub;
     // shared memory carve-up: 128-byte header | tables | residuals ; the merge area later
@@ -252,7 +237,7 @@ scan_kernel(const ScanArgs<T> a) {
     T* resid = lut + (size_t)m * 256 * QN;
 
     if (tid < QN) {
-        const int p = tid < nj ? a.sorted_pairs[first + tid] : -1;
+        const int p = tid < nj ? pairs[tid] : -1;
         s_pair[tid] = p;
         s_dc[tid] = p >= 0 ? a.dc[p] : (T)0;
         // latest published bound of this query (other CTAs update it with atomicMin)
@@ -382,6 +367,43 @@ scan_kernel(const ScanArgs<T> a) {
             // a full list bounds the query's k-th distance for every CTA that starts later
             if (mine == k) atomicMin(a.thr + pair / a.w, to_bits(kv));
         }
+    }
+}
+
+
+template <typename T, int QN, int MC, int R>
+__global__ void __launch_bounds__(STHREADS)
+scan_kernel(const ScanArgs<T> a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int nb = a.nb;
+    // ---- work item -> (bucket, group) : last bucket with group_off[b] <= item ----
+    const int item = blockIdx.x;
+    if (item >= a.group_off[nb]) return;
+    int lo = 0, hi = nb;  // invariant: group_off[lo] <= item < group_off[hi]
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (a.group_off[mid] <= item) lo = mid; else hi = mid;
+    }
+    const int b = lo;
+    const int cell = b >= a.kc ? b - a.kc : b;
+    const int g = item - a.group_off[b];
+    const int first = a.bucket_off[b] + g * QN;
+    const int nj = min(QN, a.bucket_off[b + 1] - first);
+    scan_item<T, QN, MC, R>(a, cell, a.sorted_pairs + first, nj, smem_raw);
+}
+
+// The (query, list) pairs the query-per-lane kernel could not finish (candidate overflow under
+// heavy distance ties): a persistent grid walks the redo queue, one pair per work item.
+template <typename T, int MC, int R>
+__global__ void __launch_bounds__(STHREADS)
+scan_redo_kernel(const ScanArgs<T> a, const int32_t* __restrict__ redo_pairs,
+                 const int* __restrict__ redo_cnt) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int n = *redo_cnt;
+    for (int i = blockIdx.x; i < n; i += gridDim.x) {
+        const int pair = redo_pairs[i];
+        scan_item<T, 1, MC, R>(a, a.cells[pair], redo_pairs + i, 1, smem_raw);
+        __syncthreads();
     }
 }
 

@@ -61,7 +61,7 @@ class IVFADCIndex:
                  quantization_method=DEFAULT_QUANTIZATION_METHOD,
                  coarse_maxiter=DEFAULT_COARSE_MAXITER,
                  quantization_maxiter=DEFAULT_QUANTIZATION_MAXITER, index_type=np.uint32,
-                 device=0, seed=0, shard=(0, 1)):
+                 device=0, seed=0, shard=(0, 1), flags=0):
         data = np.asarray(data)
         _dtype_code(data.dtype)
         nrows, nvectors = data.shape
@@ -83,7 +83,7 @@ class IVFADCIndex:
         centroids, assign, cb_vectors, cb_codes = training.train_quantizers(
             X, kc, k, m, coarse_maxiter, quantization_maxiter, seed)
         self._init_from_quantizers(centroids, cb_vectors, cb_codes, index_type, coarse_quantizer,
-                                   coarse_distance, quantization_distance, device, shard)
+                                   coarse_distance, quantization_distance, device, shard, flags)
         # _build_residuals + _build_inverted_index (src/index.jl:168-194): k-means' own
         # assignments, ids ascending per list
         self._add(X, _capi.LAST, assign=assign, assign_base=0)
@@ -91,7 +91,7 @@ class IVFADCIndex:
     @classmethod
     def from_quantizers(cls, centroids, cb_vectors, cb_codes=None, *, index_type=np.uint32,
                         coarse_quantizer="naive", coarse_distance="SqEuclidean",
-                        quantization_distance="SqEuclidean", device=0, shard=(0, 1)):
+                        quantization_distance="SqEuclidean", device=0, shard=(0, 1), flags=0):
         """An empty index around trained quantizers: centroids [kc, D], cb_vectors [m, k, dsub],
         cb_codes uint8 [m, k] (default 0..k-1).  What the Julia glue does after training."""
         self = cls.__new__(cls)
@@ -101,11 +101,11 @@ class IVFADCIndex:
             cb_codes = np.tile(np.arange(cb_vectors.shape[1], dtype=np.uint8), (cb_vectors.shape[0], 1))
         self._init_from_quantizers(centroids, cb_vectors, np.ascontiguousarray(cb_codes, dtype=np.uint8),
                                    np.dtype(index_type), coarse_quantizer, coarse_distance,
-                                   quantization_distance, device, shard)
+                                   quantization_distance, device, shard, flags)
         return self
 
     def _init_from_quantizers(self, centroids, cb_vectors, cb_codes, index_type, coarse_quantizer,
-                              coarse_distance, quantization_distance, device, shard):
+                              coarse_distance, quantization_distance, device, shard, flags=0):
         if str(coarse_distance) != "SqEuclidean" or str(quantization_distance) != "SqEuclidean":
             raise NotImplementedError("only SqEuclidean is on the hot path (SURVEY 8f-3)")
         self.T = centroids.dtype
@@ -119,7 +119,7 @@ class IVFADCIndex:
         cfg = _capi.Config(dim=self.nrows, kc=self.kc, m=self.m, ksub=self.k,
                            dtype=_dtype_code(self.T), id_bytes=self.I.itemsize,
                            metric_coarse=_capi.SQEUCLIDEAN, metric_resid=_capi.SQEUCLIDEAN,
-                           device=device, shard_rank=shard[0], shard_world=shard[1], reserved=0)
+                           device=device, shard_rank=shard[0], shard_world=shard[1], flags=int(flags))
         h = ctypes.c_void_p()
         rc = self._lib.ivfadc_create(ctypes.byref(h), ctypes.byref(cfg), _capi.ptr(centroids),
                                      _capi.ptr(cb_vectors), _capi.ptr(cb_codes))

@@ -16,9 +16,12 @@ pytestmark = pytest.mark.gpu
 RTOL = 1e-5  # the tolerance north_star states for ADC distances (we assert exact equality too)
 
 
-def engine_from(qz, id_type=np.uint32, X=None, assign=None, shard=(0, 1)):
+LEGACY, QLANE = 1, 2  # ivfadc_config.flags: pin the list-scan kernel (include/ivfadc.h)
+
+
+def engine_from(qz, id_type=np.uint32, X=None, assign=None, shard=(0, 1), flags=0):
     e = iv.IVFADCIndex.from_quantizers(qz.centroids, qz.cb_vectors, qz.cb_codes, index_type=id_type,
-                                       shard=shard)
+                                       shard=shard, flags=flags)
     if X is not None:
         e._add(X, 0, assign=assign, assign_base=0)
     return e
@@ -205,6 +208,60 @@ def test_search_ties_and_duplicates():
     for k, w in ((10, 3), (30, 8), (100, 2)):
         assert_search_equal(e, oidx, Q, k, w)
     e.close()
+
+
+# ------------------------------------------------------------------------------------------------
+# K2 + K3, query-per-lane kernel (large batches): same bit-exact bar, pinned with QLANE
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("D,m,ksub,kc,n,nq,k,w,identity", [
+    (128, 16, 256, 64, 20000, 500, 10, 16, True),    # config-B-shaped: ~125 queries per list
+    (96, 12, 256, 128, 30000, 300, 10, 16, True),    # config-C-shaped (m = 12: 3 table chunks)
+    (128, 8, 256, 32, 20000, 300, 10, 8, True),      # config-D-shaped (m = 8, dsub = 16)
+    (128, 16, 256, 8, 20000, 100, 16, 8, True),      # 2500-vector lists: 3 passes of 1024, k = 16
+    (40, 8, 100, 16, 5000, 200, 1, 4, False),        # dsub = 5 (generic), ksub < 256, permuted codes, k = 1
+    (35, 4, 37, 50, 3000, 77, 7, 50, False),         # trailing dims ignored, tiny lists, w = kc
+    (64, 16, 256, 700, 3000, 40, 10, 3, True),       # mostly empty / 1-2 vector lists, nearly empty groups
+])
+def test_search_qlane_bit_exact(D, m, ksub, kc, n, nq, k, w, identity):
+    from ivfadc_jl_b200 import synth
+    X = synth.blobs(n, D, kc, seed=21)
+    cent, cb, codes = synth.random_quantizers(kc, D, m, ksub, seed=6, data=X)
+    if not identity:  # code VALUE -> table entry (Q6): values are a random subset of 0..255
+        prng = np.random.default_rng(3)
+        codes = np.stack([prng.permutation(256)[:ksub].astype(np.uint8) for _ in range(m)])
+    qz = orc.Quantizers(cent, cb, codes)
+    cells, ocodes = orc.encode(qz, X, nthreads=8)
+    order = np.argsort(cells, kind="stable")
+    offsets = np.zeros(kc + 1, dtype=np.int64)
+    np.cumsum(np.bincount(cells, minlength=kc), out=offsets[1:])
+    Q = synth.blobs(nq, D, kc, seed=22)
+    oi, od, oc, scanned = orc.search_csr(qz, offsets, ocodes[order], order.astype(np.uint64), Q, k, w, nthreads=8)
+    for flags in (QLANE, LEGACY):
+        e = engine_from(qz, np.uint32, X, flags=flags)
+        gi, gd, gc = e.search_packed(Q, k, w)
+        np.testing.assert_array_equal(gc, oc, err_msg=f"flags={flags}")
+        assert np.array_equal(gd.view(np.uint8), od.view(np.uint8)), f"flags={flags}"
+        np.testing.assert_array_equal(gi, oi, err_msg=f"flags={flags}")
+        e.close()
+
+
+def test_search_qlane_ties_overflow_redo():
+    """Hundreds of identical database vectors nearest to the query: more candidates tie at the
+    k-th-distance bound than the 64 shared-memory slots hold, so the query-per-lane kernel must
+    hand those (query, list) pairs to the general kernel (redo queue) -- same answer, in the
+    reference's (distance, probe rank, position) order."""
+    rng = np.random.default_rng(9)
+    base = rng.random((30, 32)).astype(np.float32)
+    X = np.concatenate([np.repeat(base[:3], 300, axis=0), np.repeat(base[3:], 20, axis=0)])
+    rng.shuffle(X)
+    data = np.ascontiguousarray(X.T)
+    oidx, qz, assign, Xc = helpers.build_oracle_index(data, kc=4, k=16, m=8, seed=1)
+    Q = np.concatenate([base, rng.random((34, 32)).astype(np.float32)])
+    for flags in (QLANE, 0):
+        e = engine_from(qz, np.uint32, Xc, assign, flags=flags)
+        for k, w in ((10, 2), (16, 4), (1, 1)):
+            assert_search_equal(e, oidx, Q, k, w)
+        e.close()
 
 
 # ------------------------------------------------------------------------------------------------
