@@ -182,6 +182,7 @@ def main():
     ap.add_argument("--workload", default="B", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--check", type=int, default=256, help="queries verified against the oracle")
+    ap.add_argument("--flags", type=int, default=0, help="ivfadc_config.flags (1 legacy scan, 2 qlane scan, 4 exact tables)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     wl = WORKLOADS[args.workload]
@@ -221,7 +222,7 @@ def main():
     prep_s = time.perf_counter() - t0
 
     engine = iv.IVFADCIndex.from_quantizers(cent, cb, None, index_type=np.uint32, device=local_rank,
-                                            shard=(rank, world))
+                                            shard=(rank, world), flags=args.flags)
     t0 = time.perf_counter()
     iv.push_batch(engine, X)
     build_s = time.perf_counter() - t0
@@ -303,8 +304,13 @@ def main():
             oi, od, oc, _ = orc.search_csr(qz, offsets, codes_csr, ids_csr, Q[:nchk], k, w, nthreads=os.cpu_count())
             gi = out[0][:nchk].cpu().numpy().view(np.uint64)
             gd = out[1][:nchk].cpu().numpy()
-            parity = {"queries": nchk, "ids_equal": bool(np.array_equal(gi, oi)),
-                      "dists_bit_equal": bool(np.array_equal(gd.view(np.uint8), od.view(np.uint8)))}
+            gcn = out[2][:nchk].cpu().numpy()
+            parity = {"queries": nchk, "rtol": 1e-5}
+            try:
+                parity.update(orc.compare_search(gi, gd, gcn, oi, od, oc, rtol=1e-5))
+                parity["ok"] = True
+            except AssertionError as ex:
+                parity.update({"ok": False, "error": str(ex)[:200]})
         if not args.no_cpu_baseline:
             nth = os.cpu_count() or 1
             qps1, n1, dt1 = cpu_reference_qps(qz, offsets, codes_csr, ids_csr, Q, k, w, 1, budget_s=8.0)
@@ -330,7 +336,8 @@ def main():
             "data": "synthetic",
             "config": {"workload": wl["name"], "nq": nq, "k": k, "nprobe": w, "lists": "cell-sharded" if world > 1 else "one GPU",
                        "l2": "flushed between steps (256 MiB write); the 16 MB code array is L2-resident within a step",
-                       "timing": "CUDA events on the launch stream, per step, mean"},
+                       "timing": "CUDA events on the launch stream, per step, mean", "flags": args.flags,
+                       "tables": "exact direct form (fp32 chain)" if (args.flags & 5) else "tensor-core 3xTF32 GEMM form"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "kernel": "scan_kernel (K2+K3)",
                          "algorithmic_bytes_per_launch": bytes_per_launch, "kernel_ms": scan_ms,

@@ -62,6 +62,15 @@ extern "C" {
  */
 #define IVFADC_FLAG_SCAN_LEGACY 1   /* always the vector-per-lane kernel                          */
 #define IVFADC_FLAG_SCAN_QLANE  2   /* the query-per-lane kernel whenever the shape allows it     */
+/*
+ * The query-per-lane kernel builds its lookup tables on the tensor cores by default (GEMM form
+ * |w|^2 - 2 r.w, 3xTF32, fp32 accumulate): returned distances agree with the reference's direct
+ * form to ~1e-6 relative (bound 1e-5), neighbour ids except at such near-ties.  With
+ * IVFADC_FLAG_LUT_EXACT it evaluates the reference's direct form as a sequential fp32 chain and
+ * every distance is bit-identical to the CPU restatement, at roughly half the throughput.  The
+ * vector-per-lane kernel is always exact.
+ */
+#define IVFADC_FLAG_LUT_EXACT   4
 
 typedef struct ivfadc_index ivfadc_index;   /* opaque, owns all device memory */
 

@@ -236,6 +236,7 @@ int ivfadc_create(ivfadc_index** out, const ivfadc_config* cfg, const void* cent
             }
     int launches = 0;
     ok = ok && launch_codebook_norms(h, h->stream, &launches) == cudaSuccess;
+    ok = ok && scanq_prepare(h, h->stream, &launches) == cudaSuccess;
     ok = ok && cudaStreamSynchronize(h->stream) == cudaSuccess;
     std::string why;
     if (ok && !scan_supported(h, &why)) {
@@ -269,6 +270,8 @@ int ivfadc_destroy(ivfadc_index* h) {
     if (h->d_cb) cudaFree(h->d_cb);
     if (h->d_cb_codes) cudaFree(h->d_cb_codes);
     if (h->d_cb_norms) cudaFree(h->d_cb_norms);
+    if (h->d_afrag) cudaFree(h->d_afrag);
+    if (h->d_wnfrag) cudaFree(h->d_wnfrag);
     DevBuf* bufs[] = {&h->ws_q, &h->ws_cells, &h->ws_dc, &h->ws_bucket, &h->ws_sorted, &h->ws_pair_d,
                       &h->ws_pair_pos, &h->ws_pair_cnt, &h->ws_thr, &h->ws_out_ids, &h->ws_out_d,
                       &h->ws_out_cnt, &h->ws_out_keys, &h->ws_misc, &h->ws_x, &h->ws_codes, &h->ws_assign,

@@ -107,6 +107,9 @@ struct ivfadc_index {
     uint8_t* d_cb_codes = nullptr;  // uint8[m][ksub]
     void* d_cb_norms = nullptr;     // T[m][ksub]  squared norms of the codewords (oracle A2)
     int cb_identity = 0;            // codes[i][c] == c for all i, c
+    void* d_afrag = nullptr;        // codebook as mma A fragments (scanq FAST table builder)
+    void* d_wnfrag = nullptr;
+    int frag_ntiles = 0, frag_ksteps = 0;
 
     // inverted lists: device-resident CSR with slack.  List c occupies entries
     // [off[c], off[c] + len[c]) of the arenas, capacity cap[c]; off[c] is a multiple of 16 so
@@ -145,6 +148,7 @@ struct ScanPlanSizes {
     size_t bucket_bytes, sorted_bytes, pair_d_bytes, pair_pos_bytes, pair_cnt_bytes, thr_bytes;
 };
 int scan_max_k();
+cudaError_t scanq_prepare(ivfadc_index* h, cudaStream_t s, int* launches);
 bool scan_supported(const ivfadc_index* h, std::string* why);
 ScanPlanSizes scan_plan_sizes(const ivfadc_index* h, int64_t nq, int w, int k);
 // K2+K3: plan, fused LUT build + list scan + per-pair top-k, then per-query merge.

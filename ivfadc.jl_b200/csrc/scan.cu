@@ -306,12 +306,12 @@ int choose_qn_h(const ivfadc_index* h, int k) {
 // ---------------------------------------------------------------------------------------------
 // Query-per-lane path (scanq_impl.cuh): fp32, k <= 16, m in {4, 8, 12, 16}
 // ---------------------------------------------------------------------------------------------
-constexpr int kQLdw = 32;
+bool scanq_fast(const ivfadc_index* h) { return !(h->cfg.flags & IVFADC_FLAG_LUT_EXACT) && h->d_afrag; }
 
 bool scanq_shape_ok(const ivfadc_index* h, int k) {
     const int m = h->cfg.m;
     if (h->cfg.dtype != IVFADC_F32 || k > QMAXK || m % QCS != 0 || m > 16 || h->cfg.ksub > 256) return false;
-    return scanq_smem_layout(m, h->dsub, kQLdw).total <= kSmemMax;
+    return scanq_smem_layout(m, h->dsub, scanq_fast(h)).total <= kSmemMax;
 }
 
 // Which kernel serves this batch.  flags (ivfadc_config.flags): IVFADC_FLAG_SCAN_LEGACY forces the
@@ -406,15 +406,20 @@ cudaError_t search_t(ivfadc_index* h, const void* dQ, int64_t nq, int k, int w, 
             qa.bucket_off = bucket_off; qa.group_off = group_off; qa.sorted_pairs = sorted_pairs;
             qa.pair_d = pair_d; qa.pair_pos = pair_pos; qa.pair_cnt = pair_cnt;
             qa.redo_pairs = redo_pairs; qa.redo_cnt = redo_cnt;
-            const size_t qsmem = scanq_smem_layout(a.m, a.dsub, kQLdw).total;
-            auto kern = scanq_kernel<kQLdw>;
-            static size_t configured = 0;
-            if (qsmem > configured) {
-                e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)qsmem);
+            const bool fast = scanq_fast(h);
+            qa.afrag = static_cast<const float4*>(h->d_afrag);
+            qa.wnfrag = static_cast<const float2*>(h->d_wnfrag);
+            qa.ntiles = h->frag_ntiles; qa.ksteps = h->frag_ksteps;
+            const size_t qsmem = scanq_smem_layout(a.m, a.dsub, fast).total;
+            static size_t configured[2] = {0, 0};
+            if (qsmem > configured[fast]) {
+                e = fast ? cudaFuncSetAttribute(scanq_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)qsmem)
+                         : cudaFuncSetAttribute(scanq_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)qsmem);
                 if (e != cudaSuccess) return e;
-                configured = qsmem;
+                configured[fast] = qsmem;
             }
-            kern<<<(unsigned)max_items, QTHREADS, qsmem, s>>>(qa);
+            if (fast) scanq_kernel<true><<<(unsigned)max_items, QTHREADS, qsmem, s>>>(qa);
+            else scanq_kernel<false><<<(unsigned)max_items, QTHREADS, qsmem, s>>>(qa);
             if ((e = cudaGetLastError()) != cudaSuccess) return e;
             // pairs whose candidate list overflowed (heavy ties): general kernel, one pair per item
             const size_t rsmem = smem_for<T>(1, h->cfg.m, h->dsub, k);
@@ -454,6 +459,26 @@ cudaError_t search_t(ivfadc_index* h, const void* dQ, int64_t nq, int k, int w, 
 }  // namespace
 
 int scan_max_k() { return 128; }
+
+// Once at create: the codebook as tensor-core operand fragments for the FAST table builder.
+cudaError_t scanq_prepare(ivfadc_index* h, cudaStream_t s, int* launches) {
+    const int m = h->cfg.m;
+    if (h->cfg.dtype != IVFADC_F32 || m % QCS != 0 || m > 16 || h->cfg.ksub > 256) return cudaSuccess;
+    h->frag_ntiles = (h->cfg.ksub + 15) / 16;
+    h->frag_ksteps = (h->dsub + 7) / 8;
+    const size_t tiles = (size_t)m * h->frag_ntiles;
+    cudaError_t e = cudaMalloc(&h->d_afrag, tiles * h->frag_ksteps * 32 * 2 * sizeof(float4));
+    if (e != cudaSuccess) return e;
+    e = cudaMalloc(&h->d_wnfrag, tiles * 32 * sizeof(float2));
+    if (e != cudaSuccess) return e;
+    const int n = (int)tiles * 32;
+    prep_frags_kernel<<<(n + 127) / 128, 128, 0, s>>>(static_cast<const float*>(h->d_cb), m, h->cfg.ksub, h->dsub,
+                                                     h->frag_ntiles, h->frag_ksteps,
+                                                     static_cast<float4*>(h->d_afrag),
+                                                     static_cast<float2*>(h->d_wnfrag));
+    if (launches) *launches += 1;
+    return cudaGetLastError();
+}
 
 bool scan_supported(const ivfadc_index* h, std::string* why) {
     if (h->cfg.ksub > 256 || h->cfg.ksub < 1) {

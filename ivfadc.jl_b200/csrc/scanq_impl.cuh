@@ -8,15 +8,19 @@
 //   * the PQ code byte of a (vector, subspace) is warp-uniform and the lookup
 //     lut[subspace][code][lane] is one conflict-free 128-byte shared-memory wavefront: 32 lookups
 //     per LDS, the shared-memory peak (vs. ~2.6-way bank conflicts of the vector-per-lane layout);
-//   * every lane adds the table entries of ITS query in subspace order 1..m, so each distance is
-//     the same sequential chain  ((dc + l_1) + l_2) + ...  as the reference (src/index.jl:242-246)
-//     and the oracle (A3): results are bit-identical.
+//   * every lane adds the table entries of ITS query in subspace order 1..m, i.e. the sequential
+//     chain of the reference (src/index.jl:242-246).
 // A 32-query table is m*256*32*4 B (512 KB for m = 16) and cannot live in shared memory at once:
 // the subspaces are processed in chunks of 4 (128 KB), the 64 partial sums per lane stay in
 // registers across chunks.
 //
-//   K2  per chunk: lut[il][code][q] = sum_d (w_icd - r_qd)^2, r = q - centroid
-//       (src/index.jl:232-236; subspace 0 additionally carries dc = first addition of the chain);
+//   K2  per chunk, two interchangeable builders of lut[il][code][q]:
+//       EXACT  direct form  sum_d (w_icd - r_qd)^2  as one sequential fma chain per entry, subspace 0
+//              carrying dc: every returned distance is bit-identical to the oracle (A1, A3);
+//       FAST   GEMM form  |w|^2 - 2 r.w  on the tensor cores (mma.sync m16n8k8, 3xTF32 split:
+//              hi*hi + hi*lo + lo*hi, fp32 accumulate), the per-query constant dc + |r|^2 seeds the
+//              accumulators; error <= ~1e-6 relative to the returned distance, inside
+//              the 1e-5 the north_star allows.  This is the default for large batches.
 //   K3  per chunk: stream the list's code words (staged once per pass into per-chunk planes),
 //       gather-add;
 //   top-k per (query, list): k-th smallest of the 16 per-warp minima bounds the k-th distance,
@@ -58,6 +62,10 @@ struct ScanQArgs {
     int32_t* pair_cnt;           // [npairs]
     int32_t* redo_pairs;         // [npairs]
     int* redo_cnt;
+    // FAST builder: codebook pre-split into mma A fragments (see prep_frags_kernel)
+    const float4* afrag;         // [m][ntiles][ksteps][32 lanes][2]  hi(a0..a3), lo(a0..a3) of -2w
+    const float2* wnfrag;        // [m][ntiles][32 lanes]             |w|^2 of rows g, g+8
+    int ntiles, ksteps;
 };
 
 // Table chunk layout (bytes): subspace il of the chunk, code value c, query q live at
@@ -75,23 +83,30 @@ struct ScanQSmem {
     size_t lut, resid, planes, cand_d, cand_p, smin, misc, total;
 };
 
-__host__ __device__ inline ScanQSmem scanq_smem_layout(int m, int dsub, int ldw) {
+// resid: EXACT -> one [Dp][33] fp32 array; FAST -> two (tf32 hi | lo)
+__host__ __device__ inline ScanQSmem scanq_smem_layout(int m, int dsub, bool fast) {
     ScanQSmem s;
     size_t o = 0;
     s.lut = o;    o += (size_t)QCS * 256 * 32 * 4;
-    s.resid = o;  o += (size_t)m * dsub * QRS * 4;
+    s.resid = o;  o += (size_t)m * dsub * QRS * 4 * (fast ? 2 : 1);
     o = (o + 15) & ~(size_t)15;
     s.planes = o; o += (size_t)(m / QCS) * QPLANE * 4;
     s.cand_d = o; o += (size_t)QG * QCAP * 4;
     s.cand_p = o; o += (size_t)QG * QCAP * 4;
-    s.smin = o;   o += (size_t)QWARPS * QG * 4;
+    s.smin = o;   o += (size_t)QWARPS * QG * 4;   // per-warp minima; FAST also uses it for |r|^2 partials
     s.misc = o;   o += 6 * QG * 4;
     s.total = o;
     return s;
 }
 
-// ---- K2 (exact): direct-form table chunk, one sequential fma chain per entry (oracle A1) --------
-template <int DSUB, int LDW>
+__device__ __forceinline__ uint32_t to_tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return r;
+}
+
+// ---- K2 (EXACT): direct-form table chunk, one sequential fma chain per entry (oracle A1) --------
+template <int DSUB, bool IDENT>
 __device__ __forceinline__ void build_chunk_exact(const ScanQArgs& a, float* lut, const float* resid_t,
                                                   const float* s_dc, int c) {
     const int lane = threadIdx.x & 31;
@@ -109,13 +124,17 @@ __device__ __forceinline__ void build_chunk_exact(const ScanQArgs& a, float* lut
         const float* rq = resid_t + (size_t)i * dsub * QRS + lane;
         const float dc0 = i == 0 ? s_dc[lane] : 0.f;
         char* lrow = reinterpret_cast<char*>(lut) + lut_off(il, 0) + lane * 4;
+        const uint8_t* cvp = a.cb_codes + (size_t)i * a.ksub;
         if constexpr (DSUB > 0) {
             float r[DSUB > 0 ? DSUB : 1];
 #pragma unroll
             for (int d = 0; d < DSUB; ++d) r[d] = rq[d * QRS];
+            const float* wbase = a.cb + ((size_t)i * a.ksub + lo) * DSUB;
+            char* lptr = lrow + lo * 256;
+            const int n = hi - lo;
 #pragma unroll 4
-            for (int code = lo; code < hi; ++code) {
-                const float* wv = a.cb + ((size_t)i * a.ksub + code) * DSUB;
+            for (int x = 0; x < n; ++x) {
+                const float* wv = wbase + x * DSUB;
                 float wreg[DSUB > 0 ? DSUB : 1];
                 if constexpr (DSUB % 4 == 0) {
 #pragma unroll
@@ -134,8 +153,8 @@ __device__ __forceinline__ void build_chunk_exact(const ScanQArgs& a, float* lut
                     s = fma_rn(diff, diff, s);
                 }
                 if (i == 0) s = add_rn(dc0, s);  // d = dc; d += l_1
-                const int cv = a.cb_identity ? code : (int)a.cb_codes[(size_t)i * a.ksub + code];
-                *reinterpret_cast<float*>(lrow + cv * 256) = s;
+                if constexpr (IDENT) *reinterpret_cast<float*>(lptr + x * 256) = s;
+                else *reinterpret_cast<float*>(lrow + (int)cvp[lo + x] * 256) = s;
             }
         } else {
             for (int code = lo; code < hi; ++code) {
@@ -146,38 +165,147 @@ __device__ __forceinline__ void build_chunk_exact(const ScanQArgs& a, float* lut
                     s = fma_rn(diff, diff, s);
                 }
                 if (i == 0) s = add_rn(dc0, s);
-                const int cv = a.cb_identity ? code : (int)a.cb_codes[(size_t)i * a.ksub + code];
+                const int cv = IDENT ? code : (int)cvp[code];
                 *reinterpret_cast<float*>(lrow + cv * 256) = s;
             }
         }
     }
 }
 
+// ---- K2 (FAST): |w|^2 - 2 r.w on the tensor cores, 3xTF32 ---------------------------------------
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2],
+                                         const float (&c)[4]) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, "
+        "{%10,%11,%12,%13};"
+        : "=f"(d[0]), "=f"(d[1]), "=f"(d[2]), "=f"(d[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]), "f"(c[0]), "f"(c[1]), "f"(c[2]),
+          "f"(c[3]));
+}
+
+// B fragments (residuals of the 32 queries) of one subspace / k-step: column g of n-tile n is query
+// 8n + g;  b0 = r[8ks + t], b1 = r[8ks + t + 4]  (zero beyond dsub).
+__device__ __forceinline__ void load_bfrag(const uint32_t* rh, const uint32_t* rl, int i, int dsub, int ks,
+                                           int g, int t, uint32_t (&bh)[4][2], uint32_t (&bl)[4][2]) {
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+        const int d = 8 * ks + t + 4 * e;
+        const bool ok = d < dsub;
+        const int row = (i * dsub + (ok ? d : 0)) * QRS;
+#pragma unroll
+        for (int n = 0; n < 4; ++n) {
+            bh[n][e] = ok ? rh[row + 8 * n + g] : 0u;
+            bl[n][e] = ok ? rl[row + 8 * n + g] : 0u;
+        }
+    }
+}
+
+// Warp `wid` builds subspace il = wid / 4 of the chunk, 16-code tiles T = wid % 4, +4, ...
+// D fragment of lane (g, t): codes g, g+8 x queries 8n+2t, 8n+2t+1.  Rows of the table are 256 B
+// apart (same banks), so lanes with different g must write different queries at the same time:
+// lane (g, t) stores its n-tiles rotated by g & 3 -- in step s it stores n = (s + g) & 3 -- and one
+// STS.64 per step is conflict-free (each half-warp covers all 32 banks).
+template <bool IDENT, int KSTEPS>
+__device__ __forceinline__ void build_chunk_fast(const ScanQArgs& a, float* lut, const uint32_t* rh,
+                                                 const uint32_t* rl, int c) {
+    const int lane = threadIdx.x & 31;
+    const int wid = threadIdx.x >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int il = wid >> 2;
+    const int i = c * QCS + il;
+    const int ksteps = KSTEPS > 0 ? KSTEPS : a.ksteps;
+    char* lbase = reinterpret_cast<char*>(lut) + lut_off(il, 0);
+    const uint8_t* cvp = a.cb_codes + (size_t)i * a.ksub;
+    const int rot = g & 3;
+    // byte offset of the query pair stored in step s
+    int soff[4];
+#pragma unroll
+    for (int s = 0; s < 4; ++s) soff[s] = (8 * ((s + rot) & 3) + 2 * t) * 4;
+
+    uint32_t bh[4][2], bl[4][2];
+    if (KSTEPS == 1) load_bfrag(rh, rl, i, a.dsub, 0, g, t, bh, bl);
+
+    for (int T = wid & 3; T < a.ntiles; T += 4) {
+        const size_t tile = (size_t)i * a.ntiles + T;
+        const float2 wn = __ldg(a.wnfrag + tile * 32 + lane);
+        const float cw[4] = {wn.x, wn.x, wn.y, wn.y};
+        float dd[4][4];
+        for (int ks = 0; ks < ksteps; ++ks) {
+            const float4* ap = a.afrag + ((tile * ksteps + ks) * 32 + lane) * 2;
+            const float4 fh = __ldg(ap), fl = __ldg(ap + 1);
+            const uint32_t ah[4] = {__float_as_uint(fh.x), __float_as_uint(fh.y), __float_as_uint(fh.z),
+                                    __float_as_uint(fh.w)};
+            const uint32_t al[4] = {__float_as_uint(fl.x), __float_as_uint(fl.y), __float_as_uint(fl.z),
+                                    __float_as_uint(fl.w)};
+            if (KSTEPS != 1) load_bfrag(rh, rl, i, a.dsub, ks, g, t, bh, bl);
+#pragma unroll
+            for (int n = 0; n < 4; ++n) {
+                if (ks == 0) mma_tf32(dd[n], ah, bh[n], cw);
+                else mma_tf32(dd[n], ah, bh[n], dd[n]);
+                mma_tf32(dd[n], ah, bl[n], dd[n]);
+                mma_tf32(dd[n], al, bh[n], dd[n]);
+            }
+        }
+        const int code0 = 16 * T + g;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int code = code0 + 8 * h;
+            float p0[4], p1[4];
+#pragma unroll
+            for (int n = 0; n < 4; ++n) { p0[n] = dd[n][2 * h]; p1[n] = dd[n][2 * h + 1]; }
+            // rotate left by rot: r[s] = p[(s + rot) & 3]
+            float q0[4], q1[4];
+#pragma unroll
+            for (int s = 0; s < 4; ++s) {
+                q0[s] = (rot & 1) ? p0[(s + 1) & 3] : p0[s];
+                q1[s] = (rot & 1) ? p1[(s + 1) & 3] : p1[s];
+            }
+#pragma unroll
+            for (int s = 0; s < 4; ++s) {
+                p0[s] = (rot & 2) ? q0[(s + 2) & 3] : q0[s];
+                p1[s] = (rot & 2) ? q1[(s + 2) & 3] : q1[s];
+            }
+            if (code < a.ksub) {
+                const int cv = IDENT ? code : (int)cvp[code];
+                char* row = lbase + cv * 256;
+#pragma unroll
+                for (int s = 0; s < 4; ++s)
+                    *reinterpret_cast<float2*>(row + soff[s]) = make_float2(p0[s], p1[s]);
+            }
+        }
+    }
+}
+
 // ---- K3: one chunk of 4 subspaces over the 64 vectors of this warp ------------------------------
-template <bool FIRST>
-__device__ __forceinline__ float scanq_vec(const char* lutb, uint32_t lo0, uint32_t lo1, uint32_t x, float acc) {
+// FIRST: 0 = later chunk (acc += entries), 1 = first chunk, subspace-0 entry already carries dc
+// (EXACT), 2 = first chunk, acc starts from the per-query constant `base` (FAST).
+template <int FIRST>
+__device__ __forceinline__ float scanq_vec(const char* lutb, uint32_t lo0, uint32_t lo1, uint32_t x, float acc,
+                                           float base) {
 #pragma unroll
     for (int il = 0; il < QCS; ++il) {
         // address = code << 8 | (lane * 4 [+ 128]) in one PRMT: byte 1 <- byte il of the code word
         const uint32_t off = __byte_perm(x, (il & 1) ? lo1 : lo0, 0x5504 | (il << 4));
         const float v = *reinterpret_cast<const float*>(lutb + (il >> 1) * 65536 + off);
-        acc = (FIRST && il == 0) ? v : add_rn(acc, v);  // oracle A3: strictly in subspace order
+        if (il == 0 && FIRST == 1) acc = v;
+        else if (il == 0 && FIRST == 2) acc = add_rn(base, v);
+        else acc = add_rn(acc, v);  // oracle A3: strictly in subspace order
     }
     return acc;
 }
 
-template <bool FIRST>
+template <int FIRST>
 __device__ __forceinline__ void scanq_chunk(const char* lutb, uint32_t lo0, uint32_t lo1, const uint32_t* plane,
-                                            int wid, int nv, float (&acc)[QNV]) {
+                                            int wid, int nv, float base, float (&acc)[QNV]) {
 #pragma unroll
     for (int jj = 0; jj < QNV / 4; ++jj) {
         const int g = wid + QWARPS * jj;
         if (4 * g < nv) {  // warp-uniform
             const uint4 x = *reinterpret_cast<const uint4*>(plane + 4 * g);
-            acc[4 * jj + 0] = scanq_vec<FIRST>(lutb, lo0, lo1, x.x, acc[4 * jj + 0]);
-            acc[4 * jj + 1] = scanq_vec<FIRST>(lutb, lo0, lo1, x.y, acc[4 * jj + 1]);
-            acc[4 * jj + 2] = scanq_vec<FIRST>(lutb, lo0, lo1, x.z, acc[4 * jj + 2]);
-            acc[4 * jj + 3] = scanq_vec<FIRST>(lutb, lo0, lo1, x.w, acc[4 * jj + 3]);
+            acc[4 * jj + 0] = scanq_vec<FIRST>(lutb, lo0, lo1, x.x, acc[4 * jj + 0], base);
+            acc[4 * jj + 1] = scanq_vec<FIRST>(lutb, lo0, lo1, x.y, acc[4 * jj + 1], base);
+            acc[4 * jj + 2] = scanq_vec<FIRST>(lutb, lo0, lo1, x.z, acc[4 * jj + 2], base);
+            acc[4 * jj + 3] = scanq_vec<FIRST>(lutb, lo0, lo1, x.w, acc[4 * jj + 3], base);
         }
     }
 }
@@ -186,7 +314,7 @@ __device__ __forceinline__ bool cand_before(float da, uint32_t pa, float db, uin
     return da < db || (da == db && pa < pb);
 }
 
-template <int LDW>
+template <bool FAST>
 __global__ void __launch_bounds__(QTHREADS, 1)
 scanq_kernel(const ScanQArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -210,9 +338,11 @@ scanq_kernel(const ScanQArgs a) {
     const int first = a.bucket_off[cell] + (item - a.group_off[cell]) * QG;
     const int nj = min(QG, a.bucket_off[cell + 1] - first);
 
-    const ScanQSmem L = scanq_smem_layout(m, a.dsub, LDW);
+    const ScanQSmem L = scanq_smem_layout(m, a.dsub, FAST);
     float* lut = reinterpret_cast<float*>(smem_raw + L.lut);
     float* resid_t = reinterpret_cast<float*>(smem_raw + L.resid);
+    uint32_t* resid_hi = reinterpret_cast<uint32_t*>(resid_t);
+    uint32_t* resid_lo = resid_hi + (size_t)Dp * QRS;
     uint32_t* planes = reinterpret_cast<uint32_t*>(smem_raw + L.planes);
     float* cand_d = reinterpret_cast<float*>(smem_raw + L.cand_d);
     uint32_t* cand_p = reinterpret_cast<uint32_t*>(smem_raw + L.cand_p);
@@ -239,8 +369,31 @@ scanq_kernel(const ScanQArgs a) {
     for (int idx = tid; idx < QG * Dp; idx += QTHREADS) {
         const int q = idx / Dp, d = idx - q * Dp;
         const int p = s_pair[q];
-        resid_t[d * QRS + q] =
+        const float r =
             p >= 0 ? sub_rn(a.Q[(size_t)(p / a.w) * a.D + d], a.C[(size_t)cell * a.D + d]) : 0.f;
+        if (FAST) {
+            const uint32_t h = to_tf32(r);
+            resid_hi[d * QRS + q] = h;
+            resid_lo[d * QRS + q] = to_tf32(r - __uint_as_float(h));
+        } else {
+            resid_t[d * QRS + q] = r;
+        }
+    }
+    float base = 0.f;
+    if (FAST) {
+        // base_q = dc_q + |r_q|^2 over the PQ dims: warp w sums dims w, w+16, ...; fixed order
+        __syncthreads();
+        float part = 0.f;
+        for (int d = wid; d < Dp; d += QWARPS) {
+            const float r = __uint_as_float(resid_hi[d * QRS + lane]) + __uint_as_float(resid_lo[d * QRS + lane]);
+            part = fma_rn(r, r, part);
+        }
+        s_min[wid * QG + lane] = part;
+        __syncthreads();
+        float rn = 0.f;
+#pragma unroll
+        for (int w2 = 0; w2 < QWARPS; ++w2) rn = add_rn(rn, s_min[w2 * QG + lane]);
+        base = add_rn(s_dc[lane], rn);
     }
 
     const int64_t len = a.list_len[cell];
@@ -248,12 +401,12 @@ scanq_kernel(const ScanQArgs a) {
     const char* lutb = reinterpret_cast<const char*>(lut);
     const uint32_t lo0 = lane * 4, lo1 = lane * 4 + 128;
 
-    for (int64_t base = 0; base < len; base += QVP) {
-        const int nv = (int)min((int64_t)QVP, len - base);
+    for (int64_t vbase = 0; vbase < len; vbase += QVP) {
+        const int nv = (int)min((int64_t)QVP, len - vbase);
         __syncthreads();  // previous pass fully consumed (planes, candidates) / residuals written
         // stage the code words of this pass: plane[c][v] = bytes 4c..4c+3 of vector v
         {
-            const uint32_t* src = gcodes + (size_t)base * nchunks;
+            const uint32_t* src = gcodes + (size_t)vbase * nchunks;
             const int nwords = nv * nchunks;
             const int padded = ((nv + 3) & ~3) * nchunks;
             for (int idx = tid; idx < padded; idx += QTHREADS) {
@@ -267,15 +420,26 @@ scanq_kernel(const ScanQArgs a) {
 
         for (int c = 0; c < nchunks; ++c) {
             if (c > 0) __syncthreads();  // every warp is done scanning the previous table chunk
-            switch (a.dsub) {
-                case 4: build_chunk_exact<4, LDW>(a, lut, resid_t, s_dc, c); break;
-                case 8: build_chunk_exact<8, LDW>(a, lut, resid_t, s_dc, c); break;
-                case 16: build_chunk_exact<16, LDW>(a, lut, resid_t, s_dc, c); break;
-                default: build_chunk_exact<0, LDW>(a, lut, resid_t, s_dc, c); break;
+            if (FAST) {
+                if (a.cb_identity) {
+                    if (a.ksteps == 1) build_chunk_fast<true, 1>(a, lut, resid_hi, resid_lo, c);
+                    else build_chunk_fast<true, 0>(a, lut, resid_hi, resid_lo, c);
+                } else {
+                    build_chunk_fast<false, 0>(a, lut, resid_hi, resid_lo, c);
+                }
+            } else if (a.cb_identity) {
+                switch (a.dsub) {
+                    case 4: build_chunk_exact<4, true>(a, lut, resid_t, s_dc, c); break;
+                    case 8: build_chunk_exact<8, true>(a, lut, resid_t, s_dc, c); break;
+                    case 16: build_chunk_exact<16, true>(a, lut, resid_t, s_dc, c); break;
+                    default: build_chunk_exact<0, true>(a, lut, resid_t, s_dc, c); break;
+                }
+            } else {
+                build_chunk_exact<0, false>(a, lut, resid_t, s_dc, c);
             }
             __syncthreads();
-            if (c == 0) scanq_chunk<true>(lutb, lo0, lo1, planes, wid, nv, acc);
-            else scanq_chunk<false>(lutb, lo0, lo1, planes + c * QPLANE, wid, nv, acc);
+            if (c == 0) scanq_chunk<FAST ? 2 : 1>(lutb, lo0, lo1, planes, wid, nv, base, acc);
+            else scanq_chunk<0>(lutb, lo0, lo1, planes + c * QPLANE, wid, nv, base, acc);
         }
 
         // ---- per-(query, list) top-k of this pass ----
@@ -307,7 +471,7 @@ scanq_kernel(const ScanQArgs a) {
                     const int slot = atomicAdd(&s_cnt[lane], 1);
                     if (slot < QCAP) {
                         cand_d[lane * QCAP + slot] = acc[j];
-                        cand_p[lane * QCAP + slot] = (uint32_t)(base + 4 * wid + rel);
+                        cand_p[lane * QCAP + slot] = (uint32_t)(vbase + 4 * wid + rel);
                     }
                 }
             }
@@ -360,6 +524,44 @@ scanq_kernel(const ScanQArgs a) {
         } else {
             a.pair_cnt[pair] = s_cnt[tid];
         }
+    }
+}
+
+// Codebook -> mma A fragments of -2w (tf32 hi / lo) and |w|^2, once at create.
+// One thread per (subspace i, tile T, lane): rows g, g+8 of the 16-code tile, k = t, t+4 (+8 ks).
+__global__ void prep_frags_kernel(const float* __restrict__ cb, int m, int ksub, int dsub, int ntiles,
+                                  int ksteps, float4* __restrict__ afrag, float2* __restrict__ wnfrag) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= m * ntiles * 32) return;
+    const int lane = idx & 31;
+    const int tile = idx >> 5;  // i * ntiles + T
+    const int i = tile / ntiles, T = tile - i * ntiles;
+    const int g = lane >> 2, t = lane & 3;
+    float wn[2];
+    for (int h = 0; h < 2; ++h) {
+        const int code = 16 * T + g + 8 * h;
+        float s = 0.f;
+        if (code < ksub)
+            for (int d = 0; d < dsub; ++d) {
+                const float w = cb[((size_t)i * ksub + code) * dsub + d];
+                s = fma_rn(w, w, s);
+            }
+        wn[h] = s;
+    }
+    wnfrag[idx] = make_float2(wn[0], wn[1]);
+    for (int ks = 0; ks < ksteps; ++ks) {
+        float hi[4], lo[4];
+        for (int e = 0; e < 4; ++e) {  // a0: (g, t), a1: (g+8, t), a2: (g, t+4), a3: (g+8, t+4)
+            const int code = 16 * T + g + 8 * (e & 1);
+            const int d = 8 * ks + t + 4 * (e >> 1);
+            const float v = (code < ksub && d < dsub) ? -2.f * cb[((size_t)i * ksub + code) * dsub + d] : 0.f;
+            const uint32_t hb = to_tf32(v);
+            hi[e] = __uint_as_float(hb);
+            lo[e] = __uint_as_float(to_tf32(v - hi[e]));
+        }
+        float4* o = afrag + (((size_t)tile * ksteps + ks) * 32 + lane) * 2;
+        o[0] = make_float4(hi[0], hi[1], hi[2], hi[3]);
+        o[1] = make_float4(lo[0], lo[1], lo[2], lo[3]);
     }
 }
 

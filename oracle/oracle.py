@@ -282,3 +282,34 @@ def truth_search_fp64(qz: Quantizers, offsets, codes, ids, q, k: int, w: int):
     cand.sort(key=lambda t: (t[0], t[1], t[2]))
     cand = cand[:k]
     return np.array([c[3] for c in cand], dtype=np.uint64), np.array([c[0] for c in cand])
+
+
+def compare_search(gi, gd, gc, oi, od, oc, rtol: float = 1e-5):
+    """Parity of a search result (gi ids, gd dists, gc counts) against the oracle's (oi, od, oc) at
+    the bar BASELINE.json's north_star states: counts equal, ADC distances within `rtol` relative
+    rank by rank, neighbour ids equal except at near-ties (two candidates whose distances agree
+    within rtol may swap ranks, or swap across the k-th boundary).  Returns a dict with the
+    number of id mismatches (all verified to be near-ties), the largest relative distance error,
+    and whether everything is bit-identical; raises AssertionError on a real difference."""
+    gi, oi = np.asarray(gi).astype(np.uint64), np.asarray(oi).astype(np.uint64)
+    gd, od = np.asarray(gd), np.asarray(od)
+    gc, oc = np.asarray(gc), np.asarray(oc)
+    assert np.array_equal(gc, oc), "result counts differ"
+    near_ties, max_rel = 0, 0.0
+    valid = np.arange(gd.shape[1])[None, :] < gc[:, None]
+    denom = np.where(valid, np.maximum(np.abs(od), np.finfo(od.dtype).tiny), 1.0)
+    rel = np.where(valid, np.abs(gd.astype(np.float64) - od.astype(np.float64)) / denom, 0.0)
+    max_rel = float(rel.max()) if rel.size else 0.0
+    assert max_rel <= rtol, f"ADC distance off by {max_rel:.3e} relative (bar {rtol:g})"
+    for q in np.flatnonzero(((gi != oi) & valid).any(axis=1)):
+        n = int(gc[q])
+        for j in np.flatnonzero(gi[q, :n] != oi[q, :n]):
+            pos = np.flatnonzero(oi[q, :n] == gi[q, j])
+            ref = od[q, pos[0]] if len(pos) else od[q, n - 1]   # moved rank | crossed the k-th boundary
+            assert abs(float(ref) - float(gd[q, j])) <= rtol * abs(float(ref)), \
+                f"query {q} rank {j}: id {gi[q, j]} is not a near-tie of the oracle's result"
+            near_ties += 1
+    bit_equal = bool(np.array_equal(gi[valid], oi[valid]) and
+                     np.array_equal(gd[valid].view(np.uint8), od[valid].view(np.uint8)))
+    return {"near_tie_id_mismatches": near_ties, "results": int(valid.sum()), "max_rel_err": max_rel,
+            "bit_identical": bit_equal}

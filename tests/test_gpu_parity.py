@@ -16,10 +16,13 @@ pytestmark = pytest.mark.gpu
 RTOL = 1e-5  # the tolerance north_star states for ADC distances (we assert exact equality too)
 
 
-LEGACY, QLANE = 1, 2  # ivfadc_config.flags: pin the list-scan kernel (include/ivfadc.h)
+LEGACY, QLANE, LUT_EXACT = 1, 2, 4  # ivfadc_config.flags (include/ivfadc.h)
+# Default flags for the bit-exact tests: whichever scan kernel the engine picks, tables in the
+# reference's direct form.  The tensor-core (3xTF32) tables are tested at the stated tolerance in
+# test_search_qlane_* below.
 
 
-def engine_from(qz, id_type=np.uint32, X=None, assign=None, shard=(0, 1), flags=0):
+def engine_from(qz, id_type=np.uint32, X=None, assign=None, shard=(0, 1), flags=LUT_EXACT):
     e = iv.IVFADCIndex.from_quantizers(qz.centroids, qz.cb_vectors, qz.cb_codes, index_type=id_type,
                                        shard=shard, flags=flags)
     if X is not None:
@@ -236,13 +239,20 @@ def test_search_qlane_bit_exact(D, m, ksub, kc, n, nq, k, w, identity):
     np.cumsum(np.bincount(cells, minlength=kc), out=offsets[1:])
     Q = synth.blobs(nq, D, kc, seed=22)
     oi, od, oc, scanned = orc.search_csr(qz, offsets, ocodes[order], order.astype(np.uint64), Q, k, w, nthreads=8)
-    for flags in (QLANE, LEGACY):
+    for flags in (QLANE | LUT_EXACT, LEGACY):
         e = engine_from(qz, np.uint32, X, flags=flags)
         gi, gd, gc = e.search_packed(Q, k, w)
         np.testing.assert_array_equal(gc, oc, err_msg=f"flags={flags}")
         assert np.array_equal(gd.view(np.uint8), od.view(np.uint8)), f"flags={flags}"
         np.testing.assert_array_equal(gi, oi, err_msg=f"flags={flags}")
         e.close()
+    # tensor-core tables (the default for large batches): the north_star's tolerance bar
+    e = engine_from(qz, np.uint32, X, flags=QLANE)
+    gi, gd, gc = e.search_packed(Q, k, w)
+    rep = orc.compare_search(gi, gd, gc, oi, od, oc, rtol=RTOL)
+    assert rep["near_tie_id_mismatches"] <= max(2, rep["results"] // 200), rep
+    assert rep["max_rel_err"] < 3e-6, rep   # measured error budget of 3xTF32
+    e.close()
 
 
 def test_search_qlane_ties_overflow_redo():
@@ -257,11 +267,17 @@ def test_search_qlane_ties_overflow_redo():
     data = np.ascontiguousarray(X.T)
     oidx, qz, assign, Xc = helpers.build_oracle_index(data, kc=4, k=16, m=8, seed=1)
     Q = np.concatenate([base, rng.random((34, 32)).astype(np.float32)])
-    for flags in (QLANE, 0):
+    for flags in (QLANE | LUT_EXACT, LUT_EXACT):
         e = engine_from(qz, np.uint32, Xc, assign, flags=flags)
         for k, w in ((10, 2), (16, 4), (1, 1)):
             assert_search_equal(e, oidx, Q, k, w)
         e.close()
+    e = engine_from(qz, np.uint32, Xc, assign, flags=QLANE)
+    for k, w in ((10, 2), (16, 4), (1, 1)):
+        gi, gd, gc = e.search_packed(Q, k, w)
+        oi, od, oc = oidx.knn_search(Q, k, w=w, nthreads=4)
+        orc.compare_search(gi, gd, gc, oi, od, oc, rtol=RTOL)
+    e.close()
 
 
 # ------------------------------------------------------------------------------------------------
