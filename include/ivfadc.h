@@ -71,6 +71,12 @@ extern "C" {
  * vector-per-lane kernel is always exact.
  */
 #define IVFADC_FLAG_LUT_EXACT   4
+/*
+ * The default table builder of the query-per-lane kernel runs on the 5th-generation tensor cores
+ * (tcgen05.mma kind::tf32 into tensor memory, codebook streamed by TMA; fp32, dsub <= 8).  This
+ * flag selects the older warp-level mma.sync builder instead (same numerics class, 3xTF32).
+ */
+#define IVFADC_FLAG_LUT_MMASYNC 8
 
 typedef struct ivfadc_index ivfadc_index;   /* opaque, owns all device memory */
 
@@ -229,6 +235,14 @@ int ivfadc_export_quantizers(ivfadc_index* h, void* centroids_out, void* codeboo
 
 /* Override the global vector count (used by load and by sharded handles). */
 int ivfadc_set_length(ivfadc_index* h, int64_t n_total);
+
+/*
+ * Diagnostics of the tensor-core table builder (tests only).  out == NULL arms a dump; after the
+ * next search, out receives float[m][256][32] (the lookup tables of work item 0: subspace, code
+ * value, query slot; WITHOUT the per-query constant dc + |r|^2), then int32[32] (query * w + probe
+ * rank of every slot, -1 = empty) and int32 (the cell), i.e. (m * 256 * 32 + 33) * 4 bytes.
+ */
+int ivfadc_debug_tables(ivfadc_index* h, void* out);
 
 int ivfadc_get_stats(ivfadc_index* h, ivfadc_stats* out);
 int ivfadc_reset_stats(ivfadc_index* h);

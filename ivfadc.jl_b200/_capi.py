@@ -18,7 +18,7 @@ ERR_BAD_ARG, ERR_CAPACITY, ERR_CUDA, ERR_OOM, ERR_UNSUPPORTED, ERR_EMPTY = -1, -
 F32, F64 = 0, 1
 SQEUCLIDEAN = 0
 LAST, FIRST = 0, 1
-FLAG_SCAN_LEGACY, FLAG_SCAN_QLANE, FLAG_LUT_EXACT = 1, 2, 4
+FLAG_SCAN_LEGACY, FLAG_SCAN_QLANE, FLAG_LUT_EXACT, FLAG_LUT_MMASYNC = 1, 2, 4, 8
 
 # every symbol include/ivfadc.h declares (tests check that the library exports all of them)
 SYMBOLS = [
@@ -26,7 +26,7 @@ SYMBOLS = [
     "ivfadc_add", "ivfadc_encode", "ivfadc_coarse_search", "ivfadc_search", "ivfadc_search_device",
     "ivfadc_search_local_device", "ivfadc_merge_device", "ivfadc_delete", "ivfadc_pop", "ivfadc_length",
     "ivfadc_list_sizes", "ivfadc_export_list", "ivfadc_import_list", "ivfadc_export_quantizers",
-    "ivfadc_set_length", "ivfadc_get_stats", "ivfadc_reset_stats",
+    "ivfadc_set_length", "ivfadc_get_stats", "ivfadc_reset_stats", "ivfadc_debug_tables",
 ]
 
 
@@ -95,6 +95,7 @@ def load(build_if_missing: bool = True):
     lib.ivfadc_set_length.argtypes = [H, c_int64]
     lib.ivfadc_get_stats.argtypes = [H, POINTER(Stats)]
     lib.ivfadc_reset_stats.argtypes = [H]
+    lib.ivfadc_debug_tables.argtypes = [H, c_void_p]
     for name in SYMBOLS:
         fn = getattr(lib, name)
         if name not in ("ivfadc_last_error",):

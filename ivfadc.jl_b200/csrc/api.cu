@@ -84,6 +84,7 @@ int search_chunk(ivfadc_index* h, const void* dQ, int64_t nq, int k, int w, uint
     CUDA_OR_FAIL(h, h->ws_pair_pos.reserve(z.pair_pos_bytes), "workspace");
     CUDA_OR_FAIL(h, h->ws_pair_cnt.reserve(z.pair_cnt_bytes), "workspace");
     CUDA_OR_FAIL(h, h->ws_thr.reserve(z.thr_bytes), "workspace");
+    CUDA_OR_FAIL(h, h->ws_items.reserve(z.items_bytes), "workspace");
 
     Timing& tm = extra(h)->tm;
     int set = -1;
@@ -272,10 +273,13 @@ int ivfadc_destroy(ivfadc_index* h) {
     if (h->d_cb_norms) cudaFree(h->d_cb_norms);
     if (h->d_afrag) cudaFree(h->d_afrag);
     if (h->d_wnfrag) cudaFree(h->d_wnfrag);
+    if (h->d_tcB) cudaFree(h->d_tcB);
+    if (h->d_err) cudaFree(h->d_err);
+    if (h->d_dbg_lut) cudaFree(h->d_dbg_lut);
     DevBuf* bufs[] = {&h->ws_q, &h->ws_cells, &h->ws_dc, &h->ws_bucket, &h->ws_sorted, &h->ws_pair_d,
                       &h->ws_pair_pos, &h->ws_pair_cnt, &h->ws_thr, &h->ws_out_ids, &h->ws_out_d,
                       &h->ws_out_cnt, &h->ws_out_keys, &h->ws_misc, &h->ws_x, &h->ws_codes, &h->ws_assign,
-                      &h->ws_sort_tmp, &h->ws_sort_keys, &h->ws_sort_vals, &h->ws_del};
+                      &h->ws_sort_tmp, &h->ws_sort_keys, &h->ws_sort_vals, &h->ws_del, &h->ws_items};
     for (DevBuf* b : bufs) b->release();
     if (h->stream) cudaStreamDestroy(h->stream);
     cudaGetLastError();
@@ -417,6 +421,15 @@ int ivfadc_search(ivfadc_index* h, const void* Q, int64_t nq, int32_t k, int32_t
     CUDA_OR_FAIL(h, cudaMemcpyAsync(counts_out, h->ws_out_cnt.p, sizeof(int32_t) * (size_t)nq,
                                     cudaMemcpyDeviceToHost, h->stream), "D2H");
     CUDA_OR_FAIL(h, cudaStreamSynchronize(h->stream), "search");
+    if (h->d_err) {
+        int flag = 0;
+        CUDA_OR_FAIL(h, cudaMemcpy(&flag, h->d_err, sizeof(int), cudaMemcpyDeviceToHost), "D2H");
+        if (flag) {
+            cudaMemset(h->d_err, 0, sizeof(int));
+            return fail(h, IVFADC_ERR_CUDA, flag == 1 ? "tensor-core table builder: TMA operand never arrived"
+                                                      : "tensor-core table builder: MMA never completed");
+        }
+    }
     return IVFADC_OK;
 }
 
@@ -554,6 +567,21 @@ int ivfadc_export_quantizers(ivfadc_index* h, void* centroids_out, void* codeboo
 int ivfadc_set_length(ivfadc_index* h, int64_t n_total) {
     if (check_handle(h) || n_total < 0) return IVFADC_ERR_BAD_ARG;
     h->n_total = n_total;
+    return IVFADC_OK;
+}
+
+int ivfadc_debug_tables(ivfadc_index* h, void* out) {
+    if (check_handle(h)) return IVFADC_ERR_BAD_ARG;
+    cudaSetDevice(h->cfg.device);
+    const size_t bytes = ((size_t)h->cfg.m * 256 * 32 + 33) * 4;
+    if (!out) {
+        if (!h->d_dbg_lut) CUDA_OR_FAIL(h, cudaMalloc(&h->d_dbg_lut, bytes), "debug buffer");
+        CUDA_OR_FAIL(h, cudaMemset(h->d_dbg_lut, 0, bytes), "debug buffer");
+        return IVFADC_OK;
+    }
+    if (!h->d_dbg_lut) return fail(h, IVFADC_ERR_BAD_ARG, "debug dump not armed");
+    CUDA_OR_FAIL(h, cudaDeviceSynchronize(), "sync");
+    CUDA_OR_FAIL(h, cudaMemcpy(out, h->d_dbg_lut, bytes, cudaMemcpyDeviceToHost), "D2H");
     return IVFADC_OK;
 }
 

@@ -110,6 +110,9 @@ struct ivfadc_index {
     void* d_afrag = nullptr;        // codebook as mma A fragments (scanq FAST table builder)
     void* d_wnfrag = nullptr;
     int frag_ntiles = 0, frag_ksteps = 0;
+    void* d_tcB = nullptr;          // codebook as tcgen05 B-operand blocks (scant table builder)
+    int* d_err = nullptr;           // device error flag of the tcgen05 pipeline (mbarrier timeout)
+    void* d_dbg_lut = nullptr;      // optional table dump of work item 0 (tests), float[m][256][32]
 
     // inverted lists: device-resident CSR with slack.  List c occupies entries
     // [off[c], off[c] + len[c]) of the arenas, capacity cap[c]; off[c] is a multiple of 16 so
@@ -127,7 +130,7 @@ struct ivfadc_index {
     // search / mutation workspaces (grow-only)
     ivf::DevBuf ws_q, ws_cells, ws_dc, ws_bucket, ws_sorted, ws_pair_d, ws_pair_pos, ws_pair_cnt,
         ws_thr, ws_out_ids, ws_out_d, ws_out_cnt, ws_out_keys, ws_misc, ws_x, ws_codes, ws_assign,
-        ws_sort_tmp, ws_sort_keys, ws_sort_vals, ws_del;
+        ws_sort_tmp, ws_sort_keys, ws_sort_vals, ws_del, ws_items;
 
     cudaEvent_t ev[10] = {};
     bool stats_timing = true;
@@ -145,7 +148,7 @@ int coarse_max_w();
 
 // ---- scan.cu ----------------------------------------------------------------------------------
 struct ScanPlanSizes {
-    size_t bucket_bytes, sorted_bytes, pair_d_bytes, pair_pos_bytes, pair_cnt_bytes, thr_bytes;
+    size_t bucket_bytes, sorted_bytes, pair_d_bytes, pair_pos_bytes, pair_cnt_bytes, thr_bytes, items_bytes;
 };
 int scan_max_k();
 cudaError_t scanq_prepare(ivfadc_index* h, cudaStream_t s, int* launches);

@@ -1,6 +1,7 @@
 // Search planning, the scan launcher, and the final merges.  See scan_impl.cuh for K2/K3.
 #include "scan_impl.cuh"
 #include "scanq_impl.cuh"
+#include "scant_impl.cuh"
 
 namespace ivf {
 
@@ -82,6 +83,16 @@ __global__ void plan_scatter_kernel(const int32_t* __restrict__ cells, int64_t n
     const int b = ((split && (p % w)) ? kc : 0) + cell;
     const int slot = bucket_off[b] + atomicAdd(&cursor[b], 1);
     sorted_pairs[slot] = (int32_t)p;
+}
+
+// Work-item table of the query-per-lane kernels: item -> (cell, first pair slot, number of pairs).
+__global__ void plan_items_kernel(const int* __restrict__ bucket_off, const int* __restrict__ group_off, int kc,
+                                  int qn, int4* __restrict__ items) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= kc) return;
+    const int p1 = bucket_off[c + 1];
+    int g = group_off[c];
+    for (int p = bucket_off[c]; p < p1; p += qn, ++g) items[g] = make_int4(c, p, min(qn, p1 - p), 0);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -325,6 +336,13 @@ bool use_scanq(const ivfadc_index* h, int64_t npairs, int k) {
     return npairs >= (int64_t)8 * h->cfg.kc;
 }
 
+// tcgen05 table builder (scant_impl.cuh): fp32, k <= 16, m in {4, 8, 12, 16}, dsub <= 8
+bool use_scant(const ivfadc_index* h) {
+    if (h->cfg.flags & (IVFADC_FLAG_LUT_EXACT | IVFADC_FLAG_LUT_MMASYNC)) return false;
+    return h->d_tcB != nullptr && h->dsub <= 8 &&
+           scant_smem_layout(h->cfg.m).total <= kSmemMax;
+}
+
 template <typename T, int MC>
 cudaError_t launch_redo_r(const ScanArgs<T>& a, const int32_t* redo_pairs, const int* redo_cnt, int grid,
                           size_t smem, cudaStream_t s) {
@@ -396,6 +414,10 @@ cudaError_t search_t(ivfadc_index* h, const void* dQ, int64_t nq, int k, int w, 
     // upper bound on the number of work items: every bucket adds at most one partial group
     int64_t max_items = std::min<int64_t>(npairs, npairs / qn + nb);
     if (max_items < 1) max_items = 1;
+    if (qlane && use_scant(h)) {
+        plan_items_kernel<<<(kc + 255) / 256, 256, 0, s>>>(bucket_off, group_off, kc, QG, h->ws_items.as<int4>());
+        *launches += 1;
+    }
     if (h->stats_timing) cudaEventRecord(h->ev[2], s);
     if (qlane) {
         if constexpr (sizeof(T) == 4) {
@@ -406,6 +428,27 @@ cudaError_t search_t(ivfadc_index* h, const void* dQ, int64_t nq, int k, int w, 
             qa.bucket_off = bucket_off; qa.group_off = group_off; qa.sorted_pairs = sorted_pairs;
             qa.pair_d = pair_d; qa.pair_pos = pair_pos; qa.pair_cnt = pair_cnt;
             qa.redo_pairs = redo_pairs; qa.redo_cnt = redo_cnt;
+            if (use_scant(h)) {
+                ScanTArgs tq;
+                tq.q = qa;
+                tq.tcB = static_cast<const float*>(h->d_tcB);
+                tq.items = h->ws_items.as<int4>();
+                tq.err = h->d_err;
+                tq.dbg_lut = static_cast<float*>(h->d_dbg_lut);
+                const size_t tsmem = scant_smem_layout(a.m).total;
+                static size_t tconfigured[2] = {0, 0};
+                const int ident = a.cb_identity ? 1 : 0;
+                if (tsmem > tconfigured[ident]) {
+                    e = ident ? cudaFuncSetAttribute(scant_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsmem)
+                              : cudaFuncSetAttribute(scant_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsmem);
+                    if (e != cudaSuccess) return e;
+                    tconfigured[ident] = tsmem;
+                }
+                if (ident) scant_kernel<true><<<(unsigned)max_items, QTHREADS, tsmem, s>>>(tq);
+                else scant_kernel<false><<<(unsigned)max_items, QTHREADS, tsmem, s>>>(tq);
+                if ((e = cudaGetLastError()) != cudaSuccess) return e;
+                *launches += 1;
+            } else {
             const bool fast = scanq_fast(h);
             qa.afrag = static_cast<const float4*>(h->d_afrag);
             qa.wnfrag = static_cast<const float2*>(h->d_wnfrag);
@@ -421,6 +464,8 @@ cudaError_t search_t(ivfadc_index* h, const void* dQ, int64_t nq, int k, int w, 
             if (fast) scanq_kernel<true><<<(unsigned)max_items, QTHREADS, qsmem, s>>>(qa);
             else scanq_kernel<false><<<(unsigned)max_items, QTHREADS, qsmem, s>>>(qa);
             if ((e = cudaGetLastError()) != cudaSuccess) return e;
+            *launches += 1;
+            }
             // pairs whose candidate list overflowed (heavy ties): general kernel, one pair per item
             const size_t rsmem = smem_for<T>(1, h->cfg.m, h->dsub, k);
             const int rgrid = 2 * 148;
@@ -431,7 +476,7 @@ cudaError_t search_t(ivfadc_index* h, const void* dQ, int64_t nq, int k, int w, 
                 default: e = launch_redo_r<T, 0>(a, redo_pairs, redo_cnt, rgrid, rsmem, s); break;
             }
             if (e != cudaSuccess) return e;
-            *launches += 2;
+            *launches += 1;
         }
     } else {
         const size_t smem = smem_for<T>(qn, h->cfg.m, h->dsub, k);
@@ -477,6 +522,18 @@ cudaError_t scanq_prepare(ivfadc_index* h, cudaStream_t s, int* launches) {
                                                      static_cast<float4*>(h->d_afrag),
                                                      static_cast<float2*>(h->d_wnfrag));
     if (launches) *launches += 1;
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    // operand blocks of the tcgen05 builder
+    if (h->dsub <= 8 && m % 2 == 0) {
+        const size_t words = (size_t)(m / 2) * TB_NBLK * 2048;
+        if ((e = cudaMalloc(&h->d_tcB, words * sizeof(float))) != cudaSuccess) return e;
+        if ((e = cudaMalloc(&h->d_err, sizeof(int))) != cudaSuccess) return e;
+        if ((e = cudaMemsetAsync(h->d_err, 0, sizeof(int), s)) != cudaSuccess) return e;
+        prep_tc_kernel<<<(unsigned)((words + 255) / 256), 256, 0, s>>>(static_cast<const float*>(h->d_cb), m,
+                                                                      h->cfg.ksub, h->dsub,
+                                                                      static_cast<float*>(h->d_tcB));
+        if (launches) *launches += 1;
+    }
     return cudaGetLastError();
 }
 
@@ -502,6 +559,7 @@ ScanPlanSizes scan_plan_sizes(const ivfadc_index* h, int64_t nq, int w, int k) {
     z.pair_pos_bytes = sizeof(uint32_t) * (size_t)npairs * k;
     z.pair_cnt_bytes = sizeof(int32_t) * (size_t)npairs;
     z.thr_bytes = 8 * (size_t)nq;
+    z.items_bytes = sizeof(int4) * (size_t)(std::min<int64_t>(npairs, npairs / QG + h->cfg.kc) + 1);
     return z;
 }
 

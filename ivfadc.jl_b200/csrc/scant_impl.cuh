@@ -1,0 +1,533 @@
+// K2 + K3, "query-per-lane" scan with the lookup tables built by the 5th-generation tensor cores
+// (tcgen05.mma kind::tf32, accumulators in tensor memory, codebook operand streamed by TMA bulk
+// copies) -- the default batched search kernel on sm_100a (fp32, k <= 16, dsub <= 8, m % 4 == 0).
+//
+// Same work decomposition and scan loop as scanq_impl.cuh (work item = one inverted list x up to
+// 32 queries probing it, lane = query, PQ code byte warp-uniform, every lookup one conflict-free
+// 128-byte shared-memory wavefront, 64 partial distances per lane in registers); what changes is
+// K2.  The mma.sync builder of scanq spends ~190 instructions per 16x32 table tile (fragment
+// loads, lane rotations, 8-byte stores) and serialises with the scan; here
+//
+//   * the table of a GROUP of two subspaces (2 x 256 codes x 32 queries, 64 KB) is ONE accumulator
+//     tile D[128 lanes][256 columns] in tensor memory:  lane = (copy, subspace-in-group, query),
+//     column = codeword index,
+//         D = A_hi.B_hi + A_lo.B_hi + A_hi.B_lo  (3xTF32 split, fp32 accumulate)  + 1.|w|^2
+//     with A = residuals r = q - c laid out block-diagonally (rows of the other subspace are zero,
+//     rows 64..127 repeat rows 0..63 so that all four lane quarters -- hence all 16 warps -- can
+//     read the tile), B = -2 * codebook and the split squared norms.  Seven M128 N256 K8 MMAs per
+//     group, issued by one thread; nobody waits for them: they run while the previous group is
+//     being scanned;
+//   * B (40 KB per group, canonical K-major no-swizzle core-matrix layout, prepared once at
+//     create) arrives by cp.async.bulk into a two-deep shared-memory ring, completion on mbarriers;
+//   * the epilogue is one tcgen05.ld 32x32b.x32 per warp (lane = query: 32 consecutive codewords
+//     of that query) and 32 conflict-free 128-byte STS rows into the table layout the scan wants.
+//
+// Numerics: entry = |w|^2 - 2 r.w (+ per-query constant dc + |r|^2 added at scan start), the GEMM
+// form of the reference's direct form (src/index.jl:234), accurate to ~1e-6 relative of the
+// returned distance (bound 1e-5); the reference-exact chain remains available through
+// IVFADC_FLAG_LUT_EXACT (scanq_kernel<false>).
+#pragma once
+
+#include "scanq_impl.cuh"
+
+namespace ivf {
+
+constexpr int TA_BLK = 4096;                 // A block: 128 rows x 8 k (tf32), canonical layout
+constexpr int TB_BLK = 8192;                 // B block: 256 rows x 8 k
+constexpr int TB_NBLK = 5;                   // hi0, lo0, hi1, lo1, norms
+constexpr int TB_GROUP = TB_NBLK * TB_BLK;   // bytes of B per group of two subspaces
+constexpr int TA_NBLK = 5;                   // hi0, lo0, hi1, lo1, ones
+constexpr uint32_t T_TMEM_COLS = 256;
+constexpr int T_RS = 33;                     // row stride of the transposed residuals
+constexpr uint32_t T_SPIN = 1u << 22;        // bound on every mbarrier wait (no hangs: error flag instead)
+
+struct ScanTArgs {
+    ScanQArgs q;
+    const float* tcB;     // [m/2][5][2048] tf32 words: -2w hi/lo per subspace, split norms
+    const int4* items;    // [nitems] (cell, first pair slot, number of pairs, 0)
+    int* err;             // device error flag (mbarrier timeout)
+    float* dbg_lut;       // optional dump of work item 0: tables [m][256][32], then int pair[32], int cell
+};
+
+struct ScanTSmem {
+    size_t lut, bbuf, abuf, resid, planes, cand_d, cand_p, smin, misc, bars, total;
+};
+
+__host__ __device__ inline ScanTSmem scant_smem_layout(int m) {
+    ScanTSmem s;
+    size_t o = 0;
+    s.lut = o;    o += 65536;                              // [256 codes][2 subspaces][32 queries] fp32
+    s.bbuf = o;   o += 2 * (size_t)TB_GROUP;
+    s.abuf = o;   o += (size_t)TA_NBLK * TA_BLK;
+    s.resid = o;  o += (size_t)m * 8 * T_RS * 4;
+    o = (o + 15) & ~(size_t)15;
+    s.planes = o; o += (size_t)(m / QCS) * QPLANE * 4;
+    s.cand_d = o; o += (size_t)QG * QCAP * 4;
+    s.cand_p = o; o += (size_t)QG * QCAP * 4;
+    s.smin = o;   o += (size_t)QWARPS * QG * 4;
+    s.misc = o;   o += 6 * QG * 4;
+    o = (o + 15) & ~(size_t)15;
+    s.bars = o;   o += 64;
+    s.total = o;
+    return s;
+}
+
+// ---- PTX wrappers ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok;
+}
+// Bounded wait: a broken pipeline raises the error flag instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* err, int code) {
+    for (uint32_t i = 0; i < T_SPIN; ++i)
+        if (mbar_try_wait(bar, parity)) return;
+    atomicExch(err, code);
+}
+__device__ __forceinline__ void tma_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// Shared-memory matrix descriptor, K-major, SWIZZLE_NONE: 8-row x 16-byte core matrices stored as
+// 128 contiguous bytes; LBO = byte distance between the two K halves of one MMA (k 0..3 | 4..7),
+// SBO = byte distance between 8-row groups.  (cute::UMMA::SmemDescriptor, version 1 = Blackwell.)
+__device__ __forceinline__ uint64_t tc_smem_desc(uint32_t addr) {
+    constexpr uint64_t LBO = 128, SBO = 256;
+    return (uint64_t)((addr & 0x3FFFFu) >> 4) | ((LBO >> 4) << 16) | ((SBO >> 4) << 32) | (1ull << 46);
+}
+// Instruction descriptor of tcgen05.mma kind::tf32: D fp32, A/B tf32 K-major, M = 128, N = 256.
+constexpr uint32_t T_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((256u >> 3) << 17) | ((128u >> 4) << 24);
+
+__device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(T_IDESC), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// ---- K3: one group (two subspaces) over the 64 vectors of this warp ----------------------------
+// BP: which byte pair of the staged code word (subspaces 4c + 2BP, 4c + 2BP + 1).
+template <int BP, bool FIRST>
+__device__ __forceinline__ float scant_vec(const char* lutb, uint32_t lo0, uint32_t lo1, uint32_t x, float acc,
+                                           float base) {
+    // address = code << 8 | lane * 4 [+ 128] in one PRMT (table rows are 256 B: two subspaces x 32 queries)
+    const uint32_t o0 = __byte_perm(x, lo0, 0x5504 | ((2 * BP) << 4));
+    const uint32_t o1 = __byte_perm(x, lo1, 0x5504 | ((2 * BP + 1) << 4));
+    const float v0 = *reinterpret_cast<const float*>(lutb + o0);
+    const float v1 = *reinterpret_cast<const float*>(lutb + o1);
+    acc = FIRST ? add_rn(base, v0) : add_rn(acc, v0);
+    return add_rn(acc, v1);  // subspace order, as the reference's chain (src/index.jl:242-246)
+}
+
+template <int BP, bool FIRST>
+__device__ __forceinline__ void scant_group(const char* lutb, uint32_t lo0, uint32_t lo1, const uint32_t* plane,
+                                            int wid, int nv, float base, float (&acc)[QNV]) {
+#pragma unroll
+    for (int jj = 0; jj < QNV / 4; ++jj) {
+        const int g = wid + QWARPS * jj;
+        if (4 * g < nv) {  // warp-uniform
+            const uint4 x = *reinterpret_cast<const uint4*>(plane + 4 * g);
+            acc[4 * jj + 0] = scant_vec<BP, FIRST>(lutb, lo0, lo1, x.x, acc[4 * jj + 0], base);
+            acc[4 * jj + 1] = scant_vec<BP, FIRST>(lutb, lo0, lo1, x.y, acc[4 * jj + 1], base);
+            acc[4 * jj + 2] = scant_vec<BP, FIRST>(lutb, lo0, lo1, x.z, acc[4 * jj + 2], base);
+            acc[4 * jj + 3] = scant_vec<BP, FIRST>(lutb, lo0, lo1, x.w, acc[4 * jj + 3], base);
+        }
+    }
+}
+
+template <bool IDENT>
+__global__ void __launch_bounds__(QTHREADS, 1)
+scant_kernel(const ScanTArgs ta) {
+    const ScanQArgs& a = ta.q;
+    extern __shared__ __align__(1024) unsigned char smem_t[];
+    unsigned char* const smem_raw = smem_t;
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int wid = tid >> 5;
+    const int m = a.m;
+    const int k = a.k;
+    const int ng = m >> 1;          // groups of two subspaces
+    const int nplanes = m / QCS;
+
+    const int item = blockIdx.x;
+    if (item >= a.group_off[a.kc]) return;  // before any allocation
+    const int4 it = ta.items[item];
+    const int cell = it.x, first = it.y, nj = it.z;
+
+    const ScanTSmem L = scant_smem_layout(m);
+    char* lutb = reinterpret_cast<char*>(smem_raw + L.lut);
+    unsigned char* bbuf = smem_raw + L.bbuf;
+    unsigned char* abuf = smem_raw + L.abuf;
+    float* resid = reinterpret_cast<float*>(smem_raw + L.resid);
+    uint32_t* planes = reinterpret_cast<uint32_t*>(smem_raw + L.planes);
+    float* cand_d = reinterpret_cast<float*>(smem_raw + L.cand_d);
+    uint32_t* cand_p = reinterpret_cast<uint32_t*>(smem_raw + L.cand_p);
+    float* s_min = reinterpret_cast<float*>(smem_raw + L.smin);
+    float* s_dc = reinterpret_cast<float*>(smem_raw + L.misc);
+    float* s_thr = s_dc + QG;
+    float* s_run = s_thr + QG;
+    int* s_cnt = reinterpret_cast<int*>(s_run + QG);
+    int* s_pair = s_cnt + QG;
+    int* s_flag = s_pair + QG;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + L.bars);
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 4);
+    const uint32_t bar_full0 = smem_u32(&bars[0]), bar_full1 = smem_u32(&bars[1]), bar_mma = smem_u32(&bars[2]);
+    const uint32_t abuf_u32 = smem_u32(abuf), bbuf_u32 = smem_u32(bbuf);
+
+    const int64_t len = a.list_len[cell];
+    const int npass = (int)((len + QVP - 1) / QVP);
+    const int T = npass * ng;  // table builds (one per group per pass)
+
+    // ---- one-time setup: barriers, tensor memory, constant parts of A ----
+    if (tid == 0) {
+        mbar_init(bar_full0, 1);
+        mbar_init(bar_full1, 1);
+        mbar_init(bar_mma, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (wid == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)),
+                     "r"(T_TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (tid < QG) {
+        const int p = tid < nj ? a.sorted_pairs[first + tid] : -1;
+        s_pair[tid] = p;
+        s_dc[tid] = p >= 0 ? a.dc[p] : 0.f;
+        s_run[tid] = Limits<float>::inf();
+        s_cnt[tid] = 0;
+        s_flag[tid] = 0;
+    }
+    {
+        float4* A4 = reinterpret_cast<float4*>(abuf);
+        for (int i = tid; i < 4 * TA_BLK / 16; i += QTHREADS) A4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        // ones block: row (copy, j, q) selects the split norm of subspace j: k slots 2j, 2j + 1
+        for (int i = tid; i < 256; i += QTHREADS) {
+            const int r = i >> 1, half = i & 1, j = (r >> 5) & 1;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (half == 0) v = j == 0 ? make_float4(1.f, 1.f, 0.f, 0.f) : make_float4(0.f, 0.f, 1.f, 1.f);
+            *reinterpret_cast<float4*>(abuf + 4 * TA_BLK + (r >> 3) * 256 + half * 128 + (r & 7) * 16) = v;
+        }
+        fence_proxy_async();  // generic-proxy writes -> visible to the tensor core (async proxy)
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *s_tmem;
+
+    // codebook operand of the first two builds
+    if (tid == 0) {
+        mbar_expect_tx(bar_full0, TB_GROUP);
+        tma_bulk_g2s(bbuf_u32, ta.tcB, TB_GROUP, bar_full0);
+        if (T > 1) {
+            mbar_expect_tx(bar_full1, TB_GROUP);
+            tma_bulk_g2s(bbuf_u32 + TB_GROUP, ta.tcB + (size_t)(1 % ng) * (TB_GROUP / 4), TB_GROUP, bar_full1);
+        }
+    }
+
+    // residuals r_q = query - centroid (reference _closest_cluster_residuals,
+    // src/coarsequantizers.jl:40-45): warp s owns subspace s, lane q its query; transposed
+    // [s * 8 + d][q], zero-padded to 8 dims per subspace
+    {
+        float part = 0.f;
+        if (wid < m) {
+            const int p = s_pair[lane];
+            const float* qv = a.Q + (size_t)(p >= 0 ? p / a.w : 0) * a.D + wid * a.dsub;
+            const float* cv = a.C + (size_t)cell * a.D + wid * a.dsub;
+#pragma unroll
+            for (int d = 0; d < 8; ++d) {
+                const float r = (p >= 0 && d < a.dsub) ? sub_rn(qv[d], cv[d]) : 0.f;
+                resid[(wid * 8 + d) * T_RS + lane] = r;
+                part = fma_rn(r, r, part);
+            }
+        }
+        s_min[wid * QG + lane] = part;
+    }
+    __syncthreads();
+    float base;
+    {
+        float rn = 0.f;
+        for (int s = 0; s < m; ++s) rn = add_rn(rn, s_min[s * QG + lane]);  // fixed order
+        base = add_rn(s_dc[lane], rn);  // dc + |r|^2 over the PQ dims
+    }
+
+    // A rows of group g: row = (copy, j, q), block 2j = hi, 2j + 1 = lo of r[2g + j][q][0..7]
+    auto write_A = [&](int g) {
+        if (tid < 128) {
+            const int row = tid, j = (row >> 5) & 1, q = row & 31, s = 2 * g + j;
+            float hi[8], lo[8];
+#pragma unroll
+            for (int d = 0; d < 8; ++d) {
+                const float r = resid[(s * 8 + d) * T_RS + q];
+                hi[d] = __uint_as_float(to_tf32(r));
+                lo[d] = __uint_as_float(to_tf32(r - hi[d]));
+            }
+            unsigned char* ph = abuf + (2 * j) * TA_BLK + (row >> 3) * 256 + (row & 7) * 16;
+            unsigned char* pl = ph + TA_BLK;
+            *reinterpret_cast<float4*>(ph) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+            *reinterpret_cast<float4*>(ph + 128) = make_float4(hi[4], hi[5], hi[6], hi[7]);
+            *reinterpret_cast<float4*>(pl) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+            *reinterpret_cast<float4*>(pl + 128) = make_float4(lo[4], lo[5], lo[6], lo[7]);
+            fence_proxy_async();  // generic-proxy writes -> visible to the tensor core (async proxy)
+        }
+    };
+    // Build t (thread 0): the codebook operand of build t must have landed in ring slot t & 1.
+    auto issue_mma = [&](int t) {
+        const uint32_t slot = t & 1;
+        mbar_wait(slot ? bar_full1 : bar_full0, (t >> 1) & 1, ta.err, 1);
+        tc_fence_after();
+        const uint32_t bb = bbuf_u32 + slot * TB_GROUP;
+        const uint64_t A0h = tc_smem_desc(abuf_u32), A0l = tc_smem_desc(abuf_u32 + TA_BLK),
+                       A1h = tc_smem_desc(abuf_u32 + 2 * TA_BLK), A1l = tc_smem_desc(abuf_u32 + 3 * TA_BLK),
+                       A1s = tc_smem_desc(abuf_u32 + 4 * TA_BLK);
+        const uint64_t B0h = tc_smem_desc(bb), B0l = tc_smem_desc(bb + TB_BLK), B1h = tc_smem_desc(bb + 2 * TB_BLK),
+                       B1l = tc_smem_desc(bb + 3 * TB_BLK), Bn = tc_smem_desc(bb + 4 * TB_BLK);
+        tc_mma(tmem_base, A0h, B0h, 0);
+        tc_mma(tmem_base, A0l, B0h, 1);
+        tc_mma(tmem_base, A0h, B0l, 1);
+        tc_mma(tmem_base, A1h, B1h, 1);
+        tc_mma(tmem_base, A1l, B1h, 1);
+        tc_mma(tmem_base, A1h, B1l, 1);
+        tc_mma(tmem_base, A1s, Bn, 1);
+        tc_commit(bar_mma);
+    };
+    auto stage_planes = [&](int64_t vbase, int nv) {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(a.codes + (size_t)a.list_off[cell] * m) +
+                              (size_t)vbase * nplanes;
+        const int nwords = nv * nplanes;
+        const int padded = ((nv + 3) & ~3) * nplanes;
+        for (int idx = tid; idx < padded; idx += QTHREADS) {
+            const int v = idx / nplanes, c = idx - v * nplanes;
+            planes[c * QPLANE + v] = idx < nwords ? __ldg(src + idx) : 0u;
+        }
+    };
+
+    stage_planes(0, (int)min((int64_t)QVP, len));
+    write_A(0);
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) issue_mma(0);
+
+    const uint32_t lo0 = lane * 4, lo1 = lane * 4 + 128;
+    // epilogue role of this warp: lane quarter -> (copy, subspace-in-group), 32 codeword columns
+    const int quarter = wid & 3, ej = quarter & 1;
+    const int ecol0 = 32 * ((wid >> 2) * 2 + (quarter >> 1));
+    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)ecol0;
+
+    float acc[QNV];
+    int nv = 0;
+    int64_t vbase = 0;
+    for (int t = 0; t < T; ++t) {
+        const int g = t % ng;
+        if (g == 0) {
+            vbase = (int64_t)(t / ng) * QVP;
+            nv = (int)min((int64_t)QVP, len - vbase);
+            if (t > 0) stage_planes(vbase, nv);  // previous pass fully consumed (barrier below)
+        }
+        // ---- epilogue of build t: tensor memory -> table layout of the scan ----
+        mbar_wait(bar_mma, t & 1, ta.err, 2);
+        tc_fence_after();
+        {
+            uint32_t v[32];
+            tc_ld32(taddr, v);
+            tc_wait_ld();
+            const int s = 2 * g + ej;
+            char* dst = lutb + ej * 128 + lane * 4;
+            const uint8_t* cvp = a.cb_codes + (size_t)s * a.ksub;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                const int code = ecol0 + i;
+                if (code < a.ksub) {
+                    const int row = IDENT ? code : (int)cvp[code];  // code VALUE -> entry (oracle Q6)
+                    *reinterpret_cast<uint32_t*>(dst + row * 256) = v[i];
+                }
+            }
+        }
+        if (t + 1 < T) write_A((t + 1) % ng);  // build t has completed: its A operand is free
+        tc_fence_before();
+        __syncthreads();  // table complete, accumulator tile drained, next A operand written
+        if (tid == 0 && t + 1 < T) {
+            tc_fence_after();
+            if (t + 2 < T) {  // ring slot t & 1 was last read by build t (complete)
+                const uint32_t bar = (t & 1) ? bar_full1 : bar_full0;
+                mbar_expect_tx(bar, TB_GROUP);
+                tma_bulk_g2s(bbuf_u32 + (t & 1) * TB_GROUP, ta.tcB + (size_t)((t + 2) % ng) * (TB_GROUP / 4), TB_GROUP,
+                             bar);
+            }
+            issue_mma(t + 1);
+        }
+        if (ta.dbg_lut && item == 0 && t < ng) {
+            if (tid < QG) reinterpret_cast<int*>(ta.dbg_lut + (size_t)m * 256 * 32)[tid] = s_pair[tid];
+            if (tid == 0) reinterpret_cast<int*>(ta.dbg_lut + (size_t)m * 256 * 32)[QG] = cell;
+            for (int idx = tid; idx < 2 * 256 * 32; idx += QTHREADS) {
+                const int q = idx & 31, code = (idx >> 5) & 255, j = idx >> 13;
+                ta.dbg_lut[((size_t)(2 * g + j) * 256 + code) * 32 + q] =
+                    *reinterpret_cast<const float*>(lutb + code * 256 + j * 128 + q * 4);
+            }
+        }
+        // ---- K3: scan the two subspaces of this group ----
+        {
+            const uint32_t* plane = planes + (g >> 1) * QPLANE;
+            if (g == 0) scant_group<0, true>(lutb, lo0, lo1, plane, wid, nv, base, acc);
+            else if (g & 1) scant_group<1, false>(lutb, lo0, lo1, plane, wid, nv, base, acc);
+            else scant_group<0, false>(lutb, lo0, lo1, plane, wid, nv, base, acc);
+        }
+        __syncthreads();  // every warp is done with this table
+        if (g != ng - 1) continue;
+
+        // ---- per-(query, list) top-k of this pass (identical to scanq_kernel) ----
+        const int lim = nv - 4 * wid;  // slot j of this warp holds a vector iff 64*(j/4) + j%4 < lim
+        float mn = Limits<float>::inf();
+#pragma unroll
+        for (int j = 0; j < QNV; ++j) {
+            if (16 * (j & ~3) + (j & 3) < lim) mn = fminf(mn, acc[j]);
+        }
+        s_min[wid * QG + lane] = mn;
+        __syncthreads();
+        {
+            int rank = 0;
+#pragma unroll
+            for (int w2 = 0; w2 < QWARPS; ++w2) {
+                const float o = s_min[w2 * QG + lane];
+                rank += (o < mn || (o == mn && w2 < wid)) ? 1 : 0;
+            }
+            // the k-th smallest of 16 distinct candidates bounds the k-th smallest of all
+            if (rank == min(k, QWARPS) - 1) s_thr[lane] = fminf(mn, s_run[lane]);
+        }
+        __syncthreads();
+        {
+            const float thr = s_thr[lane];
+#pragma unroll
+            for (int j = 0; j < QNV; ++j) {
+                const int rel = 16 * (j & ~3) + (j & 3);
+                if (rel < lim && acc[j] <= thr) {
+                    const int slot = atomicAdd(&s_cnt[lane], 1);
+                    if (slot < QCAP) {
+                        cand_d[lane * QCAP + slot] = acc[j];
+                        cand_p[lane * QCAP + slot] = (uint32_t)(vbase + 4 * wid + rel);
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        // exact selection by (distance, position): warp w serves queries w and w + 16
+        for (int q = wid; q < QG; q += QWARPS) {
+            int n = s_cnt[q];
+            const bool ovf = n > QCAP;
+            n = min(n, QCAP);
+            float d0 = Limits<float>::inf(), d1 = Limits<float>::inf();
+            uint32_t p0 = kNoPos, p1 = kNoPos;
+            if (lane < n) { d0 = cand_d[q * QCAP + lane]; p0 = cand_p[q * QCAP + lane]; }
+            if (lane + 32 < n) { d1 = cand_d[q * QCAP + lane + 32]; p1 = cand_p[q * QCAP + lane + 32]; }
+            int r0 = 0, r1 = 0;
+            for (int e = 0; e < n; ++e) {
+                const float de = cand_d[q * QCAP + e];
+                const uint32_t pe = cand_p[q * QCAP + e];
+                r0 += cand_before(de, pe, d0, p0) ? 1 : 0;
+                r1 += cand_before(de, pe, d1, p1) ? 1 : 0;
+            }
+            __syncwarp();
+            if (lane < n && r0 < k) { cand_d[q * QCAP + r0] = d0; cand_p[q * QCAP + r0] = p0; }
+            if (lane + 32 < n && r1 < k) { cand_d[q * QCAP + r1] = d1; cand_p[q * QCAP + r1] = p1; }
+            __syncwarp();
+            if (lane == 0) {
+                const int cnt = min(n, k);
+                s_cnt[q] = cnt;
+                s_run[q] = cnt >= k ? cand_d[q * QCAP + k - 1] : Limits<float>::inf();
+                if (ovf) s_flag[q] = 1;
+            }
+        }
+        __syncthreads();
+    }
+
+    // ---- publish ----
+    for (int idx = tid; idx < nj * k; idx += QTHREADS) {
+        const int q = idx / k, e = idx - q * k;
+        const int pair = s_pair[q];
+        if (!s_flag[q] && e < s_cnt[q]) {
+            a.pair_d[(size_t)pair * k + e] = cand_d[q * QCAP + e];
+            a.pair_pos[(size_t)pair * k + e] = cand_p[q * QCAP + e];
+        }
+    }
+    if (tid < nj) {
+        const int pair = s_pair[tid];
+        if (s_flag[tid]) {
+            a.pair_cnt[pair] = 0;
+            a.redo_pairs[atomicAdd(a.redo_cnt, 1)] = pair;
+        } else {
+            a.pair_cnt[pair] = s_cnt[tid];
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (wid == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(T_TMEM_COLS)
+                     : "memory");
+    }
+}
+
+// Codebook -> B operand blocks of the tensor-core table builder, once at create.
+// Block layout (fp32 words): word(n, k) = (n >> 3) * 64 + (k >> 2) * 32 + (n & 7) * 4 + (k & 3).
+__global__ void prep_tc_kernel(const float* __restrict__ cb, int m, int ksub, int dsub, float* __restrict__ out) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int ng = m >> 1;
+    if (idx >= ng * TB_NBLK * 2048) return;
+    const int kk = idx & 7, n = (idx >> 3) & 255, b = (idx >> 11) % TB_NBLK, g = idx / (2048 * TB_NBLK);
+    float val = 0.f;
+    if (b < 4) {
+        const int s = 2 * g + (b >> 1);
+        const float v = (n < ksub && kk < dsub) ? -2.f * cb[((size_t)s * ksub + n) * dsub + kk] : 0.f;
+        const float hi = __uint_as_float(to_tf32(v));
+        val = (b & 1) ? __uint_as_float(to_tf32(v - hi)) : hi;
+    } else if (kk < 4 && n < ksub) {
+        const int s = 2 * g + (kk >> 1);
+        float nrm = 0.f;
+        for (int d = 0; d < dsub; ++d) {
+            const float w = cb[((size_t)s * ksub + n) * dsub + d];
+            nrm = fma_rn(w, w, nrm);
+        }
+        const float hi = __uint_as_float(to_tf32(nrm));
+        val = (kk & 1) ? __uint_as_float(to_tf32(nrm - hi)) : hi;
+    }
+    out[(size_t)(g * TB_NBLK + b) * 2048 + (n >> 3) * 64 + (kk >> 2) * 32 + (n & 7) * 4 + (kk & 3)] = val;
+}
+
+}  // namespace ivf

@@ -16,7 +16,7 @@ pytestmark = pytest.mark.gpu
 RTOL = 1e-5  # the tolerance north_star states for ADC distances (we assert exact equality too)
 
 
-LEGACY, QLANE, LUT_EXACT = 1, 2, 4  # ivfadc_config.flags (include/ivfadc.h)
+LEGACY, QLANE, LUT_EXACT, LUT_MMASYNC = 1, 2, 4, 8  # ivfadc_config.flags (include/ivfadc.h)
 # Default flags for the bit-exact tests: whichever scan kernel the engine picks, tables in the
 # reference's direct form.  The tensor-core (3xTF32) tables are tested at the stated tolerance in
 # test_search_qlane_* below.
@@ -246,13 +246,58 @@ def test_search_qlane_bit_exact(D, m, ksub, kc, n, nq, k, w, identity):
         assert np.array_equal(gd.view(np.uint8), od.view(np.uint8)), f"flags={flags}"
         np.testing.assert_array_equal(gi, oi, err_msg=f"flags={flags}")
         e.close()
-    # tensor-core tables (the default for large batches): the north_star's tolerance bar
+    # tensor-core tables (the default for large batches): the north_star's tolerance bar.
+    # QLANE alone = tcgen05 / tensor-memory builder where the shape allows it (dsub <= 8),
+    # QLANE | LUT_MMASYNC = the warp-level mma.sync builder.
+    for flags in (QLANE, QLANE | LUT_MMASYNC):
+        e = engine_from(qz, np.uint32, X, flags=flags)
+        gi, gd, gc = e.search_packed(Q, k, w)
+        rep = orc.compare_search(gi, gd, gc, oi, od, oc, rtol=RTOL)
+        assert rep["near_tie_id_mismatches"] <= max(2, rep["results"] // 200), (flags, rep)
+        assert rep["max_rel_err"] < 3e-6, (flags, rep)   # measured error budget of 3xTF32
+        e.close()
+
+
+@pytest.mark.parametrize("D,m,ksub,identity", [(128, 16, 256, True), (96, 12, 256, True), (40, 8, 100, False),
+                                               (16, 4, 256, True)])
+def test_tcgen05_tables_against_fp64(D, m, ksub, identity):
+    """K2 in isolation: the lookup tables the tcgen05 builder leaves in shared memory for work item 0
+    (dumped through ivfadc_debug_tables) against |w|^2 - 2 r.w evaluated in float64."""
+    import ctypes
+    from ivfadc_jl_b200 import synth
+    kc, n, nq, w = 8, 4000, 64, 2
+    X = synth.blobs(n, D, kc, seed=31)
+    cent, cb, codes = synth.random_quantizers(kc, D, m, ksub, seed=7, data=X)
+    if not identity:
+        prng = np.random.default_rng(4)
+        codes = np.stack([prng.permutation(256)[:ksub].astype(np.uint8) for _ in range(m)])
+    qz = orc.Quantizers(cent, cb, codes)
+    Q = synth.blobs(nq, D, kc, seed=32)
     e = engine_from(qz, np.uint32, X, flags=QLANE)
-    gi, gd, gc = e.search_packed(Q, k, w)
-    rep = orc.compare_search(gi, gd, gc, oi, od, oc, rtol=RTOL)
-    assert rep["near_tie_id_mismatches"] <= max(2, rep["results"] // 200), rep
-    assert rep["max_rel_err"] < 3e-6, rep   # measured error budget of 3xTF32
+    iv._capi.check(e._h, e._lib.ivfadc_debug_tables(e._h, None))
+    e.search_packed(Q, 5, w)
+    buf = np.zeros(m * 256 * 32 + 33, dtype=np.float32)
+    iv._capi.check(e._h, e._lib.ivfadc_debug_tables(e._h, buf.ctypes.data_as(ctypes.c_void_p)))
     e.close()
+    tables = buf[:m * 256 * 32].reshape(m, 256, 32)
+    meta = buf[m * 256 * 32:].view(np.int32)
+    pairs, cell = meta[:32], int(meta[32])
+    assert 0 <= cell < kc and (pairs >= 0).any()
+    dsub = D // m
+    codes_np = np.asarray(qz.cb_codes)
+    worst = 0.0
+    for slot, p in enumerate(pairs):
+        if p < 0:
+            continue
+        r = Q[p // w].astype(np.float64) - cent[cell].astype(np.float64)
+        for s in range(m):
+            rs = r[s * dsub:(s + 1) * dsub]
+            wv = cb[s].astype(np.float64)                      # [ksub, dsub]
+            want = (wv * wv).sum(1) - 2.0 * wv @ rs            # entry of codeword c lives at row codes[s][c]
+            got = tables[s, codes_np[s].astype(np.int64), slot].astype(np.float64)
+            scale = np.abs(wv * wv).sum(1) + 2.0 * np.abs(wv) @ np.abs(rs) + 1e-30
+            worst = max(worst, float(np.max(np.abs(got - want) / scale)))
+    assert worst < 2e-6, worst
 
 
 def test_search_qlane_ties_overflow_redo():
