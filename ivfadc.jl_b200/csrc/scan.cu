@@ -340,7 +340,7 @@ bool use_scanq(const ivfadc_index* h, int64_t npairs, int k) {
 bool use_scant(const ivfadc_index* h) {
     if (h->cfg.flags & (IVFADC_FLAG_LUT_EXACT | IVFADC_FLAG_LUT_MMASYNC)) return false;
     return h->d_tcB != nullptr && h->dsub <= 8 &&
-           scant_smem_layout(h->cfg.m).total <= kSmemMax;
+           scant_smem_layout(h->cfg.m, T_DYN_BASE_GUESS).total + T_DYN_BASE_GUESS <= kSmemMax;
 }
 
 template <typename T, int MC>
@@ -435,7 +435,7 @@ cudaError_t search_t(ivfadc_index* h, const void* dQ, int64_t nq, int k, int w, 
                 tq.items = h->ws_items.as<int4>();
                 tq.err = h->d_err;
                 tq.dbg_lut = static_cast<float*>(h->d_dbg_lut);
-                const size_t tsmem = scant_smem_layout(a.m).total;
+                const size_t tsmem = kSmemMax;  // the kernel places its 64 KB table at a 64 KB-aligned absolute address
                 static size_t tconfigured[2] = {0, 0};
                 const int ident = a.cb_identity ? 1 : 0;
                 if (tsmem > tconfigured[ident]) {

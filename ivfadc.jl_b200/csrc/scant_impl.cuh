@@ -49,28 +49,36 @@ struct ScanTArgs {
     float* dbg_lut;       // optional dump of work item 0: tables [m][256][32], then int pair[32], int cell
 };
 
+// Shared-memory plan, byte offsets from the start of dynamic shared memory.  The 64 KB table is placed
+// at an ABSOLUTE shared address that is a multiple of 64 KB, so that one byte-permute builds a
+// complete 32-bit lookup address  base | code << 8 | lane offset  (no add per lookup); the small
+// arrays fill the gap in front of it.
 struct ScanTSmem {
-    size_t lut, bbuf, abuf, resid, planes, cand_d, cand_p, smin, misc, bars, total;
+    uint32_t abuf, resid, planes, smin, misc, bars, front_end;  // in front of the table
+    uint32_t lut, bbuf, cand_d, cand_p, total;                  // from the table on (lut set at run time)
 };
 
-__host__ __device__ inline ScanTSmem scant_smem_layout(int m) {
+__host__ __device__ inline ScanTSmem scant_smem_layout(int m, uint32_t dyn_base) {
     ScanTSmem s;
-    size_t o = 0;
-    s.lut = o;    o += 65536;                              // [256 codes][2 subspaces][32 queries] fp32
-    s.bbuf = o;   o += 2 * (size_t)TB_GROUP;
-    s.abuf = o;   o += (size_t)TA_NBLK * TA_BLK;
-    s.resid = o;  o += (size_t)m * 8 * T_RS * 4;
-    o = (o + 15) & ~(size_t)15;
-    s.planes = o; o += (size_t)(m / QCS) * QPLANE * 4;
-    s.cand_d = o; o += (size_t)QG * QCAP * 4;
-    s.cand_p = o; o += (size_t)QG * QCAP * 4;
-    s.smin = o;   o += (size_t)QWARPS * QG * 4;
+    uint32_t o = 0;
+    s.abuf = o;   o += TA_NBLK * TA_BLK;
+    s.resid = o;  o += (uint32_t)m * 8 * T_RS * 4;
+    o = (o + 15) & ~15u;
+    s.planes = o; o += (uint32_t)(m / QCS) * QPLANE * 4;
+    s.smin = o;   o += QWARPS * QG * 4;
     s.misc = o;   o += 6 * QG * 4;
-    o = (o + 15) & ~(size_t)15;
+    o = (o + 15) & ~15u;
     s.bars = o;   o += 64;
+    s.front_end = o;
+    s.lut = ((dyn_base + o + 0xFFFFu) & ~0xFFFFu) - dyn_base;
+    o = s.lut + 65536;
+    s.bbuf = o;   o += 2 * TB_GROUP;
+    s.cand_d = o; o += QG * QCAP * 4;
+    s.cand_p = o; o += QG * QCAP * 4;
     s.total = o;
     return s;
 }
+constexpr uint32_t T_DYN_BASE_GUESS = 0x400;  // dynamic shared memory starts after the 1 KB the system reserves
 
 // ---- PTX wrappers ---------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -142,32 +150,72 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
 }
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// ---- explicit shared-memory accesses -------------------------------------------------------------
+// Every shared-memory access of this kernel goes through a 32-bit shared address held in a register.
+// With generic C++ pointers nvcc re-materialises the shared window base (S2UR SR_CgaCtaId, UMOV,
+// ULEA, IADD3) in front of almost every access once registers are tight -- 4 extra issue slots per
+// load, measured as 30% of the instructions of the first version of this kernel (profiles/).
+__device__ __forceinline__ float lds_f(uint32_t a) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds_u(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ uint4 lds_v4(uint32_t a) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts_f(uint32_t a, float v) {
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory");
+}
+__device__ __forceinline__ void sts_u(uint32_t a, uint32_t v) {
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+}
+__device__ __forceinline__ void sts_v4f(uint32_t a, float x, float y, float z, float w) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
+}
+__device__ __forceinline__ int atoms_add(uint32_t a, int v) {
+    int old;
+    asm volatile("atom.shared.add.s32 %0, [%1], %2;" : "=r"(old) : "r"(a), "r"(v) : "memory");
+    return old;
+}
+
 // ---- K3: one group (two subspaces) over the 64 vectors of this warp ----------------------------
 // BP: which byte pair of the staged code word (subspaces 4c + 2BP, 4c + 2BP + 1).
+// lo0 / lo1 = table base (multiple of 64 KB) | lane * 4 [+ 128]: ONE PRMT makes the whole address
+//   byte 0 <- lane offset, byte 1 <- code byte, bytes 2..3 <- table base.
 template <int BP, bool FIRST>
-__device__ __forceinline__ float scant_vec(const char* lutb, uint32_t lo0, uint32_t lo1, uint32_t x, float acc,
-                                           float base) {
-    // address = code << 8 | lane * 4 [+ 128] in one PRMT (table rows are 256 B: two subspaces x 32 queries)
-    const uint32_t o0 = __byte_perm(x, lo0, 0x5504 | ((2 * BP) << 4));
-    const uint32_t o1 = __byte_perm(x, lo1, 0x5504 | ((2 * BP + 1) << 4));
-    const float v0 = *reinterpret_cast<const float*>(lutb + o0);
-    const float v1 = *reinterpret_cast<const float*>(lutb + o1);
+__device__ __forceinline__ float scant_vec(uint32_t lo0, uint32_t lo1, uint32_t x, float acc, float base) {
+    const uint32_t o0 = __byte_perm(x, lo0, 0x7604 | ((2 * BP) << 4));
+    const uint32_t o1 = __byte_perm(x, lo1, 0x7604 | ((2 * BP + 1) << 4));
+    const float v0 = lds_f(o0);
+    const float v1 = lds_f(o1);
     acc = FIRST ? add_rn(base, v0) : add_rn(acc, v0);
     return add_rn(acc, v1);  // subspace order, as the reference's chain (src/index.jl:242-246)
 }
 
+// Quads of vectors are checked four at a time (planes are zero-padded, slots beyond the list are
+// masked in the selection), so the loop carries 4 warp-uniform branches per group instead of 16.
 template <int BP, bool FIRST>
-__device__ __forceinline__ void scant_group(const char* lutb, uint32_t lo0, uint32_t lo1, const uint32_t* plane,
-                                            int wid, int nv, float base, float (&acc)[QNV]) {
+__device__ __forceinline__ void scant_group(uint32_t lo0, uint32_t lo1, uint32_t plane_w, int nquads, float base,
+                                            float (&acc)[QNV]) {
 #pragma unroll
-    for (int jj = 0; jj < QNV / 4; ++jj) {
-        const int g = wid + QWARPS * jj;
-        if (4 * g < nv) {  // warp-uniform
-            const uint4 x = *reinterpret_cast<const uint4*>(plane + 4 * g);
-            acc[4 * jj + 0] = scant_vec<BP, FIRST>(lutb, lo0, lo1, x.x, acc[4 * jj + 0], base);
-            acc[4 * jj + 1] = scant_vec<BP, FIRST>(lutb, lo0, lo1, x.y, acc[4 * jj + 1], base);
-            acc[4 * jj + 2] = scant_vec<BP, FIRST>(lutb, lo0, lo1, x.z, acc[4 * jj + 2], base);
-            acc[4 * jj + 3] = scant_vec<BP, FIRST>(lutb, lo0, lo1, x.w, acc[4 * jj + 3], base);
+    for (int j4 = 0; j4 < QNV / 16; ++j4) {
+        if (4 * j4 < nquads) {  // warp-uniform
+#pragma unroll
+            for (int jq = 0; jq < 4; ++jq) {
+                const int jj = 4 * j4 + jq;
+                const uint4 x = lds_v4(plane_w + jj * (QWARPS * 16));
+                acc[4 * jj + 0] = scant_vec<BP, FIRST>(lo0, lo1, x.x, acc[4 * jj + 0], base);
+                acc[4 * jj + 1] = scant_vec<BP, FIRST>(lo0, lo1, x.y, acc[4 * jj + 1], base);
+                acc[4 * jj + 2] = scant_vec<BP, FIRST>(lo0, lo1, x.z, acc[4 * jj + 2], base);
+                acc[4 * jj + 3] = scant_vec<BP, FIRST>(lo0, lo1, x.w, acc[4 * jj + 3], base);
+            }
         }
     }
 }
@@ -177,7 +225,6 @@ __global__ void __launch_bounds__(QTHREADS, 1)
 scant_kernel(const ScanTArgs ta) {
     const ScanQArgs& a = ta.q;
     extern __shared__ __align__(1024) unsigned char smem_t[];
-    unsigned char* const smem_raw = smem_t;
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const int wid = tid >> 5;
@@ -191,25 +238,25 @@ scant_kernel(const ScanTArgs ta) {
     const int4 it = ta.items[item];
     const int cell = it.x, first = it.y, nj = it.z;
 
-    const ScanTSmem L = scant_smem_layout(m);
-    char* lutb = reinterpret_cast<char*>(smem_raw + L.lut);
-    unsigned char* bbuf = smem_raw + L.bbuf;
-    unsigned char* abuf = smem_raw + L.abuf;
-    float* resid = reinterpret_cast<float*>(smem_raw + L.resid);
-    uint32_t* planes = reinterpret_cast<uint32_t*>(smem_raw + L.planes);
-    float* cand_d = reinterpret_cast<float*>(smem_raw + L.cand_d);
-    uint32_t* cand_p = reinterpret_cast<uint32_t*>(smem_raw + L.cand_p);
-    float* s_min = reinterpret_cast<float*>(smem_raw + L.smin);
-    float* s_dc = reinterpret_cast<float*>(smem_raw + L.misc);
-    float* s_thr = s_dc + QG;
-    float* s_run = s_thr + QG;
-    int* s_cnt = reinterpret_cast<int*>(s_run + QG);
-    int* s_pair = s_cnt + QG;
-    int* s_flag = s_pair + QG;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + L.bars);
-    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 4);
-    const uint32_t bar_full0 = smem_u32(&bars[0]), bar_full1 = smem_u32(&bars[1]), bar_mma = smem_u32(&bars[2]);
-    const uint32_t abuf_u32 = smem_u32(abuf), bbuf_u32 = smem_u32(bbuf);
+    // one opaque copy of the dynamic shared-memory base; all addresses below are sb + offset
+    uint32_t sb;
+    asm volatile("mov.u32 %0, %1;" : "=r"(sb) : "r"(smem_u32(smem_t)));
+    const ScanTSmem L = scant_smem_layout(m, sb);
+    {
+        uint32_t dyn_size;
+        asm volatile("mov.u32 %0, %%dynamic_smem_size;" : "=r"(dyn_size));
+        if (L.total > dyn_size) {  // cannot happen with the 1 KB system reservation the host assumes
+            if (tid == 0) atomicExch(ta.err, 3);
+            return;
+        }
+    }
+    const uint32_t lut_u = sb + L.lut;  // multiple of 64 KB
+    const uint32_t abuf_u = sb + L.abuf, bbuf_u = sb + L.bbuf, resid_u = sb + L.resid, planes_u = sb + L.planes;
+    const uint32_t cand_d_u = sb + L.cand_d, cand_p_u = sb + L.cand_p, smin_u = sb + L.smin;
+    const uint32_t dc_u = sb + L.misc, thr_u = dc_u + QG * 4, run_u = thr_u + QG * 4, cnt_u = run_u + QG * 4,
+                   pair_u = cnt_u + QG * 4, flag_u = pair_u + QG * 4;
+    const uint32_t bar_full0 = sb + L.bars, bar_full1 = bar_full0 + 8, bar_mma = bar_full0 + 16,
+                   tmem_slot = bar_full0 + 32;
 
     const int64_t len = a.list_len[cell];
     const int npass = (int)((len + QVP - 1) / QVP);
@@ -223,43 +270,41 @@ scant_kernel(const ScanTArgs ta) {
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (wid == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)),
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot),
                      "r"(T_TMEM_COLS)
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     if (tid < QG) {
         const int p = tid < nj ? a.sorted_pairs[first + tid] : -1;
-        s_pair[tid] = p;
-        s_dc[tid] = p >= 0 ? a.dc[p] : 0.f;
-        s_run[tid] = Limits<float>::inf();
-        s_cnt[tid] = 0;
-        s_flag[tid] = 0;
+        sts_u(pair_u + tid * 4, (uint32_t)p);
+        sts_f(dc_u + tid * 4, p >= 0 ? a.dc[p] : 0.f);
+        sts_f(run_u + tid * 4, Limits<float>::inf());
+        sts_u(cnt_u + tid * 4, 0u);
+        sts_u(flag_u + tid * 4, 0u);
     }
     {
-        float4* A4 = reinterpret_cast<float4*>(abuf);
-        for (int i = tid; i < 4 * TA_BLK / 16; i += QTHREADS) A4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int i = tid; i < 4 * TA_BLK / 16; i += QTHREADS) sts_v4f(abuf_u + i * 16, 0.f, 0.f, 0.f, 0.f);
         // ones block: row (copy, j, q) selects the split norm of subspace j: k slots 2j, 2j + 1
         for (int i = tid; i < 256; i += QTHREADS) {
             const int r = i >> 1, half = i & 1, j = (r >> 5) & 1;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (half == 0) v = j == 0 ? make_float4(1.f, 1.f, 0.f, 0.f) : make_float4(0.f, 0.f, 1.f, 1.f);
-            *reinterpret_cast<float4*>(abuf + 4 * TA_BLK + (r >> 3) * 256 + half * 128 + (r & 7) * 16) = v;
+            const float a0 = (half == 0 && j == 0) ? 1.f : 0.f, a1 = (half == 0 && j == 1) ? 1.f : 0.f;
+            sts_v4f(abuf_u + 4 * TA_BLK + (r >> 3) * 256 + half * 128 + (r & 7) * 16, a0, a0, a1, a1);
         }
         fence_proxy_async();  // generic-proxy writes -> visible to the tensor core (async proxy)
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = *s_tmem;
+    const uint32_t tmem_base = lds_u(tmem_slot);
 
     // codebook operand of the first two builds
     if (tid == 0) {
         mbar_expect_tx(bar_full0, TB_GROUP);
-        tma_bulk_g2s(bbuf_u32, ta.tcB, TB_GROUP, bar_full0);
+        tma_bulk_g2s(bbuf_u, ta.tcB, TB_GROUP, bar_full0);
         if (T > 1) {
             mbar_expect_tx(bar_full1, TB_GROUP);
-            tma_bulk_g2s(bbuf_u32 + TB_GROUP, ta.tcB + (size_t)(1 % ng) * (TB_GROUP / 4), TB_GROUP, bar_full1);
+            tma_bulk_g2s(bbuf_u + TB_GROUP, ta.tcB + (size_t)(1 % ng) * (TB_GROUP / 4), TB_GROUP, bar_full1);
         }
     }
 
@@ -269,24 +314,24 @@ scant_kernel(const ScanTArgs ta) {
     {
         float part = 0.f;
         if (wid < m) {
-            const int p = s_pair[lane];
+            const int p = (int)lds_u(pair_u + lane * 4);
             const float* qv = a.Q + (size_t)(p >= 0 ? p / a.w : 0) * a.D + wid * a.dsub;
             const float* cv = a.C + (size_t)cell * a.D + wid * a.dsub;
 #pragma unroll
             for (int d = 0; d < 8; ++d) {
                 const float r = (p >= 0 && d < a.dsub) ? sub_rn(qv[d], cv[d]) : 0.f;
-                resid[(wid * 8 + d) * T_RS + lane] = r;
+                sts_f(resid_u + ((wid * 8 + d) * T_RS + lane) * 4, r);
                 part = fma_rn(r, r, part);
             }
         }
-        s_min[wid * QG + lane] = part;
+        sts_f(smin_u + (wid * QG + lane) * 4, part);
     }
     __syncthreads();
     float base;
     {
         float rn = 0.f;
-        for (int s = 0; s < m; ++s) rn = add_rn(rn, s_min[s * QG + lane]);  // fixed order
-        base = add_rn(s_dc[lane], rn);  // dc + |r|^2 over the PQ dims
+        for (int s = 0; s < m; ++s) rn = add_rn(rn, lds_f(smin_u + (s * QG + lane) * 4));  // fixed order
+        base = add_rn(lds_f(dc_u + lane * 4), rn);  // dc + |r|^2 over the PQ dims
     }
 
     // A rows of group g: row = (copy, j, q), block 2j = hi, 2j + 1 = lo of r[2g + j][q][0..7]
@@ -296,16 +341,16 @@ scant_kernel(const ScanTArgs ta) {
             float hi[8], lo[8];
 #pragma unroll
             for (int d = 0; d < 8; ++d) {
-                const float r = resid[(s * 8 + d) * T_RS + q];
+                const float r = lds_f(resid_u + ((s * 8 + d) * T_RS + q) * 4);
                 hi[d] = __uint_as_float(to_tf32(r));
                 lo[d] = __uint_as_float(to_tf32(r - hi[d]));
             }
-            unsigned char* ph = abuf + (2 * j) * TA_BLK + (row >> 3) * 256 + (row & 7) * 16;
-            unsigned char* pl = ph + TA_BLK;
-            *reinterpret_cast<float4*>(ph) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-            *reinterpret_cast<float4*>(ph + 128) = make_float4(hi[4], hi[5], hi[6], hi[7]);
-            *reinterpret_cast<float4*>(pl) = make_float4(lo[0], lo[1], lo[2], lo[3]);
-            *reinterpret_cast<float4*>(pl + 128) = make_float4(lo[4], lo[5], lo[6], lo[7]);
+            const uint32_t ph = abuf_u + (2 * j) * TA_BLK + (row >> 3) * 256 + (row & 7) * 16;
+            const uint32_t pl = ph + TA_BLK;
+            sts_v4f(ph, hi[0], hi[1], hi[2], hi[3]);
+            sts_v4f(ph + 128, hi[4], hi[5], hi[6], hi[7]);
+            sts_v4f(pl, lo[0], lo[1], lo[2], lo[3]);
+            sts_v4f(pl + 128, lo[4], lo[5], lo[6], lo[7]);
             fence_proxy_async();  // generic-proxy writes -> visible to the tensor core (async proxy)
         }
     };
@@ -314,10 +359,10 @@ scant_kernel(const ScanTArgs ta) {
         const uint32_t slot = t & 1;
         mbar_wait(slot ? bar_full1 : bar_full0, (t >> 1) & 1, ta.err, 1);
         tc_fence_after();
-        const uint32_t bb = bbuf_u32 + slot * TB_GROUP;
-        const uint64_t A0h = tc_smem_desc(abuf_u32), A0l = tc_smem_desc(abuf_u32 + TA_BLK),
-                       A1h = tc_smem_desc(abuf_u32 + 2 * TA_BLK), A1l = tc_smem_desc(abuf_u32 + 3 * TA_BLK),
-                       A1s = tc_smem_desc(abuf_u32 + 4 * TA_BLK);
+        const uint32_t bb = bbuf_u + slot * TB_GROUP;
+        const uint64_t A0h = tc_smem_desc(abuf_u), A0l = tc_smem_desc(abuf_u + TA_BLK),
+                       A1h = tc_smem_desc(abuf_u + 2 * TA_BLK), A1l = tc_smem_desc(abuf_u + 3 * TA_BLK),
+                       A1s = tc_smem_desc(abuf_u + 4 * TA_BLK);
         const uint64_t B0h = tc_smem_desc(bb), B0l = tc_smem_desc(bb + TB_BLK), B1h = tc_smem_desc(bb + 2 * TB_BLK),
                        B1l = tc_smem_desc(bb + 3 * TB_BLK), Bn = tc_smem_desc(bb + 4 * TB_BLK);
         tc_mma(tmem_base, A0h, B0h, 0);
@@ -333,10 +378,10 @@ scant_kernel(const ScanTArgs ta) {
         const uint32_t* src = reinterpret_cast<const uint32_t*>(a.codes + (size_t)a.list_off[cell] * m) +
                               (size_t)vbase * nplanes;
         const int nwords = nv * nplanes;
-        const int padded = ((nv + 3) & ~3) * nplanes;
+        const int padded = ((nv + 15) & ~15) * nplanes;  // zero-pad to whole 16-vector blocks
         for (int idx = tid; idx < padded; idx += QTHREADS) {
             const int v = idx / nplanes, c = idx - v * nplanes;
-            planes[c * QPLANE + v] = idx < nwords ? __ldg(src + idx) : 0u;
+            sts_u(planes_u + (c * QPLANE + v) * 4, idx < nwords ? __ldg(src + idx) : 0u);
         }
     };
 
@@ -346,20 +391,22 @@ scant_kernel(const ScanTArgs ta) {
     __syncthreads();
     if (tid == 0) issue_mma(0);
 
-    const uint32_t lo0 = lane * 4, lo1 = lane * 4 + 128;
+    const uint32_t lo0 = lut_u | (uint32_t)(lane * 4), lo1 = lo0 + 128;
     // epilogue role of this warp: lane quarter -> (copy, subspace-in-group), 32 codeword columns
     const int quarter = wid & 3, ej = quarter & 1;
     const int ecol0 = 32 * ((wid >> 2) * 2 + (quarter >> 1));
     const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)ecol0;
+    const uint32_t edst = lut_u + ej * 128 + lane * 4;  // + row * 256
 
     float acc[QNV];
-    int nv = 0;
+    int nv = 0, nquads = 0;
     int64_t vbase = 0;
+    int g = 0;
     for (int t = 0; t < T; ++t) {
-        const int g = t % ng;
         if (g == 0) {
             vbase = (int64_t)(t / ng) * QVP;
             nv = (int)min((int64_t)QVP, len - vbase);
+            nquads = max(0, (nv - 4 * wid + 63) >> 6);   // quads jj with 64 * jj + 4 * wid < nv
             if (t > 0) stage_planes(vbase, nv);  // previous pass fully consumed (barrier below)
         }
         // ---- epilogue of build t: tensor memory -> table layout of the scan ----
@@ -369,80 +416,82 @@ scant_kernel(const ScanTArgs ta) {
             uint32_t v[32];
             tc_ld32(taddr, v);
             tc_wait_ld();
-            const int s = 2 * g + ej;
-            char* dst = lutb + ej * 128 + lane * 4;
-            const uint8_t* cvp = a.cb_codes + (size_t)s * a.ksub;
+            if constexpr (IDENT) {
+                // rows of codewords >= ksub are never looked up: store unconditionally
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-                const int code = ecol0 + i;
-                if (code < a.ksub) {
-                    const int row = IDENT ? code : (int)cvp[code];  // code VALUE -> entry (oracle Q6)
-                    *reinterpret_cast<uint32_t*>(dst + row * 256) = v[i];
+                for (int i = 0; i < 32; ++i) sts_u(edst + (ecol0 + i) * 256, v[i]);
+            } else {
+                const uint8_t* cvp = a.cb_codes + (size_t)(2 * g + ej) * a.ksub;
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    const int code = ecol0 + i;
+                    if (code < a.ksub) sts_u(edst + (int)cvp[code] * 256, v[i]);  // code VALUE -> entry (Q6)
                 }
             }
         }
-        if (t + 1 < T) write_A((t + 1) % ng);  // build t has completed: its A operand is free
+        const int gn = g + 1 == ng ? 0 : g + 1;
+        if (t + 1 < T) write_A(gn);  // build t has completed: its A operand is free
         tc_fence_before();
         __syncthreads();  // table complete, accumulator tile drained, next A operand written
         if (tid == 0 && t + 1 < T) {
             tc_fence_after();
             if (t + 2 < T) {  // ring slot t & 1 was last read by build t (complete)
                 const uint32_t bar = (t & 1) ? bar_full1 : bar_full0;
+                const int g2 = gn + 1 == ng ? 0 : gn + 1;
                 mbar_expect_tx(bar, TB_GROUP);
-                tma_bulk_g2s(bbuf_u32 + (t & 1) * TB_GROUP, ta.tcB + (size_t)((t + 2) % ng) * (TB_GROUP / 4), TB_GROUP,
-                             bar);
+                tma_bulk_g2s(bbuf_u + (t & 1) * TB_GROUP, ta.tcB + (size_t)g2 * (TB_GROUP / 4), TB_GROUP, bar);
             }
             issue_mma(t + 1);
         }
         if (ta.dbg_lut && item == 0 && t < ng) {
-            if (tid < QG) reinterpret_cast<int*>(ta.dbg_lut + (size_t)m * 256 * 32)[tid] = s_pair[tid];
+            if (tid < QG) reinterpret_cast<int*>(ta.dbg_lut + (size_t)m * 256 * 32)[tid] = (int)lds_u(pair_u + tid * 4);
             if (tid == 0) reinterpret_cast<int*>(ta.dbg_lut + (size_t)m * 256 * 32)[QG] = cell;
             for (int idx = tid; idx < 2 * 256 * 32; idx += QTHREADS) {
                 const int q = idx & 31, code = (idx >> 5) & 255, j = idx >> 13;
-                ta.dbg_lut[((size_t)(2 * g + j) * 256 + code) * 32 + q] =
-                    *reinterpret_cast<const float*>(lutb + code * 256 + j * 128 + q * 4);
+                ta.dbg_lut[((size_t)(2 * g + j) * 256 + code) * 32 + q] = lds_f(lut_u + code * 256 + j * 128 + q * 4);
             }
         }
         // ---- K3: scan the two subspaces of this group ----
         {
-            const uint32_t* plane = planes + (g >> 1) * QPLANE;
-            if (g == 0) scant_group<0, true>(lutb, lo0, lo1, plane, wid, nv, base, acc);
-            else if (g & 1) scant_group<1, false>(lutb, lo0, lo1, plane, wid, nv, base, acc);
-            else scant_group<0, false>(lutb, lo0, lo1, plane, wid, nv, base, acc);
+            const uint32_t plane_w = planes_u + ((g >> 1) * QPLANE + 4 * wid) * 4;
+            if (g == 0) scant_group<0, true>(lo0, lo1, plane_w, nquads, base, acc);
+            else if (g & 1) scant_group<1, false>(lo0, lo1, plane_w, nquads, base, acc);
+            else scant_group<0, false>(lo0, lo1, plane_w, nquads, base, acc);
         }
         __syncthreads();  // every warp is done with this table
-        if (g != ng - 1) continue;
+        g = gn;
+        if (g != 0) continue;
 
-        // ---- per-(query, list) top-k of this pass (identical to scanq_kernel) ----
+        // ---- per-(query, list) top-k of this pass ----
         const int lim = nv - 4 * wid;  // slot j of this warp holds a vector iff 64*(j/4) + j%4 < lim
         float mn = Limits<float>::inf();
 #pragma unroll
         for (int j = 0; j < QNV; ++j) {
             if (16 * (j & ~3) + (j & 3) < lim) mn = fminf(mn, acc[j]);
         }
-        s_min[wid * QG + lane] = mn;
+        sts_f(smin_u + (wid * QG + lane) * 4, mn);
         __syncthreads();
         {
             int rank = 0;
 #pragma unroll
             for (int w2 = 0; w2 < QWARPS; ++w2) {
-                const float o = s_min[w2 * QG + lane];
+                const float o = lds_f(smin_u + (w2 * QG + lane) * 4);
                 rank += (o < mn || (o == mn && w2 < wid)) ? 1 : 0;
             }
             // the k-th smallest of 16 distinct candidates bounds the k-th smallest of all
-            if (rank == min(k, QWARPS) - 1) s_thr[lane] = fminf(mn, s_run[lane]);
+            if (rank == min(k, QWARPS) - 1) sts_f(thr_u + lane * 4, fminf(mn, lds_f(run_u + lane * 4)));
         }
         __syncthreads();
         {
-            const float thr = s_thr[lane];
+            const float thr = lds_f(thr_u + lane * 4);
 #pragma unroll
             for (int j = 0; j < QNV; ++j) {
                 const int rel = 16 * (j & ~3) + (j & 3);
                 if (rel < lim && acc[j] <= thr) {
-                    const int slot = atomicAdd(&s_cnt[lane], 1);
+                    const int slot = atoms_add(cnt_u + lane * 4, 1);
                     if (slot < QCAP) {
-                        cand_d[lane * QCAP + slot] = acc[j];
-                        cand_p[lane * QCAP + slot] = (uint32_t)(vbase + 4 * wid + rel);
+                        sts_f(cand_d_u + (lane * QCAP + slot) * 4, acc[j]);
+                        sts_u(cand_p_u + (lane * QCAP + slot) * 4, (uint32_t)(vbase + 4 * wid + rel));
                     }
                 }
             }
@@ -450,29 +499,30 @@ scant_kernel(const ScanTArgs ta) {
         __syncthreads();
         // exact selection by (distance, position): warp w serves queries w and w + 16
         for (int q = wid; q < QG; q += QWARPS) {
-            int n = s_cnt[q];
+            int n = (int)lds_u(cnt_u + q * 4);
             const bool ovf = n > QCAP;
             n = min(n, QCAP);
+            const uint32_t cd = cand_d_u + q * QCAP * 4, cp = cand_p_u + q * QCAP * 4;
             float d0 = Limits<float>::inf(), d1 = Limits<float>::inf();
             uint32_t p0 = kNoPos, p1 = kNoPos;
-            if (lane < n) { d0 = cand_d[q * QCAP + lane]; p0 = cand_p[q * QCAP + lane]; }
-            if (lane + 32 < n) { d1 = cand_d[q * QCAP + lane + 32]; p1 = cand_p[q * QCAP + lane + 32]; }
+            if (lane < n) { d0 = lds_f(cd + lane * 4); p0 = lds_u(cp + lane * 4); }
+            if (lane + 32 < n) { d1 = lds_f(cd + (lane + 32) * 4); p1 = lds_u(cp + (lane + 32) * 4); }
             int r0 = 0, r1 = 0;
             for (int e = 0; e < n; ++e) {
-                const float de = cand_d[q * QCAP + e];
-                const uint32_t pe = cand_p[q * QCAP + e];
+                const float de = lds_f(cd + e * 4);
+                const uint32_t pe = lds_u(cp + e * 4);
                 r0 += cand_before(de, pe, d0, p0) ? 1 : 0;
                 r1 += cand_before(de, pe, d1, p1) ? 1 : 0;
             }
             __syncwarp();
-            if (lane < n && r0 < k) { cand_d[q * QCAP + r0] = d0; cand_p[q * QCAP + r0] = p0; }
-            if (lane + 32 < n && r1 < k) { cand_d[q * QCAP + r1] = d1; cand_p[q * QCAP + r1] = p1; }
+            if (lane < n && r0 < k) { sts_f(cd + r0 * 4, d0); sts_u(cp + r0 * 4, p0); }
+            if (lane + 32 < n && r1 < k) { sts_f(cd + r1 * 4, d1); sts_u(cp + r1 * 4, p1); }
             __syncwarp();
             if (lane == 0) {
                 const int cnt = min(n, k);
-                s_cnt[q] = cnt;
-                s_run[q] = cnt >= k ? cand_d[q * QCAP + k - 1] : Limits<float>::inf();
-                if (ovf) s_flag[q] = 1;
+                sts_u(cnt_u + q * 4, (uint32_t)cnt);
+                sts_f(run_u + q * 4, cnt >= k ? lds_f(cd + (k - 1) * 4) : Limits<float>::inf());
+                if (ovf) sts_u(flag_u + q * 4, 1u);
             }
         }
         __syncthreads();
@@ -481,19 +531,19 @@ scant_kernel(const ScanTArgs ta) {
     // ---- publish ----
     for (int idx = tid; idx < nj * k; idx += QTHREADS) {
         const int q = idx / k, e = idx - q * k;
-        const int pair = s_pair[q];
-        if (!s_flag[q] && e < s_cnt[q]) {
-            a.pair_d[(size_t)pair * k + e] = cand_d[q * QCAP + e];
-            a.pair_pos[(size_t)pair * k + e] = cand_p[q * QCAP + e];
+        const int pair = (int)lds_u(pair_u + q * 4);
+        if (!lds_u(flag_u + q * 4) && e < (int)lds_u(cnt_u + q * 4)) {
+            a.pair_d[(size_t)pair * k + e] = lds_f(cand_d_u + (q * QCAP + e) * 4);
+            a.pair_pos[(size_t)pair * k + e] = lds_u(cand_p_u + (q * QCAP + e) * 4);
         }
     }
     if (tid < nj) {
-        const int pair = s_pair[tid];
-        if (s_flag[tid]) {
+        const int pair = (int)lds_u(pair_u + tid * 4);
+        if (lds_u(flag_u + tid * 4)) {
             a.pair_cnt[pair] = 0;
             a.redo_pairs[atomicAdd(a.redo_cnt, 1)] = pair;
         } else {
-            a.pair_cnt[pair] = s_cnt[tid];
+            a.pair_cnt[pair] = (int)lds_u(cnt_u + tid * 4);
         }
     }
     tc_fence_before();
