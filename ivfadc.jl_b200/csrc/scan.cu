@@ -524,8 +524,8 @@ cudaError_t scanq_prepare(ivfadc_index* h, cudaStream_t s, int* launches) {
     if (launches) *launches += 1;
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     // operand blocks of the tcgen05 builder
-    if (h->dsub <= 8 && m % 2 == 0) {
-        const size_t words = (size_t)(m / 2) * TB_NBLK * 2048;
+    if (h->dsub <= 8) {
+        const size_t words = (size_t)m * TB_NBLK * 2048;
         if ((e = cudaMalloc(&h->d_tcB, words * sizeof(float))) != cudaSuccess) return e;
         if ((e = cudaMalloc(&h->d_err, sizeof(int))) != cudaSuccess) return e;
         if ((e = cudaMemsetAsync(h->d_err, 0, sizeof(int), s)) != cudaSuccess) return e;

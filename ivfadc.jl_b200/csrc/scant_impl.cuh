@@ -8,19 +8,19 @@
 // K2.  The mma.sync builder of scanq spends ~190 instructions per 16x32 table tile (fragment
 // loads, lane rotations, 8-byte stores) and serialises with the scan; here
 //
-//   * the table of a GROUP of two subspaces (2 x 256 codes x 32 queries, 64 KB) is ONE accumulator
-//     tile D[128 lanes][256 columns] in tensor memory:  lane = (copy, subspace-in-group, query),
-//     column = codeword index,
+//   * the table of ONE subspace (256 codes x 32 queries, 32 KB) is an accumulator tile
+//     D[128 lanes][256 columns] in tensor memory: lane = (copy, query), column = codeword index,
 //         D = A_hi.B_hi + A_lo.B_hi + A_hi.B_lo  (3xTF32 split, fp32 accumulate)  + 1.|w|^2
-//     with A = residuals r = q - c laid out block-diagonally (rows of the other subspace are zero,
-//     rows 64..127 repeat rows 0..63 so that all four lane quarters -- hence all 16 warps -- can
-//     read the tile), B = -2 * codebook and the split squared norms.  Seven M128 N256 K8 MMAs per
-//     group, issued by one thread; nobody waits for them: they run while the previous group is
-//     being scanned;
-//   * B (40 KB per group, canonical K-major no-swizzle core-matrix layout, prepared once at
-//     create) arrives by cp.async.bulk into a two-deep shared-memory ring, completion on mbarriers;
-//   * the epilogue is one tcgen05.ld 32x32b.x32 per warp (lane = query: 32 consecutive codewords
-//     of that query) and 32 conflict-free 128-byte STS rows into the table layout the scan wants.
+//     with A = residuals r = q - c of that subspace (rows 32..127 repeat rows 0..31, so all four
+//     lane quarters -- hence all 16 warps -- can read the tile), B = -2 * codebook and the split
+//     squared norms.  Four M128 N256 K8 MMAs per subspace, issued by one thread TWO subspaces ahead
+//     of the scan into a double-buffered accumulator (512 columns): nobody waits for them;
+//   * B (24 KB per subspace, canonical K-major no-swizzle core-matrix layout, prepared once at
+//     create) arrives by cp.async.bulk into a three-deep shared-memory ring, completion on mbarriers;
+//   * the epilogue is one tcgen05.ld 32x32b.x16 per warp (lane = query: 16 consecutive codewords
+//     of that query) and 16 conflict-free 128-byte STS rows into the table layout the scan wants;
+//     the table is double-buffered, so the epilogue of subspace s + 1 and the scan of subspace s
+//     share one barrier interval and their shared-memory traffic overlaps.
 //
 // Numerics: entry = |w|^2 - 2 r.w (+ per-query constant dc + |r|^2 added at scan start), the GEMM
 // form of the reference's direct form (src/index.jl:234), accurate to ~1e-6 relative of the
@@ -34,22 +34,24 @@ namespace ivf {
 
 constexpr int TA_BLK = 4096;                 // A block: 128 rows x 8 k (tf32), canonical layout
 constexpr int TB_BLK = 8192;                 // B block: 256 rows x 8 k
-constexpr int TB_NBLK = 5;                   // hi0, lo0, hi1, lo1, norms
-constexpr int TB_GROUP = TB_NBLK * TB_BLK;   // bytes of B per group of two subspaces
-constexpr int TA_NBLK = 5;                   // hi0, lo0, hi1, lo1, ones
-constexpr uint32_t T_TMEM_COLS = 256;
+constexpr int TB_NBLK = 3;                   // hi, lo, norms
+constexpr int TB_SUB = TB_NBLK * TB_BLK;     // bytes of B per subspace
+constexpr int TB_RING = 3;                   // ring slots
+constexpr int TA_BYTES = 5 * TA_BLK;         // (hi, lo) x 2 buffers, ones
+constexpr uint32_t T_TMEM_COLS = 512;        // two accumulator tiles of 256 columns
 constexpr int T_RS = 33;                     // row stride of the transposed residuals
 constexpr uint32_t T_SPIN = 1u << 22;        // bound on every mbarrier wait (no hangs: error flag instead)
 
 struct ScanTArgs {
     ScanQArgs q;
-    const float* tcB;     // [m/2][5][2048] tf32 words: -2w hi/lo per subspace, split norms
+    const float* tcB;     // [m][3][2048] tf32 words: -2w hi | lo, split norms of one subspace
     const int4* items;    // [nitems] (cell, first pair slot, number of pairs, 0)
     int* err;             // device error flag (mbarrier timeout)
     float* dbg_lut;       // optional dump of work item 0: tables [m][256][32], then int pair[32], int cell
 };
 
-// Shared-memory plan, byte offsets from the start of dynamic shared memory.  The 64 KB table is placed
+// Shared-memory plan, byte offsets from the start of dynamic shared memory.  The 64 KB table (two
+// 32 KB buffers interleaved: 256-byte rows = [code][buffer][query]) is placed
 // at an ABSOLUTE shared address that is a multiple of 64 KB, so that one byte-permute builds a
 // complete 32-bit lookup address  base | code << 8 | lane offset  (no add per lookup); the small
 // arrays fill the gap in front of it.
@@ -61,7 +63,7 @@ struct ScanTSmem {
 __host__ __device__ inline ScanTSmem scant_smem_layout(int m, uint32_t dyn_base) {
     ScanTSmem s;
     uint32_t o = 0;
-    s.abuf = o;   o += TA_NBLK * TA_BLK;
+    s.abuf = o;   o += TA_BYTES;
     s.resid = o;  o += (uint32_t)m * 8 * T_RS * 4;
     o = (o + 15) & ~15u;
     s.planes = o; o += (uint32_t)(m / QCS) * QPLANE * 4;
@@ -72,7 +74,7 @@ __host__ __device__ inline ScanTSmem scant_smem_layout(int m, uint32_t dyn_base)
     s.front_end = o;
     s.lut = ((dyn_base + o + 0xFFFFu) & ~0xFFFFu) - dyn_base;
     o = s.lut + 65536;
-    s.bbuf = o;   o += 2 * TB_GROUP;
+    s.bbuf = o;   o += TB_RING * TB_SUB;
     s.cand_d = o; o += QG * QCAP * 4;
     s.cand_p = o; o += QG * QCAP * 4;
     s.total = o;
@@ -148,6 +150,15 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
         : "r"(taddr)
         : "memory");
 }
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr)
+        : "memory");
+}
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ---- explicit shared-memory accesses -------------------------------------------------------------
@@ -185,25 +196,20 @@ __device__ __forceinline__ int atoms_add(uint32_t a, int v) {
     return old;
 }
 
-// ---- K3: one group (two subspaces) over the 64 vectors of this warp ----------------------------
-// BP: which byte pair of the staged code word (subspaces 4c + 2BP, 4c + 2BP + 1).
-// lo0 / lo1 = table base (multiple of 64 KB) | lane * 4 [+ 128]: ONE PRMT makes the whole address
-//   byte 0 <- lane offset, byte 1 <- code byte, bytes 2..3 <- table base.
-template <int BP, bool FIRST>
-__device__ __forceinline__ float scant_vec(uint32_t lo0, uint32_t lo1, uint32_t x, float acc, float base) {
-    const uint32_t o0 = __byte_perm(x, lo0, 0x7604 | ((2 * BP) << 4));
-    const uint32_t o1 = __byte_perm(x, lo1, 0x7604 | ((2 * BP + 1) << 4));
-    const float v0 = lds_f(o0);
-    const float v1 = lds_f(o1);
-    acc = FIRST ? add_rn(base, v0) : add_rn(acc, v0);
-    return add_rn(acc, v1);  // subspace order, as the reference's chain (src/index.jl:242-246)
+// ---- K3: one subspace over the 64 vectors of this warp ------------------------------------------
+// BY: byte of the staged code word (subspace 4c + BY); the table buffer is BY & 1.
+// lob = table base (multiple of 64 KB) | buffer * 128 | lane * 4: ONE PRMT makes the whole address
+//   byte 0 <- buffer / lane offset, byte 1 <- code byte, bytes 2..3 <- table base.
+template <int BY, bool FIRST>
+__device__ __forceinline__ float scant_vec(uint32_t lob, uint32_t x, float acc, float base) {
+    const float v = lds_f(__byte_perm(x, lob, 0x7604 | (BY << 4)));
+    return FIRST ? add_rn(base, v) : add_rn(acc, v);  // subspace order, the reference's chain (src/index.jl:242-246)
 }
 
-// Quads of vectors are checked four at a time (planes are zero-padded, slots beyond the list are
-// masked in the selection), so the loop carries 4 warp-uniform branches per group instead of 16.
-template <int BP, bool FIRST>
-__device__ __forceinline__ void scant_group(uint32_t lo0, uint32_t lo1, uint32_t plane_w, int nquads, float base,
-                                            float (&acc)[QNV]) {
+// Quads of vectors are checked four at a time (slots beyond the list are masked in the selection),
+// so the loop carries 4 warp-uniform branches per subspace instead of 16.
+template <int BY, bool FIRST>
+__device__ __forceinline__ void scant_sub(uint32_t lob, uint32_t plane_w, int nquads, float base, float (&acc)[QNV]) {
 #pragma unroll
     for (int j4 = 0; j4 < QNV / 16; ++j4) {
         if (4 * j4 < nquads) {  // warp-uniform
@@ -211,10 +217,10 @@ __device__ __forceinline__ void scant_group(uint32_t lo0, uint32_t lo1, uint32_t
             for (int jq = 0; jq < 4; ++jq) {
                 const int jj = 4 * j4 + jq;
                 const uint4 x = lds_v4(plane_w + jj * (QWARPS * 16));
-                acc[4 * jj + 0] = scant_vec<BP, FIRST>(lo0, lo1, x.x, acc[4 * jj + 0], base);
-                acc[4 * jj + 1] = scant_vec<BP, FIRST>(lo0, lo1, x.y, acc[4 * jj + 1], base);
-                acc[4 * jj + 2] = scant_vec<BP, FIRST>(lo0, lo1, x.z, acc[4 * jj + 2], base);
-                acc[4 * jj + 3] = scant_vec<BP, FIRST>(lo0, lo1, x.w, acc[4 * jj + 3], base);
+                acc[4 * jj + 0] = scant_vec<BY, FIRST>(lob, x.x, acc[4 * jj + 0], base);
+                acc[4 * jj + 1] = scant_vec<BY, FIRST>(lob, x.y, acc[4 * jj + 1], base);
+                acc[4 * jj + 2] = scant_vec<BY, FIRST>(lob, x.z, acc[4 * jj + 2], base);
+                acc[4 * jj + 3] = scant_vec<BY, FIRST>(lob, x.w, acc[4 * jj + 3], base);
             }
         }
     }
@@ -230,13 +236,18 @@ scant_kernel(const ScanTArgs ta) {
     const int wid = tid >> 5;
     const int m = a.m;
     const int k = a.k;
-    const int ng = m >> 1;          // groups of two subspaces
     const int nplanes = m / QCS;
 
     const int item = blockIdx.x;
     if (item >= a.group_off[a.kc]) return;  // before any allocation
     const int4 it = ta.items[item];
     const int cell = it.x, first = it.y, nj = it.z;
+    // bring-up timeline: clock() of thread 0 of work item 300 at phase boundaries (tests/debug only)
+    long long* tstamp = (ta.dbg_lut != nullptr && item == 300 && tid == 0)
+                            ? reinterpret_cast<long long*>(ta.dbg_lut + (size_t)m * 256 * 32 + 64) : nullptr;
+    int nstamp = 0;
+    auto stamp = [&]() { if (tstamp) tstamp[nstamp++] = clock64(); };
+    stamp();
 
     // one opaque copy of the dynamic shared-memory base; all addresses below are sb + offset
     uint32_t sb;
@@ -255,19 +266,27 @@ scant_kernel(const ScanTArgs ta) {
     const uint32_t cand_d_u = sb + L.cand_d, cand_p_u = sb + L.cand_p, smin_u = sb + L.smin;
     const uint32_t dc_u = sb + L.misc, thr_u = dc_u + QG * 4, run_u = thr_u + QG * 4, cnt_u = run_u + QG * 4,
                    pair_u = cnt_u + QG * 4, flag_u = pair_u + QG * 4;
-    const uint32_t bar_full0 = sb + L.bars, bar_full1 = bar_full0 + 8, bar_mma = bar_full0 + 16,
-                   tmem_slot = bar_full0 + 32;
+    const uint32_t bar_full = sb + L.bars;         // 3 x 8 bytes: codebook operand landed in ring slot i
+    const uint32_t bar_mma = bar_full + 24;        // 2 x 8 bytes: accumulator tile i complete
+    const uint32_t tmem_slot = bar_full + 48;
 
     const int64_t len = a.list_len[cell];
     const int npass = (int)((len + QVP - 1) / QVP);
-    const int T = npass * ng;  // table builds (one per group per pass)
+    const int T = npass * m;  // table builds (one per subspace per pass); build x is subspace x % m
 
-    // ---- one-time setup: barriers, tensor memory, constant parts of A ----
+    // ---- one-time setup: barriers, tensor memory, codebook operands of the first builds ----
     if (tid == 0) {
-        mbar_init(bar_full0, 1);
-        mbar_init(bar_full1, 1);
+#pragma unroll
+        for (int i = 0; i < TB_RING; ++i) mbar_init(bar_full + 8 * i, 1);
         mbar_init(bar_mma, 1);
+        mbar_init(bar_mma + 8, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+#pragma unroll
+        for (int x = 0; x < TB_RING; ++x)
+            if (x < T) {
+                mbar_expect_tx(bar_full + 8 * x, TB_SUB);
+                tma_bulk_g2s(bbuf_u + x * TB_SUB, ta.tcB + (size_t)(x % m) * (TB_SUB / 4), TB_SUB, bar_full + 8 * x);
+            }
     }
     if (wid == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot),
@@ -283,30 +302,18 @@ scant_kernel(const ScanTArgs ta) {
         sts_u(cnt_u + tid * 4, 0u);
         sts_u(flag_u + tid * 4, 0u);
     }
-    {
-        for (int i = tid; i < 4 * TA_BLK / 16; i += QTHREADS) sts_v4f(abuf_u + i * 16, 0.f, 0.f, 0.f, 0.f);
-        // ones block: row (copy, j, q) selects the split norm of subspace j: k slots 2j, 2j + 1
-        for (int i = tid; i < 256; i += QTHREADS) {
-            const int r = i >> 1, half = i & 1, j = (r >> 5) & 1;
-            const float a0 = (half == 0 && j == 0) ? 1.f : 0.f, a1 = (half == 0 && j == 1) ? 1.f : 0.f;
-            sts_v4f(abuf_u + 4 * TA_BLK + (r >> 3) * 256 + half * 128 + (r & 7) * 16, a0, a0, a1, a1);
-        }
-        fence_proxy_async();  // generic-proxy writes -> visible to the tensor core (async proxy)
+    // ones block: every row selects the split norm in k slots 0, 1
+    for (int i = tid; i < 256; i += QTHREADS) {
+        const int r = i >> 1, half = i & 1;
+        const float one = half == 0 ? 1.f : 0.f;
+        sts_v4f(abuf_u + 4 * TA_BLK + (r >> 3) * 256 + half * 128 + (r & 7) * 16, one, one, 0.f, 0.f);
     }
+    fence_proxy_async();  // generic-proxy writes -> visible to the tensor core (async proxy)
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = lds_u(tmem_slot);
-
-    // codebook operand of the first two builds
-    if (tid == 0) {
-        mbar_expect_tx(bar_full0, TB_GROUP);
-        tma_bulk_g2s(bbuf_u, ta.tcB, TB_GROUP, bar_full0);
-        if (T > 1) {
-            mbar_expect_tx(bar_full1, TB_GROUP);
-            tma_bulk_g2s(bbuf_u + TB_GROUP, ta.tcB + (size_t)(1 % ng) * (TB_GROUP / 4), TB_GROUP, bar_full1);
-        }
-    }
+    stamp();
 
     // residuals r_q = query - centroid (reference _closest_cluster_residuals,
     // src/coarsequantizers.jl:40-45): warp s owns subspace s, lane q its query; transposed
@@ -317,9 +324,15 @@ scant_kernel(const ScanTArgs ta) {
             const int p = (int)lds_u(pair_u + lane * 4);
             const float* qv = a.Q + (size_t)(p >= 0 ? p / a.w : 0) * a.D + wid * a.dsub;
             const float* cv = a.C + (size_t)cell * a.D + wid * a.dsub;
+            float qr[8], cr[8];
 #pragma unroll
             for (int d = 0; d < 8; ++d) {
-                const float r = (p >= 0 && d < a.dsub) ? sub_rn(qv[d], cv[d]) : 0.f;
+                qr[d] = (p >= 0 && d < a.dsub) ? __ldg(qv + d) : 0.f;
+                cr[d] = (p >= 0 && d < a.dsub) ? __ldg(cv + d) : 0.f;
+            }
+#pragma unroll
+            for (int d = 0; d < 8; ++d) {
+                const float r = sub_rn(qr[d], cr[d]);
                 sts_f(resid_u + ((wid * 8 + d) * T_RS + lane) * 4, r);
                 part = fma_rn(r, r, part);
             }
@@ -327,6 +340,7 @@ scant_kernel(const ScanTArgs ta) {
         sts_f(smin_u + (wid * QG + lane) * 4, part);
     }
     __syncthreads();
+    stamp();
     float base;
     {
         float rn = 0.f;
@@ -334,135 +348,157 @@ scant_kernel(const ScanTArgs ta) {
         base = add_rn(lds_f(dc_u + lane * 4), rn);  // dc + |r|^2 over the PQ dims
     }
 
-    // A rows of group g: row = (copy, j, q), block 2j = hi, 2j + 1 = lo of r[2g + j][q][0..7]
-    auto write_A = [&](int g) {
-        if (tid < 128) {
-            const int row = tid, j = (row >> 5) & 1, q = row & 31, s = 2 * g + j;
-            float hi[8], lo[8];
+    // A operand of build x (subspace s) into A buffer x & 1: rows (copy, q), hi block then lo block
+    // ONE warp writes the whole operand (the four row copies are the same 32 rows): lane = query,
+    // 8 dims -> hi / lo, 16 stores.  The caller rotates the warp so the cost spreads evenly.
+    auto write_A = [&](int x, int s) {
+        float hi[8], lo[8];
 #pragma unroll
-            for (int d = 0; d < 8; ++d) {
-                const float r = lds_f(resid_u + ((s * 8 + d) * T_RS + q) * 4);
-                hi[d] = __uint_as_float(to_tf32(r));
-                lo[d] = __uint_as_float(to_tf32(r - hi[d]));
-            }
-            const uint32_t ph = abuf_u + (2 * j) * TA_BLK + (row >> 3) * 256 + (row & 7) * 16;
-            const uint32_t pl = ph + TA_BLK;
-            sts_v4f(ph, hi[0], hi[1], hi[2], hi[3]);
-            sts_v4f(ph + 128, hi[4], hi[5], hi[6], hi[7]);
-            sts_v4f(pl, lo[0], lo[1], lo[2], lo[3]);
-            sts_v4f(pl + 128, lo[4], lo[5], lo[6], lo[7]);
-            fence_proxy_async();  // generic-proxy writes -> visible to the tensor core (async proxy)
+        for (int d = 0; d < 8; ++d) {
+            const float r = lds_f(resid_u + ((s * 8 + d) * T_RS + lane) * 4);
+            hi[d] = __uint_as_float(to_tf32(r));
+            lo[d] = __uint_as_float(to_tf32(r - hi[d]));
         }
+        const uint32_t ph = abuf_u + (x & 1) * (2 * TA_BLK) + (lane >> 3) * 256 + (lane & 7) * 16;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {  // row = 32 c + lane
+            sts_v4f(ph + c * 1024, hi[0], hi[1], hi[2], hi[3]);
+            sts_v4f(ph + c * 1024 + 128, hi[4], hi[5], hi[6], hi[7]);
+            sts_v4f(ph + c * 1024 + TA_BLK, lo[0], lo[1], lo[2], lo[3]);
+            sts_v4f(ph + c * 1024 + TA_BLK + 128, lo[4], lo[5], lo[6], lo[7]);
+        }
+        fence_proxy_async();  // generic-proxy writes -> visible to the tensor core (async proxy)
     };
-    // Build t (thread 0): the codebook operand of build t must have landed in ring slot t & 1.
-    auto issue_mma = [&](int t) {
-        const uint32_t slot = t & 1;
-        mbar_wait(slot ? bar_full1 : bar_full0, (t >> 1) & 1, ta.err, 1);
+    // Build x (thread 0): accumulator tile x & 1, A buffer x & 1, codebook operand in ring slot x % 3.
+    auto issue_mma = [&](int x) {
+        const uint32_t slot = (uint32_t)x % TB_RING;
+        mbar_wait(bar_full + 8 * slot, ((uint32_t)x / TB_RING) & 1, ta.err, 1);
         tc_fence_after();
-        const uint32_t bb = bbuf_u + slot * TB_GROUP;
-        const uint64_t A0h = tc_smem_desc(abuf_u), A0l = tc_smem_desc(abuf_u + TA_BLK),
-                       A1h = tc_smem_desc(abuf_u + 2 * TA_BLK), A1l = tc_smem_desc(abuf_u + 3 * TA_BLK),
-                       A1s = tc_smem_desc(abuf_u + 4 * TA_BLK);
-        const uint64_t B0h = tc_smem_desc(bb), B0l = tc_smem_desc(bb + TB_BLK), B1h = tc_smem_desc(bb + 2 * TB_BLK),
-                       B1l = tc_smem_desc(bb + 3 * TB_BLK), Bn = tc_smem_desc(bb + 4 * TB_BLK);
-        tc_mma(tmem_base, A0h, B0h, 0);
-        tc_mma(tmem_base, A0l, B0h, 1);
-        tc_mma(tmem_base, A0h, B0l, 1);
-        tc_mma(tmem_base, A1h, B1h, 1);
-        tc_mma(tmem_base, A1l, B1h, 1);
-        tc_mma(tmem_base, A1h, B1l, 1);
-        tc_mma(tmem_base, A1s, Bn, 1);
-        tc_commit(bar_mma);
+        const uint32_t ab = abuf_u + (x & 1) * (2 * TA_BLK), bb = bbuf_u + slot * TB_SUB;
+        const uint32_t d = tmem_base + (uint32_t)(x & 1) * 256;
+        const uint64_t Ah = tc_smem_desc(ab), Al = tc_smem_desc(ab + TA_BLK), A1 = tc_smem_desc(abuf_u + 4 * TA_BLK);
+        const uint64_t Bh = tc_smem_desc(bb), Bl = tc_smem_desc(bb + TB_BLK), Bn = tc_smem_desc(bb + 2 * TB_BLK);
+        tc_mma(d, Ah, Bh, 0);
+        tc_mma(d, Al, Bh, 1);
+        tc_mma(d, Ah, Bl, 1);
+        tc_mma(d, A1, Bn, 1);
+        tc_commit(bar_mma + 8 * (x & 1));
+    };
+    // Epilogue of build x (subspace s): tensor memory -> table buffer x & 1 in the scan's layout.
+    // Warp w: lane quarter w & 3 (all quarters hold the same 32 queries), codewords 16w .. 16w + 15.
+    auto epilogue = [&](int x, int s) {
+        mbar_wait(bar_mma + 8 * (x & 1), ((uint32_t)x >> 1) & 1, ta.err, 2);
+        tc_fence_after();
+        uint32_t v[16];
+        tc_ld16(tmem_base + ((uint32_t)((wid & 3) * 32) << 16) + (uint32_t)((x & 1) * 256 + 16 * wid), v);
+        tc_wait_ld();
+        const uint32_t edst = lut_u + (x & 1) * 128 + lane * 4;
+        if constexpr (IDENT) {
+            // rows of codewords >= ksub are never looked up: store unconditionally
+#pragma unroll
+            for (int i = 0; i < 16; ++i) sts_u(edst + (16 * wid + i) * 256, v[i]);
+        } else {
+            const uint8_t* cvp = a.cb_codes + (size_t)s * a.ksub;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const int code = 16 * wid + i;
+                if (code < a.ksub) sts_u(edst + (int)cvp[code] * 256, v[i]);  // code VALUE -> entry (Q6)
+            }
+        }
     };
     auto stage_planes = [&](int64_t vbase, int nv) {
         const uint32_t* src = reinterpret_cast<const uint32_t*>(a.codes + (size_t)a.list_off[cell] * m) +
                               (size_t)vbase * nplanes;
         const int nwords = nv * nplanes;
-        const int padded = ((nv + 15) & ~15) * nplanes;  // zero-pad to whole 16-vector blocks
-        for (int idx = tid; idx < padded; idx += QTHREADS) {
+        for (int idx = tid; idx < nwords; idx += QTHREADS) {
             const int v = idx / nplanes, c = idx - v * nplanes;
-            sts_u(planes_u + (c * QPLANE + v) * 4, idx < nwords ? __ldg(src + idx) : 0u);
+            sts_u(planes_u + (c * QPLANE + v) * 4, __ldg(src + idx));
         }
     };
 
     stage_planes(0, (int)min((int64_t)QVP, len));
-    write_A(0);
+    if (wid == 2) write_A(0, 0);
+    if (wid == 3 && T > 1) write_A(1, 1 % m);
     tc_fence_before();
     __syncthreads();
-    if (tid == 0) issue_mma(0);
+    stamp();
+    if (tid == 0) {
+        tc_fence_after();
+        issue_mma(0);
+        if (T > 1) issue_mma(1);
+    }
+    stamp();
+    epilogue(0, 0);
+    stamp();
+    if (wid == 4 && T > 2) write_A(2, 2 % m);  // build 0 has completed: A buffer 0 is free
+    tc_fence_before();
+    __syncthreads();
 
-    const uint32_t lo0 = lut_u | (uint32_t)(lane * 4), lo1 = lo0 + 128;
-    // epilogue role of this warp: lane quarter -> (copy, subspace-in-group), 32 codeword columns
-    const int quarter = wid & 3, ej = quarter & 1;
-    const int ecol0 = 32 * ((wid >> 2) * 2 + (quarter >> 1));
-    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)ecol0;
-    const uint32_t edst = lut_u + ej * 128 + lane * 4;  // + row * 256
+    stamp();
+    const uint32_t lob0 = lut_u | (uint32_t)(lane * 4), lob1 = lob0 + 128;
+    const uint32_t plane_w0 = planes_u + 16 * wid;
 
+    const bool dbg = ta.dbg_lut != nullptr && item == 0;
     float acc[QNV];
     int nv = 0, nquads = 0;
     int64_t vbase = 0;
-    int g = 0;
+    int s = 0;  // subspace of build t
     for (int t = 0; t < T; ++t) {
-        if (g == 0) {
-            vbase = (int64_t)(t / ng) * QVP;
+        if (s == 0) {
+            vbase = (int64_t)(t / m) * QVP;
             nv = (int)min((int64_t)QVP, len - vbase);
             nquads = max(0, (nv - 4 * wid + 63) >> 6);   // quads jj with 64 * jj + 4 * wid < nv
-            if (t > 0) stage_planes(vbase, nv);  // previous pass fully consumed (barrier below)
         }
-        // ---- epilogue of build t: tensor memory -> table layout of the scan ----
-        mbar_wait(bar_mma, t & 1, ta.err, 2);
-        tc_fence_after();
-        {
-            uint32_t v[32];
-            tc_ld32(taddr, v);
-            tc_wait_ld();
-            if constexpr (IDENT) {
-                // rows of codewords >= ksub are never looked up: store unconditionally
-#pragma unroll
-                for (int i = 0; i < 32; ++i) sts_u(edst + (ecol0 + i) * 256, v[i]);
-            } else {
-                const uint8_t* cvp = a.cb_codes + (size_t)(2 * g + ej) * a.ksub;
-#pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    const int code = ecol0 + i;
-                    if (code < a.ksub) sts_u(edst + (int)cvp[code] * 256, v[i]);  // code VALUE -> entry (Q6)
-                }
-            }
-        }
-        const int gn = g + 1 == ng ? 0 : g + 1;
-        if (t + 1 < T) write_A(gn);  // build t has completed: its A operand is free
-        tc_fence_before();
-        __syncthreads();  // table complete, accumulator tile drained, next A operand written
-        if (tid == 0 && t + 1 < T) {
+        // builds run two ahead of the scan: tile / A buffer t & 1 and ring slot t % 3 are free
+        // (build t complete, its tile drained by epilogue(t) before the last barrier)
+        if (tid == 0) {
             tc_fence_after();
-            if (t + 2 < T) {  // ring slot t & 1 was last read by build t (complete)
-                const uint32_t bar = (t & 1) ? bar_full1 : bar_full0;
-                const int g2 = gn + 1 == ng ? 0 : gn + 1;
-                mbar_expect_tx(bar, TB_GROUP);
-                tma_bulk_g2s(bbuf_u + (t & 1) * TB_GROUP, ta.tcB + (size_t)g2 * (TB_GROUP / 4), TB_GROUP, bar);
+            if (t + 3 < T) {
+                const uint32_t slot = (uint32_t)t % TB_RING, bar = bar_full + 8 * slot;
+                mbar_expect_tx(bar, TB_SUB);
+                tma_bulk_g2s(bbuf_u + slot * TB_SUB, ta.tcB + (size_t)((t + 3) % m) * (TB_SUB / 4), TB_SUB, bar);
             }
-            issue_mma(t + 1);
+            if (t + 2 < T) issue_mma(t + 2);
         }
-        if (ta.dbg_lut && item == 0 && t < ng) {
+        const int s1 = s + 1 == m ? 0 : s + 1;
+        // odd warps drain the next table before scanning, even warps after: the tensor-memory load
+        // latency of one half hides behind the lookups of the other half
+        const bool epi = t + 1 < T;
+        if (epi && (wid & 1)) epilogue(t + 1, s1);
+        if (dbg && t < m) {
             if (tid < QG) reinterpret_cast<int*>(ta.dbg_lut + (size_t)m * 256 * 32)[tid] = (int)lds_u(pair_u + tid * 4);
             if (tid == 0) reinterpret_cast<int*>(ta.dbg_lut + (size_t)m * 256 * 32)[QG] = cell;
-            for (int idx = tid; idx < 2 * 256 * 32; idx += QTHREADS) {
-                const int q = idx & 31, code = (idx >> 5) & 255, j = idx >> 13;
-                ta.dbg_lut[((size_t)(2 * g + j) * 256 + code) * 32 + q] = lds_f(lut_u + code * 256 + j * 128 + q * 4);
+            for (int idx = tid; idx < 256 * 32; idx += QTHREADS) {
+                const int q = idx & 31, code = idx >> 5;
+                ta.dbg_lut[((size_t)s * 256 + code) * 32 + q] = lds_f(lut_u + code * 256 + (t & 1) * 128 + q * 4);
             }
         }
-        // ---- K3: scan the two subspaces of this group ----
+        // ---- K3: scan subspace s (table buffer t & 1 == s & 1, code byte s & 3 of plane s >> 2) ----
         {
-            const uint32_t plane_w = planes_u + ((g >> 1) * QPLANE + 4 * wid) * 4;
-            if (g == 0) scant_group<0, true>(lo0, lo1, plane_w, nquads, base, acc);
-            else if (g & 1) scant_group<1, false>(lo0, lo1, plane_w, nquads, base, acc);
-            else scant_group<0, false>(lo0, lo1, plane_w, nquads, base, acc);
+            const uint32_t plane_w = plane_w0 + (s >> 2) * (QPLANE * 4);
+            if (s == 0) scant_sub<0, true>(lob0, plane_w, nquads, base, acc);
+            else
+                switch (s & 3) {
+                    case 0: scant_sub<0, false>(lob0, plane_w, nquads, base, acc); break;
+                    case 1: scant_sub<1, false>(lob1, plane_w, nquads, base, acc); break;
+                    case 2: scant_sub<2, false>(lob0, plane_w, nquads, base, acc); break;
+                    default: scant_sub<3, false>(lob1, plane_w, nquads, base, acc); break;
+                }
         }
-        __syncthreads();  // every warp is done with this table
-        g = gn;
-        if (g != 0) continue;
+        if (epi && !(wid & 1)) epilogue(t + 1, s1);
+        if (t + 3 < T && wid == ((t + 5) & 15)) {
+            // build t + 1 has completed (A buffer (t + 1) & 1 is free); this warp has passed its own epilogue wait
+            if (!epi) mbar_wait(bar_mma + 8 * ((t + 1) & 1), ((uint32_t)(t + 1) >> 1) & 1, ta.err, 2);
+            write_A(t + 3, (s + 3) % m);
+        }
+        tc_fence_before();
+        __syncthreads();  // table buffer t & 1 consumed; table t + 1, A operand t + 3 complete; tile (t + 1) & 1 drained
+        s = s1;
+        stamp();
+        if (s != 0) continue;
 
         // ---- per-(query, list) top-k of this pass ----
+        if (t + 1 < T) stage_planes(vbase + QVP, (int)min((int64_t)QVP, len - vbase - QVP));
         const int lim = nv - 4 * wid;  // slot j of this warp holds a vector iff 64*(j/4) + j%4 < lim
         float mn = Limits<float>::inf();
 #pragma unroll
@@ -528,6 +564,7 @@ scant_kernel(const ScanTArgs ta) {
         __syncthreads();
     }
 
+    stamp();
     // ---- publish ----
     for (int idx = tid; idx < nj * k; idx += QTHREADS) {
         const int q = idx / k, e = idx - q * k;
@@ -555,29 +592,27 @@ scant_kernel(const ScanTArgs ta) {
 }
 
 // Codebook -> B operand blocks of the tensor-core table builder, once at create.
+// Per subspace: block 0 = tf32 hi of -2w, block 1 = lo, block 2 = split |w|^2 in k slots 0, 1.
 // Block layout (fp32 words): word(n, k) = (n >> 3) * 64 + (k >> 2) * 32 + (n & 7) * 4 + (k & 3).
 __global__ void prep_tc_kernel(const float* __restrict__ cb, int m, int ksub, int dsub, float* __restrict__ out) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    const int ng = m >> 1;
-    if (idx >= ng * TB_NBLK * 2048) return;
-    const int kk = idx & 7, n = (idx >> 3) & 255, b = (idx >> 11) % TB_NBLK, g = idx / (2048 * TB_NBLK);
+    if (idx >= m * TB_NBLK * 2048) return;
+    const int kk = idx & 7, n = (idx >> 3) & 255, b = (idx >> 11) % TB_NBLK, s = idx / (2048 * TB_NBLK);
     float val = 0.f;
-    if (b < 4) {
-        const int s = 2 * g + (b >> 1);
+    if (b < 2) {
         const float v = (n < ksub && kk < dsub) ? -2.f * cb[((size_t)s * ksub + n) * dsub + kk] : 0.f;
         const float hi = __uint_as_float(to_tf32(v));
-        val = (b & 1) ? __uint_as_float(to_tf32(v - hi)) : hi;
-    } else if (kk < 4 && n < ksub) {
-        const int s = 2 * g + (kk >> 1);
+        val = b ? __uint_as_float(to_tf32(v - hi)) : hi;
+    } else if (kk < 2 && n < ksub) {
         float nrm = 0.f;
         for (int d = 0; d < dsub; ++d) {
             const float w = cb[((size_t)s * ksub + n) * dsub + d];
             nrm = fma_rn(w, w, nrm);
         }
         const float hi = __uint_as_float(to_tf32(nrm));
-        val = (kk & 1) ? __uint_as_float(to_tf32(nrm - hi)) : hi;
+        val = kk ? __uint_as_float(to_tf32(nrm - hi)) : hi;
     }
-    out[(size_t)(g * TB_NBLK + b) * 2048 + (n >> 3) * 64 + (kk >> 2) * 32 + (n & 7) * 4 + (kk & 3)] = val;
+    out[(size_t)(s * TB_NBLK + b) * 2048 + (n >> 3) * 64 + (kk >> 2) * 32 + (n & 7) * 4 + (kk & 3)] = val;
 }
 
 }  // namespace ivf
