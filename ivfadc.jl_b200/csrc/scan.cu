@@ -444,8 +444,8 @@ cudaError_t search_t(ivfadc_index* h, const void* dQ, int64_t nq, int k, int w, 
                     if (e != cudaSuccess) return e;
                     tconfigured[ident] = tsmem;
                 }
-                if (ident) scant_kernel<true><<<(unsigned)max_items, QTHREADS, tsmem, s>>>(tq);
-                else scant_kernel<false><<<(unsigned)max_items, QTHREADS, tsmem, s>>>(tq);
+                if (ident) scant_kernel<true><<<(unsigned)max_items, TTHREADS, tsmem, s>>>(tq);
+                else scant_kernel<false><<<(unsigned)max_items, TTHREADS, tsmem, s>>>(tq);
                 if ((e = cudaGetLastError()) != cudaSuccess) return e;
                 *launches += 1;
             } else {

@@ -66,11 +66,11 @@ __host__ __device__ inline ScanTSmem scant_smem_layout(int m, uint32_t dyn_base)
     s.abuf = o;   o += TA_BYTES;
     s.resid = o;  o += (uint32_t)m * 8 * T_RS * 4;
     o = (o + 15) & ~15u;
-    s.planes = o; o += (uint32_t)(m / QCS) * QPLANE * 4;
+    s.planes = o; o += (uint32_t)m * QVP;                      // byte planes: plane s = code byte s of 1024 vectors
     s.smin = o;   o += QWARPS * QG * 4;
     s.misc = o;   o += 6 * QG * 4;
     o = (o + 15) & ~15u;
-    s.bars = o;   o += 64;
+    s.bars = o;   o += 96;
     s.front_end = o;
     s.lut = ((dyn_base + o + 0xFFFFu) & ~0xFFFFu) - dyn_base;
     o = s.lut + 65536;
@@ -197,7 +197,10 @@ __device__ __forceinline__ int atoms_add(uint32_t a, int v) {
 }
 
 // ---- K3: one subspace over the 64 vectors of this warp ------------------------------------------
-// BY: byte of the staged code word (subspace 4c + BY); the table buffer is BY & 1.
+// Codes are staged as BYTE PLANES (plane s = code byte s of the pass's 1024 vectors), so one uniform
+// 16-byte load delivers the codes of 16 consecutive vectors for the current subspace: 4 code loads
+// per warp and subspace (word-planes needed 16: every uniform LDS.128 costs shared-memory wavefronts,
+// measured as ~25% of the pipe in the previous version).
 // lob = table base (multiple of 64 KB) | buffer * 128 | lane * 4: ONE PRMT makes the whole address
 //   byte 0 <- buffer / lane offset, byte 1 <- code byte, bytes 2..3 <- table base.
 template <int BY, bool FIRST>
@@ -205,29 +208,36 @@ __device__ __forceinline__ float scant_vec(uint32_t lob, uint32_t x, float acc, 
     const float v = lds_f(__byte_perm(x, lob, 0x7604 | (BY << 4)));
     return FIRST ? add_rn(base, v) : add_rn(acc, v);  // subspace order, the reference's chain (src/index.jl:242-246)
 }
-
-// Quads of vectors are checked four at a time (slots beyond the list are masked in the selection),
-// so the loop carries 4 warp-uniform branches per subspace instead of 16.
-template <int BY, bool FIRST>
-__device__ __forceinline__ void scant_sub(uint32_t lob, uint32_t plane_w, int nquads, float base, float (&acc)[QNV]) {
+template <bool FIRST>
+__device__ __forceinline__ void scant_word(uint32_t lob, uint32_t x, float* acc, float base) {
+    acc[0] = scant_vec<0, FIRST>(lob, x, acc[0], base);
+    acc[1] = scant_vec<1, FIRST>(lob, x, acc[1], base);
+    acc[2] = scant_vec<2, FIRST>(lob, x, acc[2], base);
+    acc[3] = scant_vec<3, FIRST>(lob, x, acc[3], base);
+}
+// Warp w owns vectors 256 * j4 + 16 * w + i (j4 < 4, i < 16) of the pass: acc[16 * j4 + i].
+template <bool FIRST>
+__device__ __forceinline__ void scant_sub(uint32_t lob, uint32_t plane_w, int nch, float base, float (&acc)[QNV]) {
 #pragma unroll
     for (int j4 = 0; j4 < QNV / 16; ++j4) {
-        if (4 * j4 < nquads) {  // warp-uniform
-#pragma unroll
-            for (int jq = 0; jq < 4; ++jq) {
-                const int jj = 4 * j4 + jq;
-                const uint4 x = lds_v4(plane_w + jj * (QWARPS * 16));
-                acc[4 * jj + 0] = scant_vec<BY, FIRST>(lob, x.x, acc[4 * jj + 0], base);
-                acc[4 * jj + 1] = scant_vec<BY, FIRST>(lob, x.y, acc[4 * jj + 1], base);
-                acc[4 * jj + 2] = scant_vec<BY, FIRST>(lob, x.z, acc[4 * jj + 2], base);
-                acc[4 * jj + 3] = scant_vec<BY, FIRST>(lob, x.w, acc[4 * jj + 3], base);
-            }
+        if (j4 < nch) {  // warp-uniform; slots beyond the list inside a chunk are masked after the last subspace
+            const uint4 x = lds_v4(plane_w + j4 * 256);
+            scant_word<FIRST>(lob, x.x, &acc[16 * j4 + 0], base);
+            scant_word<FIRST>(lob, x.y, &acc[16 * j4 + 4], base);
+            scant_word<FIRST>(lob, x.z, &acc[16 * j4 + 8], base);
+            scant_word<FIRST>(lob, x.w, &acc[16 * j4 + 12], base);
         }
     }
 }
 
+constexpr int TTHREADS = QTHREADS + 32;  // 16 scan warps + 1 producer warp (TMA + MMA issue)
+__device__ __forceinline__ void scan_bar() { asm volatile("bar.sync 1, 512;" ::: "memory"); }  // the 16 scan warps
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
 template <bool IDENT>
-__global__ void __launch_bounds__(QTHREADS, 1)
+__global__ void __launch_bounds__(TTHREADS, 1)
 scant_kernel(const ScanTArgs ta) {
     const ScanQArgs& a = ta.q;
     extern __shared__ __align__(1024) unsigned char smem_t[];
@@ -236,7 +246,6 @@ scant_kernel(const ScanTArgs ta) {
     const int wid = tid >> 5;
     const int m = a.m;
     const int k = a.k;
-    const int nplanes = m / QCS;
 
     const int item = blockIdx.x;
     if (item >= a.group_off[a.kc]) return;  // before any allocation
@@ -266,34 +275,100 @@ scant_kernel(const ScanTArgs ta) {
     const uint32_t cand_d_u = sb + L.cand_d, cand_p_u = sb + L.cand_p, smin_u = sb + L.smin;
     const uint32_t dc_u = sb + L.misc, thr_u = dc_u + QG * 4, run_u = thr_u + QG * 4, cnt_u = run_u + QG * 4,
                    pair_u = cnt_u + QG * 4, flag_u = pair_u + QG * 4;
-    const uint32_t bar_full = sb + L.bars;         // 3 x 8 bytes: codebook operand landed in ring slot i
-    const uint32_t bar_mma = bar_full + 24;        // 2 x 8 bytes: accumulator tile i complete
-    const uint32_t tmem_slot = bar_full + 48;
+    const uint32_t bar_full = sb + L.bars;         // [3] codebook operand landed in ring slot i      (TMA tx)
+    const uint32_t bar_mma = bar_full + 24;        // [2] accumulator tile i complete                 (tcgen05.commit)
+    const uint32_t bar_aready = bar_full + 40;     // [2] A operand buffer i written                  (1 arrival)
+    const uint32_t bar_tfree = bar_full + 56;      // [2] accumulator tile i drained by the epilogue  (16 arrivals)
+    const uint32_t tmem_slot = bar_full + 72;
 
     const int64_t len = a.list_len[cell];
     const int npass = (int)((len + QVP - 1) / QVP);
     const int T = npass * m;  // table builds (one per subspace per pass); build x is subspace x % m
 
-    // ---- one-time setup: barriers, tensor memory, codebook operands of the first builds ----
-    if (tid == 0) {
+    // =============================== producer warp ===============================================
+    if (wid == QWARPS) {
+        if (lane == 0) {
 #pragma unroll
-        for (int i = 0; i < TB_RING; ++i) mbar_init(bar_full + 8 * i, 1);
-        mbar_init(bar_mma, 1);
-        mbar_init(bar_mma + 8, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            for (int i = 0; i < TB_RING; ++i) mbar_init(bar_full + 8 * i, 1);
+            mbar_init(bar_mma, 1);
+            mbar_init(bar_mma + 8, 1);
+            mbar_init(bar_aready, 1);
+            mbar_init(bar_aready + 8, 1);
+            mbar_init(bar_tfree, QWARPS);
+            mbar_init(bar_tfree + 8, QWARPS);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 #pragma unroll
-        for (int x = 0; x < TB_RING; ++x)
-            if (x < T) {
-                mbar_expect_tx(bar_full + 8 * x, TB_SUB);
-                tma_bulk_g2s(bbuf_u + x * TB_SUB, ta.tcB + (size_t)(x % m) * (TB_SUB / 4), TB_SUB, bar_full + 8 * x);
-            }
-    }
-    if (wid == 1) {
+            for (int x = 0; x < TB_RING; ++x)
+                if (x < T) {
+                    mbar_expect_tx(bar_full + 8 * x, TB_SUB);
+                    tma_bulk_g2s(bbuf_u + x * TB_SUB, ta.tcB + (size_t)(x % m) * (TB_SUB / 4), TB_SUB, bar_full + 8 * x);
+                }
+        }
+        __syncwarp();
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot),
                      "r"(T_TMEM_COLS)
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        tc_fence_before();
+        __syncthreads();  // [A]
+        tc_fence_after();
+        const uint32_t tmem_base = lds_u(tmem_slot);
+        if (lane == 0) {
+            const uint64_t A1 = tc_smem_desc(abuf_u + 4 * TA_BLK);
+            for (int x = 0; x < T; ++x) {
+                const uint32_t buf = x & 1, slot = (uint32_t)x % TB_RING;
+                if (x >= 2) mbar_wait(bar_tfree + 8 * buf, (((uint32_t)x >> 1) - 1) & 1, ta.err, 4);  // tile drained
+                mbar_wait(bar_aready + 8 * buf, ((uint32_t)x >> 1) & 1, ta.err, 5);                     // A(x) written
+                mbar_wait(bar_full + 8 * slot, ((uint32_t)x / TB_RING) & 1, ta.err, 1);                 // B(x) landed
+                tc_fence_after();
+                const uint32_t ab = abuf_u + buf * (2 * TA_BLK), bb = bbuf_u + slot * TB_SUB;
+                const uint32_t d = tmem_base + buf * 256;
+                const uint64_t Ah = tc_smem_desc(ab), Al = tc_smem_desc(ab + TA_BLK);
+                const uint64_t Bh = tc_smem_desc(bb), Bl = tc_smem_desc(bb + TB_BLK), Bn = tc_smem_desc(bb + 2 * TB_BLK);
+                tc_mma(d, Ah, Bh, 0);
+                tc_mma(d, Al, Bh, 1);
+                tc_mma(d, Ah, Bl, 1);
+                tc_mma(d, A1, Bn, 1);
+                tc_commit(bar_mma + 8 * buf);
+                if (x >= 1 && x + 2 < T) {  // ring slot of build x - 1 is free once that build has completed
+                    mbar_wait(bar_mma + 8 * ((x - 1) & 1), ((uint32_t)(x - 1) >> 1) & 1, ta.err, 6);
+                    const uint32_t s2 = (uint32_t)(x + 2) % TB_RING, bar = bar_full + 8 * s2;
+                    mbar_expect_tx(bar, TB_SUB);
+                    tma_bulk_g2s(bbuf_u + s2 * TB_SUB, ta.tcB + (size_t)((x + 2) % m) * (TB_SUB / 4), TB_SUB, bar);
+                }
+            }
+        }
+        __syncwarp();
+        __syncthreads();  // [Z] every scan warp is done with tensor memory
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(T_TMEM_COLS)
+                     : "memory");
+        return;
     }
+
+    // =============================== scan warps ==================================================
+    // Stage the codes of one pass as byte planes: a thread takes 4 consecutive vectors, transposes
+    // their code words 4 x 4 bytes at a time with byte permutes, and stores one word per subspace.
+    auto stage_planes = [&](int64_t vbase, int nv) {
+        const int nplanes = m >> 2;
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(a.codes + (size_t)a.list_off[cell] * m) +
+                              (size_t)vbase * nplanes;
+        for (int quad = tid; 4 * quad < nv; quad += QTHREADS) {
+            const int v0 = 4 * quad;
+            for (int c = 0; c < nplanes; ++c) {
+                uint32_t w[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) w[i] = v0 + i < nv ? __ldg(src + (size_t)(v0 + i) * nplanes + c) : 0u;
+                const uint32_t t01l = __byte_perm(w[0], w[1], 0x5140), t23l = __byte_perm(w[2], w[3], 0x5140);
+                const uint32_t t01h = __byte_perm(w[0], w[1], 0x7362), t23h = __byte_perm(w[2], w[3], 0x7362);
+                const uint32_t pb = planes_u + (4 * c) * QVP + v0;
+                sts_u(pb, __byte_perm(t01l, t23l, 0x5410));
+                sts_u(pb + QVP, __byte_perm(t01l, t23l, 0x7632));
+                sts_u(pb + 2 * QVP, __byte_perm(t01h, t23h, 0x5410));
+                sts_u(pb + 3 * QVP, __byte_perm(t01h, t23h, 0x7632));
+            }
+        }
+    };
+
     if (tid < QG) {
         const int p = tid < nj ? a.sorted_pairs[first + tid] : -1;
         sts_u(pair_u + tid * 4, (uint32_t)p);
@@ -309,8 +384,9 @@ scant_kernel(const ScanTArgs ta) {
         sts_v4f(abuf_u + 4 * TA_BLK + (r >> 3) * 256 + half * 128 + (r & 7) * 16, one, one, 0.f, 0.f);
     }
     fence_proxy_async();  // generic-proxy writes -> visible to the tensor core (async proxy)
+    stage_planes(0, (int)min((int64_t)QVP, len));
     tc_fence_before();
-    __syncthreads();
+    __syncthreads();  // [A] barriers initialised, tensor memory allocated, pair slots written
     tc_fence_after();
     const uint32_t tmem_base = lds_u(tmem_slot);
     stamp();
@@ -339,7 +415,7 @@ scant_kernel(const ScanTArgs ta) {
         }
         sts_f(smin_u + (wid * QG + lane) * 4, part);
     }
-    __syncthreads();
+    scan_bar();
     stamp();
     float base;
     {
@@ -348,9 +424,8 @@ scant_kernel(const ScanTArgs ta) {
         base = add_rn(lds_f(dc_u + lane * 4), rn);  // dc + |r|^2 over the PQ dims
     }
 
-    // A operand of build x (subspace s) into A buffer x & 1: rows (copy, q), hi block then lo block
-    // ONE warp writes the whole operand (the four row copies are the same 32 rows): lane = query,
-    // 8 dims -> hi / lo, 16 stores.  The caller rotates the warp so the cost spreads evenly.
+    // ONE warp writes the whole A operand of build x (the four row copies are the same 32 rows):
+    // lane = query, 8 dims -> tf32 hi / lo, 16 stores; then tells the producer.  The caller rotates the warp.
     auto write_A = [&](int x, int s) {
         float hi[8], lo[8];
 #pragma unroll
@@ -368,21 +443,8 @@ scant_kernel(const ScanTArgs ta) {
             sts_v4f(ph + c * 1024 + TA_BLK + 128, lo[4], lo[5], lo[6], lo[7]);
         }
         fence_proxy_async();  // generic-proxy writes -> visible to the tensor core (async proxy)
-    };
-    // Build x (thread 0): accumulator tile x & 1, A buffer x & 1, codebook operand in ring slot x % 3.
-    auto issue_mma = [&](int x) {
-        const uint32_t slot = (uint32_t)x % TB_RING;
-        mbar_wait(bar_full + 8 * slot, ((uint32_t)x / TB_RING) & 1, ta.err, 1);
-        tc_fence_after();
-        const uint32_t ab = abuf_u + (x & 1) * (2 * TA_BLK), bb = bbuf_u + slot * TB_SUB;
-        const uint32_t d = tmem_base + (uint32_t)(x & 1) * 256;
-        const uint64_t Ah = tc_smem_desc(ab), Al = tc_smem_desc(ab + TA_BLK), A1 = tc_smem_desc(abuf_u + 4 * TA_BLK);
-        const uint64_t Bh = tc_smem_desc(bb), Bl = tc_smem_desc(bb + TB_BLK), Bn = tc_smem_desc(bb + 2 * TB_BLK);
-        tc_mma(d, Ah, Bh, 0);
-        tc_mma(d, Al, Bh, 1);
-        tc_mma(d, Ah, Bl, 1);
-        tc_mma(d, A1, Bn, 1);
-        tc_commit(bar_mma + 8 * (x & 1));
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_aready + 8 * (x & 1));
     };
     // Epilogue of build x (subspace s): tensor memory -> table buffer x & 1 in the scan's layout.
     // Warp w: lane quarter w & 3 (all quarters hold the same 32 queries), codewords 16w .. 16w + 15.
@@ -392,6 +454,9 @@ scant_kernel(const ScanTArgs ta) {
         uint32_t v[16];
         tc_ld16(tmem_base + ((uint32_t)((wid & 3) * 32) << 16) + (uint32_t)((x & 1) * 256 + 16 * wid), v);
         tc_wait_ld();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_tfree + 8 * (x & 1));  // this warp's part of the tile is drained
         const uint32_t edst = lut_u + (x & 1) * 128 + lane * 4;
         if constexpr (IDENT) {
             // rows of codewords >= ksub are never looked up: store unconditionally
@@ -406,107 +471,75 @@ scant_kernel(const ScanTArgs ta) {
             }
         }
     };
-    auto stage_planes = [&](int64_t vbase, int nv) {
-        const uint32_t* src = reinterpret_cast<const uint32_t*>(a.codes + (size_t)a.list_off[cell] * m) +
-                              (size_t)vbase * nplanes;
-        const int nwords = nv * nplanes;
-        for (int idx = tid; idx < nwords; idx += QTHREADS) {
-            const int v = idx / nplanes, c = idx - v * nplanes;
-            sts_u(planes_u + (c * QPLANE + v) * 4, __ldg(src + idx));
-        }
-    };
 
-    stage_planes(0, (int)min((int64_t)QVP, len));
     if (wid == 2) write_A(0, 0);
     if (wid == 3 && T > 1) write_A(1, 1 % m);
-    tc_fence_before();
-    __syncthreads();
     stamp();
-    if (tid == 0) {
-        tc_fence_after();
-        issue_mma(0);
-        if (T > 1) issue_mma(1);
-    }
-    stamp();
-    epilogue(0, 0);
-    stamp();
-    if (wid == 4 && T > 2) write_A(2, 2 % m);  // build 0 has completed: A buffer 0 is free
-    tc_fence_before();
-    __syncthreads();
 
-    stamp();
     const uint32_t lob0 = lut_u | (uint32_t)(lane * 4), lob1 = lob0 + 128;
     const uint32_t plane_w0 = planes_u + 16 * wid;
-
     const bool dbg = ta.dbg_lut != nullptr && item == 0;
+
     float acc[QNV];
-    int nv = 0, nquads = 0;
+    int nv = 0, nch = 0;
     int64_t vbase = 0;
-    int s = 0;  // subspace of build t
-    for (int t = 0; t < T; ++t) {
-        if (s == 0) {
-            vbase = (int64_t)(t / m) * QVP;
-            nv = (int)min((int64_t)QVP, len - vbase);
-            nquads = max(0, (nv - 4 * wid + 63) >> 6);   // quads jj with 64 * jj + 4 * wid < nv
-        }
-        // builds run two ahead of the scan: tile / A buffer t & 1 and ring slot t % 3 are free
-        // (build t complete, its tile drained by epilogue(t) before the last barrier)
-        if (tid == 0) {
-            tc_fence_after();
-            if (t + 3 < T) {
-                const uint32_t slot = (uint32_t)t % TB_RING, bar = bar_full + 8 * slot;
-                mbar_expect_tx(bar, TB_SUB);
-                tma_bulk_g2s(bbuf_u + slot * TB_SUB, ta.tcB + (size_t)((t + 3) % m) * (TB_SUB / 4), TB_SUB, bar);
-            }
-            if (t + 2 < T) issue_mma(t + 2);
-        }
+    int s = m - 1;  // subspace of build t; the loop starts one step early (t = -1: only the first epilogue)
+    for (int t = -1; t < T; ++t) {
         const int s1 = s + 1 == m ? 0 : s + 1;
+        if (s1 == 0 && t + 1 < T) {  // the next build opens a pass
+            vbase = (int64_t)((t + 1) / m) * QVP;
+        }
         // odd warps drain the next table before scanning, even warps after: the tensor-memory load
         // latency of one half hides behind the lookups of the other half
         const bool epi = t + 1 < T;
-        if (epi && (wid & 1)) epilogue(t + 1, s1);
-        if (dbg && t < m) {
-            if (tid < QG) reinterpret_cast<int*>(ta.dbg_lut + (size_t)m * 256 * 32)[tid] = (int)lds_u(pair_u + tid * 4);
-            if (tid == 0) reinterpret_cast<int*>(ta.dbg_lut + (size_t)m * 256 * 32)[QG] = cell;
-            for (int idx = tid; idx < 256 * 32; idx += QTHREADS) {
-                const int q = idx & 31, code = idx >> 5;
-                ta.dbg_lut[((size_t)s * 256 + code) * 32 + q] = lds_f(lut_u + code * 256 + (t & 1) * 128 + q * 4);
+        if (epi && ((wid & 1) || t < 0)) epilogue(t + 1, s1);
+        if (t >= 0) {
+            if (s == 0) {
+                nv = (int)min((int64_t)QVP, len - vbase);
+                nch = min(4, max(0, (nv - 16 * wid + 255) >> 8));  // chunks j4 with 256 * j4 + 16 * wid < nv
             }
-        }
-        // ---- K3: scan subspace s (table buffer t & 1 == s & 1, code byte s & 3 of plane s >> 2) ----
-        {
-            const uint32_t plane_w = plane_w0 + (s >> 2) * (QPLANE * 4);
-            if (s == 0) scant_sub<0, true>(lob0, plane_w, nquads, base, acc);
-            else
-                switch (s & 3) {
-                    case 0: scant_sub<0, false>(lob0, plane_w, nquads, base, acc); break;
-                    case 1: scant_sub<1, false>(lob1, plane_w, nquads, base, acc); break;
-                    case 2: scant_sub<2, false>(lob0, plane_w, nquads, base, acc); break;
-                    default: scant_sub<3, false>(lob1, plane_w, nquads, base, acc); break;
+            if (dbg && t < m) {
+                if (tid < QG) reinterpret_cast<int*>(ta.dbg_lut + (size_t)m * 256 * 32)[tid] = (int)lds_u(pair_u + tid * 4);
+                if (tid == 0) reinterpret_cast<int*>(ta.dbg_lut + (size_t)m * 256 * 32)[QG] = cell;
+                for (int idx = tid; idx < 256 * 32; idx += QTHREADS) {
+                    const int q = idx & 31, code = idx >> 5;
+                    ta.dbg_lut[((size_t)s * 256 + code) * 32 + q] = lds_f(lut_u + code * 256 + (t & 1) * 128 + q * 4);
                 }
+            }
+            // ---- K3: scan subspace s (table buffer t & 1 == s & 1, byte plane s) ----
+            const uint32_t plane_w = plane_w0 + s * QVP;
+            if (s == 0) scant_sub<true>(lob0, plane_w, nch, base, acc);
+            else scant_sub<false>((s & 1) ? lob1 : lob0, plane_w, nch, base, acc);
+            if (epi && !(wid & 1)) epilogue(t + 1, s1);
         }
-        if (epi && !(wid & 1)) epilogue(t + 1, s1);
-        if (t + 3 < T && wid == ((t + 5) & 15)) {
-            // build t + 1 has completed (A buffer (t + 1) & 1 is free); this warp has passed its own epilogue wait
-            if (!epi) mbar_wait(bar_mma + 8 * ((t + 1) & 1), ((uint32_t)(t + 1) >> 1) & 1, ta.err, 2);
-            write_A(t + 3, (s + 3) % m);
-        }
-        tc_fence_before();
-        __syncthreads();  // table buffer t & 1 consumed; table t + 1, A operand t + 3 complete; tile (t + 1) & 1 drained
+        if (t + 3 < T && wid == ((t + 5) & 15)) write_A(t + 3, (s + 3) % m);  // build t + 1 complete: its A buffer is free
+        scan_bar();  // table buffer t & 1 consumed, table t + 1 complete
         s = s1;
         stamp();
-        if (s != 0) continue;
+        if (t < 0 || s != 0) continue;
 
         // ---- per-(query, list) top-k of this pass ----
-        if (t + 1 < T) stage_planes(vbase + QVP, (int)min((int64_t)QVP, len - vbase - QVP));
-        const int lim = nv - 4 * wid;  // slot j of this warp holds a vector iff 64*(j/4) + j%4 < lim
+        // mask the slots beyond the list (only the chunk that straddles the end has any)
+        {
+            const int lim = nv - 16 * wid;  // slot 16 * j4 + i holds a vector iff 256 * j4 + i < lim
+#pragma unroll
+            for (int j4 = 0; j4 < QNV / 16; ++j4) {
+                if (256 * j4 + 16 > lim) {  // warp-uniform: chunk not completely inside the list
+#pragma unroll
+                    for (int i = 0; i < 16; ++i)
+                        if (256 * j4 + i >= lim) acc[16 * j4 + i] = Limits<float>::inf();
+                }
+            }
+        }
+        if (t + 1 < T) {  // planes of the next pass (this pass's scan is complete)
+            stage_planes(vbase, (int)min((int64_t)QVP, len - vbase));
+        }
+        const int64_t pbase = (int64_t)(t / m) * QVP + 16 * wid;  // position of slot 0 of this warp
         float mn = Limits<float>::inf();
 #pragma unroll
-        for (int j = 0; j < QNV; ++j) {
-            if (16 * (j & ~3) + (j & 3) < lim) mn = fminf(mn, acc[j]);
-        }
+        for (int j = 0; j < QNV; ++j) mn = fminf(mn, acc[j]);
         sts_f(smin_u + (wid * QG + lane) * 4, mn);
-        __syncthreads();
+        scan_bar();
         {
             int rank = 0;
 #pragma unroll
@@ -517,22 +550,22 @@ scant_kernel(const ScanTArgs ta) {
             // the k-th smallest of 16 distinct candidates bounds the k-th smallest of all
             if (rank == min(k, QWARPS) - 1) sts_f(thr_u + lane * 4, fminf(mn, lds_f(run_u + lane * 4)));
         }
-        __syncthreads();
+        scan_bar();
         {
             const float thr = lds_f(thr_u + lane * 4);
+            const bool any_real = thr < Limits<float>::inf();  // fewer than k vectors so far: keep every real slot
 #pragma unroll
             for (int j = 0; j < QNV; ++j) {
-                const int rel = 16 * (j & ~3) + (j & 3);
-                if (rel < lim && acc[j] <= thr) {
+                if (acc[j] <= thr && (any_real || acc[j] < Limits<float>::inf())) {
                     const int slot = atoms_add(cnt_u + lane * 4, 1);
                     if (slot < QCAP) {
                         sts_f(cand_d_u + (lane * QCAP + slot) * 4, acc[j]);
-                        sts_u(cand_p_u + (lane * QCAP + slot) * 4, (uint32_t)(vbase + 4 * wid + rel));
+                        sts_u(cand_p_u + (lane * QCAP + slot) * 4, (uint32_t)(pbase + 256 * (j >> 4) + (j & 15)));
                     }
                 }
             }
         }
-        __syncthreads();
+        scan_bar();
         // exact selection by (distance, position): warp w serves queries w and w + 16
         for (int q = wid; q < QG; q += QWARPS) {
             int n = (int)lds_u(cnt_u + q * 4);
@@ -561,10 +594,10 @@ scant_kernel(const ScanTArgs ta) {
                 if (ovf) sts_u(flag_u + q * 4, 1u);
             }
         }
-        __syncthreads();
+        scan_bar();
+        stamp();
     }
 
-    stamp();
     // ---- publish ----
     for (int idx = tid; idx < nj * k; idx += QTHREADS) {
         const int q = idx / k, e = idx - q * k;
@@ -584,11 +617,7 @@ scant_kernel(const ScanTArgs ta) {
         }
     }
     tc_fence_before();
-    __syncthreads();
-    if (wid == 1) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(T_TMEM_COLS)
-                     : "memory");
-    }
+    __syncthreads();  // [Z]
 }
 
 // Codebook -> B operand blocks of the tensor-core table builder, once at create.
