@@ -444,8 +444,8 @@ cudaError_t search_t(ivfadc_index* h, const void* dQ, int64_t nq, int k, int w, 
                     if (e != cudaSuccess) return e;
                     tconfigured[ident] = tsmem;
                 }
-                if (ident) scant_kernel<true><<<(unsigned)max_items, TTHREADS, tsmem, s>>>(tq);
-                else scant_kernel<false><<<(unsigned)max_items, TTHREADS, tsmem, s>>>(tq);
+                if (ident) scant_kernel<true><<<(unsigned)max_items, QTHREADS, tsmem, s>>>(tq);
+                else scant_kernel<false><<<(unsigned)max_items, QTHREADS, tsmem, s>>>(tq);
                 if ((e = cudaGetLastError()) != cudaSuccess) return e;
                 *launches += 1;
             } else {
@@ -524,8 +524,8 @@ cudaError_t scanq_prepare(ivfadc_index* h, cudaStream_t s, int* launches) {
     if (launches) *launches += 1;
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     // operand blocks of the tcgen05 builder
-    if (h->dsub <= 8) {
-        const size_t words = (size_t)m * TB_NBLK * 2048;
+    if (h->dsub <= 8 && m % 2 == 0) {
+        const size_t words = (size_t)(m / 2) * TB_NBLK * 2048;
         if ((e = cudaMalloc(&h->d_tcB, words * sizeof(float))) != cudaSuccess) return e;
         if ((e = cudaMalloc(&h->d_err, sizeof(int))) != cudaSuccess) return e;
         if ((e = cudaMemsetAsync(h->d_err, 0, sizeof(int), s)) != cudaSuccess) return e;

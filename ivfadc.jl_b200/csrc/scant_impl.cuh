@@ -8,19 +8,22 @@
 // K2.  The mma.sync builder of scanq spends ~190 instructions per 16x32 table tile (fragment
 // loads, lane rotations, 8-byte stores) and serialises with the scan; here
 //
-//   * the table of ONE subspace (256 codes x 32 queries, 32 KB) is an accumulator tile
-//     D[128 lanes][256 columns] in tensor memory: lane = (copy, query), column = codeword index,
+//   * the table of a GROUP of two subspaces (2 x 256 codes x 32 queries, 64 KB) is ONE accumulator
+//     tile D[128 lanes][256 columns] in tensor memory:  lane = (copy, subspace-in-group, query),
+//     column = codeword index,
 //         D = A_hi.B_hi + A_lo.B_hi + A_hi.B_lo  (3xTF32 split, fp32 accumulate)  + 1.|w|^2
-//     with A = residuals r = q - c of that subspace (rows 32..127 repeat rows 0..31, so all four
-//     lane quarters -- hence all 16 warps -- can read the tile), B = -2 * codebook and the split
-//     squared norms.  Four M128 N256 K8 MMAs per subspace, issued by one thread TWO subspaces ahead
-//     of the scan into a double-buffered accumulator (512 columns): nobody waits for them;
-//   * B (24 KB per subspace, canonical K-major no-swizzle core-matrix layout, prepared once at
-//     create) arrives by cp.async.bulk into a three-deep shared-memory ring, completion on mbarriers;
-//   * the epilogue is one tcgen05.ld 32x32b.x16 per warp (lane = query: 16 consecutive codewords
-//     of that query) and 16 conflict-free 128-byte STS rows into the table layout the scan wants;
-//     the table is double-buffered, so the epilogue of subspace s + 1 and the scan of subspace s
-//     share one barrier interval and their shared-memory traffic overlaps.
+//     with A = residuals r = q - c laid out block-diagonally (rows of the other subspace are zero,
+//     rows 64..127 repeat rows 0..63 so that all four lane quarters -- hence all 16 warps -- can
+//     read the tile), B = -2 * codebook and the split squared norms.  Seven M128 N256 K8 MMAs per
+//     group, issued by ONE lane of the warp that carries half a scan share, while the others
+//     already scan the previous group;
+//   * B (40 KB per group, canonical K-major no-swizzle core-matrix layout, prepared once at
+//     create) arrives by cp.async.bulk into a two-deep shared-memory ring, completion on mbarriers;
+//   * the epilogue is one tcgen05.ld 32x32b.x32 per warp (lane = query: 32 consecutive codewords
+//     of that query) and 32 conflict-free 128-byte STS rows into the table layout the scan wants.
+// (Two other schedules were measured and rejected, see DESIGN.md: per-subspace builds two ahead
+// with a double-buffered table, and a 17th producer warp -- 5 warps on one scheduler cap the kernel
+// at 96 registers.)
 //
 // Numerics: entry = |w|^2 - 2 r.w (+ per-query constant dc + |r|^2 added at scan start), the GEMM
 // form of the reference's direct form (src/index.jl:234), accurate to ~1e-6 relative of the
@@ -34,24 +37,29 @@ namespace ivf {
 
 constexpr int TA_BLK = 4096;                 // A block: 128 rows x 8 k (tf32), canonical layout
 constexpr int TB_BLK = 8192;                 // B block: 256 rows x 8 k
-constexpr int TB_NBLK = 3;                   // hi, lo, norms
-constexpr int TB_SUB = TB_NBLK * TB_BLK;     // bytes of B per subspace
-constexpr int TB_RING = 3;                   // ring slots
-constexpr int TA_BYTES = 5 * TA_BLK;         // (hi, lo) x 2 buffers, ones
-constexpr uint32_t T_TMEM_COLS = 512;        // two accumulator tiles of 256 columns
+constexpr int TB_NBLK = 5;                   // hi0, lo0, hi1, lo1, norms
+constexpr int TB_GROUP = TB_NBLK * TB_BLK;   // bytes of B per group of two subspaces
+constexpr int TA_BYTES = 5 * TA_BLK;         // hi0, lo0, hi1, lo1, ones
+constexpr uint32_t T_TMEM_COLS = 256;
 constexpr int T_RS = 33;                     // row stride of the transposed residuals
 constexpr uint32_t T_SPIN = 1u << 22;        // bound on every mbarrier wait (no hangs: error flag instead)
+// Vectors of a pass are dealt in chunks of 16: warp w owns chunks w, w + 16, w + 32, w + 48.  One lane
+// of the ISSUER warp issues the TMA / MMA work of the next group.  (Giving that warp half a scan
+// share -- 992-vector passes -- was measured: it turns every list of 993..1024 vectors into two passes.)
+constexpr int T_ISSUER = QWARPS - 1;
+constexpr int T_VP = QVP;                    // 1024 vectors per pass
+constexpr int T_PLANE = 1024;                // bytes per byte plane
 
 struct ScanTArgs {
     ScanQArgs q;
-    const float* tcB;     // [m][3][2048] tf32 words: -2w hi | lo, split norms of one subspace
+    const float* tcB;     // [m/2][5][2048] tf32 words: -2w hi/lo per subspace, split norms
     const int4* items;    // [nitems] (cell, first pair slot, number of pairs, 0)
     int* err;             // device error flag (mbarrier timeout)
     float* dbg_lut;       // optional dump of work item 0: tables [m][256][32], then int pair[32], int cell
 };
 
-// Shared-memory plan, byte offsets from the start of dynamic shared memory.  The 64 KB table (two
-// 32 KB buffers interleaved: 256-byte rows = [code][buffer][query]) is placed
+// Shared-memory plan, byte offsets from the start of dynamic shared memory.  The 64 KB table
+// (256-byte rows = [code][subspace-in-group][query]) is placed
 // at an ABSOLUTE shared address that is a multiple of 64 KB, so that one byte-permute builds a
 // complete 32-bit lookup address  base | code << 8 | lane offset  (no add per lookup); the small
 // arrays fill the gap in front of it.
@@ -66,7 +74,7 @@ __host__ __device__ inline ScanTSmem scant_smem_layout(int m, uint32_t dyn_base)
     s.abuf = o;   o += TA_BYTES;
     s.resid = o;  o += (uint32_t)m * 8 * T_RS * 4;
     o = (o + 15) & ~15u;
-    s.planes = o; o += (uint32_t)m * QVP;                      // byte planes: plane s = code byte s of 1024 vectors
+    s.planes = o; o += (uint32_t)m * T_PLANE;                  // byte planes: plane s = code byte s of the pass's vectors
     s.smin = o;   o += QWARPS * QG * 4;
     s.misc = o;   o += 6 * QG * 4;
     o = (o + 15) & ~15u;
@@ -74,7 +82,7 @@ __host__ __device__ inline ScanTSmem scant_smem_layout(int m, uint32_t dyn_base)
     s.front_end = o;
     s.lut = ((dyn_base + o + 0xFFFFu) & ~0xFFFFu) - dyn_base;
     o = s.lut + 65536;
-    s.bbuf = o;   o += TB_RING * TB_SUB;
+    s.bbuf = o;   o += 2 * TB_GROUP;
     s.cand_d = o; o += QG * QCAP * 4;
     s.cand_p = o; o += QG * QCAP * 4;
     s.total = o;
@@ -104,6 +112,7 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity)
 }
 // Bounded wait: a broken pipeline raises the error flag instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* err, int code) {
+#pragma unroll 1
     for (uint32_t i = 0; i < T_SPIN; ++i)
         if (mbar_try_wait(bar, parity)) return;
     atomicExch(err, code);
@@ -196,48 +205,47 @@ __device__ __forceinline__ int atoms_add(uint32_t a, int v) {
     return old;
 }
 
-// ---- K3: one subspace over the 64 vectors of this warp ------------------------------------------
-// Codes are staged as BYTE PLANES (plane s = code byte s of the pass's 1024 vectors), so one uniform
-// 16-byte load delivers the codes of 16 consecutive vectors for the current subspace: 4 code loads
-// per warp and subspace (word-planes needed 16: every uniform LDS.128 costs shared-memory wavefronts,
-// measured as ~25% of the pipe in the previous version).
-// lob = table base (multiple of 64 KB) | buffer * 128 | lane * 4: ONE PRMT makes the whole address
-//   byte 0 <- buffer / lane offset, byte 1 <- code byte, bytes 2..3 <- table base.
+// ---- K3: one group (two subspaces) over the vectors of this warp -------------------------------
+// Codes are staged as BYTE PLANES (plane s = code byte s of the pass's vectors), so one uniform
+// 16-byte load delivers the codes of 16 consecutive vectors for one subspace.
+// lob = table base (multiple of 64 KB) | subspace-in-group * 128 | lane * 4: ONE PRMT makes the
+// whole lookup address: byte 0 <- lane offset, byte 1 <- code byte, bytes 2..3 <- table base.
 template <int BY, bool FIRST>
-__device__ __forceinline__ float scant_vec(uint32_t lob, uint32_t x, float acc, float base) {
-    const float v = lds_f(__byte_perm(x, lob, 0x7604 | (BY << 4)));
-    return FIRST ? add_rn(base, v) : add_rn(acc, v);  // subspace order, the reference's chain (src/index.jl:242-246)
+__device__ __forceinline__ float scant_vec(uint32_t lo0, uint32_t lo1, uint32_t x0, uint32_t x1, float acc, float base) {
+    const float v0 = lds_f(__byte_perm(x0, lo0, 0x7604 | (BY << 4)));
+    const float v1 = lds_f(__byte_perm(x1, lo1, 0x7604 | (BY << 4)));
+    acc = FIRST ? add_rn(base, v0) : add_rn(acc, v0);
+    return add_rn(acc, v1);  // subspace order, the reference's chain (src/index.jl:242-246)
 }
 template <bool FIRST>
-__device__ __forceinline__ void scant_word(uint32_t lob, uint32_t x, float* acc, float base) {
-    acc[0] = scant_vec<0, FIRST>(lob, x, acc[0], base);
-    acc[1] = scant_vec<1, FIRST>(lob, x, acc[1], base);
-    acc[2] = scant_vec<2, FIRST>(lob, x, acc[2], base);
-    acc[3] = scant_vec<3, FIRST>(lob, x, acc[3], base);
+__device__ __forceinline__ void scant_word(uint32_t lo0, uint32_t lo1, uint32_t x0, uint32_t x1, float* acc, float base) {
+    acc[0] = scant_vec<0, FIRST>(lo0, lo1, x0, x1, acc[0], base);
+    acc[1] = scant_vec<1, FIRST>(lo0, lo1, x0, x1, acc[1], base);
+    acc[2] = scant_vec<2, FIRST>(lo0, lo1, x0, x1, acc[2], base);
+    acc[3] = scant_vec<3, FIRST>(lo0, lo1, x0, x1, acc[3], base);
 }
-// Warp w owns vectors 256 * j4 + 16 * w + i (j4 < 4, i < 16) of the pass: acc[16 * j4 + i].
 template <bool FIRST>
-__device__ __forceinline__ void scant_sub(uint32_t lob, uint32_t plane_w, int nch, float base, float (&acc)[QNV]) {
+__device__ __forceinline__ void scant_chunk(uint32_t lo0, uint32_t lo1, uint32_t pa, float* acc, float base) {
+    const uint4 x0 = lds_v4(pa), x1 = lds_v4(pa + T_PLANE);
+    scant_word<FIRST>(lo0, lo1, x0.x, x1.x, acc + 0, base);
+    scant_word<FIRST>(lo0, lo1, x0.y, x1.y, acc + 4, base);
+    scant_word<FIRST>(lo0, lo1, x0.z, x1.z, acc + 8, base);
+    scant_word<FIRST>(lo0, lo1, x0.w, x1.w, acc + 12, base);
+}
+// Slot 16 * j4 + i of a warp = vector 16 * (c0 + cs * j4) + i of the pass.  FULL: all four chunks are
+// inside the list -> straight-line code (the code loads of all chunks can be issued up front).
+template <bool FIRST, bool FULL>
+__device__ __forceinline__ void scant_group(uint32_t lo0, uint32_t lo1, uint32_t plane_w, uint32_t pstride, int nch,
+                                            float base, float (&acc)[QNV]) {
 #pragma unroll
     for (int j4 = 0; j4 < QNV / 16; ++j4) {
-        if (j4 < nch) {  // warp-uniform; slots beyond the list inside a chunk are masked after the last subspace
-            const uint4 x = lds_v4(plane_w + j4 * 256);
-            scant_word<FIRST>(lob, x.x, &acc[16 * j4 + 0], base);
-            scant_word<FIRST>(lob, x.y, &acc[16 * j4 + 4], base);
-            scant_word<FIRST>(lob, x.z, &acc[16 * j4 + 8], base);
-            scant_word<FIRST>(lob, x.w, &acc[16 * j4 + 12], base);
-        }
+        if (FULL || j4 < nch)  // warp-uniform; slots beyond the list inside a chunk are masked after the last group
+            scant_chunk<FIRST>(lo0, lo1, plane_w + j4 * pstride, &acc[16 * j4], base);
     }
 }
 
-constexpr int TTHREADS = QTHREADS + 32;  // 16 scan warps + 1 producer warp (TMA + MMA issue)
-__device__ __forceinline__ void scan_bar() { asm volatile("bar.sync 1, 512;" ::: "memory"); }  // the 16 scan warps
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-
 template <bool IDENT>
-__global__ void __launch_bounds__(TTHREADS, 1)
+__global__ void __launch_bounds__(QTHREADS, 1)
 scant_kernel(const ScanTArgs ta) {
     const ScanQArgs& a = ta.q;
     extern __shared__ __align__(1024) unsigned char smem_t[];
@@ -246,11 +254,14 @@ scant_kernel(const ScanTArgs ta) {
     const int wid = tid >> 5;
     const int m = a.m;
     const int k = a.k;
+    const int ng = m >> 1;  // groups of two subspaces
 
     const int item = blockIdx.x;
     if (item >= a.group_off[a.kc]) return;  // before any allocation
     const int4 it = ta.items[item];
     const int cell = it.x, first = it.y, nj = it.z;
+    // query slot of this lane and the start of its data: issued first, consumed after the setup
+    const int my_pair = lane < nj ? a.sorted_pairs[first + lane] : -1;
     // bring-up timeline: clock() of thread 0 of work item 300 at phase boundaries (tests/debug only)
     long long* tstamp = (ta.dbg_lut != nullptr && item == 300 && tid == 0)
                             ? reinterpret_cast<long long*>(ta.dbg_lut + (size_t)m * 256 * 32 + 64) : nullptr;
@@ -275,137 +286,111 @@ scant_kernel(const ScanTArgs ta) {
     const uint32_t cand_d_u = sb + L.cand_d, cand_p_u = sb + L.cand_p, smin_u = sb + L.smin;
     const uint32_t dc_u = sb + L.misc, thr_u = dc_u + QG * 4, run_u = thr_u + QG * 4, cnt_u = run_u + QG * 4,
                    pair_u = cnt_u + QG * 4, flag_u = pair_u + QG * 4;
-    const uint32_t bar_full = sb + L.bars;         // [3] codebook operand landed in ring slot i      (TMA tx)
-    const uint32_t bar_mma = bar_full + 24;        // [2] accumulator tile i complete                 (tcgen05.commit)
-    const uint32_t bar_aready = bar_full + 40;     // [2] A operand buffer i written                  (1 arrival)
-    const uint32_t bar_tfree = bar_full + 56;      // [2] accumulator tile i drained by the epilogue  (16 arrivals)
-    const uint32_t tmem_slot = bar_full + 72;
+    const uint32_t bar_full0 = sb + L.bars, bar_full1 = bar_full0 + 8, bar_mma = bar_full0 + 16,
+                   tmem_slot = bar_full0 + 32;
 
     const int64_t len = a.list_len[cell];
-    const int npass = (int)((len + QVP - 1) / QVP);
-    const int T = npass * m;  // table builds (one per subspace per pass); build x is subspace x % m
+    const int npass = (int)((len + T_VP - 1) / T_VP);
+    const int T = npass * ng;  // table builds (one per group per pass)
 
-    // =============================== producer warp ===============================================
-    if (wid == QWARPS) {
-        if (lane == 0) {
-#pragma unroll
-            for (int i = 0; i < TB_RING; ++i) mbar_init(bar_full + 8 * i, 1);
-            mbar_init(bar_mma, 1);
-            mbar_init(bar_mma + 8, 1);
-            mbar_init(bar_aready, 1);
-            mbar_init(bar_aready + 8, 1);
-            mbar_init(bar_tfree, QWARPS);
-            mbar_init(bar_tfree + 8, QWARPS);
-            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-#pragma unroll
-            for (int x = 0; x < TB_RING; ++x)
-                if (x < T) {
-                    mbar_expect_tx(bar_full + 8 * x, TB_SUB);
-                    tma_bulk_g2s(bbuf_u + x * TB_SUB, ta.tcB + (size_t)(x % m) * (TB_SUB / 4), TB_SUB, bar_full + 8 * x);
-                }
+    // ---- setup: barriers + first codebook operands (issuer lane), tensor memory, residuals, codes ----
+    if (wid == T_ISSUER && lane == 0) {
+        mbar_init(bar_full0, 1);
+        mbar_init(bar_full1, 1);
+        mbar_init(bar_mma, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        mbar_expect_tx(bar_full0, TB_GROUP);
+        tma_bulk_g2s(bbuf_u, ta.tcB, TB_GROUP, bar_full0);
+        if (T > 1) {
+            mbar_expect_tx(bar_full1, TB_GROUP);
+            tma_bulk_g2s(bbuf_u + TB_GROUP, ta.tcB + (size_t)(1 % ng) * (TB_GROUP / 4), TB_GROUP, bar_full1);
         }
-        __syncwarp();
+    }
+    if (wid == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot),
                      "r"(T_TMEM_COLS)
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-        tc_fence_before();
-        __syncthreads();  // [A]
-        tc_fence_after();
-        const uint32_t tmem_base = lds_u(tmem_slot);
-        if (lane == 0) {
-            const uint64_t A1 = tc_smem_desc(abuf_u + 4 * TA_BLK);
-            for (int x = 0; x < T; ++x) {
-                const uint32_t buf = x & 1, slot = (uint32_t)x % TB_RING;
-                if (x >= 2) mbar_wait(bar_tfree + 8 * buf, (((uint32_t)x >> 1) - 1) & 1, ta.err, 4);  // tile drained
-                mbar_wait(bar_aready + 8 * buf, ((uint32_t)x >> 1) & 1, ta.err, 5);                     // A(x) written
-                mbar_wait(bar_full + 8 * slot, ((uint32_t)x / TB_RING) & 1, ta.err, 1);                 // B(x) landed
-                tc_fence_after();
-                const uint32_t ab = abuf_u + buf * (2 * TA_BLK), bb = bbuf_u + slot * TB_SUB;
-                const uint32_t d = tmem_base + buf * 256;
-                const uint64_t Ah = tc_smem_desc(ab), Al = tc_smem_desc(ab + TA_BLK);
-                const uint64_t Bh = tc_smem_desc(bb), Bl = tc_smem_desc(bb + TB_BLK), Bn = tc_smem_desc(bb + 2 * TB_BLK);
-                tc_mma(d, Ah, Bh, 0);
-                tc_mma(d, Al, Bh, 1);
-                tc_mma(d, Ah, Bl, 1);
-                tc_mma(d, A1, Bn, 1);
-                tc_commit(bar_mma + 8 * buf);
-                if (x >= 1 && x + 2 < T) {  // ring slot of build x - 1 is free once that build has completed
-                    mbar_wait(bar_mma + 8 * ((x - 1) & 1), ((uint32_t)(x - 1) >> 1) & 1, ta.err, 6);
-                    const uint32_t s2 = (uint32_t)(x + 2) % TB_RING, bar = bar_full + 8 * s2;
-                    mbar_expect_tx(bar, TB_SUB);
-                    tma_bulk_g2s(bbuf_u + s2 * TB_SUB, ta.tcB + (size_t)((x + 2) % m) * (TB_SUB / 4), TB_SUB, bar);
-                }
+    }
+    // residuals r_q = query - centroid (reference _closest_cluster_residuals,
+    // src/coarsequantizers.jl:40-45): warp s owns subspace s, lane q its query; transposed
+    // [s * 8 + d][q], zero-padded to 8 dims per subspace
+    float qr[8], cr[8];
+    if (wid < m) {
+        const float* qv = a.Q + (size_t)(my_pair >= 0 ? my_pair / a.w : 0) * a.D + wid * a.dsub;
+        const float* cv = a.C + (size_t)cell * a.D + wid * a.dsub;
+        if (a.dsub == 8 && (a.D & 3) == 0) {
+            const float4 q0 = __ldg(reinterpret_cast<const float4*>(qv)), q1 = __ldg(reinterpret_cast<const float4*>(qv) + 1);
+            const float4 e0 = __ldg(reinterpret_cast<const float4*>(cv)), e1 = __ldg(reinterpret_cast<const float4*>(cv) + 1);
+            qr[0] = q0.x; qr[1] = q0.y; qr[2] = q0.z; qr[3] = q0.w; qr[4] = q1.x; qr[5] = q1.y; qr[6] = q1.z; qr[7] = q1.w;
+            cr[0] = e0.x; cr[1] = e0.y; cr[2] = e0.z; cr[3] = e0.w; cr[4] = e1.x; cr[5] = e1.y; cr[6] = e1.z; cr[7] = e1.w;
+            if (my_pair < 0) {
+#pragma unroll
+                for (int d = 0; d < 8; ++d) qr[d] = cr[d] = 0.f;
+            }
+        } else {
+#pragma unroll
+            for (int d = 0; d < 8; ++d) {
+                qr[d] = (my_pair >= 0 && d < a.dsub) ? __ldg(qv + d) : 0.f;
+                cr[d] = (my_pair >= 0 && d < a.dsub) ? __ldg(cv + d) : 0.f;
             }
         }
-        __syncwarp();
-        __syncthreads();  // [Z] every scan warp is done with tensor memory
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(T_TMEM_COLS)
-                     : "memory");
-        return;
     }
-
-    // =============================== scan warps ==================================================
+    if (wid == 0) {
+        sts_u(pair_u + lane * 4, (uint32_t)my_pair);
+        sts_f(dc_u + lane * 4, my_pair >= 0 ? a.dc[my_pair] : 0.f);
+        sts_f(run_u + lane * 4, Limits<float>::inf());
+        sts_u(cnt_u + lane * 4, 0u);
+        sts_u(flag_u + lane * 4, 0u);
+    }
+    // A operand: zero rows stay zero for the whole item; ones block: row (copy, j, q) selects the
+    // split norm of subspace j (k slots 2j, 2j + 1)
+    for (int i = tid; i < 4 * TA_BLK / 16; i += QTHREADS) sts_v4f(abuf_u + i * 16, 0.f, 0.f, 0.f, 0.f);
+    for (int i = tid; i < 256; i += QTHREADS) {
+        const int r = i >> 1, half = i & 1, j = (r >> 5) & 1;
+        const float a0 = (half == 0 && j == 0) ? 1.f : 0.f, a1 = (half == 0 && j == 1) ? 1.f : 0.f;
+        sts_v4f(abuf_u + 4 * TA_BLK + (r >> 3) * 256 + half * 128 + (r & 7) * 16, a0, a0, a1, a1);
+    }
     // Stage the codes of one pass as byte planes: a thread takes 4 consecutive vectors, transposes
     // their code words 4 x 4 bytes at a time with byte permutes, and stores one word per subspace.
     auto stage_planes = [&](int64_t vbase, int nv) {
         const int nplanes = m >> 2;
         const uint32_t* src = reinterpret_cast<const uint32_t*>(a.codes + (size_t)a.list_off[cell] * m) +
                               (size_t)vbase * nplanes;
+        auto put = [&](int c, int v0, const uint32_t (&w)[4]) {
+            const uint32_t t01l = __byte_perm(w[0], w[1], 0x5140), t23l = __byte_perm(w[2], w[3], 0x5140);
+            const uint32_t t01h = __byte_perm(w[0], w[1], 0x7362), t23h = __byte_perm(w[2], w[3], 0x7362);
+            const uint32_t pb = planes_u + (4 * c) * T_PLANE + v0;
+            sts_u(pb, __byte_perm(t01l, t23l, 0x5410));
+            sts_u(pb + T_PLANE, __byte_perm(t01l, t23l, 0x7632));
+            sts_u(pb + 2 * T_PLANE, __byte_perm(t01h, t23h, 0x5410));
+            sts_u(pb + 3 * T_PLANE, __byte_perm(t01h, t23h, 0x7632));
+        };
         for (int quad = tid; 4 * quad < nv; quad += QTHREADS) {
             const int v0 = 4 * quad;
-            for (int c = 0; c < nplanes; ++c) {
-                uint32_t w[4];
+            if (nplanes == 4) {  // m = 16: one 128-bit load per vector (lists start 16-byte aligned)
+                uint4 r[4];
 #pragma unroll
-                for (int i = 0; i < 4; ++i) w[i] = v0 + i < nv ? __ldg(src + (size_t)(v0 + i) * nplanes + c) : 0u;
-                const uint32_t t01l = __byte_perm(w[0], w[1], 0x5140), t23l = __byte_perm(w[2], w[3], 0x5140);
-                const uint32_t t01h = __byte_perm(w[0], w[1], 0x7362), t23h = __byte_perm(w[2], w[3], 0x7362);
-                const uint32_t pb = planes_u + (4 * c) * QVP + v0;
-                sts_u(pb, __byte_perm(t01l, t23l, 0x5410));
-                sts_u(pb + QVP, __byte_perm(t01l, t23l, 0x7632));
-                sts_u(pb + 2 * QVP, __byte_perm(t01h, t23h, 0x5410));
-                sts_u(pb + 3 * QVP, __byte_perm(t01h, t23h, 0x7632));
+                for (int i = 0; i < 4; ++i)
+                    r[i] = v0 + i < nv ? __ldg(reinterpret_cast<const uint4*>(src) + v0 + i) : make_uint4(0u, 0u, 0u, 0u);
+                { const uint32_t w[4] = {r[0].x, r[1].x, r[2].x, r[3].x}; put(0, v0, w); }
+                { const uint32_t w[4] = {r[0].y, r[1].y, r[2].y, r[3].y}; put(1, v0, w); }
+                { const uint32_t w[4] = {r[0].z, r[1].z, r[2].z, r[3].z}; put(2, v0, w); }
+                { const uint32_t w[4] = {r[0].w, r[1].w, r[2].w, r[3].w}; put(3, v0, w); }
+            } else {
+                for (int c = 0; c < nplanes; ++c) {
+                    uint32_t w[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) w[i] = v0 + i < nv ? __ldg(src + (size_t)(v0 + i) * nplanes + c) : 0u;
+                    put(c, v0, w);
+                }
             }
         }
     };
-
-    if (tid < QG) {
-        const int p = tid < nj ? a.sorted_pairs[first + tid] : -1;
-        sts_u(pair_u + tid * 4, (uint32_t)p);
-        sts_f(dc_u + tid * 4, p >= 0 ? a.dc[p] : 0.f);
-        sts_f(run_u + tid * 4, Limits<float>::inf());
-        sts_u(cnt_u + tid * 4, 0u);
-        sts_u(flag_u + tid * 4, 0u);
-    }
-    // ones block: every row selects the split norm in k slots 0, 1
-    for (int i = tid; i < 256; i += QTHREADS) {
-        const int r = i >> 1, half = i & 1;
-        const float one = half == 0 ? 1.f : 0.f;
-        sts_v4f(abuf_u + 4 * TA_BLK + (r >> 3) * 256 + half * 128 + (r & 7) * 16, one, one, 0.f, 0.f);
-    }
-    fence_proxy_async();  // generic-proxy writes -> visible to the tensor core (async proxy)
-    stage_planes(0, (int)min((int64_t)QVP, len));
-    tc_fence_before();
-    __syncthreads();  // [A] barriers initialised, tensor memory allocated, pair slots written
-    tc_fence_after();
-    const uint32_t tmem_base = lds_u(tmem_slot);
-    stamp();
-
-    // residuals r_q = query - centroid (reference _closest_cluster_residuals,
-    // src/coarsequantizers.jl:40-45): warp s owns subspace s, lane q its query; transposed
-    // [s * 8 + d][q], zero-padded to 8 dims per subspace
+    stage_planes(0, (int)min((int64_t)T_VP, len));
     {
         float part = 0.f;
         if (wid < m) {
-            const int p = (int)lds_u(pair_u + lane * 4);
-            const float* qv = a.Q + (size_t)(p >= 0 ? p / a.w : 0) * a.D + wid * a.dsub;
-            const float* cv = a.C + (size_t)cell * a.D + wid * a.dsub;
-            float qr[8], cr[8];
-#pragma unroll
-            for (int d = 0; d < 8; ++d) {
-                qr[d] = (p >= 0 && d < a.dsub) ? __ldg(qv + d) : 0.f;
-                cr[d] = (p >= 0 && d < a.dsub) ? __ldg(cv + d) : 0.f;
-            }
 #pragma unroll
             for (int d = 0; d < 8; ++d) {
                 const float r = sub_rn(qr[d], cr[d]);
@@ -415,7 +400,11 @@ scant_kernel(const ScanTArgs ta) {
         }
         sts_f(smin_u + (wid * QG + lane) * 4, part);
     }
-    scan_bar();
+    fence_proxy_async();  // generic-proxy writes (A constants) -> visible to the tensor core (async proxy)
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = lds_u(tmem_slot);
     stamp();
     float base;
     {
@@ -424,122 +413,161 @@ scant_kernel(const ScanTArgs ta) {
         base = add_rn(lds_f(dc_u + lane * 4), rn);  // dc + |r|^2 over the PQ dims
     }
 
-    // ONE warp writes the whole A operand of build x (the four row copies are the same 32 rows):
-    // lane = query, 8 dims -> tf32 hi / lo, 16 stores; then tells the producer.  The caller rotates the warp.
-    auto write_A = [&](int x, int s) {
-        float hi[8], lo[8];
+    // ONE warp writes the A operand of group g: rows (copy, j, q), block 2j = hi, 2j + 1 = lo of
+    // r[2g + j][q][0..7]; lane = query.  The caller rotates the warp.
+    auto write_A = [&](int g) {
 #pragma unroll
-        for (int d = 0; d < 8; ++d) {
-            const float r = lds_f(resid_u + ((s * 8 + d) * T_RS + lane) * 4);
-            hi[d] = __uint_as_float(to_tf32(r));
-            lo[d] = __uint_as_float(to_tf32(r - hi[d]));
-        }
-        const uint32_t ph = abuf_u + (x & 1) * (2 * TA_BLK) + (lane >> 3) * 256 + (lane & 7) * 16;
+        for (int j = 0; j < 2; ++j) {
+            float hi[8], lo[8];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {  // row = 32 c + lane
-            sts_v4f(ph + c * 1024, hi[0], hi[1], hi[2], hi[3]);
-            sts_v4f(ph + c * 1024 + 128, hi[4], hi[5], hi[6], hi[7]);
-            sts_v4f(ph + c * 1024 + TA_BLK, lo[0], lo[1], lo[2], lo[3]);
-            sts_v4f(ph + c * 1024 + TA_BLK + 128, lo[4], lo[5], lo[6], lo[7]);
-        }
-        fence_proxy_async();  // generic-proxy writes -> visible to the tensor core (async proxy)
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar_aready + 8 * (x & 1));
-    };
-    // Epilogue of build x (subspace s): tensor memory -> table buffer x & 1 in the scan's layout.
-    // Warp w: lane quarter w & 3 (all quarters hold the same 32 queries), codewords 16w .. 16w + 15.
-    auto epilogue = [&](int x, int s) {
-        mbar_wait(bar_mma + 8 * (x & 1), ((uint32_t)x >> 1) & 1, ta.err, 2);
-        tc_fence_after();
-        uint32_t v[16];
-        tc_ld16(tmem_base + ((uint32_t)((wid & 3) * 32) << 16) + (uint32_t)((x & 1) * 256 + 16 * wid), v);
-        tc_wait_ld();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar_tfree + 8 * (x & 1));  // this warp's part of the tile is drained
-        const uint32_t edst = lut_u + (x & 1) * 128 + lane * 4;
-        if constexpr (IDENT) {
-            // rows of codewords >= ksub are never looked up: store unconditionally
+            for (int d = 0; d < 8; ++d) {
+                const float r = lds_f(resid_u + (((2 * g + j) * 8 + d) * T_RS + lane) * 4);
+                hi[d] = __uint_as_float(to_tf32(r));
+                lo[d] = __uint_as_float(to_tf32(r - hi[d]));
+            }
+            const uint32_t ph = abuf_u + (2 * j) * TA_BLK + (4 * j + (lane >> 3)) * 256 + (lane & 7) * 16;
 #pragma unroll
-            for (int i = 0; i < 16; ++i) sts_u(edst + (16 * wid + i) * 256, v[i]);
-        } else {
-            const uint8_t* cvp = a.cb_codes + (size_t)s * a.ksub;
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                const int code = 16 * wid + i;
-                if (code < a.ksub) sts_u(edst + (int)cvp[code] * 256, v[i]);  // code VALUE -> entry (Q6)
+            for (int c = 0; c < 2; ++c) {  // row = 64 c + 32 j + lane
+                sts_v4f(ph + c * 2048, hi[0], hi[1], hi[2], hi[3]);
+                sts_v4f(ph + c * 2048 + 128, hi[4], hi[5], hi[6], hi[7]);
+                sts_v4f(ph + c * 2048 + TA_BLK, lo[0], lo[1], lo[2], lo[3]);
+                sts_v4f(ph + c * 2048 + TA_BLK + 128, lo[4], lo[5], lo[6], lo[7]);
             }
         }
+        fence_proxy_async();  // generic-proxy writes -> visible to the tensor core (async proxy)
+    };
+    // Build t (issuer lane): the codebook operand of build t must have landed in ring slot t & 1.
+    auto issue_mma = [&](int t) {
+        const uint32_t slot = t & 1;
+        mbar_wait(slot ? bar_full1 : bar_full0, ((uint32_t)t >> 1) & 1, ta.err, 1);
+        tc_fence_after();
+        const uint32_t bb = bbuf_u + slot * TB_GROUP;
+        const uint64_t A0h = tc_smem_desc(abuf_u), A0l = tc_smem_desc(abuf_u + TA_BLK),
+                       A1h = tc_smem_desc(abuf_u + 2 * TA_BLK), A1l = tc_smem_desc(abuf_u + 3 * TA_BLK),
+                       A1s = tc_smem_desc(abuf_u + 4 * TA_BLK);
+        const uint64_t B0h = tc_smem_desc(bb), B0l = tc_smem_desc(bb + TB_BLK), B1h = tc_smem_desc(bb + 2 * TB_BLK),
+                       B1l = tc_smem_desc(bb + 3 * TB_BLK), Bn = tc_smem_desc(bb + 4 * TB_BLK);
+        tc_mma(tmem_base, A0h, B0h, 0);
+        tc_mma(tmem_base, A0l, B0h, 1);
+        tc_mma(tmem_base, A0h, B0l, 1);
+        tc_mma(tmem_base, A1h, B1h, 1);
+        tc_mma(tmem_base, A1l, B1h, 1);
+        tc_mma(tmem_base, A1h, B1l, 1);
+        tc_mma(tmem_base, A1s, Bn, 1);
+        tc_commit(bar_mma);
     };
 
-    if (wid == 2) write_A(0, 0);
-    if (wid == 3 && T > 1) write_A(1, 1 % m);
+    if (wid == 2) write_A(0);
+    tc_fence_before();
+    __syncthreads();
+    if (wid == T_ISSUER && lane == 0) {
+        tc_fence_after();
+        issue_mma(0);
+    }
     stamp();
 
-    const uint32_t lob0 = lut_u | (uint32_t)(lane * 4), lob1 = lob0 + 128;
-    const uint32_t plane_w0 = planes_u + 16 * wid;
+    const uint32_t lo0 = lut_u | (uint32_t)(lane * 4), lo1 = lo0 + 128;
+    // epilogue role of this warp: lane quarter -> (copy, subspace-in-group), 32 codeword columns
+    const int quarter = wid & 3, ej = quarter & 1;
+    const int ecol0 = 32 * ((wid >> 2) * 2 + (quarter >> 1));
+    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)ecol0;
+    const uint32_t edst = lut_u + ej * 128 + lane * 4;  // + row * 256
+    // scan role: first chunk, chunk stride, chunks owned
+    const int c0 = wid, cs = QWARPS;
+    const int maxch = 4;
+    const uint32_t pstride = 16 * cs;
+    const uint32_t plane_w0 = planes_u + 16 * c0;
     const bool dbg = ta.dbg_lut != nullptr && item == 0;
 
     float acc[QNV];
     int nv = 0, nch = 0;
     int64_t vbase = 0;
-    int s = m - 1;  // subspace of build t; the loop starts one step early (t = -1: only the first epilogue)
-    for (int t = -1; t < T; ++t) {
-        const int s1 = s + 1 == m ? 0 : s + 1;
-        if (s1 == 0 && t + 1 < T) {  // the next build opens a pass
-            vbase = (int64_t)((t + 1) / m) * QVP;
+    int g = 0;
+    for (int t = 0; t < T; ++t) {
+        if (g == 0) {
+            vbase = (int64_t)(t / ng) * T_VP;
+            nv = (int)min((int64_t)T_VP, len - vbase);
+            nch = min(maxch, max(0, (nv - 16 * c0 + (int)pstride - 1) / (int)pstride));  // chunks j4 with 16 (c0 + cs j4) < nv
         }
-        // odd warps drain the next table before scanning, even warps after: the tensor-memory load
-        // latency of one half hides behind the lookups of the other half
-        const bool epi = t + 1 < T;
-        if (epi && ((wid & 1) || t < 0)) epilogue(t + 1, s1);
-        if (t >= 0) {
-            if (s == 0) {
-                nv = (int)min((int64_t)QVP, len - vbase);
-                nch = min(4, max(0, (nv - 16 * wid + 255) >> 8));  // chunks j4 with 256 * j4 + 16 * wid < nv
-            }
-            if (dbg && t < m) {
-                if (tid < QG) reinterpret_cast<int*>(ta.dbg_lut + (size_t)m * 256 * 32)[tid] = (int)lds_u(pair_u + tid * 4);
-                if (tid == 0) reinterpret_cast<int*>(ta.dbg_lut + (size_t)m * 256 * 32)[QG] = cell;
-                for (int idx = tid; idx < 256 * 32; idx += QTHREADS) {
-                    const int q = idx & 31, code = idx >> 5;
-                    ta.dbg_lut[((size_t)s * 256 + code) * 32 + q] = lds_f(lut_u + code * 256 + (t & 1) * 128 + q * 4);
+        // ---- epilogue of build t: tensor memory -> table layout of the scan ----
+        mbar_wait(bar_mma, t & 1, ta.err, 2);
+        tc_fence_after();
+        {
+            uint32_t v[32];
+            tc_ld32(taddr, v);
+            tc_wait_ld();
+            if constexpr (IDENT) {
+                // rows of codewords >= ksub are never looked up: store unconditionally
+#pragma unroll
+                for (int i = 0; i < 32; ++i) sts_u(edst + (ecol0 + i) * 256, v[i]);
+            } else {
+                const uint8_t* cvp = a.cb_codes + (size_t)(2 * g + ej) * a.ksub;
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    const int code = ecol0 + i;
+                    if (code < a.ksub) sts_u(edst + (int)cvp[code] * 256, v[i]);  // code VALUE -> entry (Q6)
                 }
             }
-            // ---- K3: scan subspace s (table buffer t & 1 == s & 1, byte plane s) ----
-            const uint32_t plane_w = plane_w0 + s * QVP;
-            if (s == 0) scant_sub<true>(lob0, plane_w, nch, base, acc);
-            else scant_sub<false>((s & 1) ? lob1 : lob0, plane_w, nch, base, acc);
-            if (epi && !(wid & 1)) epilogue(t + 1, s1);
         }
-        if (t + 3 < T && wid == ((t + 5) & 15)) write_A(t + 3, (s + 3) % m);  // build t + 1 complete: its A buffer is free
-        scan_bar();  // table buffer t & 1 consumed, table t + 1 complete
-        s = s1;
+        const int gn = g + 1 == ng ? 0 : g + 1;
+        if (t + 1 < T && wid == ((t + 3) & 7)) write_A(gn);  // build t has completed: its A operand is free
+        tc_fence_before();
+        __syncthreads();  // table complete, accumulator tile drained, next A operand written
+        if (wid == T_ISSUER && lane == 0 && t + 1 < T) {
+            tc_fence_after();
+            if (t + 2 < T) {  // ring slot t & 1 was last read by build t (complete)
+                const uint32_t bar = (t & 1) ? bar_full1 : bar_full0;
+                const int g2 = gn + 1 == ng ? 0 : gn + 1;
+                mbar_expect_tx(bar, TB_GROUP);
+                tma_bulk_g2s(bbuf_u + (t & 1) * TB_GROUP, ta.tcB + (size_t)g2 * (TB_GROUP / 4), TB_GROUP, bar);
+            }
+            issue_mma(t + 1);
+        }
+        __syncwarp();
+        if (dbg && t < ng) {
+            if (tid < QG) reinterpret_cast<int*>(ta.dbg_lut + (size_t)m * 256 * 32)[tid] = (int)lds_u(pair_u + tid * 4);
+            if (tid == 0) reinterpret_cast<int*>(ta.dbg_lut + (size_t)m * 256 * 32)[QG] = cell;
+            for (int idx = tid; idx < 2 * 256 * 32; idx += QTHREADS) {
+                const int q = idx & 31, code = (idx >> 5) & 255, j = idx >> 13;
+                ta.dbg_lut[((size_t)(2 * g + j) * 256 + code) * 32 + q] = lds_f(lut_u + code * 256 + j * 128 + q * 4);
+            }
+        }
+        // ---- K3: scan the two subspaces of this group (byte planes 2g, 2g + 1) ----
+        {
+            const uint32_t plane_w = plane_w0 + (2 * g) * T_PLANE;
+            if (nch == 4) {
+                if (g == 0) scant_group<true, true>(lo0, lo1, plane_w, pstride, nch, base, acc);
+                else scant_group<false, true>(lo0, lo1, plane_w, pstride, nch, base, acc);
+            } else {
+                if (g == 0) scant_group<true, false>(lo0, lo1, plane_w, pstride, nch, base, acc);
+                else scant_group<false, false>(lo0, lo1, plane_w, pstride, nch, base, acc);
+            }
+        }
+        __syncthreads();  // every warp is done with this table
+        g = gn;
         stamp();
-        if (t < 0 || s != 0) continue;
+        if (g != 0) continue;
 
         // ---- per-(query, list) top-k of this pass ----
-        // mask the slots beyond the list (only the chunk that straddles the end has any)
+        // mask the slots beyond the list (chunks not owned / not reached, and the chunk that straddles the end)
         {
-            const int lim = nv - 16 * wid;  // slot 16 * j4 + i holds a vector iff 256 * j4 + i < lim
+            const int lim = nv - 16 * c0;  // slot 16 * j4 + i holds a vector iff pstride * j4 + i < lim
 #pragma unroll
             for (int j4 = 0; j4 < QNV / 16; ++j4) {
-                if (256 * j4 + 16 > lim) {  // warp-uniform: chunk not completely inside the list
+                if (j4 >= maxch || (int)pstride * j4 + 16 > lim) {  // warp-uniform
 #pragma unroll
                     for (int i = 0; i < 16; ++i)
-                        if (256 * j4 + i >= lim) acc[16 * j4 + i] = Limits<float>::inf();
+                        if (j4 >= maxch || (int)pstride * j4 + i >= lim) acc[16 * j4 + i] = Limits<float>::inf();
                 }
             }
         }
-        if (t + 1 < T) {  // planes of the next pass (this pass's scan is complete)
-            stage_planes(vbase, (int)min((int64_t)QVP, len - vbase));
-        }
-        const int64_t pbase = (int64_t)(t / m) * QVP + 16 * wid;  // position of slot 0 of this warp
+        const int64_t pbase = vbase + 16 * c0;  // position of slot 0 of this warp
+        if (t + 1 < T) stage_planes(vbase + T_VP, (int)min((int64_t)T_VP, len - vbase - T_VP));  // next pass
         float mn = Limits<float>::inf();
 #pragma unroll
         for (int j = 0; j < QNV; ++j) mn = fminf(mn, acc[j]);
         sts_f(smin_u + (wid * QG + lane) * 4, mn);
-        scan_bar();
+        __syncthreads();
         {
             int rank = 0;
 #pragma unroll
@@ -550,22 +578,27 @@ scant_kernel(const ScanTArgs ta) {
             // the k-th smallest of 16 distinct candidates bounds the k-th smallest of all
             if (rank == min(k, QWARPS) - 1) sts_f(thr_u + lane * 4, fminf(mn, lds_f(run_u + lane * 4)));
         }
-        scan_bar();
+        __syncthreads();
         {
             const float thr = lds_f(thr_u + lane * 4);
-            const bool any_real = thr < Limits<float>::inf();  // fewer than k vectors so far: keep every real slot
+            // keep d <= bound; while fewer than k vectors have been seen (bound = +inf) keep every real slot
+            const float cut = thr < Limits<float>::inf() ? thr : 3.402823466e+38f;
+            int c = 0;
+#pragma unroll
+            for (int j = 0; j < QNV; ++j) c += acc[j] <= cut ? 1 : 0;
+            int slot = c ? atoms_add(cnt_u + lane * 4, c) : 0;  // ONE shared-memory atomic per (warp, query)
 #pragma unroll
             for (int j = 0; j < QNV; ++j) {
-                if (acc[j] <= thr && (any_real || acc[j] < Limits<float>::inf())) {
-                    const int slot = atoms_add(cnt_u + lane * 4, 1);
+                if (acc[j] <= cut) {
                     if (slot < QCAP) {
                         sts_f(cand_d_u + (lane * QCAP + slot) * 4, acc[j]);
-                        sts_u(cand_p_u + (lane * QCAP + slot) * 4, (uint32_t)(pbase + 256 * (j >> 4) + (j & 15)));
+                        sts_u(cand_p_u + (lane * QCAP + slot) * 4, (uint32_t)(pbase + (int)pstride * (j >> 4) + (j & 15)));
                     }
+                    ++slot;
                 }
             }
         }
-        scan_bar();
+        __syncthreads();
         // exact selection by (distance, position): warp w serves queries w and w + 16
         for (int q = wid; q < QG; q += QWARPS) {
             int n = (int)lds_u(cnt_u + q * 4);
@@ -577,6 +610,7 @@ scant_kernel(const ScanTArgs ta) {
             if (lane < n) { d0 = lds_f(cd + lane * 4); p0 = lds_u(cp + lane * 4); }
             if (lane + 32 < n) { d1 = lds_f(cd + (lane + 32) * 4); p1 = lds_u(cp + (lane + 32) * 4); }
             int r0 = 0, r1 = 0;
+#pragma unroll 4
             for (int e = 0; e < n; ++e) {
                 const float de = lds_f(cd + e * 4);
                 const uint32_t pe = lds_u(cp + e * 4);
@@ -594,7 +628,7 @@ scant_kernel(const ScanTArgs ta) {
                 if (ovf) sts_u(flag_u + q * 4, 1u);
             }
         }
-        scan_bar();
+        __syncthreads();
         stamp();
     }
 
@@ -617,31 +651,37 @@ scant_kernel(const ScanTArgs ta) {
         }
     }
     tc_fence_before();
-    __syncthreads();  // [Z]
+    __syncthreads();
+    if (wid == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(T_TMEM_COLS)
+                     : "memory");
+    }
 }
 
 // Codebook -> B operand blocks of the tensor-core table builder, once at create.
-// Per subspace: block 0 = tf32 hi of -2w, block 1 = lo, block 2 = split |w|^2 in k slots 0, 1.
 // Block layout (fp32 words): word(n, k) = (n >> 3) * 64 + (k >> 2) * 32 + (n & 7) * 4 + (k & 3).
 __global__ void prep_tc_kernel(const float* __restrict__ cb, int m, int ksub, int dsub, float* __restrict__ out) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= m * TB_NBLK * 2048) return;
-    const int kk = idx & 7, n = (idx >> 3) & 255, b = (idx >> 11) % TB_NBLK, s = idx / (2048 * TB_NBLK);
+    const int ng = m >> 1;
+    if (idx >= ng * TB_NBLK * 2048) return;
+    const int kk = idx & 7, n = (idx >> 3) & 255, b = (idx >> 11) % TB_NBLK, g = idx / (2048 * TB_NBLK);
     float val = 0.f;
-    if (b < 2) {
+    if (b < 4) {
+        const int s = 2 * g + (b >> 1);
         const float v = (n < ksub && kk < dsub) ? -2.f * cb[((size_t)s * ksub + n) * dsub + kk] : 0.f;
         const float hi = __uint_as_float(to_tf32(v));
-        val = b ? __uint_as_float(to_tf32(v - hi)) : hi;
-    } else if (kk < 2 && n < ksub) {
+        val = (b & 1) ? __uint_as_float(to_tf32(v - hi)) : hi;
+    } else if (kk < 4 && n < ksub) {
+        const int s = 2 * g + (kk >> 1);
         float nrm = 0.f;
         for (int d = 0; d < dsub; ++d) {
             const float w = cb[((size_t)s * ksub + n) * dsub + d];
             nrm = fma_rn(w, w, nrm);
         }
         const float hi = __uint_as_float(to_tf32(nrm));
-        val = kk ? __uint_as_float(to_tf32(nrm - hi)) : hi;
+        val = (kk & 1) ? __uint_as_float(to_tf32(nrm - hi)) : hi;
     }
-    out[(size_t)(s * TB_NBLK + b) * 2048 + (n >> 3) * 64 + (kk >> 2) * 32 + (n & 7) * 4 + (kk & 3)] = val;
+    out[(size_t)(g * TB_NBLK + b) * 2048 + (n >> 3) * 64 + (kk >> 2) * 32 + (n & 7) * 4 + (kk & 3)] = val;
 }
 
 }  // namespace ivf
