@@ -1,0 +1,70 @@
+"""Golden fixtures (tests/golden/*.npz, made by tests/golden/make_golden.py from the oracle).
+
+CPU: the oracle must reproduce its own pinned outputs bit for bit (guards the checker against
+silent drift -- the reference itself ships no golden vectors).
+GPU: the CUDA path, through the C ABI, must reproduce the same fixtures bit for bit
+(reference-exact tables) and within 1e-5 relative / ids equal except near-ties (default tables).
+"""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import oracle as orc
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+FIXTURES = ["readme_f32", "reftest_f64"]
+
+
+def load(name):
+    z = np.load(os.path.join(HERE, "golden", name + ".npz"))
+    qz = orc.Quantizers(z["centroids"], z["cb_vectors"], z["cb_codes"])
+    return z, qz
+
+
+@pytest.mark.parametrize("name", FIXTURES)
+def test_oracle_reproduces_golden(name):
+    z, qz = load(name)
+    X, Q, assign = z["X"], z["Q"], z["assign"]
+    cells, codes = orc.encode(qz, X, nthreads=2)
+    np.testing.assert_array_equal(cells, z["enc_cells"])
+    np.testing.assert_array_equal(codes, z["enc_codes"])
+    _, bcodes = orc.encode(qz, X, assign=assign, assign_base=0, nthreads=2)
+    np.testing.assert_array_equal(bcodes, z["build_codes"])
+    ccells, cdc = orc.coarse_search(qz, Q, z["coarse_cells"].shape[1], nthreads=2)
+    np.testing.assert_array_equal(ccells, z["coarse_cells"])
+    assert np.array_equal(cdc.view(np.uint8), z["coarse_dc"].view(np.uint8))
+    oidx = orc.OracleIndex(qz, id_bytes=4).build(X, assign, assign_base=0)
+    for kk, w in z["searches"]:
+        oi, od, oc = oidx.knn_search(Q, int(kk), w=int(w), nthreads=2)
+        np.testing.assert_array_equal(oc, z[f"counts_k{kk}_w{w}"])
+        np.testing.assert_array_equal(oi, z[f"ids_k{kk}_w{w}"])
+        assert np.array_equal(od.view(np.uint8), z[f"dists_k{kk}_w{w}"].view(np.uint8))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", FIXTURES)
+@pytest.mark.parametrize("flags", [4, 0, 1])   # reference-exact tables | engine default | vector-per-lane kernel
+def test_cuda_reproduces_golden(name, flags):
+    import ivfadc_jl_b200 as iv
+    z, qz = load(name)
+    X, Q, assign = z["X"], z["Q"], z["assign"]
+    e = iv.IVFADCIndex.from_quantizers(qz.centroids, qz.cb_vectors, qz.cb_codes, index_type=np.uint32, flags=flags)
+    gcell, gcode = e.encode(X)
+    np.testing.assert_array_equal(gcell, z["enc_cells"])
+    np.testing.assert_array_equal(gcode, z["enc_codes"])
+    w8 = z["coarse_cells"].shape[1]
+    ccells, cdc = e.coarse_search(Q, w8)
+    np.testing.assert_array_equal(ccells, z["coarse_cells"])
+    assert np.array_equal(cdc.view(np.uint8), z["coarse_dc"].view(np.uint8))
+    e._add(X, 0, assign=assign, assign_base=0)
+    for kk, w in z["searches"]:
+        gi, gd, gc = e.search_packed(Q, int(kk), int(w))
+        oi, od, oc = z[f"ids_k{kk}_w{w}"], z[f"dists_k{kk}_w{w}"], z[f"counts_k{kk}_w{w}"]
+        if flags in (4, 1) or X.dtype == np.float64:
+            np.testing.assert_array_equal(gc, oc)
+            np.testing.assert_array_equal(gi, oi)
+            assert np.array_equal(gd.view(np.uint8), od.view(np.uint8))
+        else:
+            orc.compare_search(gi, gd, gc, oi, od, oc, rtol=1e-5)
+    e.close()
