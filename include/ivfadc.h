@@ -191,6 +191,20 @@ int ivfadc_search_local_device(ivfadc_index* h, const void* dQ, int64_t nq, int3
                                int32_t* d_counts, void* stream);
 
 /*
+ * Sharded search with the coarse step sharded BY QUERY (device pointers): rank r runs
+ * ivfadc_coarse_search_device on its slice of the batch, the host all-gathers the probe lists
+ * (cells int32[nq][w], dc T[nq][w], both in query order) and every rank calls
+ * ivfadc_search_probes_local_device -- step 1 with the probes supplied instead of recomputed, so
+ * the replicated coarse_search (src/coarsequantizers.jl:33-37) no longer limits scaling.
+ * w must already be clamped to kc (src/index.jl:216).
+ */
+int ivfadc_coarse_search_device(ivfadc_index* h, const void* dQ, int64_t nq, int32_t w, int32_t* d_cells,
+                                void* d_dc, void* stream);
+int ivfadc_search_probes_local_device(ivfadc_index* h, const void* dQ, int64_t nq, int32_t k, int32_t w,
+                                      const int32_t* d_cells, const void* d_dc, uint64_t* d_ids, void* d_dists,
+                                      uint64_t* d_keys, int32_t* d_counts, void* stream);
+
+/*
  * Sharded search, step 2 (device pointers): merge `parts` candidate sets laid out
  * [parts][nq][k] (as gathered from the ranks) into the final [nq][k] by (dist, key).
  */

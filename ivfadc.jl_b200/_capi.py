@@ -24,7 +24,8 @@ FLAG_SCAN_LEGACY, FLAG_SCAN_QLANE, FLAG_LUT_EXACT, FLAG_LUT_MMASYNC = 1, 2, 4, 8
 SYMBOLS = [
     "ivfadc_abi_version", "ivfadc_device_count", "ivfadc_create", "ivfadc_destroy", "ivfadc_last_error",
     "ivfadc_add", "ivfadc_encode", "ivfadc_coarse_search", "ivfadc_search", "ivfadc_search_device",
-    "ivfadc_search_local_device", "ivfadc_merge_device", "ivfadc_delete", "ivfadc_pop", "ivfadc_length",
+    "ivfadc_search_local_device", "ivfadc_coarse_search_device", "ivfadc_search_probes_local_device",
+    "ivfadc_merge_device", "ivfadc_delete", "ivfadc_pop", "ivfadc_length",
     "ivfadc_list_sizes", "ivfadc_export_list", "ivfadc_import_list", "ivfadc_export_quantizers",
     "ivfadc_set_length", "ivfadc_get_stats", "ivfadc_reset_stats", "ivfadc_debug_tables",
 ]
@@ -83,6 +84,9 @@ def load(build_if_missing: bool = True):
                                          c_void_p, c_void_p]
     lib.ivfadc_search_local_device.argtypes = [H, c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p,
                                                c_void_p, c_void_p, c_void_p]
+    lib.ivfadc_coarse_search_device.argtypes = [H, c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_void_p]
+    lib.ivfadc_search_probes_local_device.argtypes = [H, c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p,
+                                                      c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
     lib.ivfadc_merge_device.argtypes = [H, c_int32, c_int64, c_int32, c_void_p, c_void_p, c_void_p,
                                         c_void_p, c_void_p, c_void_p, c_void_p]
     lib.ivfadc_delete.argtypes = [H, c_void_p, c_int64]

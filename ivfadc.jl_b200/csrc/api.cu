@@ -74,7 +74,8 @@ int check_handle(const ivfadc_index* h) { return h ? IVFADC_OK : IVFADC_ERR_BAD_
 
 // One chunk of queries, everything on the device, asynchronous on `s`.
 int search_chunk(ivfadc_index* h, const void* dQ, int64_t nq, int k, int w, uint64_t* d_ids, void* d_dists,
-                 uint64_t* d_keys, int32_t* d_counts, cudaStream_t s) {
+                 uint64_t* d_keys, int32_t* d_counts, cudaStream_t s, const int32_t* ext_cells = nullptr,
+                 const void* ext_dc = nullptr) {
     const ScanPlanSizes z = scan_plan_sizes(h, nq, w, k);
     CUDA_OR_FAIL(h, h->ws_cells.reserve(sizeof(int32_t) * (size_t)nq * w), "workspace");
     CUDA_OR_FAIL(h, h->ws_dc.reserve(h->tsize * (size_t)nq * w), "workspace");
@@ -97,12 +98,17 @@ int search_chunk(ivfadc_index* h, const void* dQ, int64_t nq, int k, int w, uint
         cudaEventRecord(tm.ev[set][0], s);
     }
     int launches = 0;
-    int32_t* d_cells = h->ws_cells.as<int32_t>();
-    CUDA_OR_FAIL(h, launch_coarse(h, dQ, nq, w, d_cells, h->ws_dc.p, s, &launches), "coarse kernel");
+    const int32_t* d_cells = ext_cells;
+    const void* d_dc = ext_dc;
+    if (!ext_cells) {  // probes supplied by the caller when the coarse step is sharded by query across ranks
+        CUDA_OR_FAIL(h, launch_coarse(h, dQ, nq, w, h->ws_cells.as<int32_t>(), h->ws_dc.p, s, &launches), "coarse kernel");
+        d_cells = h->ws_cells.as<int32_t>();
+        d_dc = h->ws_dc.p;
+    }
     if (set >= 0) cudaEventRecord(tm.ev[set][1], s);
     const bool timing = h->stats_timing;
     h->stats_timing = set >= 0;
-    cudaError_t e = launch_search(h, dQ, nq, k, w, d_cells, h->ws_dc.p, d_ids, d_dists, d_keys, d_counts,
+    cudaError_t e = launch_search(h, dQ, nq, k, w, d_cells, d_dc, d_ids, d_dists, d_keys, d_counts,
                                   extra(h)->d_scanned, s, &launches);
     h->stats_timing = timing;
     CUDA_OR_FAIL(h, e, "scan kernels");
@@ -116,11 +122,13 @@ int search_chunk(ivfadc_index* h, const void* dQ, int64_t nq, int k, int w, uint
 }
 
 int search_core(ivfadc_index* h, const void* dQ, int64_t nq, int k, int w, uint64_t* d_ids, void* d_dists,
-                uint64_t* d_keys, int32_t* d_counts, cudaStream_t s) {
+                uint64_t* d_keys, int32_t* d_counts, cudaStream_t s, const int32_t* ext_cells = nullptr,
+                const void* ext_dc = nullptr) {
     if (!dQ || !d_ids || !d_dists || !d_counts) return fail(h, IVFADC_ERR_BAD_ARG, "null pointer");
     if (nq < 0) return fail(h, IVFADC_ERR_BAD_ARG, "nq < 0");
     if (k < 1) return fail(h, IVFADC_ERR_BAD_ARG, "Number of neighbors must be k >= 1");
     if (w < 1) return fail(h, IVFADC_ERR_BAD_ARG, "Number of clusters to search in must be w >= 1");
+    if (ext_cells && w > h->cfg.kc) return fail(h, IVFADC_ERR_BAD_ARG, "w > kc with caller-supplied probes");
     w = std::min(w, h->cfg.kc);  // reference src/index.jl:216
     if (k > scan_max_k()) return fail(h, IVFADC_ERR_UNSUPPORTED, "k > 128 is not supported by the scan kernel yet");
     if (w > coarse_max_w()) return fail(h, IVFADC_ERR_UNSUPPORTED, "w > 128 is not supported by the coarse kernel yet");
@@ -134,7 +142,9 @@ int search_core(ivfadc_index* h, const void* dQ, int64_t nq, int k, int w, uint6
         const int64_t n = std::min(chunk, nq - q0);
         int rc = search_chunk(h, static_cast<const char*>(dQ) + (size_t)q0 * h->cfg.dim * h->tsize, n, k, w,
                               d_ids + q0 * k, static_cast<char*>(d_dists) + (size_t)q0 * k * h->tsize,
-                              d_keys ? d_keys + q0 * k : nullptr, d_counts + q0, s);
+                              d_keys ? d_keys + q0 * k : nullptr, d_counts + q0, s,
+                              ext_cells ? ext_cells + q0 * w : nullptr,
+                              ext_dc ? static_cast<const char*>(ext_dc) + (size_t)q0 * w * h->tsize : nullptr);
         if (rc != IVFADC_OK) return rc;
     }
     return IVFADC_OK;
@@ -447,6 +457,31 @@ int ivfadc_search_local_device(ivfadc_index* h, const void* dQ, int64_t nq, int3
     if (!d_keys) return fail(h, IVFADC_ERR_BAD_ARG, "null keys");
     cudaSetDevice(h->cfg.device);
     return search_core(h, dQ, nq, k, w, d_ids, d_dists, d_keys, d_counts, static_cast<cudaStream_t>(stream));
+}
+
+int ivfadc_coarse_search_device(ivfadc_index* h, const void* dQ, int64_t nq, int32_t w, int32_t* d_cells,
+                                void* d_dc, void* stream) {
+    if (check_handle(h)) return IVFADC_ERR_BAD_ARG;
+    if (nq < 0 || (nq > 0 && (!dQ || !d_cells || !d_dc))) return fail(h, IVFADC_ERR_BAD_ARG, "null pointer");
+    if (w < 1 || w > h->cfg.kc) return fail(h, IVFADC_ERR_BAD_ARG, "w outside 1..kc (clamp before calling)");
+    if (w > coarse_max_w()) return fail(h, IVFADC_ERR_UNSUPPORTED, "w > 128");
+    if (nq == 0) return IVFADC_OK;
+    cudaSetDevice(h->cfg.device);
+    int launches = 0;
+    CUDA_OR_FAIL(h, launch_coarse(h, dQ, nq, w, d_cells, d_dc, static_cast<cudaStream_t>(stream), &launches),
+                 "coarse kernel");
+    h->stats.gpu_launches += launches;
+    return IVFADC_OK;
+}
+
+int ivfadc_search_probes_local_device(ivfadc_index* h, const void* dQ, int64_t nq, int32_t k, int32_t w,
+                                      const int32_t* d_cells, const void* d_dc, uint64_t* d_ids, void* d_dists,
+                                      uint64_t* d_keys, int32_t* d_counts, void* stream) {
+    if (check_handle(h)) return IVFADC_ERR_BAD_ARG;
+    if (!d_keys || !d_cells || !d_dc) return fail(h, IVFADC_ERR_BAD_ARG, "null pointer");
+    cudaSetDevice(h->cfg.device);
+    return search_core(h, dQ, nq, k, w, d_ids, d_dists, d_keys, d_counts, static_cast<cudaStream_t>(stream), d_cells,
+                       d_dc);
 }
 
 int ivfadc_merge_device(ivfadc_index* h, int32_t parts, int64_t nq, int32_t k, const uint64_t* d_ids_in,

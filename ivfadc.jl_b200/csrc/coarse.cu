@@ -5,8 +5,9 @@
 //
 // Distances are the DIRECT form sum_d (c_d - q_d)^2 evaluated as one sequential fma chain per
 // (query, centroid) pair -- bit-identical to the oracle (A1) -- on the FFMA pipe, register-tiled
-// 2 queries x 4 centroids per thread from padded shared-memory tiles; the top-w selection is
-// fused: after each 64-centroid tile every warp updates the warp-distributed sorted lists of its
+// 2 queries x 8 centroids per thread from padded shared-memory tiles (a 2 x 4 tile was
+// shared-memory-bandwidth bound: 6 LDS.128 per 32 fma pairs; 2 x 8 needs 10 per 64); the top-w selection is
+// fused: after each 128-centroid tile every warp updates the warp-distributed sorted lists of its
 // 4 queries.  FP32 FFMA was chosen over 3xTF32 tcgen05 because selection must agree with the
 // oracle bit for bit and the whole step is < 10% of the search ("K1").
 #include "common.cuh"
@@ -17,7 +18,8 @@ namespace ivf {
 namespace {
 
 constexpr int TQ = 32;        // queries per CTA
-constexpr int TC = 64;        // centroids per tile
+constexpr int TC = 128;       // centroids per tile
+constexpr int TCJ = TC / 16;  // centroids per thread
 constexpr int CTHREADS = 256;
 
 template <typename T> struct CoarseCfg;
@@ -69,11 +71,11 @@ coarse_kernel(const T* __restrict__ Q, const T* __restrict__ C, int64_t nq, int 
     for (int a = 0; a < 4; ++a) kth[a] = Limits<T>::inf();
 
     for (int c0 = 0; c0 < kc; c0 += TC) {
-        T acc[2][4];
+        T acc[2][TCJ];
 #pragma unroll
         for (int a = 0; a < 2; ++a)
 #pragma unroll
-            for (int j = 0; j < 4; ++j) acc[a][j] = (T)0;
+            for (int j = 0; j < TCJ; ++j) acc[a][j] = (T)0;
 
         for (int d0 = 0; d0 < D; d0 += DK) {
             __syncthreads();  // previous chunk / distance tile fully consumed
@@ -90,17 +92,17 @@ coarse_kernel(const T* __restrict__ Q, const T* __restrict__ C, int64_t nq, int 
                 sC[row * LD + col] = (c < kc && d < D) ? C[(int64_t)c * D + d] : (T)0;
             }
             __syncthreads();
-#pragma unroll 4
+#pragma unroll 2
             for (int d = 0; d < DK; d += VEC) {
-                T qv[2][VEC], cv[4][VEC];
+                T qv[2][VEC], cv[TCJ][VEC];
 #pragma unroll
                 for (int a = 0; a < 2; ++a) ld16(&sQ[(ty * 2 + a) * LD + d], qv[a]);
 #pragma unroll
-                for (int j = 0; j < 4; ++j) ld16(&sC[(tx + 16 * j) * LD + d], cv[j]);
+                for (int j = 0; j < TCJ; ++j) ld16(&sC[(tx + 16 * j) * LD + d], cv[j]);
 #pragma unroll
                 for (int a = 0; a < 2; ++a)
 #pragma unroll
-                    for (int j = 0; j < 4; ++j)
+                    for (int j = 0; j < TCJ; ++j)
 #pragma unroll
                         for (int e = 0; e < VEC; ++e) {
                             const T diff = sub_rn(cv[j][e], qv[a][e]);  // oracle A1: a[i] - b[i]
@@ -112,7 +114,7 @@ coarse_kernel(const T* __restrict__ Q, const T* __restrict__ C, int64_t nq, int 
 #pragma unroll
         for (int a = 0; a < 2; ++a)
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
+            for (int j = 0; j < TCJ; ++j) {
                 const int c = c0 + tx + 16 * j;
                 sDist[(ty * 2 + a) * LDD + tx + 16 * j] = c < kc ? acc[a][j] : Limits<T>::inf();
             }
@@ -124,7 +126,7 @@ coarse_kernel(const T* __restrict__ Q, const T* __restrict__ C, int64_t nq, int 
         for (int a = 0; a < 4; ++a) {
             const int ql = wid * 4 + a;
 #pragma unroll
-            for (int half = 0; half < 2; ++half) {
+            for (int half = 0; half < TC / 32; ++half) {
                 const T val = sDist[ql * LDD + lane + 32 * half];
                 const int cidx = c0 + lane + 32 * half;
                 unsigned mask = __ballot_sync(0xffffffffu, val < kth[a]);

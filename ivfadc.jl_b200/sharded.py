@@ -2,7 +2,8 @@
 
 The inverted lists shard by cell (cell c lives on rank c % world; the quantizers are replicated),
 lists are independent, and a query's answer is the top-k over the union of its probed lists, so
-the path has exactly one exchange step: every rank scans the probed cells it owns and produces its
+the path has one exchange step for the results (and a small one for the probe lists, so that the
+coarse assignment is computed once across the ranks instead of once per rank): every rank scans the probed cells it owns and produces its
 k best candidates per query with their merge keys (probe rank << 32 | position); one all-gather
 (NCCL over NVLink; 8 B + 8 B + 4..8 B per candidate, ~1 MB per rank for a 10k-query batch) brings
 the candidate sets together and a merge kernel keeps the k smallest by (distance, key) -- the
@@ -62,6 +63,35 @@ def search_local(engine, dQ: torch.Tensor, k: int, w: int = 1):
     return ids, dists, keys, counts
 
 
+def coarse_device(engine, dQ: torch.Tensor, w: int):
+    """ivfadc_coarse_search_device: (cells int32 [nq, w], dc [nq, w]) device tensors."""
+    assert dQ.is_cuda and dQ.is_contiguous() and dQ.dtype == _tdtype(engine)
+    nq = dQ.shape[0]
+    cells = torch.empty((nq, w), dtype=torch.int32, device=dQ.device)
+    dc = torch.empty((nq, w), dtype=dQ.dtype, device=dQ.device)
+    rc = engine._lib.ivfadc_coarse_search_device(engine._h, ctypes.c_void_p(dQ.data_ptr()), nq, w,
+                                                 ctypes.c_void_p(cells.data_ptr()), ctypes.c_void_p(dc.data_ptr()),
+                                                 _stream_ptr())
+    _capi.check(engine._h, rc)
+    return cells, dc
+
+
+def search_local_probes(engine, dQ: torch.Tensor, k: int, w: int, cells: torch.Tensor, dc: torch.Tensor):
+    """Step 1 with caller-supplied probe lists (the coarse step was sharded by query)."""
+    assert dQ.is_cuda and dQ.is_contiguous() and cells.is_contiguous() and dc.is_contiguous()
+    nq = dQ.shape[0]
+    ids = torch.empty((nq, k), dtype=torch.int64, device=dQ.device)
+    keys = torch.empty((nq, k), dtype=torch.int64, device=dQ.device)
+    dists = torch.empty((nq, k), dtype=dQ.dtype, device=dQ.device)
+    counts = torch.empty((nq,), dtype=torch.int32, device=dQ.device)
+    rc = engine._lib.ivfadc_search_probes_local_device(
+        engine._h, ctypes.c_void_p(dQ.data_ptr()), nq, k, w, ctypes.c_void_p(cells.data_ptr()),
+        ctypes.c_void_p(dc.data_ptr()), ctypes.c_void_p(ids.data_ptr()), ctypes.c_void_p(dists.data_ptr()),
+        ctypes.c_void_p(keys.data_ptr()), ctypes.c_void_p(counts.data_ptr()), _stream_ptr())
+    _capi.check(engine._h, rc)
+    return ids, dists, keys, counts
+
+
 def merge_gathered(engine, ids_all, dists_all, keys_all, k: int):
     """Step 2: [parts, nq, k] gathered candidates -> final (ids, dists, counts)."""
     parts, nq, _ = ids_all.shape
@@ -93,6 +123,16 @@ class CudaShardEngine:
     def search_local(self, dQ, k, w):
         return search_local(self.index, dQ, k, w)[:3]
 
+    def coarse(self, dQ, w):
+        return coarse_device(self.index, dQ, w)
+
+    def search_local_probes(self, dQ, k, w, cells, dc):
+        return search_local_probes(self.index, dQ, k, w, cells, dc)[:3]
+
+    @property
+    def kc(self):
+        return self.index.kc
+
     def merge(self, ids_all, dists_all, keys_all, k):
         return merge_gathered(self.index, ids_all, dists_all, keys_all, k)
 
@@ -120,10 +160,29 @@ class ShardedSearcher:
 
     def search(self, Q, k: int, w: int = 1):
         """Q is the full (replicated / broadcast) query batch on every rank."""
-        ids, dists, keys = self.engine.search_local(Q, k, w)
+        nq = Q.shape[0]
+        if self.world > 1 and hasattr(self.engine, "coarse") and nq >= self.world:
+            # coarse step sharded by query: rank r assigns its slice, one all-gather of the probe lists
+            w = min(w, self.engine.kc)
+            per = (nq + self.world - 1) // self.world
+            lo = min(nq, self.rank * per)
+            hi = min(nq, lo + per)
+            cells_l = torch.zeros((per, w), dtype=torch.int32, device=Q.device)
+            dc_l = torch.zeros((per, w), dtype=Q.dtype, device=Q.device)
+            if hi > lo:
+                c, d = self.engine.coarse(Q[lo:hi].contiguous(), w)
+                cells_l[:hi - lo] = c
+                dc_l[:hi - lo] = d
+            cells_all = torch.empty((self.world * per, w), dtype=torch.int32, device=Q.device)
+            dc_all = torch.empty((self.world * per, w), dtype=Q.dtype, device=Q.device)
+            self.dist.all_gather_into_tensor(cells_all, cells_l, group=self.group)
+            self.dist.all_gather_into_tensor(dc_all, dc_l, group=self.group)
+            ids, dists, keys = self.engine.search_local_probes(Q, k, w, cells_all[:nq].contiguous(),
+                                                               dc_all[:nq].contiguous())
+        else:
+            ids, dists, keys = self.engine.search_local(Q, k, w)
         if self.world == 1:
             return self.engine.merge(ids[None], dists[None], keys[None], k)
-        nq = ids.shape[0]
         # rank-major concatenation along dim 0 == [world, nq, k] (the layout ivfadc_merge_device takes)
         ids_all = torch.empty((self.world * nq, k), dtype=ids.dtype, device=ids.device)
         dists_all = torch.empty((self.world * nq, k), dtype=dists.dtype, device=ids.device)

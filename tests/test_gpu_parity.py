@@ -500,6 +500,20 @@ def test_two_shards_merge_equals_unsharded():
     np.testing.assert_array_equal(counts.cpu().numpy(), oc)
     assert np.array_equal(dists.cpu().numpy().view(np.uint8), od.view(np.uint8))
     np.testing.assert_array_equal(ids.cpu().numpy().astype(np.uint64), oi)
+    # coarse step sharded by query: each shard assigns half of the batch, probe lists are concatenated
+    # (what the all-gather does) and handed to ivfadc_search_probes_local_device
+    half = 170
+    c0, d0 = sharded.coarse_device(shards[0], dQ[:half].contiguous(), w)
+    c1, d1 = sharded.coarse_device(shards[1], dQ[half:].contiguous(), w)
+    cells, dc = torch.cat([c0, c1]).contiguous(), torch.cat([d0, d1]).contiguous()
+    ocells, odc = orc.coarse_search(qz, Q, w, nthreads=4)
+    np.testing.assert_array_equal(cells.cpu().numpy(), ocells)
+    assert np.array_equal(dc.cpu().numpy().view(np.uint8), odc.view(np.uint8))
+    parts = [sharded.search_local_probes(s, dQ, k, w, cells, dc) for s in shards]
+    ids2, dists2, counts2 = sharded.merge_parts(shards[0], parts, k)
+    np.testing.assert_array_equal(counts2.cpu().numpy(), oc)
+    assert np.array_equal(dists2.cpu().numpy().view(np.uint8), od.view(np.uint8))
+    np.testing.assert_array_equal(ids2.cpu().numpy().astype(np.uint64), oi)
     # mutation on shards: delete + pushfirst keep the global numbering
     dele = [5, 17, 400, 5999, 6000]
     oidx.delete_from_index(dele)

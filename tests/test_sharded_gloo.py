@@ -21,11 +21,25 @@ class OracleShardEngine:
         self.qz, self.rank, self.world = qz, rank, world
         self.offsets, self.codes, self.ids = offsets, codes, ids
 
+    @property
+    def kc(self):
+        return self.qz.kc
+
+    def coarse(self, Q, w):
+        from oracle import oracle as orc
+        cells, dc = orc.coarse_search(self.qz, Q.numpy(), w)
+        return torch.from_numpy(cells), torch.from_numpy(dc)
+
     def search_local(self, Q, k, w):
+        from oracle import oracle as orc
+        cells, _ = orc.coarse_search(self.qz, Q.numpy(), w)
+        return self.search_local_probes(Q, k, w, torch.from_numpy(cells), None)
+
+    def search_local_probes(self, Q, k, w, cells, dc):
         from oracle import oracle as orc
         Qn = Q.numpy()
         nq = Qn.shape[0]
-        cells, dc = orc.coarse_search(self.qz, Qn, w)
+        cells = cells.numpy()
         ids = np.full((nq, k), -1, dtype=np.int64)
         keys = np.full((nq, k), -1, dtype=np.int64)
         dists = np.full((nq, k), np.inf, dtype=Qn.dtype)
