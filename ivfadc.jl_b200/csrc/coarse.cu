@@ -5,9 +5,9 @@
 //
 // Distances are the DIRECT form sum_d (c_d - q_d)^2 evaluated as one sequential fma chain per
 // (query, centroid) pair -- bit-identical to the oracle (A1) -- on the FFMA pipe, register-tiled
-// 2 queries x 8 centroids per thread from padded shared-memory tiles (a 2 x 4 tile was
-// shared-memory-bandwidth bound: 6 LDS.128 per 32 fma pairs; 2 x 8 needs 10 per 64); the top-w selection is
-// fused: after each 128-centroid tile every warp updates the warp-distributed sorted lists of its
+// 2 queries x 4 centroids per thread from padded shared-memory tiles (a 2 x 8 tile, TC = 128, was
+// measured slower on config B: 0.335 vs 0.277 ms, fewer resident CTAs for a 313-CTA grid); the top-w selection is
+// fused: after each 64-centroid tile every warp updates the warp-distributed sorted lists of its
 // 4 queries.  FP32 FFMA was chosen over 3xTF32 tcgen05 because selection must agree with the
 // oracle bit for bit and the whole step is < 10% of the search ("K1").
 #include "common.cuh"
@@ -18,7 +18,7 @@ namespace ivf {
 namespace {
 
 constexpr int TQ = 32;        // queries per CTA
-constexpr int TC = 128;       // centroids per tile
+constexpr int TC = 64;        // centroids per tile
 constexpr int TCJ = TC / 16;  // centroids per thread
 constexpr int CTHREADS = 256;
 
@@ -92,7 +92,7 @@ coarse_kernel(const T* __restrict__ Q, const T* __restrict__ C, int64_t nq, int 
                 sC[row * LD + col] = (c < kc && d < D) ? C[(int64_t)c * D + d] : (T)0;
             }
             __syncthreads();
-#pragma unroll 2
+#pragma unroll 4
             for (int d = 0; d < DK; d += VEC) {
                 T qv[2][VEC], cv[TCJ][VEC];
 #pragma unroll
