@@ -162,33 +162,48 @@ class ShardedSearcher:
         """Q is the full (replicated / broadcast) query batch on every rank."""
         nq = Q.shape[0]
         if self.world > 1 and hasattr(self.engine, "coarse") and nq >= self.world:
-            # coarse step sharded by query: rank r assigns its slice, one all-gather of the probe lists
+            # coarse step sharded by query: rank r assigns its slice; ONE all-gather of the probe lists
+            # (cells and dc are both 4-byte elements when T is float32: packed side by side as int32)
             w = min(w, self.engine.kc)
             per = (nq + self.world - 1) // self.world
             lo = min(nq, self.rank * per)
             hi = min(nq, lo + per)
-            cells_l = torch.zeros((per, w), dtype=torch.int32, device=Q.device)
-            dc_l = torch.zeros((per, w), dtype=Q.dtype, device=Q.device)
-            if hi > lo:
-                c, d = self.engine.coarse(Q[lo:hi].contiguous(), w)
-                cells_l[:hi - lo] = c
-                dc_l[:hi - lo] = d
-            cells_all = torch.empty((self.world * per, w), dtype=torch.int32, device=Q.device)
-            dc_all = torch.empty((self.world * per, w), dtype=Q.dtype, device=Q.device)
-            self.dist.all_gather_into_tensor(cells_all, cells_l, group=self.group)
-            self.dist.all_gather_into_tensor(dc_all, dc_l, group=self.group)
-            ids, dists, keys = self.engine.search_local_probes(Q, k, w, cells_all[:nq].contiguous(),
-                                                               dc_all[:nq].contiguous())
+            if Q.dtype == torch.float32:
+                packed = torch.zeros((per, 2, w), dtype=torch.int32, device=Q.device)
+                if hi > lo:
+                    c, d = self.engine.coarse(Q[lo:hi].contiguous(), w)
+                    packed[:hi - lo, 0] = c
+                    packed[:hi - lo, 1] = d.view(torch.int32)
+                allp = torch.empty((self.world * per, 2, w), dtype=torch.int32, device=Q.device)
+                self.dist.all_gather_into_tensor(allp, packed, group=self.group)
+                cells_all = allp[:nq, 0].contiguous()
+                dc_all = allp[:nq, 1].contiguous().view(torch.float32)
+            else:
+                cells_l = torch.zeros((per, w), dtype=torch.int32, device=Q.device)
+                dc_l = torch.zeros((per, w), dtype=Q.dtype, device=Q.device)
+                if hi > lo:
+                    c, d = self.engine.coarse(Q[lo:hi].contiguous(), w)
+                    cells_l[:hi - lo] = c
+                    dc_l[:hi - lo] = d
+                cells_all = torch.empty((self.world * per, w), dtype=torch.int32, device=Q.device)
+                dc_all = torch.empty((self.world * per, w), dtype=Q.dtype, device=Q.device)
+                self.dist.all_gather_into_tensor(cells_all, cells_l, group=self.group)
+                self.dist.all_gather_into_tensor(dc_all, dc_l, group=self.group)
+                cells_all, dc_all = cells_all[:nq].contiguous(), dc_all[:nq].contiguous()
+            ids, dists, keys = self.engine.search_local_probes(Q, k, w, cells_all, dc_all)
         else:
             ids, dists, keys = self.engine.search_local(Q, k, w)
         if self.world == 1:
             return self.engine.merge(ids[None], dists[None], keys[None], k)
-        # rank-major concatenation along dim 0 == [world, nq, k] (the layout ivfadc_merge_device takes)
+        # rank-major concatenation along dim 0 == [world, nq, k] (the layout ivfadc_merge_device takes);
+        # the three gathers are issued back to back (asynchronously) and awaited together
         ids_all = torch.empty((self.world * nq, k), dtype=ids.dtype, device=ids.device)
         dists_all = torch.empty((self.world * nq, k), dtype=dists.dtype, device=ids.device)
         keys_all = torch.empty((self.world * nq, k), dtype=keys.dtype, device=ids.device)
-        self.dist.all_gather_into_tensor(ids_all, ids.contiguous(), group=self.group)
-        self.dist.all_gather_into_tensor(dists_all, dists.contiguous(), group=self.group)
-        self.dist.all_gather_into_tensor(keys_all, keys.contiguous(), group=self.group)
+        works = [self.dist.all_gather_into_tensor(ids_all, ids.contiguous(), group=self.group, async_op=True),
+                 self.dist.all_gather_into_tensor(dists_all, dists.contiguous(), group=self.group, async_op=True),
+                 self.dist.all_gather_into_tensor(keys_all, keys.contiguous(), group=self.group, async_op=True)]
+        for wk in works:
+            wk.wait()
         shape = (self.world, nq, k)
         return self.engine.merge(ids_all.view(shape), dists_all.view(shape), keys_all.view(shape), k)

@@ -548,3 +548,53 @@ def test_device_api_matches_host_api():
     assert np.array_equal(dd.cpu().numpy(), hd)
     np.testing.assert_array_equal(dcn.cpu().numpy(), hc)
     e.close()
+
+
+# ------------------------------------------------------------------------------------------------
+# Full BASELINE.json size (config B: 1M x 128-d, kc = 1024, m = 16, 10k queries, nprobe 16, k 10):
+# size-independent properties + a sample against the oracle
+# ------------------------------------------------------------------------------------------------
+def test_config_b_full_size_properties():
+    from ivfadc_jl_b200 import synth
+    D, N, kc, m, ksub, nq, k, w = 128, 1_000_000, 1024, 16, 256, 10_000, 10, 16
+    X = synth.blobs(N, D, kc, seed=1002)
+    Q = synth.blobs(nq, D, kc, seed=2001)
+    cent = synth.blob_centres(D, kc)
+    _, cb, _ = synth.random_quantizers(kc, D, m, ksub, seed=5, data=X[:200_000])
+    qz = orc.Quantizers(cent, cb, None)
+    e = iv.IVFADCIndex.from_quantizers(cent, cb, None, index_type=np.uint32)           # engine default (tcgen05 tables)
+    x = iv.IVFADCIndex.from_quantizers(cent, cb, None, index_type=np.uint32, flags=LUT_EXACT)
+    iv.push_batch(e, X)
+    iv.push_batch(x, X)
+    assert len(e) == N and int(e.list_sizes().sum()) == N
+    gi, gd, gc = e.search_packed(Q, k, w)
+    xi, xd, xc = x.search_packed(Q, k, w)
+    # shape / order properties (src/index.jl:247-257): k results, ascending, ids in range and unique per query
+    assert (gc == k).all() and (xc == k).all()
+    assert (np.diff(gd, axis=1) >= 0).all() and (np.diff(xd, axis=1) >= 0).all()
+    assert gi.max() < N and all(len(set(r)) == k for r in gi[:500])
+    # default tables vs reference-exact tables: the north_star tolerance on every one of the 100k results
+    rep = orc.compare_search(gi, gd, gc, xi, xd, xc, rtol=RTOL)
+    assert rep["near_tie_id_mismatches"] <= 50, rep
+    # checksum of checksums: the exact engine is deterministic across kernels (query-per-lane vs vector-per-lane)
+    y = iv.IVFADCIndex.from_quantizers(cent, cb, None, index_type=np.uint32, flags=LEGACY)
+    iv.push_batch(y, X)
+    yi, yd, yc = y.search_packed(Q[:2000], k, w)
+    assert np.array_equal(yi, xi[:2000]) and np.array_equal(yd.view(np.uint8), xd[:2000].view(np.uint8))
+    # a sample against the oracle on the exported lists
+    sizes = x.list_sizes()
+    off = np.zeros(kc + 1, dtype=np.int64)
+    np.cumsum(sizes, out=off[1:])
+    ids = np.empty(N, dtype=np.uint64)
+    codes = np.empty((N, m), dtype=np.uint8)
+    for c in range(kc):
+        if sizes[c]:
+            i, cd = x.export_list(c)
+            ids[off[c]:off[c + 1]], codes[off[c]:off[c + 1]] = i, cd
+    oi, od, oc, _ = orc.search_csr(qz, off, codes, ids, Q[:128], k, w, nthreads=8)
+    assert np.array_equal(xi[:128], oi) and np.array_equal(xd[:128].view(np.uint8), od.view(np.uint8))
+    # delete 1000 vectors: none of them may come back, counts stay k
+    dele = np.unique(gi[:100].ravel())[:1000]
+    iv.delete_from_index(e, (dele + 1).tolist())       # 1-based, as the reference takes them
+    assert len(e) == N - len(dele)
+    e.close(); x.close(); y.close()
