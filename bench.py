@@ -182,6 +182,9 @@ def main():
     ap.add_argument("--workload", default="B", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--check", type=int, default=256, help="queries verified against the oracle")
+    ap.add_argument("--graph", action="store_true",
+                    help="N > 1: replay the sharded step from a CUDA graph (opt-in: measured gain at N = 2 is 3%%, and "
+                         "tearing down a process group with captured NCCL work hung once)")
     ap.add_argument("--flags", type=int, default=0,
                     help="ivfadc_config.flags (1 vector-per-lane scan, 2 query-per-lane scan, 4 exact tables, 8 mma.sync tables)")
     args = ap.parse_args()
@@ -233,9 +236,26 @@ def main():
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
     searcher = sharded.ShardedSearcher(sharded.CudaShardEngine(engine)) if world > 1 else None
 
+    use_graph = world > 1 and args.graph
+    breakdown = None
+    if use_graph:
+        # per-kernel breakdown / roofline from a few eager steps (event timing on), then the headline
+        # timing replays the whole sharded step (coarse slice, gathers, scan, merge) from a CUDA graph
+        for _ in range(args.warmup):
+            searcher.search(dQ, k, w)
+        torch.cuda.synchronize()
+        engine.stats(reset=True)
+        for _ in range(5):
+            flush.zero_()
+            searcher.search(dQ, k, w)
+        torch.cuda.synchronize()
+        breakdown = engine.stats()
+        searcher.search_graphed(dQ, k, w)   # capture
+        torch.cuda.synchronize()
+
     def step_device():
         if world > 1:
-            return searcher.search(dQ, k, w)
+            return searcher.search_graphed(dQ, k, w) if use_graph else searcher.search(dQ, k, w)
         return sharded.search_device(engine, dQ, k, w)
 
     # ---- device-resident timing -------------------------------------------------------------
@@ -260,6 +280,11 @@ def main():
         dist.barrier()
     dev_ms = sum(a.elapsed_time(b) for a, b in evs) / args.steps
     st = engine.stats()
+    nbreak = args.steps
+    if breakdown is not None:   # graph replays carry no per-kernel events: use the eager steps measured above
+        st, nbreak = dict(st), 5
+        for key_ in ("coarse_ms", "plan_ms", "scan_ms", "merge_ms", "scan_launches", "scan_code_bytes", "scanned_vectors"):
+            st[key_] = breakdown[key_]
     clocks = sampler.stop()
     if world > 1:
         t = torch.tensor([dev_ms], device=dev, dtype=torch.float64)
@@ -303,7 +328,7 @@ def main():
 
         def step_host():
             dQ2.copy_(hQ, non_blocking=True)
-            o = searcher.search(dQ2, k, w)
+            o = searcher.search_graphed(dQ2, k, w) if use_graph else searcher.search(dQ2, k, w)
             h_ids.copy_(o[0], non_blocking=True)
             h_d.copy_(o[1], non_blocking=True)
             h_c.copy_(o[2], non_blocking=True)
@@ -370,6 +395,7 @@ def main():
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
             "config": {"workload": wl["name"], "nq": nq, "k": k, "nprobe": w, "lists": "cell-sharded" if world > 1 else "one GPU",
+                       "launch": "CUDA graph replay of the sharded step" if use_graph else "eager",
                        "l2": "flushed between steps (256 MiB write); the 16 MB code array is L2-resident within a step",
                        "timing": "CUDA events on the launch stream, per step, mean", "flags": args.flags,
                        "tables": ("exact direct form (fp32 chain)" if (args.flags & 5) else
@@ -384,15 +410,20 @@ def main():
                          "per_rank": world > 1},
             "cpu_baseline": cpu,
             "e2e": e2e,
-            "gpu_launches": int(st["gpu_launches"]),
+            # graph replays re-issue the captured kernels: launches per eager step x timed steps
+            "gpu_launches": (int(breakdown["gpu_launches"] / 5 * args.steps) if breakdown is not None
+                             else int(st["gpu_launches"])),
             "clocks": clocks,
-            "breakdown_ms": {"coarse": st["coarse_ms"] / args.steps, "plan": st["plan_ms"] / args.steps,
-                             "scan": st["scan_ms"] / args.steps, "merge": st["merge_ms"] / args.steps},
+            "breakdown_ms": {"coarse": st["coarse_ms"] / nbreak, "plan": st["plan_ms"] / nbreak,
+                             "scan": st["scan_ms"] / nbreak, "merge": st["merge_ms"] / nbreak},
             "build": {"vectors": wl["N"], "seconds": build_s, "vectors_per_s": wl["N"] / build_s, "prep_s": prep_s},
             "parity": parity,
         }
         print(json.dumps(line))
     if world > 1:
+        if searcher is not None and hasattr(searcher, "_graphs"):
+            searcher._graphs.clear()   # captured NCCL work must be gone before the group is destroyed
+        torch.cuda.synchronize()
         dist.barrier()
         dist.destroy_process_group()
     engine.close()

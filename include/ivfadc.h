@@ -258,6 +258,13 @@ int ivfadc_set_length(ivfadc_index* h, int64_t n_total);
  */
 int ivfadc_debug_tables(ivfadc_index* h, void* out);
 
+/*
+ * Per-kernel CUDA-event timing of the search path (ivfadc_stats.*_ms) on / off (default on).
+ * Switch it off before capturing *_device calls into a CUDA graph: event queries are not
+ * capturable.  Counters (queries, scanned vectors, launches) keep running.
+ */
+int ivfadc_set_stats_timing(ivfadc_index* h, int32_t enable);
+
 int ivfadc_get_stats(ivfadc_index* h, ivfadc_stats* out);
 int ivfadc_reset_stats(ivfadc_index* h);
 

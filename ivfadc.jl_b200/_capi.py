@@ -27,7 +27,7 @@ SYMBOLS = [
     "ivfadc_search_local_device", "ivfadc_coarse_search_device", "ivfadc_search_probes_local_device",
     "ivfadc_merge_device", "ivfadc_delete", "ivfadc_pop", "ivfadc_length",
     "ivfadc_list_sizes", "ivfadc_export_list", "ivfadc_import_list", "ivfadc_export_quantizers",
-    "ivfadc_set_length", "ivfadc_get_stats", "ivfadc_reset_stats", "ivfadc_debug_tables",
+    "ivfadc_set_length", "ivfadc_get_stats", "ivfadc_reset_stats", "ivfadc_debug_tables", "ivfadc_set_stats_timing",
 ]
 
 
@@ -100,6 +100,7 @@ def load(build_if_missing: bool = True):
     lib.ivfadc_get_stats.argtypes = [H, POINTER(Stats)]
     lib.ivfadc_reset_stats.argtypes = [H]
     lib.ivfadc_debug_tables.argtypes = [H, c_void_p]
+    lib.ivfadc_set_stats_timing.argtypes = [H, c_int32]
     for name in SYMBOLS:
         fn = getattr(lib, name)
         if name not in ("ivfadc_last_error",):

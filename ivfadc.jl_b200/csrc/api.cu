@@ -620,6 +620,14 @@ int ivfadc_debug_tables(ivfadc_index* h, void* out) {
     return IVFADC_OK;
 }
 
+int ivfadc_set_stats_timing(ivfadc_index* h, int32_t enable) {
+    if (check_handle(h)) return IVFADC_ERR_BAD_ARG;
+    cudaSetDevice(h->cfg.device);
+    flush_all(h);
+    h->stats_timing = enable != 0;
+    return IVFADC_OK;
+}
+
 int ivfadc_get_stats(ivfadc_index* h, ivfadc_stats* out) {
     if (check_handle(h) || !out) return IVFADC_ERR_BAD_ARG;
     cudaSetDevice(h->cfg.device);

@@ -133,6 +133,9 @@ class CudaShardEngine:
     def kc(self):
         return self.index.kc
 
+    def set_timing(self, enable: bool):
+        _capi.check(self.index._h, self.index._lib.ivfadc_set_stats_timing(self.index._h, 1 if enable else 0))
+
     def merge(self, ids_all, dists_all, keys_all, k):
         return merge_gathered(self.index, ids_all, dists_all, keys_all, k)
 
@@ -157,6 +160,34 @@ class ShardedSearcher:
     @staticmethod
     def owner(cell: int, world: int) -> int:
         return cell % world
+
+    def search_graphed(self, Q, k: int, w: int = 1):
+        """`search` replayed from a CUDA graph (one graph per batch shape): the step is ~20 small
+        launches and four collectives, so at multi-GPU step times below a millisecond the Python /
+        launch overhead would otherwise set the pace.  Q is copied into a static buffer; the returned
+        tensors are the graph's static outputs (valid until the next call)."""
+        key = (tuple(Q.shape), Q.dtype, k, w)
+        if not hasattr(self, "_graphs"):
+            self._graphs = {}
+        if key not in self._graphs:
+            static_q = Q.clone()
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(3):          # warm-up: workspaces grow, kernel attributes are set
+                    self.search(static_q, k, w)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            if hasattr(self.engine, "set_timing"):
+                self.engine.set_timing(False)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                out = self.search(static_q, k, w)
+            self._graphs[key] = (g, static_q, out)
+        g, static_q, out = self._graphs[key]
+        static_q.copy_(Q, non_blocking=True)
+        g.replay()
+        return out
 
     def search(self, Q, k: int, w: int = 1):
         """Q is the full (replicated / broadcast) query batch on every rank."""
