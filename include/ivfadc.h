@@ -77,6 +77,12 @@ extern "C" {
  * flag selects the older warp-level mma.sync builder instead (same numerics class, 3xTF32).
  */
 #define IVFADC_FLAG_LUT_MMASYNC 8
+/*
+ * The default query-per-lane kernel keeps the lookup tables in tensor memory and looks them up with
+ * tcgen05.ld at column = code byte (persistent CTAs).  This flag selects the previous generation,
+ * which copies every table from tensor memory to shared memory and gathers with LDS.
+ */
+#define IVFADC_FLAG_SCAN_SMEMLUT 16
 
 typedef struct ivfadc_index ivfadc_index;   /* opaque, owns all device memory */
 

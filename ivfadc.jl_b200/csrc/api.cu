@@ -284,6 +284,7 @@ int ivfadc_destroy(ivfadc_index* h) {
     if (h->d_afrag) cudaFree(h->d_afrag);
     if (h->d_wnfrag) cudaFree(h->d_wnfrag);
     if (h->d_tcB) cudaFree(h->d_tcB);
+    if (h->d_tcU) cudaFree(h->d_tcU);
     if (h->d_err) cudaFree(h->d_err);
     if (h->d_dbg_lut) cudaFree(h->d_dbg_lut);
     DevBuf* bufs[] = {&h->ws_q, &h->ws_cells, &h->ws_dc, &h->ws_bucket, &h->ws_sorted, &h->ws_pair_d,

@@ -111,6 +111,7 @@ struct ivfadc_index {
     void* d_wnfrag = nullptr;
     int frag_ntiles = 0, frag_ksteps = 0;
     void* d_tcB = nullptr;          // codebook as tcgen05 B-operand blocks (scant table builder)
+    void* d_tcU = nullptr;          // codebook as per-subspace B-operand blocks, rows = code values (scanu)
     int* d_err = nullptr;           // device error flag of the tcgen05 pipeline (mbarrier timeout)
     void* d_dbg_lut = nullptr;      // optional table dump of work item 0 (tests), float[m][256][32]
 

@@ -2,6 +2,7 @@
 #include "scan_impl.cuh"
 #include "scanq_impl.cuh"
 #include "scant_impl.cuh"
+#include "scanu_impl.cuh"
 
 namespace ivf {
 
@@ -184,6 +185,167 @@ merge_probes_kernel(int64_t nq, int w, int k, const int32_t* __restrict__ cells,
     if (lane == 0) out_cnt[q] = e;
 }
 
+// Final selection over UNSORTED candidate rows (the tensor-memory lookup kernel dumps every vector
+// whose distance is within the list's k-th-distance bound; the redo kernel writes exact sorted
+// rows): one warp per query picks the k smallest of the union of its w rows by
+// (distance, probe rank, position) -- the reference's order, src/index.jl:247-257.
+//   1. lane minima over a strided share of the candidates; the k-th smallest of the 32 minima bounds
+//      the k-th distance of the query;
+//   2. candidates within the bound are compacted into shared memory (ballot prefix);
+//   3. k rounds of warp arg-min over the compacted set held in registers.  A set larger than
+//      MC_CAP (heavy ties) is selected by k filtered sweeps over the rows in global memory.
+constexpr int MC_CAP = 128;
+
+__device__ __forceinline__ bool key_less(float da, uint64_t ka, float db, uint64_t kb) {
+    return da < db || (da == db && ka < kb);
+}
+
+template <typename IdT>
+__global__ void __launch_bounds__(128)
+merge_cands_kernel(int64_t nq, int w, int k, int ps, const int32_t* __restrict__ cells,
+                   const float* __restrict__ pair_d, const uint32_t* __restrict__ pair_pos,
+                   const int32_t* __restrict__ pair_cnt, const int64_t* __restrict__ list_off,
+                   const IdT* __restrict__ ids_arena, uint64_t* __restrict__ out_ids,
+                   float* __restrict__ out_d, uint64_t* __restrict__ out_keys, int32_t* __restrict__ out_cnt) {
+    __shared__ float s_d[4][MC_CAP];
+    __shared__ uint64_t s_k[4][MC_CAP];
+    const int lane = threadIdx.x & 31, wq = threadIdx.x >> 5;
+    const int64_t q = (int64_t)blockIdx.x * 4 + wq;
+    if (q >= nq) return;
+    const float inf = Limits<float>::inf();
+    int cnt[MERGE_NL];
+#pragma unroll
+    for (int s = 0; s < MERGE_NL; ++s) {
+        const int r = lane + 32 * s;
+        cnt[s] = r < w ? min(pair_cnt[q * w + r], ps) : 0;
+    }
+    auto count_of = [&](int r) {
+        int c = 0;
+#pragma unroll
+        for (int s = 0; s < MERGE_NL; ++s)
+            if (s == (r >> 5)) c = __shfl_sync(0xffffffffu, cnt[s], r & 31);
+        return c;
+    };
+    // 1. bound
+    float lmin = inf;
+#pragma unroll 4
+    for (int r = 0; r < w; ++r) {
+        const int c = count_of(r);
+        const float* row = pair_d + (size_t)(q * w + r) * ps;
+        for (int e = lane; e < c; e += 32) lmin = fminf(lmin, row[e]);
+    }
+    int rank = 0;
+#pragma unroll
+    for (int l = 0; l < 32; ++l) {
+        const float o = __shfl_sync(0xffffffffu, lmin, l);
+        rank += (o < lmin || (o == lmin && l < lane)) ? 1 : 0;
+    }
+    const int src = __ffs(__ballot_sync(0xffffffffu, rank == min(k, 32) - 1)) - 1;
+    const float bound = __shfl_sync(0xffffffffu, lmin, src);
+    // 2. compaction of the candidates within the bound
+    int M = 0;
+    for (int r = 0; r < w; ++r) {
+        const int c = count_of(r);
+        const size_t rb = (size_t)(q * w + r) * ps;
+        for (int e0 = 0; e0 < c; e0 += 32) {
+            const int e = e0 + lane;
+            const float d = e < c ? pair_d[rb + e] : inf;
+            const bool pred = e < c && d <= bound && d < inf;
+            const unsigned mask = __ballot_sync(0xffffffffu, pred);
+            if (pred) {
+                const int slot = M + __popc(mask & ((1u << lane) - 1u));
+                if (slot < MC_CAP) {
+                    s_d[wq][slot] = d;
+                    s_k[wq][slot] = ((uint64_t)r << 32) | pair_pos[rb + e];
+                }
+            }
+            M += __popc(mask);
+        }
+    }
+    __syncwarp();
+    int e = 0;
+    if (M <= MC_CAP) {
+        // 3. k rounds of warp arg-min; lane holds entries lane, lane + 32, lane + 64, lane + 96
+        float d[4];
+        uint64_t key[4];
+#pragma unroll
+        for (int s = 0; s < 4; ++s) {
+            const int i = lane + 32 * s;
+            d[s] = i < M ? s_d[wq][i] : inf;
+            key[s] = i < M ? s_k[wq][i] : ~0ull;
+        }
+        for (; e < k; ++e) {
+            float bd = inf;
+            uint64_t bk = ~0ull;
+#pragma unroll
+            for (int s = 0; s < 4; ++s)
+                if (key[s] != ~0ull && key_less(d[s], key[s], bd, bk)) { bd = d[s]; bk = key[s]; }
+            const uint64_t mine = bk;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const float od = __shfl_xor_sync(0xffffffffu, bd, o);
+                const uint64_t ok = __shfl_xor_sync(0xffffffffu, bk, o);
+                if (ok != ~0ull && (bk == ~0ull || key_less(od, ok, bd, bk))) { bd = od; bk = ok; }
+            }
+            if (bk == ~0ull) break;  // every candidate taken
+            if (mine == bk) {        // keys are unique: exactly one lane owns the winner
+#pragma unroll
+                for (int s = 0; s < 4; ++s)
+                    if (key[s] == bk) key[s] = ~0ull;
+            }
+            if (lane == 0) {
+                const int r = (int)(bk >> 32);
+                const int cell = cells[q * w + r];
+                out_ids[q * k + e] = (uint64_t)ids_arena[list_off[cell] + (uint32_t)bk];
+                out_d[q * k + e] = bd;
+                if (out_keys) out_keys[q * k + e] = bk;
+            }
+        }
+    } else {
+        // heavy ties: k filtered sweeps over the rows (each sweep finds the smallest candidate after the last winner)
+        float ld = 0.f;
+        uint64_t lk = 0;
+        for (; e < k; ++e) {
+            float bd = inf;
+            uint64_t bk = ~0ull;
+            for (int r = 0; r < w; ++r) {
+                const int c = count_of(r);
+                const size_t rb = (size_t)(q * w + r) * ps;
+                for (int i = lane; i < c; i += 32) {
+                    const float dd = pair_d[rb + i];
+                    const uint64_t kk = ((uint64_t)r << 32) | pair_pos[rb + i];
+                    if (dd < inf && (e == 0 || key_less(ld, lk, dd, kk)) && (bk == ~0ull || key_less(dd, kk, bd, bk))) {
+                        bd = dd;
+                        bk = kk;
+                    }
+                }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const float od = __shfl_xor_sync(0xffffffffu, bd, o);
+                const uint64_t ok = __shfl_xor_sync(0xffffffffu, bk, o);
+                if (ok != ~0ull && (bk == ~0ull || key_less(od, ok, bd, bk))) { bd = od; bk = ok; }
+            }
+            if (bk == ~0ull) break;
+            ld = bd;
+            lk = bk;
+            if (lane == 0) {
+                const int r = (int)(bk >> 32);
+                const int cell = cells[q * w + r];
+                out_ids[q * k + e] = (uint64_t)ids_arena[list_off[cell] + (uint32_t)bk];
+                out_d[q * k + e] = bd;
+                if (out_keys) out_keys[q * k + e] = bk;
+            }
+        }
+    }
+    for (int x = e + lane; x < k; x += 32) {
+        out_ids[q * k + x] = ~0ull;
+        out_d[q * k + x] = inf;
+        if (out_keys) out_keys[q * k + x] = ~0ull;
+    }
+    if (lane == 0) out_cnt[q] = e;
+}
+
 // Merge `parts` candidate sets [parts][nq][k] (sorted rows padded with key = ~0) into [nq][k].
 template <typename T>
 __global__ void __launch_bounds__(128)
@@ -336,11 +498,40 @@ bool use_scanq(const ivfadc_index* h, int64_t npairs, int k) {
     return npairs >= (int64_t)8 * h->cfg.kc;
 }
 
-// tcgen05 table builder (scant_impl.cuh): fp32, k <= 16, m in {4, 8, 12, 16}, dsub <= 8
+// tensor-memory lookup kernel (scanu_impl.cuh), the default: fp32, k <= 16, m in {4, 8, 12, 16}, dsub <= 8
+bool use_scanu(const ivfadc_index* h) {
+    if (h->cfg.flags & (IVFADC_FLAG_LUT_EXACT | IVFADC_FLAG_LUT_MMASYNC | IVFADC_FLAG_SCAN_SMEMLUT)) return false;
+    return h->d_tcU != nullptr && h->dsub <= 8 && h->cfg.m % 4 == 0 && h->cfg.m <= 16 &&
+           scanu_smem_layout(h->cfg.m).total + 1024 <= kSmemMax;
+}
+
+template <int NP, bool DBG>
+cudaError_t launch_scanu_inst(const ScanUArgs& ua, unsigned grid, size_t smem, cudaStream_t s) {
+    static size_t configured = 0;
+    if (smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(scanu_kernel<NP, DBG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured = smem;
+    }
+    scanu_kernel<NP, DBG><<<grid, QTHREADS, smem, s>>>(ua);
+    return cudaGetLastError();
+}
+template <int NP>
+cudaError_t launch_scanu_np(const ScanUArgs& ua, unsigned grid, size_t smem, cudaStream_t s) {
+    return ua.dbg ? launch_scanu_inst<NP, true>(ua, grid, smem, s) : launch_scanu_inst<NP, false>(ua, grid, smem, s);
+}
+
+// tcgen05 table builder with shared-memory tables (scant_impl.cuh): fp32, k <= 16, m in {4, 8, 12, 16}, dsub <= 8
 bool use_scant(const ivfadc_index* h) {
     if (h->cfg.flags & (IVFADC_FLAG_LUT_EXACT | IVFADC_FLAG_LUT_MMASYNC)) return false;
     return h->d_tcB != nullptr && h->dsub <= 8 &&
            scant_smem_layout(h->cfg.m, T_DYN_BASE_GUESS).total + T_DYN_BASE_GUESS <= kSmemMax;
+}
+
+// Row stride of the per-pair candidate arrays: k sorted entries, or U_CAP unsorted candidates when
+// the tensor-memory lookup kernel serves the batch.
+int pair_stride(const ivfadc_index* h, int64_t npairs, int k) {
+    return (use_scanq(h, npairs, k) && use_scanu(h)) ? std::max(k, U_CAP) : k;
 }
 
 template <typename T, int MC>
@@ -375,6 +566,7 @@ cudaError_t search_t(ivfadc_index* h, const void* dQ, int64_t nq, int k, int w, 
     int* bucket_off = cursor + 2 * kc;
     int* group_off = bucket_off + 2 * kc + 1;
     int* redo_cnt = group_off + 2 * kc + 1;
+    int* item_counter = redo_cnt + 1;
     int32_t* sorted_pairs = h->ws_sorted.as<int32_t>();
     int32_t* redo_pairs = sorted_pairs + npairs;
     T* pair_d = h->ws_pair_d.as<T>();
@@ -382,7 +574,7 @@ cudaError_t search_t(ivfadc_index* h, const void* dQ, int64_t nq, int k, int w, 
     int32_t* pair_cnt = h->ws_pair_cnt.as<int32_t>();
     bits_t* thr = h->ws_thr.as<bits_t>();
 
-    if ((e = cudaMemsetAsync(bucket_cnt, 0, sizeof(int) * (size_t)(8 * kc + 3), s)) != cudaSuccess) return e;
+    if ((e = cudaMemsetAsync(bucket_cnt, 0, sizeof(int) * (size_t)(8 * kc + 4), s)) != cudaSuccess) return e;
     if ((e = cudaMemsetAsync(pair_cnt, 0, sizeof(int32_t) * npairs, s)) != cudaSuccess) return e;
 
     const int pthreads = 256;
@@ -410,11 +602,13 @@ cudaError_t search_t(ivfadc_index* h, const void* dQ, int64_t nq, int k, int w, 
     a.cells = d_cells; a.dc = static_cast<const T*>(d_dc);
     a.bucket_off = bucket_off; a.group_off = group_off; a.nb = nb; a.sorted_pairs = sorted_pairs;
     a.pair_d = pair_d; a.pair_pos = pair_pos; a.pair_cnt = pair_cnt; a.thr = thr;
+    const int ps = pair_stride(h, npairs, k);
+    a.pstride = ps;
 
     // upper bound on the number of work items: every bucket adds at most one partial group
     int64_t max_items = std::min<int64_t>(npairs, npairs / qn + nb);
     if (max_items < 1) max_items = 1;
-    if (qlane && use_scant(h)) {
+    if (qlane && (use_scanu(h) || use_scant(h))) {
         plan_items_kernel<<<(kc + 255) / 256, 256, 0, s>>>(bucket_off, group_off, kc, QG, h->ws_items.as<int4>());
         *launches += 1;
     }
@@ -428,7 +622,32 @@ cudaError_t search_t(ivfadc_index* h, const void* dQ, int64_t nq, int k, int w, 
             qa.bucket_off = bucket_off; qa.group_off = group_off; qa.sorted_pairs = sorted_pairs;
             qa.pair_d = pair_d; qa.pair_pos = pair_pos; qa.pair_cnt = pair_cnt;
             qa.redo_pairs = redo_pairs; qa.redo_cnt = redo_cnt;
-            if (use_scant(h)) {
+            if (use_scanu(h)) {
+                ScanUArgs uq;
+                uq.q = qa;
+                uq.tcU = static_cast<const float*>(h->d_tcU);
+                uq.items = h->ws_items.as<int4>();
+                uq.item_counter = item_counter;
+                uq.pstride = ps;
+                uq.err = h->d_err;
+                uq.dbg = static_cast<float*>(h->d_dbg_lut);
+                static int num_sms = 0;
+                if (!num_sms) {
+                    int dev = 0;
+                    cudaGetDevice(&dev);
+                    if ((e = cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
+                }
+                const size_t usmem = scanu_smem_layout(a.m).total;
+                const unsigned ugrid = (unsigned)std::min<int64_t>(max_items, num_sms);  // persistent: one CTA per SM
+                switch (a.m) {
+                    case 4: e = launch_scanu_np<1>(uq, ugrid, usmem, s); break;
+                    case 8: e = launch_scanu_np<2>(uq, ugrid, usmem, s); break;
+                    case 12: e = launch_scanu_np<3>(uq, ugrid, usmem, s); break;
+                    default: e = launch_scanu_np<4>(uq, ugrid, usmem, s); break;
+                }
+                if (e != cudaSuccess) return e;
+                *launches += 1;
+            } else if (use_scant(h)) {
                 ScanTArgs tq;
                 tq.q = qa;
                 tq.tcB = static_cast<const float*>(h->d_tcB);
@@ -489,7 +708,18 @@ cudaError_t search_t(ivfadc_index* h, const void* dQ, int64_t nq, int k, int w, 
     if (h->stats_timing) cudaEventRecord(h->ev[3], s);
 
     const unsigned mgrid = (unsigned)((nq + 3) / 4);
-    if (h->id_dev_bytes == 4)
+    if (ps != k) {  // unsorted candidate rows (fp32 only)
+        if constexpr (sizeof(T) == 4) {
+            if (h->id_dev_bytes == 4)
+                merge_cands_kernel<uint32_t><<<mgrid, 128, 0, s>>>(
+                    nq, w, k, ps, d_cells, pair_d, pair_pos, pair_cnt, h->d_off, static_cast<const uint32_t*>(h->d_ids),
+                    d_ids, static_cast<float*>(d_dists), d_keys, d_counts);
+            else
+                merge_cands_kernel<uint64_t><<<mgrid, 128, 0, s>>>(
+                    nq, w, k, ps, d_cells, pair_d, pair_pos, pair_cnt, h->d_off, static_cast<const uint64_t*>(h->d_ids),
+                    d_ids, static_cast<float*>(d_dists), d_keys, d_counts);
+        }
+    } else if (h->id_dev_bytes == 4)
         merge_probes_kernel<T, uint32_t><<<mgrid, 128, 0, s>>>(
             nq, w, k, d_cells, pair_d, pair_pos, pair_cnt, h->d_off, static_cast<const uint32_t*>(h->d_ids),
             d_ids, static_cast<T*>(d_dists), d_keys, d_counts);
@@ -534,6 +764,17 @@ cudaError_t scanq_prepare(ivfadc_index* h, cudaStream_t s, int* launches) {
                                                                       static_cast<float*>(h->d_tcB));
         if (launches) *launches += 1;
     }
+    // operand blocks of the tensor-memory lookup kernel (rows = code values)
+    if (h->dsub <= 8 && m % 4 == 0) {
+        const size_t bytes = (size_t)m * U_BSUB;
+        if ((e = cudaMalloc(&h->d_tcU, bytes)) != cudaSuccess) return e;
+        if ((e = cudaMemsetAsync(h->d_tcU, 0, bytes, s)) != cudaSuccess) return e;
+        const int n = m * h->cfg.ksub;
+        prep_tcu_kernel<<<(n + 255) / 256, 256, 0, s>>>(static_cast<const float*>(h->d_cb), h->d_cb_codes,
+                                                        h->cb_identity ? 1 : 0, m, h->cfg.ksub, h->dsub,
+                                                        static_cast<float*>(h->d_tcU));
+        if (launches) *launches += 1;
+    }
     return cudaGetLastError();
 }
 
@@ -553,10 +794,11 @@ ScanPlanSizes scan_plan_sizes(const ivfadc_index* h, int64_t nq, int w, int k) {
     ScanPlanSizes z;
     const int64_t npairs = nq * w;
     const int nb = 2 * h->cfg.kc;
-    z.bucket_bytes = sizeof(int) * (size_t)(4 * nb + 3);
+    z.bucket_bytes = sizeof(int) * (size_t)(4 * nb + 4);
     z.sorted_bytes = sizeof(int32_t) * (size_t)npairs * 2;  // sorted pairs | redo queue
-    z.pair_d_bytes = h->tsize * (size_t)npairs * k;
-    z.pair_pos_bytes = sizeof(uint32_t) * (size_t)npairs * k;
+    const int ps = pair_stride(h, npairs, k);
+    z.pair_d_bytes = h->tsize * (size_t)npairs * ps;
+    z.pair_pos_bytes = sizeof(uint32_t) * (size_t)npairs * ps;
     z.pair_cnt_bytes = sizeof(int32_t) * (size_t)npairs;
     z.thr_bytes = 8 * (size_t)nq;
     z.items_bytes = sizeof(int4) * (size_t)(std::min<int64_t>(npairs, npairs / QG + h->cfg.kc) + 1);

@@ -46,6 +46,7 @@ template <typename T> struct ScanArgs {
     T* pair_d;                  // [npairs][k]
     uint32_t* pair_pos;         // [npairs][k]
     int32_t* pair_cnt;          // [npairs]
+    int pstride;                // row stride of pair_d / pair_pos (>= k)
     typename Limits<T>::bits_t* thr;  // [nq] running inclusive bound on the k-th distance
 };
 
@@ -355,8 +356,8 @@ __device__ __forceinline__ void scan_item(const ScanArgs<T>& a, const int cell, 
         for (int r = 0; r < R; ++r) {
             const int e = lane * R + r;
             if (e < k) {
-                a.pair_d[(size_t)pair * k + e] = fin.v[r];
-                a.pair_pos[(size_t)pair * k + e] = fin.p[r];
+                a.pair_d[(size_t)pair * a.pstride + e] = fin.v[r];
+                a.pair_pos[(size_t)pair * a.pstride + e] = fin.p[r];
                 mine += fin.p[r] != kNoPos;
             }
         }

@@ -16,7 +16,7 @@ pytestmark = pytest.mark.gpu
 RTOL = 1e-5  # the tolerance north_star states for ADC distances (we assert exact equality too)
 
 
-LEGACY, QLANE, LUT_EXACT, LUT_MMASYNC = 1, 2, 4, 8  # ivfadc_config.flags (include/ivfadc.h)
+LEGACY, QLANE, LUT_EXACT, LUT_MMASYNC, SMEMLUT = 1, 2, 4, 8, 16  # ivfadc_config.flags (include/ivfadc.h)
 # Default flags for the bit-exact tests: whichever scan kernel the engine picks, tables in the
 # reference's direct form.  The tensor-core (3xTF32) tables are tested at the stated tolerance in
 # test_search_qlane_* below.
@@ -247,9 +247,10 @@ def test_search_qlane_bit_exact(D, m, ksub, kc, n, nq, k, w, identity):
         np.testing.assert_array_equal(gi, oi, err_msg=f"flags={flags}")
         e.close()
     # tensor-core tables (the default for large batches): the north_star's tolerance bar.
-    # QLANE alone = tcgen05 / tensor-memory builder where the shape allows it (dsub <= 8),
+    # QLANE alone = tensor-memory lookup kernel (tcgen05.mma tables looked up with tcgen05.ld) where the
+    # shape allows it (dsub <= 8), QLANE | SMEMLUT = tcgen05 tables copied to shared memory,
     # QLANE | LUT_MMASYNC = the warp-level mma.sync builder.
-    for flags in (QLANE, QLANE | LUT_MMASYNC):
+    for flags in (QLANE, QLANE | SMEMLUT, QLANE | LUT_MMASYNC):
         e = engine_from(qz, np.uint32, X, flags=flags)
         gi, gd, gc = e.search_packed(Q, k, w)
         rep = orc.compare_search(gi, gd, gc, oi, od, oc, rtol=RTOL)
@@ -317,12 +318,13 @@ def test_search_qlane_ties_overflow_redo():
         for k, w in ((10, 2), (16, 4), (1, 1)):
             assert_search_equal(e, oidx, Q, k, w)
         e.close()
-    e = engine_from(qz, np.uint32, Xc, assign, flags=QLANE)
-    for k, w in ((10, 2), (16, 4), (1, 1)):
-        gi, gd, gc = e.search_packed(Q, k, w)
-        oi, od, oc = oidx.knn_search(Q, k, w=w, nthreads=4)
-        orc.compare_search(gi, gd, gc, oi, od, oc, rtol=RTOL)
-    e.close()
+    for flags in (QLANE, QLANE | SMEMLUT):
+        e = engine_from(qz, np.uint32, Xc, assign, flags=flags)
+        for k, w in ((10, 2), (16, 4), (1, 1)):
+            gi, gd, gc = e.search_packed(Q, k, w)
+            oi, od, oc = oidx.knn_search(Q, k, w=w, nthreads=4)
+            orc.compare_search(gi, gd, gc, oi, od, oc, rtol=RTOL)
+        e.close()
 
 
 # ------------------------------------------------------------------------------------------------
