@@ -609,7 +609,7 @@ int ivfadc_set_length(ivfadc_index* h, int64_t n_total) {
 int ivfadc_debug_tables(ivfadc_index* h, void* out) {
     if (check_handle(h)) return IVFADC_ERR_BAD_ARG;
     cudaSetDevice(h->cfg.device);
-    const size_t bytes = ((size_t)h->cfg.m * 256 * 32 + 64 + 256) * 4;  // tables, slots, cell, timeline stamps
+    const size_t bytes = ((size_t)h->cfg.m * 256 * 32 + 64 + 1024) * 4;  // tables, slots, cell, timeline stamps
     if (!out) {
         if (!h->d_dbg_lut) CUDA_OR_FAIL(h, cudaMalloc(&h->d_dbg_lut, bytes), "debug buffer");
         CUDA_OR_FAIL(h, cudaMemset(h->d_dbg_lut, 0, bytes), "debug buffer");

@@ -51,6 +51,14 @@ constexpr int U_BSUB = 3 * U_BBLK;           // hi, lo, norms of one subspace
 constexpr int U_NB = 3;                      // B ring depth
 constexpr uint32_t U_TMEM_COLS = 512;
 constexpr int U_CW = 16;                     // candidate slots per (query, warp)
+constexpr bool U_CTA_SYNC = true;             // per-table CTA barrier (true) or mbarrier release collected by the issuer (false)
+#ifndef U_DEPTH
+#define U_DEPTH 32                           // lookups in flight per tcgen05.wait::ld (16 or 32)
+#endif
+// Vectors of a pass are dealt in chunks of 16: warp w owns chunks w, w + U_SW, w + 2 U_SW, w + 3 U_SW.
+constexpr int U_SW = QWARPS;                  // full-share warps (U_SW = 15: the issuing warp keeps a half share and a pass
+                                             // holds 992 vectors -- measured slower: lists of 993..1024 vectors take two passes)
+constexpr int U_VP = U_SW == QWARPS ? 16 * 4 * QWARPS : 16 * (4 * U_SW + 2);
 constexpr int U_CAP = 64;                    // candidate row of a (query, list) pair in global memory (more -> redo queue)
 
 struct ScanUArgs {
@@ -76,7 +84,7 @@ __host__ __device__ inline ScanUSmem scanu_smem_layout(int m) {
     s.bring = o;   o += U_NB * U_BSUB;
     s.cand = o;    o += QG * QWARPS * U_CW * 8;
     s.planes = o;  o += (uint32_t)m * T_PLANE;
-    s.raw = o;     o += (uint32_t)m * T_VP;      // code words of the next pass as they lie in the list
+    s.raw = o;     o += (uint32_t)m * U_VP;      // code words of the next pass as they lie in the list
     s.resid = o;   o += (uint32_t)m * 8 * T_RS * 4;
     o = (o + 15) & ~15u;
     s.smin = o;    o += QWARPS * QG * 4;
@@ -91,6 +99,25 @@ __host__ __device__ inline ScanUSmem scanu_smem_layout(int m) {
     return s;
 }
 
+// Warp-converged issue: every lane executes these with warp-uniform operands and ONE elected lane issues.
+// (Under `if (lane == 0)` ptxas wraps each tcgen05.mma in an elect / R2UR.BROADCAST loop that moves the
+// five operands into uniform registers one by one.)
+__device__ __forceinline__ void tc_mma_elect(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(T_IDESC), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tc_commit_elect(uint32_t bar) {
+    asm volatile(
+        "{\n\t.reg .pred q;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(bar)
+        : "memory");
+}
 __device__ __forceinline__ float tc_ld1(uint32_t taddr) {
     uint32_t v;
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(v) : "r"(taddr) : "memory");
@@ -131,11 +158,11 @@ __device__ __forceinline__ void scanu_issue(uint32_t tb, const uint4& x, float* 
 // FULL: all four chunks of the warp are inside the list -> two chunks (32 lookups) in flight per wait;
 // the wait costs a fixed ~200 cycles per warp, so the depth of a batch sets the pace of the scan.
 template <bool FIRST, bool FULL>
-__device__ __forceinline__ void scanu_sub(uint32_t tb, uint32_t plane_w, int nch, float base, float (&acc)[QNV]) {
-    if constexpr (FULL) {
+__device__ __forceinline__ void scanu_sub(uint32_t tb, uint32_t plane_w, uint32_t cstep, int nch, float base, float (&acc)[QNV]) {
+    if constexpr (FULL && U_DEPTH == 32) {
 #pragma unroll
         for (int j2 = 0; j2 < QNV / 32; ++j2) {
-            const uint4 x0 = lds_v4(plane_w + (2 * j2) * (16 * QWARPS)), x1 = lds_v4(plane_w + (2 * j2 + 1) * (16 * QWARPS));
+            const uint4 x0 = lds_v4(plane_w + (2 * j2) * cstep), x1 = lds_v4(plane_w + (2 * j2 + 1) * cstep);
             float t[32];
             scanu_issue<0>(tb, x0, t);
             scanu_issue<0>(tb, x1, t + 16);
@@ -146,8 +173,8 @@ __device__ __forceinline__ void scanu_sub(uint32_t tb, uint32_t plane_w, int nch
     } else {
 #pragma unroll
         for (int j4 = 0; j4 < QNV / 16; ++j4) {
-            if (j4 < nch) {  // warp-uniform; slots beyond the list are masked after the last subspace
-                const uint4 x = lds_v4(plane_w + j4 * (16 * QWARPS));
+            if (FULL || j4 < nch) {  // warp-uniform; slots beyond the list are masked after the last subspace
+                const uint4 x = lds_v4(plane_w + j4 * cstep);
                 float t[16];
                 scanu_issue<0>(tb, x, t);
                 tc_wait_ld();
@@ -172,6 +199,7 @@ scanu_kernel(const ScanUArgs ua) {
     const int wid = __shfl_sync(0xffffffffu, tid >> 5, 0);
     const int k = a.k;
     const int ps = ua.pstride;
+    const bool fastq = a.dsub == 8 && (a.D & 3) == 0;  // 16-byte aligned query / centroid slices
     const int nitems = a.group_off[a.kc];
     if ((int)blockIdx.x >= nitems) return;  // before any allocation
 
@@ -185,7 +213,8 @@ scanu_kernel(const ScanUArgs ua) {
     const uint32_t bar_full = sb + L.bars;          // 3 x 8 bytes
     const uint32_t bar_mma = bar_full + 24;         // 2 x 8 bytes
     const uint32_t bar_a = bar_full + 40;           // A operands of the first two builds of a segment
-    const uint32_t tmem_slot = bar_full + 48, next_slot = bar_full + 56;
+    const uint32_t bar_free = bar_full + 48;        // 2 x 8 bytes: all 16 warps are done with a table buffer
+    const uint32_t tmem_slot = bar_full + 64, next_slot = bar_full + 72;
 
     // ---- one-time setup ----
     if (wid == T_ISSUER && lane == 0) {
@@ -193,6 +222,8 @@ scanu_kernel(const ScanUArgs ua) {
         mbar_init(bar_mma, 1);
         mbar_init(bar_mma + 8, 1);
         mbar_init(bar_a, 2);
+        mbar_init(bar_free, QWARPS);
+        mbar_init(bar_free + 8, QWARPS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         for (int i = 0; i < U_NB; ++i) {
             mbar_expect_tx(bar_full + 8 * i, U_BSUB);
@@ -259,7 +290,23 @@ scanu_kernel(const ScanUArgs ua) {
         { const uint2 v = lds_v2u(desc_u + 24); off_n = (int64_t)(((uint64_t)v.y << 32) | v.x); }
         if (new_item) {
             const int my_pair = (int)lds_u(desc_u + 64 + lane * 4);
-            if (wid < m) {
+            if (fastq) {
+                // Query rows, coalesced: warp w copies the PQ dims of rows w and w + 16 (m * 32 contiguous bytes,
+                // 16 per lane) into rawq[row][chunk ^ (row & 7)] (overlaid on the free A ring; the XOR keeps the
+                // transposing reads of seg_stage at 4-way bank conflicts).  One row = 4 cache lines per request
+                // instead of the 32 lines a lane-per-query gather touches.
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int q = wid + QWARPS * h;
+                    const int pq = (int)lds_u(desc_u + 64 + q * 4);
+                    if (lane < 2 * m) {
+                        const uint32_t dst = aring_u + q * (m * 32) + ((lane ^ (q & 7)) * 16);
+                        if (pq >= 0) cp_async(dst, a.Q + (size_t)(pq / a.w) * a.D + lane * 4, 16);
+                        else sts_v4f(dst, 0.f, 0.f, 0.f, 0.f);
+                    }
+                }
+                if (wid < m && lane < 2) cp_async(cbuf_u + wid * 32 + lane * 16, a.C + (size_t)cell_n * a.D + wid * 8 + lane * 4, 16);
+            } else if (wid < m) {
                 const float* qv = a.Q + (size_t)(my_pair >= 0 ? my_pair / a.w : 0) * a.D + wid * a.dsub;
                 const float* cv = a.C + (size_t)cell_n * a.D + wid * a.dsub;
 #pragma unroll
@@ -283,9 +330,9 @@ scanu_kernel(const ScanUArgs ua) {
                 sts_u(mu + 4 * QG * 4, 0u);
             }
         }
-        if (tid < T_VP / 4) {
-            const int64_t vb = (int64_t)pass_n * T_VP;
-            const int nvn = (int)min((int64_t)T_VP, len_n - vb);
+        if (tid < U_VP / 4) {
+            const int64_t vb = (int64_t)pass_n * U_VP;
+            const int nvn = (int)min((int64_t)U_VP, len_n - vb);
             const uint32_t* src = reinterpret_cast<const uint32_t*>(a.codes + (size_t)off_n * m) + (size_t)vb * NP;
             const int v0 = 4 * tid;
 #pragma unroll
@@ -309,9 +356,8 @@ scanu_kernel(const ScanUArgs ua) {
     // (plane s = code byte s of the pass's vectors; 4 x 4 byte transposes), and for a new item the
     // residuals r = q - c (reference _closest_cluster_residuals, src/coarsequantizers.jl:40-45; warp s
     // owns subspace s, lane q its query) with their squared norms.
-    auto seg_stage = [&](bool new_item) {
-        cp_wait();
-        if (tid < T_VP / 4) {
+    auto seg_stage = [&](bool new_item) {  // the caller has waited for the copies (cp_wait) and passed a CTA barrier
+        if (tid < U_VP / 4) {
             const int v0 = 4 * tid;
             uint32_t cw[4][NP];
 #pragma unroll
@@ -337,14 +383,22 @@ scanu_kernel(const ScanUArgs ua) {
             }
         }
         if (new_item) {
-            __syncwarp();  // centroid slice copied by lanes 0..7 of this warp
             float part = 0.f;
             if (wid < m) {
+                float qd[8];
+                if (fastq) {  // rows copied by other warps: visible after the barrier the caller placed before this call
+                    const uint32_t rq = aring_u + lane * (m * 32);
+                    const uint4 u0 = lds_v4(rq + (((2 * wid) ^ (lane & 7)) * 16)), u1 = lds_v4(rq + (((2 * wid + 1) ^ (lane & 7)) * 16));
+                    qd[0] = __uint_as_float(u0.x); qd[1] = __uint_as_float(u0.y); qd[2] = __uint_as_float(u0.z); qd[3] = __uint_as_float(u0.w);
+                    qd[4] = __uint_as_float(u1.x); qd[5] = __uint_as_float(u1.y); qd[6] = __uint_as_float(u1.z); qd[7] = __uint_as_float(u1.w);
+                } else {
+#pragma unroll
+                    for (int d = 0; d < 8; ++d) qd[d] = lds_f(resid_u + ((wid * 8 + d) * T_RS + lane) * 4);
+                }
 #pragma unroll
                 for (int d = 0; d < 8; ++d) {
-                    const uint32_t ra = resid_u + ((wid * 8 + d) * T_RS + lane) * 4;
-                    const float r = sub_rn(lds_f(ra), lds_f(cbuf_u + (wid * 8 + d) * 4));
-                    sts_f(ra, r);
+                    const float r = sub_rn(qd[d], lds_f(cbuf_u + (wid * 8 + d) * 4));
+                    sts_f(resid_u + ((wid * 8 + d) * T_RS + lane) * 4, r);
                     part = fma_rn(r, r, part);
                 }
             }
@@ -352,7 +406,8 @@ scanu_kernel(const ScanUArgs ua) {
         }
     };
     // ONE warp writes the A operand of subspace s into ring slot s & 1: rows (copy, q), hi / lo of
-    // r[s][q][0..7]; lane = query
+    // r[s][q][0..7]; lane = query.  (Spreading the stores over all 512 threads was measured: the scan of
+    // every warp slows down by more than the writer warp gains.)
     auto write_A = [&](int s) {
         float hi[8], lo[8];
 #pragma unroll
@@ -371,29 +426,53 @@ scanu_kernel(const ScanUArgs ua) {
         }
         fence_proxy_async();  // generic-proxy writes -> visible to the tensor core (async proxy)
     };
-    uint32_t tmem_base = 0;
-    // Build number t (global count) = subspace s of the running segment, issued by ONE lane: the codebook
-    // operand of build t is in ring slot t % 3 (the ring is refilled three builds ahead).
-    auto issue_mma = [&](uint32_t t, int s) {
-        const uint32_t slot = t % U_NB;
-        mbar_wait(bar_full + 8 * slot, (t / U_NB) & 1, ua.err, 1);
-        tc_fence_after();
-        const uint32_t bb = bring_u + slot * U_BSUB, ab = aring_u + (s & 1) * U_ASUB;
-        const uint64_t Ah = tc_smem_desc(ab), Al = tc_smem_desc(ab + U_ABLK), A1 = tc_smem_desc(aone_u);
-        const uint64_t Bh = tc_smem_desc(bb), Bl = tc_smem_desc(bb + U_BBLK), Bn = tc_smem_desc(bb + 2 * U_BBLK);
-        const uint32_t d = tmem_base + (t & 1) * 256;
-        tc_mma(d, Ah, Bh, 0);
-        tc_mma(d, Al, Bh, 1);
-        tc_mma(d, Ah, Bl, 1);
-        tc_mma(d, A1, Bn, 1);
-        tc_commit(bar_mma + 8 * (t & 1));
+    // One lane waits (mbarrier.try_wait: the hardware SUSPENDS the waiting thread, so the 15 waiting warps
+    // do not take issue slots from the warp that is issuing the next build -- a test_wait spin was measured
+    // to starve it), the warp reconverges behind it.  Bounded: a broken pipeline raises the error flag.
+    auto warp_wait = [&](uint32_t bar, uint32_t parity, int code) {
+        if (lane == 0) mbar_wait(bar, parity, ua.err, code);
+        __syncwarp();
     };
-    auto refill_B = [&](uint32_t t) {  // build t has completed: its ring slot takes the operand of build t + 3
-        const uint32_t slot = t % U_NB, bar = bar_full + 8 * slot;
+    uint32_t tmem_base = 0;
+    // bring-up: fine-grained clock stamps of the issuing lane (DBG instantiation only)
+    long long* fstamp_p = nullptr;
+    int fstamp_n = 0, fstamp_on = 0;
+#define U_STAMP_F() do { if (DBG && fstamp_p && fstamp_on && fstamp_n < 200) fstamp_p[fstamp_n++] = clock64(); } while (0)
+    // Build number t (global count) = subspace s of the running segment, issued by ONE lane: the codebook
+    // operand of build t is in ring slot t % 3 (the ring is refilled three builds ahead).  The issuing warp
+    // shares its scheduler with three scanning warps, so every instruction here costs ~4 cycles of the
+    // critical path: the descriptors are offsets from three precomputed ones (the address field is
+    // bits 0..13 in units of 16 bytes; no carry leaves it), slot and phase are carried, not divided.
+    const uint64_t descA0 = tc_smem_desc(aring_u), descB0 = tc_smem_desc(bring_u), desc1 = tc_smem_desc(aone_u);
+    uint32_t bslot = 0, bphase = 0;  // ring slot / phase of the next build (issuer lane only)
+    auto issue_mma = [&](uint32_t t, int s) {  // called by ALL lanes of the issuing warp
+        const uint32_t slot_u = __shfl_sync(0xffffffffu, bslot, 0), par_u = __shfl_sync(0xffffffffu, bphase, 0);
+        const uint32_t t_u = __shfl_sync(0xffffffffu, t, 0), s_u = (uint32_t)__shfl_sync(0xffffffffu, s, 0);
+        warp_wait(bar_full + 8 * slot_u, par_u, 1);
+        tc_fence_after();
+        const uint64_t Ah = descA0 + (uint64_t)((s_u & 1) * (U_ASUB >> 4)), Al = Ah + (U_ABLK >> 4);
+        const uint64_t Bh = descB0 + (uint64_t)(slot_u * (U_BSUB >> 4)), Bl = Bh + (U_BBLK >> 4), Bn = Bl + (U_BBLK >> 4);
+        const uint32_t d = tmem_base + (t_u & 1) * 256;
+        tc_mma_elect(d, Ah, Bh, 0);
+        tc_mma_elect(d, Al, Bh, 1);
+        tc_mma_elect(d, Ah, Bl, 1);
+        tc_mma_elect(d, desc1, Bn, 1);
+        tc_commit_elect(bar_mma + 8 * (t_u & 1));
+        if (++bslot == U_NB) { bslot = 0; bphase ^= 1; }
+    };
+    uint32_t rslot = 0, rsub = U_NB % m;  // ring slot to refill next / subspace whose operand goes there (issuer lane only)
+    auto refill_B = [&](uint32_t) {  // build t (in order) has completed: its ring slot takes the operand of build t + 3
+        const uint32_t bar = bar_full + 8 * rslot;
+        U_STAMP_F();
         mbar_expect_tx(bar, U_BSUB);
-        tma_bulk_g2s(bring_u + slot * U_BSUB, ua.tcU + (size_t)((t + U_NB) % m) * (U_BSUB / 4), U_BSUB, bar);
+        U_STAMP_F();
+        tma_bulk_g2s(bring_u + rslot * U_BSUB, ua.tcU + (size_t)rsub * (U_BSUB / 4), U_BSUB, bar);
+        U_STAMP_F();
+        if (++rslot == U_NB) rslot = 0;
+        if (++rsub == (uint32_t)m) rsub = 0;
     };
     // after a staging barrier: warps 2, 3 write the first two A operands, the issuer starts builds 0, 1
+    // (no CTA barrier: the other warps go on to the candidate dump)
     auto seg_start_builds = [&]() {
         if (wid == 2 || wid == 3) {
             write_A(wid - 2);
@@ -401,13 +480,10 @@ scanu_kernel(const ScanUArgs ua) {
             if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_a) : "memory");
         }
         if (wid == T_ISSUER) {
-            if (lane == 0) {
-                mbar_wait(bar_a, nstage & 1, ua.err, 4);
-                tc_fence_after();
-                issue_mma(tglob, 0);
-                issue_mma(tglob + 1, 1);
-            }
-            __syncwarp();
+            warp_wait(bar_a, nstage & 1, 4);
+            tc_fence_after();
+            issue_mma(tglob, 0);
+            issue_mma(tglob + 1, 1);
         }
         ++nstage;
     };
@@ -424,10 +500,12 @@ scanu_kernel(const ScanUArgs ua) {
         {
             const uint2 v = lds_v2u(desc_u + 16);
             const int64_t len = (int64_t)(((uint64_t)v.y << 32) | v.x);
-            npass = (int)((len + T_VP - 1) / T_VP);
-            nv = (int)min((int64_t)T_VP, len);
+            npass = (int)((len + U_VP - 1) / U_VP);
+            nv = (int)min((int64_t)U_VP, len);
         }
         seg_load(true, 0, 0);
+        cp_wait();
+        __syncthreads();
         seg_stage(true);
         if (tid == 0) sts_u(next_slot, (uint32_t)(gridDim.x + atomicAdd(ua.item_counter, 1)));
         fence_proxy_async();  // A ones block
@@ -442,7 +520,11 @@ scanu_kernel(const ScanUArgs ua) {
     }
     const int quarter = wid & 3;
     const uint32_t tq = tmem_base + ((uint32_t)(quarter * 32) << 16);
-    const uint32_t plane_w0 = planes_u + 16 * wid;
+    const int c0 = wid < U_SW ? wid : 4 * U_SW;          // first chunk of this warp
+    const int cs = wid < U_SW ? U_SW : 1;                // chunk stride
+    const int maxch = wid < U_SW ? 4 : 2;                // chunks owned
+    const uint32_t cstep = 16u * cs;
+    const uint32_t plane_w0 = planes_u + 16 * c0;
     // bring-up (DBG instantiation only): table dump of the first item of CTA 0, and clock64 of
     // thread 0 of CTA 0 at the phase boundaries of its 4th segment
     bool dbg_first = DBG && blockIdx.x == 0;
@@ -450,11 +532,22 @@ scanu_kernel(const ScanUArgs ua) {
                             ? reinterpret_cast<long long*>(ua.dbg + (size_t)m * 256 * 32 + 64) : nullptr;
     int nstamp = 0, nseg = 0;
     auto stamp = [&]() { if (DBG && tstamp && nseg == 3 && nstamp < 30) tstamp[nstamp++] = clock64(); };
+    // issuer lane of CTA 0, same segment: after the table wait / own scan done / buffer free / MMAs issued, per subspace
+    long long* istamp = (DBG && blockIdx.x == 0 && tid == (U_CTA_SYNC ? 32 : T_ISSUER * 32))
+                            ? reinterpret_cast<long long*>(ua.dbg + (size_t)m * 256 * 32 + 64) + 32 : nullptr;
+    int nistamp = 0;
+    auto stamp_i = [&]() { if (DBG && istamp && nseg == 3 && nistamp < 80) istamp[nistamp++] = clock64(); };
+    // every warp of CTA 0, subspaces 5 and 6 of the same segment: before the table wait / after it / scan done / past the barrier
+    long long* wstamp = (DBG && blockIdx.x == 0 && lane == 0)
+                            ? reinterpret_cast<long long*>(ua.dbg + (size_t)m * 256 * 32 + 64) + 112 + wid * 8 : nullptr;
+    if (DBG && blockIdx.x == 0 && tid == T_ISSUER * 32) fstamp_p = reinterpret_cast<long long*>(ua.dbg + (size_t)m * 256 * 32 + 64) + 240;
+    auto stamp_w = [&](int s, int i) { if (DBG && wstamp && nseg == 3 && (s == 5 || s == 6)) wstamp[(s - 5) * 4 + i] = clock64(); };
 
     float acc[QNV];
     for (;;) {
         stamp();
-        const int nch = min(4, max(0, (nv - 16 * wid + 16 * QWARPS - 1) / (16 * QWARPS)));  // chunks j4 with 16 (wid + 16 j4) < nv
+        fstamp_on = DBG && nseg == 3;
+        const int nch = min(maxch, max(0, (nv - 16 * c0 + 16 * cs - 1) / (16 * cs)));  // chunks j4 with 16 (c0 + cs j4) < nv
         const bool same_item = pass + 1 < npass;
         // the item after this one (its index was published before the last barrier of the previous boundary)
         const int nitem = same_item ? item : (int)lds_u(next_slot);
@@ -462,6 +555,8 @@ scanu_kernel(const ScanUArgs ua) {
         const bool fetch_desc = !same_item && has_next && wid == 0;
 
         // ---- the m subspaces of this segment ----
+#pragma unroll
+        for (int j = 0; j < QNV; ++j) acc[j] = base;  // dc + |r|^2, then the table entries in subspace order
 #pragma unroll 1
         for (int s = 0; s < m; ++s) {
             const uint32_t t = tglob + s;
@@ -470,19 +565,21 @@ scanu_kernel(const ScanUArgs ua) {
                 else if (s == SB) desc_b();
                 else if (s == SC) desc_c();
             }
-            mbar_wait(bar_mma + 8 * (t & 1), (t >> 1) & 1, ua.err, 2);
+            if (U_CTA_SYNC) stamp_i();
+            stamp_w(s, 0);
+            warp_wait(bar_mma + 8 * (t & 1), (t >> 1) & 1, 2);
             tc_fence_after();
-            if (s + 2 < m && wid == ((s + 2) & 7) + 4) write_A(s + 2);  // build s has completed: its A slot is free
+            if (wid == 0 && lane == 0) refill_B(t);  // as early as possible (the copy needs its two table periods), and not by the issuing warp
+            stamp_i();
+            stamp_w(s, 1);
+            if (s + 2 < m && wid == T_ISSUER - 1) write_A(s + 2);  // build s has completed: its A slot is free (warps 14, 15 own the fewest vectors)
             // s and t are warp-uniform, but ptxas keeps the loop counter in a vector register unless told (one SHFL each)
             const uint32_t tb = tq + (__shfl_sync(0xffffffffu, t, 0) & 1) * 256;
             const uint32_t plane_w = plane_w0 + __shfl_sync(0xffffffffu, s, 0) * T_PLANE;
-            if (nch == 4) {
-                if (s == 0) scanu_sub<true, true>(tb, plane_w, nch, base, acc);
-                else scanu_sub<false, true>(tb, plane_w, nch, base, acc);
-            } else {
-                if (s == 0) scanu_sub<true, false>(tb, plane_w, nch, base, acc);
-                else scanu_sub<false, false>(tb, plane_w, nch, base, acc);
-            }
+            // ONE code path for every subspace (the accumulators start at dc + |r|^2): the loop body stays
+            // within the instruction cache
+            if (nch == 4) scanu_sub<false, true>(tb, plane_w, cstep, nch, base, acc);
+            else scanu_sub<false, false>(tb, plane_w, cstep, nch, base, acc);
             if (DBG && dbg_first) {  // bring-up: dump the table of subspace s of the first item (the four quarters agree)
                 if (wid < 4) {
                     for (int c = wid; c < 256; c += 4) {
@@ -494,15 +591,36 @@ scanu_kernel(const ScanUArgs ua) {
                 if (s == 0 && tid < QG) reinterpret_cast<int*>(ua.dbg + (size_t)m * 256 * 32)[tid] = (int)lds_u(misc_u + ipar * U_MISC + tid * 4);
                 if (s == 0 && tid == 0) reinterpret_cast<int*>(ua.dbg + (size_t)m * 256 * 32)[QG] = ua.items[item].x;
             }
-            tc_fence_before();
-            __syncthreads();  // every warp is done with this table; A operand of build s + 2 written
-            if (wid == T_ISSUER) {
-                if (lane == 0) {
+            if constexpr (U_CTA_SYNC) {
+                stamp_i();
+                stamp_w(s, 2);
+                tc_fence_before();
+                __syncthreads();  // every warp is done with this table; A operand of build s + 2 written
+                stamp_i();
+                // the barrier instruction defers blocking: read the clock through a shared-memory round trip that cannot pass it
+                if (DBG) { sts_u(thr_u + 0 * lane, lds_u(thr_u)); }
+                stamp_w(s, 3);
+                if (wid == T_ISSUER && s + 2 < m) {
                     tc_fence_after();
-                    if (s + 2 < m) issue_mma(t + 2, s + 2);
-                    refill_B(t);
+                    issue_mma(t + 2, s + 2);
                 }
+            } else {
+                // this warp is done with the table (and, if it was the writer, with the A operand of build s + 2):
+                // no CTA-wide barrier -- the warps run ahead into the next table, only the issuer collects the arrivals
+                tc_fence_before();
                 __syncwarp();
+                if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_free + 8 * (t & 1)) : "memory");
+                stamp_i();
+                if (wid == T_ISSUER) {
+                    if (s + 2 < m) {
+                        warp_wait(bar_free + 8 * (t & 1), (t >> 1) & 1, 6);
+                        stamp_i();
+                        tc_fence_after();
+                        issue_mma(t + 2, s + 2);
+                        stamp_i();
+                    }
+                    __syncwarp();
+                }
             }
             stamp();
         }
@@ -510,6 +628,9 @@ scanu_kernel(const ScanUArgs ua) {
         dbg_first = false;
 
         // ---- segment boundary ----
+        // A warp gets here once builds m - 2, m - 1 have completed, i.e. every warp has finished subspace
+        // m - 3: the residuals and both A slots are free, and (m >= 8) warp 0 has published the descriptor.
+        if (m < 8) __syncthreads();
         // vectors of the next pass / item (desc: the running item while it has passes left, else the next one)
         int nj_n = nj, npass_n = npass, nv_n = 0;
         if (has_next) {
@@ -517,9 +638,9 @@ scanu_kernel(const ScanUArgs ua) {
             const int64_t len_n = (int64_t)(((uint64_t)v.y << 32) | v.x);
             if (!same_item) {
                 nj_n = (int)lds_u(desc_u + 8);
-                npass_n = (int)((len_n + T_VP - 1) / T_VP);
+                npass_n = (int)((len_n + U_VP - 1) / U_VP);
             }
-            nv_n = (int)min((int64_t)T_VP, len_n - (same_item ? (int64_t)(pass + 1) * T_VP : 0));
+            nv_n = (int)min((int64_t)U_VP, len_n - (same_item ? (int64_t)(pass + 1) * U_VP : 0));
         }
         int nx = 0;
         const bool fetch_next = tid == 0 && has_next && !same_item;
@@ -528,13 +649,13 @@ scanu_kernel(const ScanUArgs ua) {
 
         // mask the slots beyond the list (chunks not reached, and the chunk that straddles the end)
         {
-            const int lim = nv - 16 * wid;  // slot 16 * j4 + i holds a vector iff 256 * j4 + i < lim
+            const int lim = nv - 16 * c0;  // slot 16 * j4 + i holds a vector iff 16 * cs * j4 + i < lim (and j4 < maxch)
 #pragma unroll
             for (int j4 = 0; j4 < QNV / 16; ++j4) {
-                if (16 * QWARPS * j4 + 16 > lim) {  // warp-uniform
+                if (j4 >= maxch || 16 * cs * j4 + 16 > lim) {  // warp-uniform
 #pragma unroll
                     for (int i = 0; i < 16; ++i)
-                        if (16 * QWARPS * j4 + i >= lim) acc[16 * j4 + i] = Limits<float>::inf();
+                        if (j4 >= maxch || 16 * cs * j4 + i >= lim) acc[16 * j4 + i] = Limits<float>::inf();
                 }
             }
         }
@@ -561,6 +682,7 @@ scanu_kernel(const ScanUArgs ua) {
                 sts_f(run_u + lane * 4, thr);
             }
         }
+        cp_wait();  // the asynchronous copies of the next segment (issued before the previous barrier) have landed
         __syncthreads();
         stamp();
         {
@@ -615,10 +737,11 @@ scanu_kernel(const ScanUArgs ua) {
             if (!bad) {
                 const uint32_t src = cand_u + ((q * QWARPS + w2) * U_CW + half * (U_CW / 2)) * 8;
                 const size_t dst = (size_t)pair * ps + cf + (incl - nl);
-                const uint32_t pbase = (uint32_t)pass * T_VP + 16 * w2;  // position of register slot 0 of warp w2
+                const uint32_t pbase = (uint32_t)pass * U_VP + 16 * (w2 < U_SW ? w2 : 4 * U_SW);  // position of register slot 0 of warp w2
+                const uint32_t pstep = 16 * (w2 < U_SW ? U_SW : 1);
                 for (int i = 0; i < nl; ++i) {
                     const uint2 v = lds_v2u(src + i * 8);
-                    a.pair_pos[dst + i] = pbase + 16 * QWARPS * (v.x >> 4) + (v.x & 15);
+                    a.pair_pos[dst + i] = pbase + pstep * (v.x >> 4) + (v.x & 15);
                     a.pair_d[dst + i] = __uint_as_float(v.y);
                 }
             }

@@ -19,7 +19,7 @@ try:
 except Exception as ex:
     print("SEARCH FAILED:", ex)
     gi = None
-buf = np.zeros(m * 256 * 32 + 64 + 256, dtype=np.float32)
+buf = np.zeros(m * 256 * 32 + 64 + 1024, dtype=np.float32)
 iv._capi.check(e._h, e._lib.ivfadc_debug_tables(e._h, buf.ctypes.data_as(ctypes.c_void_p)))
 tables = buf[:m * 256 * 32].reshape(m, 256, 32)
 meta = buf[m * 256 * 32:].view(np.int32)

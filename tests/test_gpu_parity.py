@@ -277,7 +277,7 @@ def test_tcgen05_tables_against_fp64(D, m, ksub, identity):
     e = engine_from(qz, np.uint32, X, flags=QLANE)
     iv._capi.check(e._h, e._lib.ivfadc_debug_tables(e._h, None))
     e.search_packed(Q, 5, w)
-    buf = np.zeros(m * 256 * 32 + 64 + 256, dtype=np.float32)   # tables, slots, cell, timeline stamps
+    buf = np.zeros(m * 256 * 32 + 64 + 1024, dtype=np.float32)   # tables, slots, cell, timeline stamps
     iv._capi.check(e._h, e._lib.ivfadc_debug_tables(e._h, buf.ctypes.data_as(ctypes.c_void_p)))
     e.close()
     tables = buf[:m * 256 * 32].reshape(m, 256, 32)
