@@ -398,13 +398,16 @@ def main():
                        "launch": "CUDA graph replay of the sharded step" if use_graph else "eager",
                        "l2": "flushed between steps (256 MiB write); the 16 MB code array is L2-resident within a step",
                        "timing": "CUDA events on the launch stream, per step, mean", "flags": args.flags,
+                       "scan": ("tensor-memory lookups: tcgen05.mma tables stay in TMEM, tcgen05.ld at column = code byte, "
+                                "persistent CTAs" if not (args.flags & 29) else "see flags"),
                        "tables": ("exact direct form (fp32 chain)" if (args.flags & 5) else
                                   "mma.sync 3xTF32 GEMM form" if (args.flags & 8) else
                                   "tcgen05 kind::tf32 3xTF32 GEMM form, accumulators in tensor memory, codebook operand by TMA")},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic,
                          "kernel": ("scan_kernel" if (args.flags & 1) else "scanq_kernel" if (args.flags & 12) else
-                                    "scant_kernel") + " (K2 lookup tables + K3 list scan + per-list top-k)",
+                                    "scant_kernel" if (args.flags & 16) else "scanu_kernel") +
+                                   " (K2 lookup tables + K3 list scan + per-list candidate selection)",
                          "algorithmic_bytes_per_launch": bytes_per_launch, "kernel_ms": scan_ms,
                          "peak_source": peak_src,
                          "per_rank": world > 1},

@@ -83,6 +83,11 @@ extern "C" {
  * which copies every table from tensor memory to shared memory and gathers with LDS.
  */
 #define IVFADC_FLAG_SCAN_SMEMLUT 16
+/*
+ * The fp32 coarse step (D <= 128) uses packed FP32 instructions on transposed centroids; this flag
+ * selects the scalar FFMA kernel instead (identical results, both bit-exact against the reference form).
+ */
+#define IVFADC_FLAG_COARSE_SCALAR 32
 
 typedef struct ivfadc_index ivfadc_index;   /* opaque, owns all device memory */
 

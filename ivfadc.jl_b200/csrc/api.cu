@@ -248,6 +248,7 @@ int ivfadc_create(ivfadc_index** out, const ivfadc_config* cfg, const void* cent
     int launches = 0;
     ok = ok && launch_codebook_norms(h, h->stream, &launches) == cudaSuccess;
     ok = ok && scanq_prepare(h, h->stream, &launches) == cudaSuccess;
+    ok = ok && coarse_prepare(h, h->stream, &launches) == cudaSuccess;
     ok = ok && cudaStreamSynchronize(h->stream) == cudaSuccess;
     std::string why;
     if (ok && !scan_supported(h, &why)) {
@@ -278,6 +279,7 @@ int ivfadc_destroy(ivfadc_index* h) {
     }
     lists_free(h);
     if (h->d_centroids) cudaFree(h->d_centroids);
+    if (h->d_centroids_t) cudaFree(h->d_centroids_t);
     if (h->d_cb) cudaFree(h->d_cb);
     if (h->d_cb_codes) cudaFree(h->d_cb_codes);
     if (h->d_cb_norms) cudaFree(h->d_cb_norms);

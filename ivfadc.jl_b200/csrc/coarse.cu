@@ -13,6 +13,8 @@
 #include "common.cuh"
 #include "warp_topk.cuh"
 
+#include <algorithm>
+
 namespace ivf {
 
 namespace {
@@ -158,6 +160,193 @@ coarse_kernel(const T* __restrict__ Q, const T* __restrict__ C, int64_t nq, int 
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// fp32 fast path (D <= 128): packed FP32 arithmetic (add.rn.f32x2 / fma.rn.f32x2, sm_100).
+//   * same arithmetic as coarse_kernel -- diff = c - q, acc = fma(diff, diff, acc) in ascending d,
+//     one sequential chain per (query, centroid) pair: bit-identical to the oracle (A1); the two halves
+//     of a packed operation are two different centroids, never two steps of one chain;
+//   * operands arrive as ready-made register pairs: centroids are kept TRANSPOSED in HBM
+//     (Ct[d][kc], once at create), so a tile row holds 64 consecutive centroids of one dim and one
+//     128-bit shared load yields two centroid pairs; queries are staged once per CTA (all D dims)
+//     as negated duplicates {-q, -q}, so c - q is one packed add with no register shuffling;
+//   * 4 queries x 4 centroids per thread: 3 LDS.128 feed 16 packed instructions per dim;
+//   * TQ (queries per CTA: 16 / 24 / 32) is picked per batch so that the query blocks fill the SMs'
+//     resident-CTA slots evenly (10 000 queries: TQ = 24 -> 417 blocks on 444 slots instead of 313).
+// Selection as in coarse_kernel (distance tile -> warp-distributed sorted lists, ascending cell order).
+// ---------------------------------------------------------------------------------------------
+constexpr int PC = 64;               // centroids per tile
+constexpr int PLDC = PC + 4;         // tile row stride in floats (16-byte aligned rows, conflict-free LDS.128)
+constexpr int PMAXD = 256;
+
+__device__ __forceinline__ unsigned long long add2(unsigned long long a, unsigned long long b) {
+    unsigned long long d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+    unsigned long long d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+
+constexpr int PDK = 64;              // dims per centroid chunk (double-buffered through cp.async)
+
+template <int NTY, int R>
+__global__ void __launch_bounds__(16 * NTY)
+coarse2_kernel(const float* __restrict__ Q, const float* __restrict__ Ct, int64_t nq, int kc, int kcp, int D, int w,
+               int32_t* __restrict__ cells_out, float* __restrict__ dc_out) {
+    constexpr int TQ2 = 4 * NTY, NT = 16 * NTY, NW = NT / 32, QPW = TQ2 / NW;  // 8 queries per warp
+    constexpr int LDQ = 2 * TQ2 + 4;  // floats per dim row of the duplicated queries (16-byte aligned rows)
+    constexpr int LDD = PC + 1;
+    extern __shared__ __align__(16) float smem_c[];
+    float* sQ = smem_c;                                  // [D][LDQ]: {-q, -q} pairs
+    float* sC = smem_c + (size_t)D * LDQ;                // 2 x [PDK][PLDC]: centroid chunks, double-buffered
+    float* sDist = sC + 2 * PDK * PLDC;                  // [TQ2][LDD] distance tile
+
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int tx = tid & 15;   // centroids 4 tx .. 4 tx + 3 of the tile
+    const int ty = tid >> 4;   // queries 4 ty .. 4 ty + 3 of the block
+    const int64_t q0 = (int64_t)blockIdx.x * TQ2;
+    const int nck = (D + PDK - 1) / PDK;                 // chunks per tile
+    const int ntile = (kc + PC - 1) / PC;
+    const int nchunks = ntile * nck;
+
+    // chunk k = dims [PDK (k % nck), +PDK) of centroids [PC (k / nck), +PC): asynchronous copy, 16 bytes per request
+    auto prefetch = [&](int k) {
+        const int c0 = (k / nck) * PC, d0 = (k % nck) * PDK;
+        float* dst = sC + (k & 1) * (PDK * PLDC);
+        for (int idx = tid; idx < PDK * (PC / 4); idx += NT) {
+            const int dd = idx >> 4, c4 = idx & 15;
+            const uint32_t sa = (uint32_t)__cvta_generic_to_shared(dst + dd * PLDC + 4 * c4);
+            if (d0 + dd < D)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(Ct + (size_t)(d0 + dd) * kcp + c0 + 4 * c4) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    prefetch(0);
+
+    // queries: coalesced along d, stored transposed, negated and duplicated
+    for (int idx = tid; idx < TQ2 * D; idx += NT) {
+        const int row = idx / D, d = idx - row * D;
+        const int64_t q = q0 + row;
+        const float v = q < nq ? -Q[q * D + d] : 0.f;
+        *reinterpret_cast<float2*>(&sQ[d * LDQ + 2 * row]) = make_float2(v, v);
+    }
+
+    WarpList<float, int, R> lst[QPW];
+#pragma unroll
+    for (int a = 0; a < QPW; ++a) lst[a].init(0x7fffffff);
+    float kth[QPW];
+#pragma unroll
+    for (int a = 0; a < QPW; ++a) kth[a] = Limits<float>::inf();
+
+    unsigned long long acc[4][2];
+    for (int k = 0; k < nchunks; ++k) {
+        const int ck = k % nck;
+        if (ck == 0) {
+#pragma unroll
+            for (int a = 0; a < 4; ++a) acc[a][0] = acc[a][1] = 0ull;
+        }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();  // chunk k landed (and the queries, first time); every warp is done with chunk k - 1
+        if (k + 1 < nchunks) prefetch(k + 1);  // into the buffer chunk k - 1 occupied
+        const int d0 = ck * PDK;
+        const int dn = min(PDK, D - d0);
+        const float* pc = sC + (k & 1) * (PDK * PLDC) + 4 * tx;
+        const float* pq = sQ + (size_t)d0 * LDQ + 8 * ty;
+#pragma unroll 8
+        for (int d = 0; d < dn; ++d) {
+            const ulonglong2 cv = *reinterpret_cast<const ulonglong2*>(pc + d * PLDC);          // {c0, c1}, {c2, c3}
+            const ulonglong2 qa = *reinterpret_cast<const ulonglong2*>(pq + d * LDQ);           // {-q0, -q0}, {-q1, -q1}
+            const ulonglong2 qb = *reinterpret_cast<const ulonglong2*>(pq + d * LDQ + 4);       // {-q2, -q2}, {-q3, -q3}
+            const unsigned long long qn[4] = {qa.x, qa.y, qb.x, qb.y};
+#pragma unroll
+            for (int a = 0; a < 4; ++a) {
+                const unsigned long long d0p = add2(cv.x, qn[a]), d1p = add2(cv.y, qn[a]);  // oracle A1: c - q
+                acc[a][0] = fma2(d0p, d0p, acc[a][0]);
+                acc[a][1] = fma2(d1p, d1p, acc[a][1]);
+            }
+        }
+        if (ck != nck - 1) continue;
+        // ---- tile complete: distances -> shared tile -> fused selection ----
+        const int c0 = (k / nck) * PC;
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const unsigned long long pr = acc[a][j >> 1];
+                const float v = __uint_as_float((j & 1) ? (unsigned)(pr >> 32) : (unsigned)pr);
+                const int c = c0 + 4 * tx + j;
+                sDist[(4 * ty + a) * LDD + 4 * tx + j] = c < kc ? v : Limits<float>::inf();
+            }
+        __syncthreads();
+        // warp `wid` owns queries QPW * wid ..; candidates are offered in ascending cell order, so the
+        // stable (value-only) insertion reproduces sortperm's ties.  (The next tile's first chunk is in flight.)
+#pragma unroll
+        for (int a = 0; a < QPW; ++a) {
+            const int ql = wid * QPW + a;
+#pragma unroll
+            for (int half = 0; half < PC / 32; ++half) {
+                const float val = sDist[ql * LDD + lane + 32 * half];
+                const int cidx = c0 + lane + 32 * half;
+                unsigned mask = __ballot_sync(0xffffffffu, val < kth[a]);
+                while (mask) {
+                    const int src = __ffs(mask) - 1;
+                    const float nv = __shfl_sync(0xffffffffu, val, src);
+                    const int np = __shfl_sync(0xffffffffu, cidx, src);
+                    lst[a].template insert<false>(nv, np);
+                    kth[a] = lst[a].value_at(w - 1);
+                    const unsigned done = (2u << src) - 1u;  // lanes <= src
+                    mask = __ballot_sync(0xffffffffu, val < kth[a]) & ~done;
+                }
+            }
+        }
+        // the distance tile is rewritten only after the next tile's chunks have passed their barriers
+    }
+#pragma unroll
+    for (int a = 0; a < QPW; ++a) {
+        const int64_t q = q0 + wid * QPW + a;
+        if (q >= nq) continue;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int e = lane * R + r;
+            if (e < w) {
+                cells_out[q * w + e] = lst[a].p[r];
+                dc_out[q * w + e] = lst[a].v[r];
+            }
+        }
+    }
+}
+
+__global__ void transpose_centroids_kernel(const float* __restrict__ C, int kc, int kcp, int D, float* __restrict__ Ct) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= kcp * D) return;
+    const int d = idx / kcp, c = idx - d * kcp;
+    Ct[idx] = c < kc ? C[(size_t)c * D + d] : 0.f;
+}
+
+template <int NTY, int R>
+cudaError_t launch_coarse2_inst(const float* Q, const float* Ct, int64_t nq, int kc, int kcp, int D, int w,
+                                int32_t* cells, float* dc, cudaStream_t s) {
+    constexpr int TQ2 = 4 * NTY;
+    const size_t smem = ((size_t)D * (2 * TQ2 + 4) + 2 * (size_t)PDK * PLDC + (size_t)TQ2 * (PC + 1)) * sizeof(float);
+    static size_t configured = 0;
+    if (smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(coarse2_kernel<NTY, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured = smem;
+    }
+    coarse2_kernel<NTY, R><<<(unsigned)((nq + TQ2 - 1) / TQ2), 16 * NTY, smem, s>>>(Q, Ct, nq, kc, kcp, D, w, cells, dc);
+    return cudaGetLastError();
+}
+template <int R>
+cudaError_t launch_coarse2_r(int nty, const float* Q, const float* Ct, int64_t nq, int kc, int kcp, int D, int w,
+                             int32_t* cells, float* dc, cudaStream_t s) {
+    if (nty == 4) return launch_coarse2_inst<4, R>(Q, Ct, nq, kc, kcp, D, w, cells, dc, s);
+    if (nty == 6) return launch_coarse2_inst<6, R>(Q, Ct, nq, kc, kcp, D, w, cells, dc, s);
+    return launch_coarse2_inst<8, R>(Q, Ct, nq, kc, kcp, D, w, cells, dc, s);
+}
+
 template <typename T>
 cudaError_t launch_coarse_t(const ivfadc_index* h, const void* dQ, int64_t nq, int w,
                             int32_t* d_cells, void* d_dc, cudaStream_t s) {
@@ -179,10 +368,54 @@ cudaError_t launch_coarse_t(const ivfadc_index* h, const void* dQ, int64_t nq, i
 
 int coarse_max_w() { return 128; }
 
+// Once at create (fp32): the centroids transposed, Ct[d][kc_pad], kc padded to the tile width.
+cudaError_t coarse_prepare(ivfadc_index* h, cudaStream_t s, int* launches) {
+    if (h->cfg.dtype != IVFADC_F32) return cudaSuccess;
+    h->kc_pad = (h->cfg.kc + PC - 1) / PC * PC;
+    const size_t n = (size_t)h->kc_pad * h->cfg.dim;
+    cudaError_t e = cudaMalloc(&h->d_centroids_t, n * sizeof(float));
+    if (e != cudaSuccess) return e;
+    transpose_centroids_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(static_cast<const float*>(h->d_centroids), h->cfg.kc,
+                                                                        h->kc_pad, h->cfg.dim,
+                                                                        static_cast<float*>(h->d_centroids_t));
+    if (launches) *launches += 1;
+    return cudaGetLastError();
+}
+
 cudaError_t launch_coarse(const ivfadc_index* h, const void* dQ, int64_t nq, int w, int32_t* d_cells,
                           void* d_dc, cudaStream_t s, int* launches) {
     if (nq <= 0) return cudaSuccess;
     if (launches) *launches += 1;
+    if (h->cfg.dtype == IVFADC_F32 && h->d_centroids_t && h->cfg.dim <= PMAXD && (h->cfg.dim & 3) == 0 &&
+        !(h->cfg.flags & IVFADC_FLAG_COARSE_SCALAR)) {
+        // queries per CTA: the block count that fills the resident-CTA slots of the SMs most evenly
+        static int num_sms = 0;
+        if (!num_sms) {
+            int dev = 0;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+        }
+        const int D = h->cfg.dim;
+        int best = 8;
+        double best_eff = -1.0;
+        for (int nty : {8, 6, 4}) {
+            const int tq = 4 * nty;
+            const size_t smem = ((size_t)D * (2 * tq + 4) + 2 * (size_t)PDK * PLDC + (size_t)tq * (PC + 1)) * sizeof(float) + 1024;
+            const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(16, (size_t)(227 * 1024) / smem));
+            const int64_t blocks = (nq + tq - 1) / tq;
+            const int64_t slots = (int64_t)num_sms * per_sm;
+            const int64_t rounds = (blocks + slots - 1) / slots;
+            // useful query slots / provisioned query slots, smaller blocks re-stream the centroids more often
+            const double eff = (double)nq / ((double)rounds * slots * tq) * (nty == 8 ? 1.0 : nty == 6 ? 0.97 : 0.93);
+            if (eff > best_eff) { best_eff = eff; best = nty; }
+        }
+        const float* Q = static_cast<const float*>(dQ);
+        const float* Ct = static_cast<const float*>(h->d_centroids_t);
+        float* dc = static_cast<float*>(d_dc);
+        if (w <= 32) return launch_coarse2_r<1>(best, Q, Ct, nq, h->cfg.kc, h->kc_pad, D, w, d_cells, dc, s);
+        if (w <= 64) return launch_coarse2_r<2>(best, Q, Ct, nq, h->cfg.kc, h->kc_pad, D, w, d_cells, dc, s);
+        return launch_coarse2_r<4>(best, Q, Ct, nq, h->cfg.kc, h->kc_pad, D, w, d_cells, dc, s);
+    }
     if (h->cfg.dtype == IVFADC_F32) return launch_coarse_t<float>(h, dQ, nq, w, d_cells, d_dc, s);
     return launch_coarse_t<double>(h, dQ, nq, w, d_cells, d_dc, s);
 }

@@ -103,6 +103,8 @@ struct ivfadc_index {
 
     // quantizers (device)
     void* d_centroids = nullptr;    // T[kc][D]
+    void* d_centroids_t = nullptr;  // fp32 only: centroids transposed [D][kc_pad] (packed-FP32 coarse kernel)
+    int kc_pad = 0;
     void* d_cb = nullptr;           // T[m][ksub][dsub]
     uint8_t* d_cb_codes = nullptr;  // uint8[m][ksub]
     void* d_cb_norms = nullptr;     // T[m][ksub]  squared norms of the codewords (oracle A2)
@@ -146,6 +148,7 @@ namespace ivf {
 cudaError_t launch_coarse(const ivfadc_index* h, const void* dQ, int64_t nq, int w, int32_t* d_cells,
                           void* d_dc, cudaStream_t s, int* launches);
 int coarse_max_w();
+cudaError_t coarse_prepare(ivfadc_index* h, cudaStream_t s, int* launches);
 
 // ---- scan.cu ----------------------------------------------------------------------------------
 struct ScanPlanSizes {

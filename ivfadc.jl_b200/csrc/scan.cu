@@ -226,13 +226,21 @@ merge_cands_kernel(int64_t nq, int w, int k, int ps, const int32_t* __restrict__
             if (s == (r >> 5)) c = __shfl_sync(0xffffffffu, cnt[s], r & 31);
         return c;
     };
-    // 1. bound
+    // 1. bound.  Four rows at a time: the loads of a group are independent and issued together (rows are
+    // short -- typically 20..30 candidates -- so one load per row and lane covers them; the tail loop is rare)
     float lmin = inf;
-#pragma unroll 4
-    for (int r = 0; r < w; ++r) {
-        const int c = count_of(r);
-        const float* row = pair_d + (size_t)(q * w + r) * ps;
-        for (int e = lane; e < c; e += 32) lmin = fminf(lmin, row[e]);
+    for (int r0 = 0; r0 < w; r0 += 4) {
+        int c[4];
+        float v[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) c[i] = r0 + i < w ? count_of(r0 + i) : 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) v[i] = lane < c[i] ? pair_d[(size_t)(q * w + r0 + i) * ps + lane] : inf;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            lmin = fminf(lmin, v[i]);
+            for (int e = lane + 32; e < c[i]; e += 32) lmin = fminf(lmin, pair_d[(size_t)(q * w + r0 + i) * ps + e]);
+        }
     }
     int rank = 0;
 #pragma unroll
@@ -242,24 +250,41 @@ merge_cands_kernel(int64_t nq, int w, int k, int ps, const int32_t* __restrict__
     }
     const int src = __ffs(__ballot_sync(0xffffffffu, rank == min(k, 32) - 1)) - 1;
     const float bound = __shfl_sync(0xffffffffu, lmin, src);
-    // 2. compaction of the candidates within the bound
+    // 2. compaction of the candidates within the bound (rows in rank order, so equal keys cannot occur)
     int M = 0;
-    for (int r = 0; r < w; ++r) {
-        const int c = count_of(r);
-        const size_t rb = (size_t)(q * w + r) * ps;
-        for (int e0 = 0; e0 < c; e0 += 32) {
-            const int e = e0 + lane;
-            const float d = e < c ? pair_d[rb + e] : inf;
-            const bool pred = e < c && d <= bound && d < inf;
-            const unsigned mask = __ballot_sync(0xffffffffu, pred);
-            if (pred) {
-                const int slot = M + __popc(mask & ((1u << lane) - 1u));
-                if (slot < MC_CAP) {
-                    s_d[wq][slot] = d;
-                    s_k[wq][slot] = ((uint64_t)r << 32) | pair_pos[rb + e];
-                }
+    auto offer = [&](int r, int e, int c, float d, uint32_t pos) {
+        const bool pred = e < c && d <= bound && d < inf;
+        const unsigned mask = __ballot_sync(0xffffffffu, pred);
+        if (pred) {
+            const int slot = M + __popc(mask & ((1u << lane) - 1u));
+            if (slot < MC_CAP) {
+                s_d[wq][slot] = d;
+                s_k[wq][slot] = ((uint64_t)r << 32) | pos;
             }
-            M += __popc(mask);
+        }
+        M += __popc(mask);
+    };
+    for (int r0 = 0; r0 < w; r0 += 4) {
+        int c[4];
+        float v[4];
+        uint32_t pp[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) c[i] = r0 + i < w ? count_of(r0 + i) : 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const size_t o = (size_t)(q * w + r0 + i) * ps + lane;
+            v[i] = lane < c[i] ? pair_d[o] : inf;
+            pp[i] = lane < c[i] ? pair_pos[o] : 0u;
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            if (c[i] == 0) continue;  // warp-uniform
+            offer(r0 + i, lane, c[i], v[i], pp[i]);
+            for (int e0 = 32; e0 < c[i]; e0 += 32) {
+                const int e = e0 + lane;
+                const size_t o = (size_t)(q * w + r0 + i) * ps + e;
+                offer(r0 + i, e, c[i], e < c[i] ? pair_d[o] : inf, e < c[i] ? pair_pos[o] : 0u);
+            }
         }
     }
     __syncwarp();

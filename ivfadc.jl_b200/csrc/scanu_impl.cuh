@@ -53,7 +53,7 @@ constexpr uint32_t U_TMEM_COLS = 512;
 constexpr int U_CW = 16;                     // candidate slots per (query, warp)
 constexpr bool U_CTA_SYNC = true;             // per-table CTA barrier (true) or mbarrier release collected by the issuer (false)
 #ifndef U_DEPTH
-#define U_DEPTH 32                           // lookups in flight per tcgen05.wait::ld (16 or 32)
+#define U_DEPTH 16                           // lookups in flight per tcgen05.wait::ld (16 or 32; 32 measured 2% slower)
 #endif
 // Vectors of a pass are dealt in chunks of 16: warp w owns chunks w, w + U_SW, w + 2 U_SW, w + 3 U_SW.
 constexpr int U_SW = QWARPS;                  // full-share warps (U_SW = 15: the issuing warp keeps a half share and a pass

@@ -16,7 +16,7 @@ pytestmark = pytest.mark.gpu
 RTOL = 1e-5  # the tolerance north_star states for ADC distances (we assert exact equality too)
 
 
-LEGACY, QLANE, LUT_EXACT, LUT_MMASYNC, SMEMLUT = 1, 2, 4, 8, 16  # ivfadc_config.flags (include/ivfadc.h)
+LEGACY, QLANE, LUT_EXACT, LUT_MMASYNC, SMEMLUT, COARSE_SCALAR = 1, 2, 4, 8, 16, 32  # ivfadc_config.flags (include/ivfadc.h)
 # Default flags for the bit-exact tests: whichever scan kernel the engine picks, tables in the
 # reference's direct form.  The tensor-core (3xTF32) tables are tested at the stated tolerance in
 # test_search_qlane_* below.
@@ -55,7 +55,8 @@ def assert_search_equal(engine, oidx, Q, k, w, nthreads=4):
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
 @pytest.mark.parametrize("D,kc,nq,w", [(50, 100, 37, 1), (10, 100, 64, 2), (128, 1024, 300, 16),
                                        (2, 3, 5, 3), (96, 257, 33, 33), (17, 70, 9, 64),
-                                       (128, 300, 130, 128), (200, 64, 40, 7)])
+                                       (128, 300, 130, 128), (200, 64, 40, 7), (64, 500, 1000, 16),
+                                       (128, 1024, 2500, 16), (32, 64, 4000, 8)])
 def test_coarse_search_bit_exact(dtype, D, kc, nq, w):
     rng = np.random.default_rng(D * 1000 + kc)
     cent = rng.random((kc, D)).astype(dtype)
@@ -64,12 +65,15 @@ def test_coarse_search_bit_exact(dtype, D, kc, nq, w):
     cb = rng.standard_normal((1, 4, D)).astype(dtype)
     qz = orc.Quantizers(cent, cb)
     Q = rng.random((nq, D)).astype(dtype)
-    e = engine_from(qz)
-    gc, gd = e.coarse_search(Q, w)
     oc, od = orc.coarse_search(qz, Q, w, nthreads=4)
-    np.testing.assert_array_equal(gc, oc)
-    assert np.array_equal(gd.view(np.uint8), od.view(np.uint8))
-    e.close()
+    # default: packed-FP32 kernel on transposed centroids where the shape allows it (fp32, D % 4 == 0,
+    # D <= 128); COARSE_SCALAR: the scalar FFMA kernel.  Same bits either way.
+    for flags in (LUT_EXACT, LUT_EXACT | COARSE_SCALAR):
+        e = engine_from(qz, flags=flags)
+        gc, gd = e.coarse_search(Q, w)
+        np.testing.assert_array_equal(gc, oc, err_msg=f"flags={flags}")
+        assert np.array_equal(gd.view(np.uint8), od.view(np.uint8)), f"flags={flags}"
+        e.close()
 
 
 # ------------------------------------------------------------------------------------------------
