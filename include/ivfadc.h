@@ -88,6 +88,12 @@ extern "C" {
  * selects the scalar FFMA kernel instead (identical results, both bit-exact against the reference form).
  */
 #define IVFADC_FLAG_COARSE_SCALAR 32
+/*
+ * Test switch: the final per-query selection over candidate rows normally ranks up to 128 candidates
+ * within the k-th-distance bound in registers and falls back to k filtered sweeps over the rows beyond
+ * that (heavy distance ties); with this flag the fallback takes over at 4, so ordinary data exercises it.
+ */
+#define IVFADC_FLAG_TEST_MERGE_SWEEP 64
 
 typedef struct ivfadc_index ivfadc_index;   /* opaque, owns all device memory */
 

@@ -19,6 +19,7 @@ F32, F64 = 0, 1
 SQEUCLIDEAN = 0
 LAST, FIRST = 0, 1
 FLAG_SCAN_LEGACY, FLAG_SCAN_QLANE, FLAG_LUT_EXACT, FLAG_LUT_MMASYNC, FLAG_SCAN_SMEMLUT, FLAG_COARSE_SCALAR = 1, 2, 4, 8, 16, 32
+FLAG_TEST_MERGE_SWEEP = 64
 
 # every symbol include/ivfadc.h declares (tests check that the library exports all of them)
 SYMBOLS = [

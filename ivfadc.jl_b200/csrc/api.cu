@@ -288,6 +288,7 @@ int ivfadc_destroy(ivfadc_index* h) {
     if (h->d_tcB) cudaFree(h->d_tcB);
     if (h->d_tcU) cudaFree(h->d_tcU);
     if (h->d_err) cudaFree(h->d_err);
+    if (h->h_err) cudaFreeHost(h->h_err);
     if (h->d_dbg_lut) cudaFree(h->d_dbg_lut);
     DevBuf* bufs[] = {&h->ws_q, &h->ws_cells, &h->ws_dc, &h->ws_bucket, &h->ws_sorted, &h->ws_pair_d,
                       &h->ws_pair_pos, &h->ws_pair_cnt, &h->ws_thr, &h->ws_out_ids, &h->ws_out_d,
@@ -433,14 +434,26 @@ int ivfadc_search(ivfadc_index* h, const void* Q, int64_t nq, int32_t k, int32_t
                                     h->stream), "D2H");
     CUDA_OR_FAIL(h, cudaMemcpyAsync(counts_out, h->ws_out_cnt.p, sizeof(int32_t) * (size_t)nq,
                                     cudaMemcpyDeviceToHost, h->stream), "D2H");
+    // the error flag of the tensor-core pipeline rides in the same asynchronous batch (pinned word)
+    if (h->d_err && !h->h_err) {
+        if (cudaMallocHost(reinterpret_cast<void**>(&h->h_err), sizeof(int)) != cudaSuccess) h->h_err = nullptr;
+    }
+    if (h->d_err && h->h_err)
+        CUDA_OR_FAIL(h, cudaMemcpyAsync(h->h_err, h->d_err, sizeof(int), cudaMemcpyDeviceToHost, h->stream), "D2H");
     CUDA_OR_FAIL(h, cudaStreamSynchronize(h->stream), "search");
     if (h->d_err) {
         int flag = 0;
-        CUDA_OR_FAIL(h, cudaMemcpy(&flag, h->d_err, sizeof(int), cudaMemcpyDeviceToHost), "D2H");
+        if (h->h_err) flag = *h->h_err;
+        else CUDA_OR_FAIL(h, cudaMemcpy(&flag, h->d_err, sizeof(int), cudaMemcpyDeviceToHost), "D2H");
         if (flag) {
             cudaMemset(h->d_err, 0, sizeof(int));
-            return fail(h, IVFADC_ERR_CUDA, flag == 1 ? "tensor-core table builder: TMA operand never arrived"
-                                                      : "tensor-core table builder: MMA never completed");
+            const char* what = flag == 1 ? "tensor-core table builder: TMA operand never arrived"
+                             : flag == 2 ? "tensor-core table builder: MMA never completed"
+                             : flag == 3 ? "tensor-core table builder: shared-memory plan does not fit"
+                             : flag == 4 ? "tensor-core table builder: first A operands of a work item never written"
+                             : flag == 5 ? "tensor-core table builder: codebook ring did not drain"
+                                         : "tensor-core table builder: table buffer never released";
+            return fail(h, IVFADC_ERR_CUDA, what);
         }
     }
     return IVFADC_OK;

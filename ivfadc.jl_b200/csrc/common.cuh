@@ -114,6 +114,7 @@ struct ivfadc_index {
     int frag_ntiles = 0, frag_ksteps = 0;
     void* d_tcB = nullptr;          // codebook as tcgen05 B-operand blocks (scant table builder)
     void* d_tcU = nullptr;          // codebook as per-subspace B-operand blocks, rows = code values (scanu)
+    int* h_err = nullptr;           // pinned host copy of d_err (read back with the results)
     int* d_err = nullptr;           // device error flag of the tcgen05 pipeline (mbarrier timeout)
     void* d_dbg_lut = nullptr;      // optional table dump of work item 0 (tests), float[m][256][32]
 

@@ -202,7 +202,7 @@ __device__ __forceinline__ bool key_less(float da, uint64_t ka, float db, uint64
 
 template <typename IdT>
 __global__ void __launch_bounds__(128)
-merge_cands_kernel(int64_t nq, int w, int k, int ps, const int32_t* __restrict__ cells,
+merge_cands_kernel(int64_t nq, int w, int k, int ps, int cap, const int32_t* __restrict__ cells,
                    const float* __restrict__ pair_d, const uint32_t* __restrict__ pair_pos,
                    const int32_t* __restrict__ pair_cnt, const int64_t* __restrict__ list_off,
                    const IdT* __restrict__ ids_arena, uint64_t* __restrict__ out_ids,
@@ -257,7 +257,7 @@ merge_cands_kernel(int64_t nq, int w, int k, int ps, const int32_t* __restrict__
         const unsigned mask = __ballot_sync(0xffffffffu, pred);
         if (pred) {
             const int slot = M + __popc(mask & ((1u << lane) - 1u));
-            if (slot < MC_CAP) {
+            if (slot < cap) {
                 s_d[wq][slot] = d;
                 s_k[wq][slot] = ((uint64_t)r << 32) | pos;
             }
@@ -289,7 +289,7 @@ merge_cands_kernel(int64_t nq, int w, int k, int ps, const int32_t* __restrict__
     }
     __syncwarp();
     int e = 0;
-    if (M <= MC_CAP) {
+    if (M <= cap) {  // cap = MC_CAP (tests lower it to drive ordinary data through the sweep path)
         // 3. k rounds of warp arg-min; lane holds entries lane, lane + 32, lane + 64, lane + 96
         float d[4];
         uint64_t key[4];
@@ -734,14 +734,15 @@ cudaError_t search_t(ivfadc_index* h, const void* dQ, int64_t nq, int k, int w, 
 
     const unsigned mgrid = (unsigned)((nq + 3) / 4);
     if (ps != k) {  // unsorted candidate rows (fp32 only)
+        const int mcap = (h->cfg.flags & IVFADC_FLAG_TEST_MERGE_SWEEP) ? 4 : MC_CAP;
         if constexpr (sizeof(T) == 4) {
             if (h->id_dev_bytes == 4)
                 merge_cands_kernel<uint32_t><<<mgrid, 128, 0, s>>>(
-                    nq, w, k, ps, d_cells, pair_d, pair_pos, pair_cnt, h->d_off, static_cast<const uint32_t*>(h->d_ids),
+                    nq, w, k, ps, mcap, d_cells, pair_d, pair_pos, pair_cnt, h->d_off, static_cast<const uint32_t*>(h->d_ids),
                     d_ids, static_cast<float*>(d_dists), d_keys, d_counts);
             else
                 merge_cands_kernel<uint64_t><<<mgrid, 128, 0, s>>>(
-                    nq, w, k, ps, d_cells, pair_d, pair_pos, pair_cnt, h->d_off, static_cast<const uint64_t*>(h->d_ids),
+                    nq, w, k, ps, mcap, d_cells, pair_d, pair_pos, pair_cnt, h->d_off, static_cast<const uint64_t*>(h->d_ids),
                     d_ids, static_cast<float*>(d_dists), d_keys, d_counts);
         }
     } else if (h->id_dev_bytes == 4)

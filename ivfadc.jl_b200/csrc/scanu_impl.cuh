@@ -144,6 +144,14 @@ __device__ __forceinline__ float f_unflip(uint32_t u) {
 // tb = tensor-memory address of the table (lane quarter of this warp, column 0 of the buffer; the
 // low byte is zero, so ONE uniform byte-permute forms the lookup address), pa = shared address of
 // the 16 code bytes of the chunk.  Everything here is warp-uniform except acc / base.
+// acc[0..1] += t[0..1] as ONE packed add (add.rn.f32x2: each half is an ordinary IEEE fp32 add of its own chain)
+__device__ __forceinline__ void add_pair(float& a0, float& a1, float t0, float t1) {
+    unsigned long long a, t;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "f"(a0), "f"(a1));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(t) : "f"(t0), "f"(t1));
+    asm("add.rn.f32x2 %0, %0, %1;" : "+l"(a) : "l"(t));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(a0), "=f"(a1) : "l"(a));
+}
 template <int N>
 __device__ __forceinline__ void scanu_issue(uint32_t tb, const uint4& x, float* t) {
     t[0] = tc_ld1(__byte_perm(x.x, tb, 0x7650));  t[1] = tc_ld1(__byte_perm(x.x, tb, 0x7651));
@@ -168,7 +176,7 @@ __device__ __forceinline__ void scanu_sub(uint32_t tb, uint32_t plane_w, uint32_
             scanu_issue<0>(tb, x1, t + 16);
             tc_wait_ld();
 #pragma unroll
-            for (int i = 0; i < 32; ++i) acc[32 * j2 + i] = FIRST ? add_rn(base, t[i]) : add_rn(acc[32 * j2 + i], t[i]);
+            for (int i = 0; i < 32; i += 2) add_pair(acc[32 * j2 + i], acc[32 * j2 + i + 1], t[i], t[i + 1]);
         }
     } else {
 #pragma unroll
@@ -179,7 +187,7 @@ __device__ __forceinline__ void scanu_sub(uint32_t tb, uint32_t plane_w, uint32_
                 scanu_issue<0>(tb, x, t);
                 tc_wait_ld();
 #pragma unroll
-                for (int i = 0; i < 16; ++i) acc[16 * j4 + i] = FIRST ? add_rn(base, t[i]) : add_rn(acc[16 * j4 + i], t[i]);
+                for (int i = 0; i < 16; i += 2) add_pair(acc[16 * j4 + i], acc[16 * j4 + i + 1], t[i], t[i + 1]);
             }
         }
     }
@@ -221,7 +229,7 @@ scanu_kernel(const ScanUArgs ua) {
         for (int i = 0; i < U_NB; ++i) mbar_init(bar_full + 8 * i, 1);
         mbar_init(bar_mma, 1);
         mbar_init(bar_mma + 8, 1);
-        mbar_init(bar_a, 2);
+        mbar_init(bar_a, 8);
         mbar_init(bar_free, QWARPS);
         mbar_init(bar_free + 8, QWARPS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -405,10 +413,11 @@ scanu_kernel(const ScanUArgs ua) {
             sts_f(rnorm_u + (wid * QG + lane) * 4, part);
         }
     };
-    // ONE warp writes the A operand of subspace s into ring slot s & 1: rows (copy, q), hi / lo of
-    // r[s][q][0..7]; lane = query.  (Spreading the stores over all 512 threads was measured: the scan of
-    // every warp slows down by more than the writer warp gains.)
-    auto write_A = [&](int s) {
+    // The A operand of subspace s (ring slot s & 1): rows (copy, q), hi / lo of r[s][q][0..7]; lane = query,
+    // one row copy per call (four warps share a table's operand).  No proxy fence here (it costs a writer
+    // several hundred cycles of its scan): the issuing warp fences once, after the barrier that makes these
+    // writes visible to it and before the MMAs that read them.
+    auto write_A = [&](int s, int c) {
         float hi[8], lo[8];
 #pragma unroll
         for (int d = 0; d < 8; ++d) {
@@ -416,15 +425,11 @@ scanu_kernel(const ScanUArgs ua) {
             hi[d] = __uint_as_float(to_tf32(r));
             lo[d] = __uint_as_float(to_tf32(r - hi[d]));
         }
-        const uint32_t ph = aring_u + (s & 1) * U_ASUB + (lane >> 3) * 256 + (lane & 7) * 16;
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {  // row = 32 c + lane
-            sts_v4f(ph + c * 1024, hi[0], hi[1], hi[2], hi[3]);
-            sts_v4f(ph + c * 1024 + 128, hi[4], hi[5], hi[6], hi[7]);
-            sts_v4f(ph + c * 1024 + U_ABLK, lo[0], lo[1], lo[2], lo[3]);
-            sts_v4f(ph + c * 1024 + U_ABLK + 128, lo[4], lo[5], lo[6], lo[7]);
-        }
-        fence_proxy_async();  // generic-proxy writes -> visible to the tensor core (async proxy)
+        const uint32_t ph = aring_u + (s & 1) * U_ASUB + c * 1024 + (lane >> 3) * 256 + (lane & 7) * 16;  // row = 32 c + lane
+        sts_v4f(ph, hi[0], hi[1], hi[2], hi[3]);
+        sts_v4f(ph + 128, hi[4], hi[5], hi[6], hi[7]);
+        sts_v4f(ph + U_ABLK, lo[0], lo[1], lo[2], lo[3]);
+        sts_v4f(ph + U_ABLK + 128, lo[4], lo[5], lo[6], lo[7]);
     };
     // One lane waits (mbarrier.try_wait: the hardware SUSPENDS the waiting thread, so the 15 waiting warps
     // do not take issue slots from the warp that is issuing the next build -- a test_wait spin was measured
@@ -450,6 +455,7 @@ scanu_kernel(const ScanUArgs ua) {
         const uint32_t t_u = __shfl_sync(0xffffffffu, t, 0), s_u = (uint32_t)__shfl_sync(0xffffffffu, s, 0);
         warp_wait(bar_full + 8 * slot_u, par_u, 1);
         tc_fence_after();
+        fence_proxy_async();  // A operand: generic-proxy writes of four warps (ordered before this point by a barrier) -> async proxy
         const uint64_t Ah = descA0 + (uint64_t)((s_u & 1) * (U_ASUB >> 4)), Al = Ah + (U_ABLK >> 4);
         const uint64_t Bh = descB0 + (uint64_t)(slot_u * (U_BSUB >> 4)), Bl = Bh + (U_BBLK >> 4), Bn = Bl + (U_BBLK >> 4);
         const uint32_t d = tmem_base + (t_u & 1) * 256;
@@ -474,8 +480,8 @@ scanu_kernel(const ScanUArgs ua) {
     // after a staging barrier: warps 2, 3 write the first two A operands, the issuer starts builds 0, 1
     // (no CTA barrier: the other warps go on to the candidate dump)
     auto seg_start_builds = [&]() {
-        if (wid == 2 || wid == 3) {
-            write_A(wid - 2);
+        if (wid < 8) {  // warps 0..3: operand of subspace 0, warps 4..7: subspace 1; one row copy each
+            write_A(wid >> 2, wid & 3);
             __syncwarp();
             if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_a) : "memory");
         }
@@ -572,7 +578,7 @@ scanu_kernel(const ScanUArgs ua) {
             if (wid == 0 && lane == 0) refill_B(t);  // as early as possible (the copy needs its two table periods), and not by the issuing warp
             stamp_i();
             stamp_w(s, 1);
-            if (s + 2 < m && wid == T_ISSUER - 1) write_A(s + 2);  // build s has completed: its A slot is free (warps 14, 15 own the fewest vectors)
+            if (s + 2 < m && wid >= QWARPS - 4) write_A(s + 2, wid - (QWARPS - 4));  // build s has completed: its A slot is free
             // s and t are warp-uniform, but ptxas keeps the loop counter in a vector register unless told (one SHFL each)
             const uint32_t tb = tq + (__shfl_sync(0xffffffffu, t, 0) & 1) * 256;
             const uint32_t plane_w = plane_w0 + __shfl_sync(0xffffffffu, s, 0) * T_PLANE;

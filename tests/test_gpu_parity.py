@@ -16,7 +16,7 @@ pytestmark = pytest.mark.gpu
 RTOL = 1e-5  # the tolerance north_star states for ADC distances (we assert exact equality too)
 
 
-LEGACY, QLANE, LUT_EXACT, LUT_MMASYNC, SMEMLUT, COARSE_SCALAR = 1, 2, 4, 8, 16, 32  # ivfadc_config.flags (include/ivfadc.h)
+LEGACY, QLANE, LUT_EXACT, LUT_MMASYNC, SMEMLUT, COARSE_SCALAR, MERGE_SWEEP = 1, 2, 4, 8, 16, 32, 64  # ivfadc_config.flags (include/ivfadc.h)
 # Default flags for the bit-exact tests: whichever scan kernel the engine picks, tables in the
 # reference's direct form.  The tensor-core (3xTF32) tables are tested at the stated tolerance in
 # test_search_qlane_* below.
@@ -254,20 +254,29 @@ def test_search_qlane_bit_exact(D, m, ksub, kc, n, nq, k, w, identity):
     # QLANE alone = tensor-memory lookup kernel (tcgen05.mma tables looked up with tcgen05.ld) where the
     # shape allows it (dsub <= 8), QLANE | SMEMLUT = tcgen05 tables copied to shared memory,
     # QLANE | LUT_MMASYNC = the warp-level mma.sync builder.
-    for flags in (QLANE, QLANE | SMEMLUT, QLANE | LUT_MMASYNC):
+    # QLANE | MERGE_SWEEP: the heavy-tie fallback of the final selection on ordinary data.
+    first = None
+    for flags in (QLANE, QLANE | MERGE_SWEEP, QLANE | SMEMLUT, QLANE | LUT_MMASYNC):
         e = engine_from(qz, np.uint32, X, flags=flags)
         gi, gd, gc = e.search_packed(Q, k, w)
         rep = orc.compare_search(gi, gd, gc, oi, od, oc, rtol=RTOL)
         assert rep["near_tie_id_mismatches"] <= max(2, rep["results"] // 200), (flags, rep)
         assert rep["max_rel_err"] < 3e-6, (flags, rep)   # measured error budget of 3xTF32
+        if flags == QLANE:
+            first = (gi.copy(), gd.copy(), gc.copy())
+        elif flags == QLANE | MERGE_SWEEP:  # same candidates, other selection path: identical bits
+            np.testing.assert_array_equal(gi, first[0])
+            assert np.array_equal(gd.view(np.uint8), first[1].view(np.uint8))
+            np.testing.assert_array_equal(gc, first[2])
         e.close()
 
 
 @pytest.mark.parametrize("D,m,ksub,identity", [(128, 16, 256, True), (96, 12, 256, True), (40, 8, 100, False),
                                                (16, 4, 256, True)])
 def test_tcgen05_tables_against_fp64(D, m, ksub, identity):
-    """K2 in isolation: the lookup tables the tcgen05 builder leaves in shared memory for work item 0
-    (dumped through ivfadc_debug_tables) against |w|^2 - 2 r.w evaluated in float64."""
+    """K2 in isolation: the lookup tables the tcgen05 builder leaves in tensor memory for the first work
+    item (read back with tcgen05.ld and dumped through ivfadc_debug_tables) against |w|^2 - 2 r.w
+    evaluated in float64."""
     import ctypes
     from ivfadc_jl_b200 import synth
     kc, n, nq, w = 8, 4000, 64, 2
@@ -322,7 +331,7 @@ def test_search_qlane_ties_overflow_redo():
         for k, w in ((10, 2), (16, 4), (1, 1)):
             assert_search_equal(e, oidx, Q, k, w)
         e.close()
-    for flags in (QLANE, QLANE | SMEMLUT):
+    for flags in (QLANE, QLANE | MERGE_SWEEP, QLANE | SMEMLUT):
         e = engine_from(qz, np.uint32, Xc, assign, flags=flags)
         for k, w in ((10, 2), (16, 4), (1, 1)):
             gi, gd, gc = e.search_packed(Q, k, w)
