@@ -94,6 +94,15 @@ extern "C" {
  * that (heavy distance ties); with this flag the fallback takes over at 4, so ordinary data exercises it.
  */
 #define IVFADC_FLAG_TEST_MERGE_SWEEP 64
+/*
+ * The fp32 coarse step (kc >= 256, D % 16 == 0, D <= 128, w <= 32) runs on the tensor cores: TF32
+ * scores prune the centroids to a provable superset of the exact top-w, which is then re-ranked with
+ * the reference's direct form (results bit-identical to the FFMA kernels).  This flag keeps the
+ * packed-FP32 kernel as the coarse step.
+ */
+#define IVFADC_FLAG_COARSE_FFMA 128
+/* Test switch: the tensor-core coarse kernel flags EVERY query for the FFMA redo pass. */
+#define IVFADC_FLAG_TEST_COARSE_REDO 256
 
 typedef struct ivfadc_index ivfadc_index;   /* opaque, owns all device memory */
 

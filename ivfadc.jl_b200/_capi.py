@@ -20,6 +20,7 @@ SQEUCLIDEAN = 0
 LAST, FIRST = 0, 1
 FLAG_SCAN_LEGACY, FLAG_SCAN_QLANE, FLAG_LUT_EXACT, FLAG_LUT_MMASYNC, FLAG_SCAN_SMEMLUT, FLAG_COARSE_SCALAR = 1, 2, 4, 8, 16, 32
 FLAG_TEST_MERGE_SWEEP = 64
+FLAG_COARSE_FFMA, FLAG_TEST_COARSE_REDO = 128, 256
 
 # every symbol include/ivfadc.h declares (tests check that the library exports all of them)
 SYMBOLS = [

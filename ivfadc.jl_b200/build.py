@@ -11,7 +11,7 @@ CSRC = os.path.join(HERE, "csrc")
 OBJDIR = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libivfadc_cuda.so")
 SOURCES = ["api.cu", "coarse.cu", "scan.cu", "encode.cu", "lists.cu"]
-HEADERS = ["common.cuh", "warp_topk.cuh", "scan_impl.cuh", "scanq_impl.cuh", "scant_impl.cuh", "scanu_impl.cuh"]
+HEADERS = ["common.cuh", "warp_topk.cuh", "scan_impl.cuh", "scanq_impl.cuh", "scant_impl.cuh", "scanu_impl.cuh", "coarse_tc.cuh"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "-I" + os.path.join(ROOT, "include"), "-I" + CSRC,

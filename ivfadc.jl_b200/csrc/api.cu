@@ -280,6 +280,9 @@ int ivfadc_destroy(ivfadc_index* h) {
     lists_free(h);
     if (h->d_centroids) cudaFree(h->d_centroids);
     if (h->d_centroids_t) cudaFree(h->d_centroids_t);
+    if (h->d_tcC) cudaFree(h->d_tcC);
+    if (h->d_ccn) cudaFree(h->d_ccn);
+    h->ws_coarse_redo.release();
     if (h->d_cb) cudaFree(h->d_cb);
     if (h->d_cb_codes) cudaFree(h->d_cb_codes);
     if (h->d_cb_norms) cudaFree(h->d_cb_norms);

@@ -12,6 +12,7 @@
 // oracle bit for bit and the whole step is < 10% of the search ("K1").
 #include "common.cuh"
 #include "warp_topk.cuh"
+#include "coarse_tc.cuh"
 
 #include <algorithm>
 
@@ -194,7 +195,7 @@ constexpr int PDK = 64;              // dims per centroid chunk (double-buffered
 template <int NTY, int R>
 __global__ void __launch_bounds__(16 * NTY)
 coarse2_kernel(const float* __restrict__ Q, const float* __restrict__ Ct, int64_t nq, int kc, int kcp, int D, int w,
-               int32_t* __restrict__ cells_out, float* __restrict__ dc_out) {
+               int32_t* __restrict__ cells_out, float* __restrict__ dc_out, const uint8_t* __restrict__ redo) {
     constexpr int TQ2 = 4 * NTY, NT = 16 * NTY, NW = NT / 32, QPW = TQ2 / NW;  // 8 queries per warp
     constexpr int LDQ = 2 * TQ2 + 4;  // floats per dim row of the duplicated queries (16-byte aligned rows)
     constexpr int LDD = PC + 1;
@@ -207,6 +208,11 @@ coarse2_kernel(const float* __restrict__ Q, const float* __restrict__ Ct, int64_
     const int tx = tid & 15;   // centroids 4 tx .. 4 tx + 3 of the tile
     const int ty = tid >> 4;   // queries 4 ty .. 4 ty + 3 of the block
     const int64_t q0 = (int64_t)blockIdx.x * TQ2;
+    if (redo) {  // second pass behind the tensor-core kernel: only the queries it flagged (normally none)
+        bool any = false;
+        for (int i = tid; i < TQ2; i += NT) any = any || (q0 + i < nq && redo[q0 + i]);
+        if (!__syncthreads_or(any)) return;
+    }
     const int nck = (D + PDK - 1) / PDK;                 // chunks per tile
     const int ntile = (kc + PC - 1) / PC;
     const int nchunks = ntile * nck;
@@ -307,6 +313,7 @@ coarse2_kernel(const float* __restrict__ Q, const float* __restrict__ Ct, int64_
     for (int a = 0; a < QPW; ++a) {
         const int64_t q = q0 + wid * QPW + a;
         if (q >= nq) continue;
+        if (redo && !redo[q]) continue;
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             const int e = lane * R + r;
@@ -327,7 +334,7 @@ __global__ void transpose_centroids_kernel(const float* __restrict__ C, int kc, 
 
 template <int NTY, int R>
 cudaError_t launch_coarse2_inst(const float* Q, const float* Ct, int64_t nq, int kc, int kcp, int D, int w,
-                                int32_t* cells, float* dc, cudaStream_t s) {
+                                int32_t* cells, float* dc, cudaStream_t s, const uint8_t* redo) {
     constexpr int TQ2 = 4 * NTY;
     const size_t smem = ((size_t)D * (2 * TQ2 + 4) + 2 * (size_t)PDK * PLDC + (size_t)TQ2 * (PC + 1)) * sizeof(float);
     static size_t configured = 0;
@@ -336,15 +343,15 @@ cudaError_t launch_coarse2_inst(const float* Q, const float* Ct, int64_t nq, int
         if (e != cudaSuccess) return e;
         configured = smem;
     }
-    coarse2_kernel<NTY, R><<<(unsigned)((nq + TQ2 - 1) / TQ2), 16 * NTY, smem, s>>>(Q, Ct, nq, kc, kcp, D, w, cells, dc);
+    coarse2_kernel<NTY, R><<<(unsigned)((nq + TQ2 - 1) / TQ2), 16 * NTY, smem, s>>>(Q, Ct, nq, kc, kcp, D, w, cells, dc, redo);
     return cudaGetLastError();
 }
 template <int R>
 cudaError_t launch_coarse2_r(int nty, const float* Q, const float* Ct, int64_t nq, int kc, int kcp, int D, int w,
-                             int32_t* cells, float* dc, cudaStream_t s) {
-    if (nty == 4) return launch_coarse2_inst<4, R>(Q, Ct, nq, kc, kcp, D, w, cells, dc, s);
-    if (nty == 6) return launch_coarse2_inst<6, R>(Q, Ct, nq, kc, kcp, D, w, cells, dc, s);
-    return launch_coarse2_inst<8, R>(Q, Ct, nq, kc, kcp, D, w, cells, dc, s);
+                             int32_t* cells, float* dc, cudaStream_t s, const uint8_t* redo = nullptr) {
+    if (nty == 4) return launch_coarse2_inst<4, R>(Q, Ct, nq, kc, kcp, D, w, cells, dc, s, redo);
+    if (nty == 6) return launch_coarse2_inst<6, R>(Q, Ct, nq, kc, kcp, D, w, cells, dc, s, redo);
+    return launch_coarse2_inst<8, R>(Q, Ct, nq, kc, kcp, D, w, cells, dc, s, redo);
 }
 
 template <typename T>
@@ -379,8 +386,46 @@ cudaError_t coarse_prepare(ivfadc_index* h, cudaStream_t s, int* launches) {
                                                                         h->kc_pad, h->cfg.dim,
                                                                         static_cast<float*>(h->d_centroids_t));
     if (launches) *launches += 1;
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    // operands of the tensor-core kernel (coarse_tc.cuh): TF32 centroid blocks, squared norms, max norm
+    const int kc = h->cfg.kc, D = h->cfg.dim;
+    if (kc >= ctc::NC && D % 16 == 0 && D <= 128) {
+        h->kc_pad256 = (kc + ctc::NC - 1) / ctc::NC * ctc::NC;
+        const int ksteps = D / 8;
+        const size_t words = (size_t)h->kc_pad256 * ksteps * 8;
+        if ((e = cudaMalloc(&h->d_tcC, words * sizeof(float))) != cudaSuccess) return e;
+        if ((e = cudaMalloc(&h->d_ccn, ((size_t)h->kc_pad256 + 4) * sizeof(float))) != cudaSuccess) return e;
+        if ((e = cudaMemsetAsync(h->d_ccn, 0, ((size_t)h->kc_pad256 + 4) * sizeof(float), s)) != cudaSuccess) return e;
+        if (!h->d_err) {
+            if ((e = cudaMalloc(&h->d_err, sizeof(int))) != cudaSuccess) return e;
+            if ((e = cudaMemsetAsync(h->d_err, 0, sizeof(int), s)) != cudaSuccess) return e;
+        }
+        const int64_t nthr = (int64_t)h->kc_pad256 * ksteps;
+        ctc::prep_tcc_kernel<<<(unsigned)((nthr + 255) / 256), 256, 0, s>>>(static_cast<const float*>(h->d_centroids), kc,
+                                                                           h->kc_pad256, D, ksteps,
+                                                                           static_cast<float*>(h->d_tcC));
+        ctc::prep_cn_kernel<<<(unsigned)((h->kc_pad256 + 255) / 256), 256, 0, s>>>(static_cast<const float*>(h->d_centroids), kc,
+                                                                                  h->kc_pad256, D,
+                                                                                  static_cast<float*>(h->d_ccn));
+        if (launches) *launches += 2;
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+}
+
+namespace {
+template <int WL>
+cudaError_t launch_coarse3_inst(const ctc::Args& a, unsigned grid, size_t smem, cudaStream_t s) {
+    static size_t configured = 0;
+    if (smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(ctc::coarse3_kernel<WL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured = smem;
+    }
+    ctc::coarse3_kernel<WL><<<grid, ctc::THREADS, smem, s>>>(a);
     return cudaGetLastError();
 }
+}  // namespace
 
 cudaError_t launch_coarse(const ivfadc_index* h, const void* dQ, int64_t nq, int w, int32_t* d_cells,
                           void* d_dc, cudaStream_t s, int* launches) {
@@ -412,6 +457,34 @@ cudaError_t launch_coarse(const ivfadc_index* h, const void* dQ, int64_t nq, int
         const float* Q = static_cast<const float*>(dQ);
         const float* Ct = static_cast<const float*>(h->d_centroids_t);
         float* dc = static_cast<float*>(d_dc);
+        // tensor-core pruning + exact re-rank (coarse_tc.cuh); the FFMA kernel below redoes flagged queries
+        if (h->d_tcC && w <= 32 && w <= h->cfg.kc && !(h->cfg.flags & IVFADC_FLAG_COARSE_FFMA) &&
+            (reinterpret_cast<uintptr_t>(dQ) & 15) == 0 &&
+            ctc::smem_layout(D / 8).total <= (size_t)(227 * 1024)) {
+            // redo flags [nq] | candidate counts [nq] | candidate rows [nq][CAP]
+            const size_t off_cnt = ((size_t)nq + 255) / 256 * 256, off_cand = off_cnt + (size_t)nq * 4;
+            cudaError_t e = h->ws_coarse_redo.reserve(off_cand + (size_t)nq * ctc::CAP * 4);
+            if (e != cudaSuccess) return e;
+            ctc::Args ca;
+            ca.Q = Q; ca.C = static_cast<const float*>(h->d_centroids);
+            ca.tcC = static_cast<const float*>(h->d_tcC); ca.cn = static_cast<const float*>(h->d_ccn);
+            ca.nq = nq; ca.kc = h->cfg.kc; ca.kcp = h->kc_pad256; ca.D = D; ca.ksteps = D / 8; ca.w = w;
+            ca.cells_out = d_cells; ca.dc_out = dc; ca.redo = h->ws_coarse_redo.as<uint8_t>(); ca.err = h->d_err;
+            ca.cnt_out = reinterpret_cast<int32_t*>(ca.redo + off_cnt);
+            ca.cand_out = reinterpret_cast<int32_t*>(ca.redo + off_cand);
+            ca.force_redo = (h->cfg.flags & IVFADC_FLAG_TEST_COARSE_REDO) ? 1 : 0;
+            const unsigned grid = (unsigned)((nq + ctc::MQ - 1) / ctc::MQ);
+            const size_t smem = ctc::smem_layout(D / 8).total;
+            if (w <= 1) e = launch_coarse3_inst<1>(ca, grid, smem, s);
+            else if (w <= 8) e = launch_coarse3_inst<8>(ca, grid, smem, s);
+            else if (w <= 16) e = launch_coarse3_inst<16>(ca, grid, smem, s);
+            else e = launch_coarse3_inst<32>(ca, grid, smem, s);
+            if (e != cudaSuccess) return e;
+            ctc::coarse3_rerank_kernel<<<(unsigned)((nq + ctc::RR_WARPS - 1) / ctc::RR_WARPS), ctc::RR_WARPS * 32, 0, s>>>(ca);
+            if ((e = cudaGetLastError()) != cudaSuccess) return e;
+            if (launches) *launches += 2;
+            return launch_coarse2_r<1>(best, Q, Ct, nq, h->cfg.kc, h->kc_pad, D, w, d_cells, dc, s, ca.redo);
+        }
         if (w <= 32) return launch_coarse2_r<1>(best, Q, Ct, nq, h->cfg.kc, h->kc_pad, D, w, d_cells, dc, s);
         if (w <= 64) return launch_coarse2_r<2>(best, Q, Ct, nq, h->cfg.kc, h->kc_pad, D, w, d_cells, dc, s);
         return launch_coarse2_r<4>(best, Q, Ct, nq, h->cfg.kc, h->kc_pad, D, w, d_cells, dc, s);

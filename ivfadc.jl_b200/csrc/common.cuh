@@ -105,6 +105,10 @@ struct ivfadc_index {
     void* d_centroids = nullptr;    // T[kc][D]
     void* d_centroids_t = nullptr;  // fp32 only: centroids transposed [D][kc_pad] (packed-FP32 coarse kernel)
     int kc_pad = 0;
+    void* d_tcC = nullptr;          // fp32 only: centroids as tcgen05 B-operand blocks [kc_pad256 / 256][D / 8][2048] (coarse_tc.cuh)
+    void* d_ccn = nullptr;          // fp32 only: squared centroid norms [kc_pad256] (+inf padding), then max |c|^2
+    int kc_pad256 = 0;
+    mutable ivf::DevBuf ws_coarse_redo;  // uint8[nq]: queries the tensor-core coarse kernel hands to the FFMA kernel
     void* d_cb = nullptr;           // T[m][ksub][dsub]
     uint8_t* d_cb_codes = nullptr;  // uint8[m][ksub]
     void* d_cb_norms = nullptr;     // T[m][ksub]  squared norms of the codewords (oracle A2)

@@ -17,6 +17,7 @@ RTOL = 1e-5  # the tolerance north_star states for ADC distances (we assert exac
 
 
 LEGACY, QLANE, LUT_EXACT, LUT_MMASYNC, SMEMLUT, COARSE_SCALAR, MERGE_SWEEP = 1, 2, 4, 8, 16, 32, 64  # ivfadc_config.flags (include/ivfadc.h)
+COARSE_FFMA, COARSE_REDO = 128, 256
 # Default flags for the bit-exact tests: whichever scan kernel the engine picks, tables in the
 # reference's direct form.  The tensor-core (3xTF32) tables are tested at the stated tolerance in
 # test_search_qlane_* below.
@@ -68,7 +69,41 @@ def test_coarse_search_bit_exact(dtype, D, kc, nq, w):
     oc, od = orc.coarse_search(qz, Q, w, nthreads=4)
     # default: packed-FP32 kernel on transposed centroids where the shape allows it (fp32, D % 4 == 0,
     # D <= 128); COARSE_SCALAR: the scalar FFMA kernel.  Same bits either way.
-    for flags in (LUT_EXACT, LUT_EXACT | COARSE_SCALAR):
+    for flags in (LUT_EXACT, LUT_EXACT | COARSE_SCALAR, LUT_EXACT | COARSE_FFMA):
+        e = engine_from(qz, flags=flags)
+        gc, gd = e.coarse_search(Q, w)
+        np.testing.assert_array_equal(gc, oc, err_msg=f"flags={flags}")
+        assert np.array_equal(gd.view(np.uint8), od.view(np.uint8)), f"flags={flags}"
+        e.close()
+
+
+@pytest.mark.parametrize("data", ["uniform", "blobs", "large_norm", "ties"])
+@pytest.mark.parametrize("D,kc,nq,w", [(128, 1024, 1000, 16), (128, 1024, 129, 1), (96, 4096, 300, 16),
+                                       (64, 300, 500, 8), (128, 256, 128, 32), (16, 700, 260, 5),
+                                       (128, 2048, 4000, 16)])
+def test_coarse_tensor_core_bit_exact(data, D, kc, nq, w):
+    """coarse_tc.cuh: TF32 tensor-core scores only prune; cells and distances must be bit-identical to the
+    oracle's direct form (src/coarsequantizers.jl:33-37), stable ties included.  COARSE_REDO sends every
+    query through the FFMA redo pass that serves candidate overflows."""
+    rng = np.random.default_rng(D * 7 + kc + w)
+    if data == "uniform":
+        cent = rng.random((kc, D)).astype(np.float32)
+        Q = rng.random((nq, D)).astype(np.float32)
+    elif data == "blobs":
+        cent = rng.random((kc, D)).astype(np.float32)
+        Q = (cent[rng.integers(0, kc, nq)] + 0.05 * rng.standard_normal((nq, D))).astype(np.float32)
+    elif data == "large_norm":  # distances small against the norms: the pruning margin is wide
+        cent = (100.0 + rng.random((kc, D))).astype(np.float32)
+        Q = (100.0 + rng.random((nq, D))).astype(np.float32)
+    else:  # many exact duplicates: more candidates than slots -> redo pass; lower cell index wins
+        base = rng.random((8, D)).astype(np.float32)
+        cent = base[rng.integers(0, 8, kc)].copy()
+        cent[::3] = rng.random((len(cent[::3]), D)).astype(np.float32)
+        Q = rng.random((nq, D)).astype(np.float32)
+    cb = rng.standard_normal((1, 4, D)).astype(np.float32)
+    qz = orc.Quantizers(cent, cb)
+    oc, od = orc.coarse_search(qz, Q, w, nthreads=4)
+    for flags in (LUT_EXACT, LUT_EXACT | COARSE_REDO):
         e = engine_from(qz, flags=flags)
         gc, gd = e.coarse_search(Q, w)
         np.testing.assert_array_equal(gc, oc, err_msg=f"flags={flags}")
