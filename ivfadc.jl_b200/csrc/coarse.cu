@@ -392,7 +392,7 @@ cudaError_t coarse_prepare(ivfadc_index* h, cudaStream_t s, int* launches) {
     if (kc >= ctc::NC && D % 16 == 0 && D <= 128) {
         h->kc_pad256 = (kc + ctc::NC - 1) / ctc::NC * ctc::NC;
         const int ksteps = D / 8;
-        const size_t words = (size_t)h->kc_pad256 * ksteps * 8;
+        const size_t words = (size_t)h->kc_pad256 * (ksteps + 1) * 8;
         if ((e = cudaMalloc(&h->d_tcC, words * sizeof(float))) != cudaSuccess) return e;
         if ((e = cudaMalloc(&h->d_ccn, ((size_t)h->kc_pad256 + 4) * sizeof(float))) != cudaSuccess) return e;
         if ((e = cudaMemsetAsync(h->d_ccn, 0, ((size_t)h->kc_pad256 + 4) * sizeof(float), s)) != cudaSuccess) return e;
@@ -400,7 +400,7 @@ cudaError_t coarse_prepare(ivfadc_index* h, cudaStream_t s, int* launches) {
             if ((e = cudaMalloc(&h->d_err, sizeof(int))) != cudaSuccess) return e;
             if ((e = cudaMemsetAsync(h->d_err, 0, sizeof(int), s)) != cudaSuccess) return e;
         }
-        const int64_t nthr = (int64_t)h->kc_pad256 * ksteps;
+        const int64_t nthr = (int64_t)h->kc_pad256 * (ksteps + 1);
         ctc::prep_tcc_kernel<<<(unsigned)((nthr + 255) / 256), 256, 0, s>>>(static_cast<const float*>(h->d_centroids), kc,
                                                                            h->kc_pad256, D, ksteps,
                                                                            static_cast<float*>(h->d_tcC));
@@ -458,7 +458,8 @@ cudaError_t launch_coarse(const ivfadc_index* h, const void* dQ, int64_t nq, int
         const float* Ct = static_cast<const float*>(h->d_centroids_t);
         float* dc = static_cast<float*>(d_dc);
         // tensor-core pruning + exact re-rank (coarse_tc.cuh); the FFMA kernel below redoes flagged queries
-        if (h->d_tcC && w <= 32 && w <= h->cfg.kc && !(h->cfg.flags & IVFADC_FLAG_COARSE_FFMA) &&
+        const int wl = w <= 1 ? 1 : w <= 8 ? 8 : w <= 16 ? 16 : 32;  // the bound needs wl finite group minima
+        if (h->d_tcC && w <= 32 && h->cfg.kc >= wl * ctc::GRP && !(h->cfg.flags & IVFADC_FLAG_COARSE_FFMA) &&
             (reinterpret_cast<uintptr_t>(dQ) & 15) == 0 &&
             ctc::smem_layout(D / 8).total <= (size_t)(227 * 1024)) {
             // redo flags [nq] | candidate counts [nq] | candidate rows [nq][CAP]
@@ -480,7 +481,14 @@ cudaError_t launch_coarse(const ivfadc_index* h, const void* dQ, int64_t nq, int
             else if (w <= 16) e = launch_coarse3_inst<16>(ca, grid, smem, s);
             else e = launch_coarse3_inst<32>(ca, grid, smem, s);
             if (e != cudaSuccess) return e;
-            ctc::coarse3_rerank_kernel<<<(unsigned)((nq + ctc::RR_WARPS - 1) / ctc::RR_WARPS), ctc::RR_WARPS * 32, 0, s>>>(ca);
+            const size_t rsmem = ctc::RR_WARPS * ctc::rr_warp_floats(D) * sizeof(float);
+            static size_t rr_configured = 0;
+            if (rsmem > rr_configured) {
+                e = cudaFuncSetAttribute(ctc::coarse3_rerank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem);
+                if (e != cudaSuccess) return e;
+                rr_configured = rsmem;
+            }
+            ctc::coarse3_rerank_kernel<<<(unsigned)((nq + ctc::RR_WARPS - 1) / ctc::RR_WARPS), ctc::RR_WARPS * 32, rsmem, s>>>(ca);
             if ((e = cudaGetLastError()) != cudaSuccess) return e;
             if (launches) *launches += 2;
             return launch_coarse2_r<1>(best, Q, Ct, nq, h->cfg.kc, h->kc_pad, D, w, d_cells, dc, s, ca.redo);
