@@ -186,7 +186,8 @@ def main():
                     help="N > 1: replay the sharded step from a CUDA graph (opt-in: measured gain at N = 2 is 3%%, and "
                          "tearing down a process group with captured NCCL work hung once)")
     ap.add_argument("--flags", type=int, default=0,
-                    help="ivfadc_config.flags (1 vector-per-lane scan, 2 query-per-lane scan, 4 exact tables, 8 mma.sync tables)")
+                    help="ivfadc_config.flags (1 vector-per-lane scan, 2 query-per-lane scan, 4 exact tables, 8 mma.sync tables, "
+                         "16 shared-memory tables, 32 scalar coarse, 128 packed-FP32 coarse)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     wl = WORKLOADS[args.workload]
@@ -400,6 +401,8 @@ def main():
                        "timing": "CUDA events on the launch stream, per step, mean", "flags": args.flags,
                        "scan": ("tensor-memory lookups: tcgen05.mma tables stay in TMEM, tcgen05.ld at column = code byte, "
                                 "persistent CTAs" if not (args.flags & 29) else "see flags"),
+                       "coarse": ("packed-FP32 FFMA kernel" if (args.flags & 160) else
+                                  "tcgen05 kind::tf32 scores prune to a provable superset of the top-w, exact direct-form re-rank"),
                        "tables": ("exact direct form (fp32 chain)" if (args.flags & 5) else
                                   "mma.sync 3xTF32 GEMM form" if (args.flags & 8) else
                                   "tcgen05 kind::tf32 3xTF32 GEMM form, accumulators in tensor memory, codebook operand by TMA")},

@@ -450,7 +450,8 @@ int ivfadc_search(ivfadc_index* h, const void* Q, int64_t nq, int32_t k, int32_t
         else CUDA_OR_FAIL(h, cudaMemcpy(&flag, h->d_err, sizeof(int), cudaMemcpyDeviceToHost), "D2H");
         if (flag) {
             cudaMemset(h->d_err, 0, sizeof(int));
-            const char* what = flag == 1 ? "tensor-core table builder: TMA operand never arrived"
+            const char* what = flag >= 11 ? "tensor-core coarse kernel: pipeline wait timed out (TMA / MMA / accumulator tile)"
+                             : flag == 1 ? "tensor-core table builder: TMA operand never arrived"
                              : flag == 2 ? "tensor-core table builder: MMA never completed"
                              : flag == 3 ? "tensor-core table builder: shared-memory plan does not fit"
                              : flag == 4 ? "tensor-core table builder: first A operands of a work item never written"

@@ -4,12 +4,15 @@
 // as a documented deviation, the approximate HNSW variant (src/coarsequantizers.jl:73-76).
 //
 // Distances are the DIRECT form sum_d (c_d - q_d)^2 evaluated as one sequential fma chain per
-// (query, centroid) pair -- bit-identical to the oracle (A1) -- on the FFMA pipe, register-tiled
-// 2 queries x 4 centroids per thread from padded shared-memory tiles (a 2 x 8 tile, TC = 128, was
-// measured slower on config B: 0.335 vs 0.277 ms, fewer resident CTAs for a 313-CTA grid); the top-w selection is
-// fused: after each 64-centroid tile every warp updates the warp-distributed sorted lists of its
-// 4 queries.  FP32 FFMA was chosen over 3xTF32 tcgen05 because selection must agree with the
-// oracle bit for bit and the whole step is < 10% of the search ("K1").
+// (query, centroid) pair -- bit-identical to the oracle (A1).  Three kernels, same bits:
+//   * coarse_tc.cuh (default where the shape allows): tcgen05 TF32 scores prune the centroids to a
+//     provable superset of the exact top-w, a second kernel re-ranks the survivors with the chain;
+//   * coarse2_kernel: packed-FP32 (FADD2 / FFMA2) on transposed centroids; also the redo pass of the
+//     tensor-core kernel (queries whose candidate slots overflowed);
+//   * coarse_kernel: scalar FFMA, any T / D; register-tiled 2 queries x 4 centroids per thread from padded
+//     shared-memory tiles (a 2 x 8 tile, TC = 128, was measured slower on config B: 0.335 vs 0.277 ms).
+// The FFMA kernels fuse the top-w selection: after each 64-centroid tile every warp updates the
+// warp-distributed sorted lists of its queries.
 #include "common.cuh"
 #include "warp_topk.cuh"
 #include "coarse_tc.cuh"
@@ -488,7 +491,9 @@ cudaError_t launch_coarse(const ivfadc_index* h, const void* dQ, int64_t nq, int
                 if (e != cudaSuccess) return e;
                 rr_configured = rsmem;
             }
-            ctc::coarse3_rerank_kernel<<<(unsigned)((nq + ctc::RR_WARPS - 1) / ctc::RR_WARPS), ctc::RR_WARPS * 32, rsmem, s>>>(ca);
+            const unsigned rr_need = (unsigned)((nq + ctc::RR_WARPS - 1) / ctc::RR_WARPS);
+            const unsigned rr_slots = (unsigned)num_sms * (unsigned)std::max<size_t>(1, (size_t)(227 * 1024) / (rsmem + 1024));
+            ctc::coarse3_rerank_kernel<<<std::min(rr_need, rr_slots), ctc::RR_WARPS * 32, rsmem, s>>>(ca);
             if ((e = cudaGetLastError()) != cudaSuccess) return e;
             if (launches) *launches += 2;
             return launch_coarse2_r<1>(best, Q, Ct, nq, h->cfg.kc, h->kc_pad, D, w, d_cells, dc, s, ca.redo);

@@ -250,7 +250,7 @@ __global__ void __launch_bounds__(THREADS, 1) coarse3_kernel(const Args a) {
     //      word(n, k) = (n >> 3) * 64 + (k >> 2) * 32 + (n & 7) * 4 + (k & 3)
     {
         const int nchunk = MQ * 2 * KS;  // 16-byte chunks (4 dims of one row)
-        constexpr int UNR = 8;           // loads in flight per thread
+        constexpr int UNR = 16;          // loads in flight per thread (D = 128: the whole share of a thread in one batch)
         for (int base = tid; base < nchunk; base += THREADS * UNR) {
             float4 v[UNR];
 #pragma unroll
@@ -458,23 +458,37 @@ __host__ __device__ inline size_t rr_warp_floats(int D) { return (size_t)32 * rr
 __global__ void __launch_bounds__(RR_WARPS * 32) coarse3_rerank_kernel(const Args a) {
     extern __shared__ __align__(16) float rr_smem[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int64_t q = (int64_t)blockIdx.x * RR_WARPS + wid;
-    if (q >= a.nq) return;
     const int w = a.w, D = a.D, D4 = D >> 2, stride = rr_stride(D);
-    // candidate row and count are fetched together (one round trip)
-    int cand_r[CAP / 32];
-#pragma unroll
-    for (int h = 0; h < CAP / 32; ++h) cand_r[h] = __ldg(a.cand_out + q * CAP + lane + 32 * h);
-    const int total = __ldg(a.cnt_out + q);
-    if (total < w) {  // overflow (-1); fewer than w cannot happen (the candidates contain the top w), never return garbage
-        if (lane == 0) a.redo[q] = 1;
-        return;
-    }
-    if (lane == 0) a.redo[q] = 0;
     float* rows = rr_smem + (size_t)wid * rr_warp_floats(D);
     float* qs = rows + 32 * stride;
     int* scratch = reinterpret_cast<int*>(qs + D);
     const uint32_t rows_u = smem_u32(rows), qs_u = smem_u32(qs);
+    // persistent warps: candidate row and count of the NEXT query are fetched (one round trip, together)
+    // while the current one is ranked
+    const int64_t qstep = (int64_t)gridDim.x * RR_WARPS;
+    int64_t q = (int64_t)blockIdx.x * RR_WARPS + wid;
+    int cand_n[CAP / 32], total_n = 0;
+    if (q < a.nq) {
+#pragma unroll
+        for (int h = 0; h < CAP / 32; ++h) cand_n[h] = __ldg(a.cand_out + q * CAP + lane + 32 * h);
+        total_n = __ldg(a.cnt_out + q);
+    }
+    for (; q < a.nq; q += qstep) {
+    int cand_r[CAP / 32];
+#pragma unroll
+    for (int h = 0; h < CAP / 32; ++h) cand_r[h] = cand_n[h];
+    const int total = total_n;
+    if (q + qstep < a.nq) {
+#pragma unroll
+        for (int h = 0; h < CAP / 32; ++h) cand_n[h] = __ldg(a.cand_out + (q + qstep) * CAP + lane + 32 * h);
+        total_n = __ldg(a.cnt_out + q + qstep);
+    }
+    if (total < w) {  // overflow (-1); fewer than w cannot happen (the candidates contain the top w), never return garbage
+        if (lane == 0) a.redo[q] = 1;
+        continue;
+    }
+    if (lane == 0) a.redo[q] = 0;
+    __syncwarp();  // the previous query's reads of scratch / qs are done
 #pragma unroll
     for (int h = 0; h < CAP / 32; ++h)
         if (lane + 32 * h < total) scratch[lane + 32 * h] = cand_r[h];
@@ -544,6 +558,7 @@ __global__ void __launch_bounds__(RR_WARPS * 32) coarse3_rerank_kernel(const Arg
             a.dc_out[q * w + rank[h]] = __uint_as_float((unsigned)(key[h] >> 32));
         }
     }
+    }  // queries of this warp
 }
 
 // Centroids -> B operand blocks [tile][k-steps + 1][2048 words], once at create: TF32(-2 c) per k-step of 8 dims,
