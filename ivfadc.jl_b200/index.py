@@ -315,6 +315,19 @@ def popfirst(ivfadc: IVFADCIndex):
 def delete_from_index(ivfadc: IVFADCIndex, points):
     """`points` are 1-based integers like in the reference."""
     maxid = 2 ** _TYPE_TO_BITS[ivfadc.I] - 1
+    arr = np.asarray(points)
+    if arr.ndim == 1 and arr.dtype.kind in "iu" and arr.dtype.itemsize <= 8 and arr.dtype != np.uint64:
+        # integer arrays: the same checks, vectorised (a 1 M-id delete is one C-ABI call, not 1 M Python steps)
+        v = arr.astype(np.int64) - 1
+        bad = (v < 0) | (v > maxid) if maxid < 2 ** 63 else (v < 0)
+        if bad.any():
+            raise OverflowError(f"InexactError: cannot convert {int(v[np.argmax(bad)])} to {ivfadc.I}")  # I.(points .- 1), :93
+        ids = v.astype(np.uint64)
+        if ids.size == 0:
+            return None
+        ids = np.ascontiguousarray(ids)
+        _capi.check(ivfadc._h, ivfadc._lib.ivfadc_delete(ivfadc._h, _capi.ptr(ids), len(ids)))
+        return None
     shifted = []
     for p in points:
         v = int(p) - 1
