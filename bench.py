@@ -37,6 +37,9 @@ WORKLOADS = {
               D=128, N=1_000_000, kc=1024, m=16, ksub=256, nq=10_000, k=10, w=16),
     "C": dict(name="Deep10M-shaped synthetic: 96-d, 10M vectors, kc=4096, m=12, SqEuclidean",
               D=96, N=10_000_000, kc=4096, m=12, ksub=256, nq=10_000, k=10, w=16),
+    "D8": dict(name="per-GPU shard of the 100M-vector config at 8 GPUs: 128-d, 12.5M vectors in 2048 of the 16384 cells, "
+                    "m=8 (dsub=16), 2 of a query's 16 probes land on this GPU",
+               D=128, N=12_500_000, kc=2048, m=8, ksub=256, nq=10_000, k=10, w=2),
     "S": dict(name="small smoke workload (not a bench line)",
               D=64, N=100_000, kc=128, m=16, ksub=256, nq=2_000, k=10, w=8),
 }
@@ -400,7 +403,7 @@ def main():
                        "l2": "flushed between steps (256 MiB write); the 16 MB code array is L2-resident within a step",
                        "timing": "CUDA events on the launch stream, per step, mean", "flags": args.flags,
                        "scan": ("tensor-memory lookups: tcgen05.mma tables stay in TMEM, tcgen05.ld at column = code byte, "
-                                "persistent CTAs" if not (args.flags & 29) else "see flags"),
+                                "persistent CTAs" if int(st.get("last_scan_kernel", 0)) == 4 else "see roofline.kernel"),
                        "coarse": ("packed-FP32 FFMA kernel" if (args.flags & 160) else
                                   "tcgen05 kind::tf32 scores prune to a provable superset of the top-w, exact direct-form re-rank"),
                        "tables": ("exact direct form (fp32 chain)" if (args.flags & 5) else
@@ -408,8 +411,8 @@ def main():
                                   "tcgen05 kind::tf32 3xTF32 GEMM form, accumulators in tensor memory, codebook operand by TMA")},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic,
-                         "kernel": ("scan_kernel" if (args.flags & 1) else "scanq_kernel" if (args.flags & 12) else
-                                    "scant_kernel" if (args.flags & 16) else "scanu_kernel") +
+                         "kernel": {1: "scan_kernel (vector per lane, exact tables)", 2: "scanq_kernel", 3: "scant_kernel",
+                                    4: "scanu_kernel"}.get(int(st.get("last_scan_kernel", 0)), "?") +
                                    " (K2 lookup tables + K3 list scan + per-list candidate selection)",
                          "algorithmic_bytes_per_launch": bytes_per_launch, "kernel_ms": scan_ms,
                          "peak_source": peak_src,

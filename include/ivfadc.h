@@ -133,7 +133,8 @@ typedef struct ivfadc_stats {
     double   merge_ms;
     double   encode_ms;
     uint64_t scan_launches;
-    uint64_t reserved[4];
+    uint64_t last_scan_kernel;  /* kernel of the last search: 1 vector-per-lane, 2 query-per-lane (scanq), 3 scant, 4 scanu */
+    uint64_t reserved[3];
 } ivfadc_stats;
 
 int ivfadc_abi_version(void);

@@ -28,7 +28,7 @@ struct Extra {
     uint64_t scanned_flushed = 0;
 };
 
-Extra* extra(ivfadc_index* h) { return reinterpret_cast<Extra*>(h->stats.reserved[3]); }
+Extra* extra(ivfadc_index* h) { return reinterpret_cast<Extra*>(h->stats.reserved[2]); }
 
 int fail(ivfadc_index* h, int code, const char* msg, cudaError_t e = cudaSuccess) {
     if (h) {
@@ -213,7 +213,7 @@ int ivfadc_create(ivfadc_index** out, const ivfadc_config* cfg, const void* cent
     h->dsub = cfg->dim / cfg->m;  // QuantizedArrays.rowrange: floor(D / m)
     h->tsize = cfg->dtype == IVFADC_F32 ? 4 : 8;
     h->id_dev_bytes = cfg->id_bytes <= 4 ? 4 : 8;
-    h->stats.reserved[3] = reinterpret_cast<uint64_t>(x);
+    h->stats.reserved[2] = reinterpret_cast<uint64_t>(x);
 
     const size_t cbytes = (size_t)cfg->kc * cfg->dim * h->tsize;
     const size_t vbytes = (size_t)cfg->m * cfg->ksub * h->dsub * h->tsize;
@@ -659,7 +659,7 @@ int ivfadc_get_stats(ivfadc_index* h, ivfadc_stats* out) {
         h->stats.scan_code_bytes = scanned * (uint64_t)h->cfg.m;
     }
     *out = h->stats;
-    out->reserved[3] = 0;
+    out->reserved[2] = 0;
     return IVFADC_OK;
 }
 
@@ -667,9 +667,9 @@ int ivfadc_reset_stats(ivfadc_index* h) {
     if (check_handle(h)) return IVFADC_ERR_BAD_ARG;
     cudaSetDevice(h->cfg.device);
     flush_all(h);
-    const uint64_t keep = h->stats.reserved[3];
+    const uint64_t keep = h->stats.reserved[2];
     h->stats = ivfadc_stats{};
-    h->stats.reserved[3] = keep;
+    h->stats.reserved[2] = keep;
     cudaMemset(extra(h)->d_scanned, 0, sizeof(uint64_t));
     return IVFADC_OK;
 }

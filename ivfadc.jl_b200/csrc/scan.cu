@@ -516,34 +516,53 @@ bool scanq_shape_ok(const ivfadc_index* h, int k) {
 // vector-per-lane kernel, IVFADC_FLAG_SCAN_QLANE forces the query-per-lane kernel whenever the
 // shape allows it; otherwise the query-per-lane kernel is used when its 32-query groups are
 // reasonably full (>= 8 probes per list on average).
+int scanu_dup(const ivfadc_index* h);
 bool use_scanq(const ivfadc_index* h, int64_t npairs, int k) {
     if (h->cfg.flags & IVFADC_FLAG_SCAN_LEGACY) return false;
     if (!scanq_shape_ok(h, k)) return false;
     if (h->cfg.flags & IVFADC_FLAG_SCAN_QLANE) return true;
-    return npairs >= (int64_t)8 * h->cfg.kc;
+    if (npairs < (int64_t)8 * h->cfg.kc) return false;
+    // Cost model from the measured runs ("which scan kernel"): a query-per-lane work item costs the
+    // same whether 5 or 32 queries share it -- kc (n/32 + 1/2) items of ceil(L / 1024) passes of `tables` table
+    // builds + scans at ~0.0099 us of GPU time each -- while the vector-per-lane kernel streams the pairs' code
+    // bytes at ~1.3 TB/s.  Few queries per (long) list, as in config D (10 per list of 6100), favour the latter.
+    const double kc = (double)h->cfg.kc, nbar = (double)npairs / kc;
+    const double lbar = std::max(1.0, (double)h->n_local / kc);
+    const int tables = h->cfg.m * ((h->dsub <= 8 || h->dsub == 16) ? scanu_dup(h) : 1);
+    const double est_q = kc * (nbar / 32.0 + 0.5) * std::ceil(lbar / 1024.0) * tables * 0.0099;
+    const double est_v = (double)npairs * lbar * h->cfg.m / 1.3e6;
+    return est_q < est_v;
 }
 
-// tensor-memory lookup kernel (scanu_impl.cuh), the default: fp32, k <= 16, m in {4, 8, 12, 16}, dsub <= 8
+// tensor-memory lookup kernel (scanu_impl.cuh), the default: fp32, k <= 16, m in {4, 8, 12, 16} with dsub <= 8,
+// or m in {4, 8} with dsub = 16 (two 8-dim tables per code byte)
+int scanu_dup(const ivfadc_index* h) { return h->dsub == 16 ? 2 : 1; }
+bool scanu_shape_ok(const ivfadc_index* h) {
+    const int mt = h->cfg.m * scanu_dup(h);
+    return (h->dsub <= 8 || h->dsub == 16) && h->cfg.m % 4 == 0 && mt <= 16 && scanu_smem_layout(mt).total + 1024 <= kSmemMax;
+}
 bool use_scanu(const ivfadc_index* h) {
     if (h->cfg.flags & (IVFADC_FLAG_LUT_EXACT | IVFADC_FLAG_LUT_MMASYNC | IVFADC_FLAG_SCAN_SMEMLUT)) return false;
-    return h->d_tcU != nullptr && h->dsub <= 8 && h->cfg.m % 4 == 0 && h->cfg.m <= 16 &&
-           scanu_smem_layout(h->cfg.m).total + 1024 <= kSmemMax;
+    return h->d_tcU != nullptr && scanu_shape_ok(h);
 }
 
-template <int NP, bool DBG>
+template <int NP, bool DBG, int DUP>
 cudaError_t launch_scanu_inst(const ScanUArgs& ua, unsigned grid, size_t smem, cudaStream_t s) {
     static size_t configured = 0;
     if (smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(scanu_kernel<NP, DBG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(scanu_kernel<NP, DBG, DUP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         configured = smem;
     }
-    scanu_kernel<NP, DBG><<<grid, QTHREADS, smem, s>>>(ua);
+    scanu_kernel<NP, DBG, DUP><<<grid, QTHREADS, smem, s>>>(ua);
     return cudaGetLastError();
 }
-template <int NP>
+template <int NP, int DUP = 1>
 cudaError_t launch_scanu_np(const ScanUArgs& ua, unsigned grid, size_t smem, cudaStream_t s) {
-    return ua.dbg ? launch_scanu_inst<NP, true>(ua, grid, smem, s) : launch_scanu_inst<NP, false>(ua, grid, smem, s);
+    if constexpr (DUP == 1) {
+        if (ua.dbg) return launch_scanu_inst<NP, true, 1>(ua, grid, smem, s);  // table dump / timeline (bring-up, dsub <= 8)
+    }
+    return launch_scanu_inst<NP, false, DUP>(ua, grid, smem, s);
 }
 
 // tcgen05 table builder with shared-memory tables (scant_impl.cuh): fp32, k <= 16, m in {4, 8, 12, 16}, dsub <= 8
@@ -638,6 +657,7 @@ cudaError_t search_t(ivfadc_index* h, const void* dQ, int64_t nq, int k, int w, 
         *launches += 1;
     }
     if (h->stats_timing) cudaEventRecord(h->ev[2], s);
+    h->stats.last_scan_kernel = !qlane ? 1 : use_scanu(h) ? 4 : use_scant(h) ? 3 : 2;
     if (qlane) {
         if constexpr (sizeof(T) == 4) {
             ScanQArgs qa;
@@ -662,13 +682,20 @@ cudaError_t search_t(ivfadc_index* h, const void* dQ, int64_t nq, int k, int w, 
                     cudaGetDevice(&dev);
                     if ((e = cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
                 }
-                const size_t usmem = scanu_smem_layout(a.m).total;
+                const int dup = scanu_dup(h);
+                const size_t usmem = scanu_smem_layout(a.m * dup).total;
                 const unsigned ugrid = (unsigned)std::min<int64_t>(max_items, num_sms);  // persistent: one CTA per SM
-                switch (a.m) {
-                    case 4: e = launch_scanu_np<1>(uq, ugrid, usmem, s); break;
-                    case 8: e = launch_scanu_np<2>(uq, ugrid, usmem, s); break;
-                    case 12: e = launch_scanu_np<3>(uq, ugrid, usmem, s); break;
-                    default: e = launch_scanu_np<4>(uq, ugrid, usmem, s); break;
+                if (dup == 2) {  // dsub = 16: two 8-dim tables per code byte
+                    uq.q.dsub = 8;
+                    if (a.m == 4) e = launch_scanu_np<1, 2>(uq, ugrid, usmem, s);
+                    else e = launch_scanu_np<2, 2>(uq, ugrid, usmem, s);
+                } else {
+                    switch (a.m) {
+                        case 4: e = launch_scanu_np<1>(uq, ugrid, usmem, s); break;
+                        case 8: e = launch_scanu_np<2>(uq, ugrid, usmem, s); break;
+                        case 12: e = launch_scanu_np<3>(uq, ugrid, usmem, s); break;
+                        default: e = launch_scanu_np<4>(uq, ugrid, usmem, s); break;
+                    }
                 }
                 if (e != cudaSuccess) return e;
                 *launches += 1;
@@ -791,13 +818,18 @@ cudaError_t scanq_prepare(ivfadc_index* h, cudaStream_t s, int* launches) {
         if (launches) *launches += 1;
     }
     // operand blocks of the tensor-memory lookup kernel (rows = code values)
-    if (h->dsub <= 8 && m % 4 == 0) {
-        const size_t bytes = (size_t)m * U_BSUB;
+    if (scanu_shape_ok(h)) {
+        const int dup = scanu_dup(h);
+        const size_t bytes = (size_t)m * dup * U_BSUB;
         if ((e = cudaMalloc(&h->d_tcU, bytes)) != cudaSuccess) return e;
         if ((e = cudaMemsetAsync(h->d_tcU, 0, bytes, s)) != cudaSuccess) return e;
-        const int n = m * h->cfg.ksub;
+        if (!h->d_err) {
+            if ((e = cudaMalloc(&h->d_err, sizeof(int))) != cudaSuccess) return e;
+            if ((e = cudaMemsetAsync(h->d_err, 0, sizeof(int), s)) != cudaSuccess) return e;
+        }
+        const int n = m * dup * h->cfg.ksub;
         prep_tcu_kernel<<<(n + 255) / 256, 256, 0, s>>>(static_cast<const float*>(h->d_cb), h->d_cb_codes,
-                                                        h->cb_identity ? 1 : 0, m, h->cfg.ksub, h->dsub,
+                                                        h->cb_identity ? 1 : 0, m, h->cfg.ksub, h->dsub, dup,
                                                         static_cast<float*>(h->d_tcU));
         if (launches) *launches += 1;
     }

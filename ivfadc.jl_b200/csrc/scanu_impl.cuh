@@ -193,13 +193,17 @@ __device__ __forceinline__ void scanu_sub(uint32_t tb, uint32_t plane_w, uint32_
     }
 }
 
-// NP = m / 4: 32-bit code words per database vector
-template <int NP, bool DBG>
+// NP = (code bytes per vector) / 4: 32-bit code words per database vector.
+// DUP = 2 serves dsub = 16 (config D: m = 8): a 16-dim subspace is scanned as TWO tables of 8 dims that share
+// the code byte -- |r - w|^2 splits over the dims, so entry(code) = entry_lo(code) + entry_hi(code); the kernel
+// runs m = 2 * (code bytes) tables of 8 dims, table s reads byte plane s / 2 (a.dsub is passed as 8).
+template <int NP, bool DBG, int DUP = 1>
 __global__ void __launch_bounds__(QTHREADS, 1)
 scanu_kernel(const ScanUArgs ua) {
     const ScanQArgs& a = ua.q;
     extern __shared__ __align__(1024) unsigned char smem_u[];
-    constexpr int m = 4 * NP;
+    constexpr int mc = 4 * NP;      // code bytes per vector
+    constexpr int m = mc * DUP;     // tables per work item
     constexpr int SB = m / 4, SC = m / 2;  // subspace iterations at which warp 0 advances the descriptor prefetch
     const int tid = threadIdx.x;
     const int lane = tid & 31;
@@ -341,7 +345,7 @@ scanu_kernel(const ScanUArgs ua) {
         if (tid < U_VP / 4) {
             const int64_t vb = (int64_t)pass_n * U_VP;
             const int nvn = (int)min((int64_t)U_VP, len_n - vb);
-            const uint32_t* src = reinterpret_cast<const uint32_t*>(a.codes + (size_t)off_n * m) + (size_t)vb * NP;
+            const uint32_t* src = reinterpret_cast<const uint32_t*>(a.codes + (size_t)off_n * mc) + (size_t)vb * NP;
             const int v0 = 4 * tid;
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
@@ -581,7 +585,7 @@ scanu_kernel(const ScanUArgs ua) {
             if (s + 2 < m && wid >= QWARPS - 4) write_A(s + 2, wid - (QWARPS - 4));  // build s has completed: its A slot is free
             // s and t are warp-uniform, but ptxas keeps the loop counter in a vector register unless told (one SHFL each)
             const uint32_t tb = tq + (__shfl_sync(0xffffffffu, t, 0) & 1) * 256;
-            const uint32_t plane_w = plane_w0 + __shfl_sync(0xffffffffu, s, 0) * T_PLANE;
+            const uint32_t plane_w = plane_w0 + (__shfl_sync(0xffffffffu, s, 0) / DUP) * T_PLANE;
             // ONE code path for every subspace (the accumulators start at dc + |r|^2): the loop body stays
             // within the instruction cache
             if (nch == 4) scanu_sub<false, true>(tb, plane_w, cstep, nch, base, acc);
@@ -794,16 +798,18 @@ scanu_kernel(const ScanUArgs ua) {
 // is the codeword whose code VALUE is n (reference: LittleDict keyed by cb.codes, src/index.jl:235),
 // so that the scan addresses the accumulator tile with the stored code byte directly.
 // Block layout (fp32 words): word(n, k) = (n >> 3) * 64 + (k >> 2) * 32 + (n & 7) * 4 + (k & 3).
+// dup = 2 (dsub = 16): table t = 2 s + half holds dims 8 half .. 8 half + 7 of subspace s.
 __global__ void prep_tcu_kernel(const float* __restrict__ cb, const uint8_t* __restrict__ cb_codes, int identity,
-                                int m, int ksub, int dsub, float* __restrict__ out) {
+                                int m, int ksub, int dsub, int dup, float* __restrict__ out) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= m * ksub) return;
-    const int s = idx / ksub, n = idx - s * ksub;
+    if (idx >= m * dup * ksub) return;
+    const int t = idx / ksub, n = idx - t * ksub;
+    const int s = t / dup, d0 = (t - s * dup) * 8;
     const int row = identity ? n : (int)cb_codes[(size_t)s * ksub + n];
-    float* o = out + (size_t)s * (U_BSUB / 4);
+    float* o = out + (size_t)t * (U_BSUB / 4);
     float nrm = 0.f;
     for (int kk = 0; kk < 8; ++kk) {
-        const float w = kk < dsub ? cb[((size_t)s * ksub + n) * dsub + kk] : 0.f;
+        const float w = d0 + kk < dsub ? cb[((size_t)s * ksub + n) * dsub + d0 + kk] : 0.f;
         nrm = fma_rn(w, w, nrm);
         const float v = -2.f * w;
         const float hi = __uint_as_float(to_tf32(v));

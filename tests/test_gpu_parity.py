@@ -258,7 +258,8 @@ def test_search_ties_and_duplicates():
 @pytest.mark.parametrize("D,m,ksub,kc,n,nq,k,w,identity", [
     (128, 16, 256, 64, 20000, 500, 10, 16, True),    # config-B-shaped: ~125 queries per list
     (96, 12, 256, 128, 30000, 300, 10, 16, True),    # config-C-shaped (m = 12: 3 table chunks)
-    (128, 8, 256, 32, 20000, 300, 10, 8, True),      # config-D-shaped (m = 8, dsub = 16)
+    (128, 8, 256, 32, 20000, 300, 10, 8, True),      # config-D-shaped (m = 8, dsub = 16: two 8-dim tables per code byte)
+    (64, 4, 200, 40, 10000, 200, 10, 8, False),      # m = 4, dsub = 16, permuted code values, ksub < 256
     (128, 16, 256, 8, 20000, 100, 16, 8, True),      # 2500-vector lists: 3 passes of 1024, k = 16
     (40, 8, 100, 16, 5000, 200, 1, 4, False),        # dsub = 5 (generic), ksub < 256, permuted codes, k = 1
     (35, 4, 37, 50, 3000, 77, 7, 50, False),         # trailing dims ignored, tiny lists, w = kc
