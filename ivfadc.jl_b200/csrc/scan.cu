@@ -289,8 +289,33 @@ merge_cands_kernel(int64_t nq, int w, int k, int ps, int cap, const int32_t* __r
     }
     __syncwarp();
     int e = 0;
-    if (M <= cap) {  // cap = MC_CAP (tests lower it to drive ordinary data through the sweep path)
-        // 3. k rounds of warp arg-min; lane holds entries lane, lane + 32, lane + 64, lane + 96
+    bool done = false;
+    if (M <= 32 && M <= cap) {
+        // 3a. the common case -- at most one candidate per lane, no two equal distances: every lane counts the
+        // smaller distances (independent shuffles of the order-preserving bit pattern) and the lanes of rank < k
+        // write their result, id gathers in parallel.  Same order as 3b: (distance, probe rank, position).
+        const bool have = lane < M;
+        const float dm = have ? s_d[wq][lane] : inf;
+        const uint64_t km = have ? s_k[wq][lane] : ~0ull;
+        const uint32_t kd = have ? f_flip(dm + 0.f) : 0xFFFFFFFFu;   // + 0: -0 and +0 compare equal, as in key_less
+        const unsigned same = __match_any_sync(0xffffffffu, kd);
+        if (__all_sync(0xffffffffu, !have || __popc(same) == 1)) {
+            int rk = 0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) rk += __shfl_sync(0xffffffffu, kd, j) < kd ? 1 : 0;
+            if (have && rk < k) {
+                const int cell = cells[q * w + (int)(km >> 32)];
+                out_ids[q * k + rk] = (uint64_t)ids_arena[list_off[cell] + (uint32_t)km];
+                out_d[q * k + rk] = dm;
+                if (out_keys) out_keys[q * k + rk] = km;
+            }
+            e = min(M, k);
+            done = true;
+        }
+    }
+    if (done) {
+    } else if (M <= cap) {  // cap = MC_CAP (tests lower it to drive ordinary data through the sweep path)
+        // 3b. k rounds of warp arg-min; lane holds entries lane, lane + 32, lane + 64, lane + 96
         float d[4];
         uint64_t key[4];
 #pragma unroll
