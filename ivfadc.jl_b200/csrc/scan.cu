@@ -29,16 +29,21 @@ __global__ void plan_count_kernel(const int32_t* __restrict__ cells, int64_t npa
             mylen = (unsigned long long)len;
         }
     }
-    if (scanned) {
+    if (scanned) {  // one global atomic per block (a per-warp atomic on one address serialises 5 000 of them per batch)
+        __shared__ unsigned long long blk;
+        if (threadIdx.x == 0) blk = 0ull;
+        __syncthreads();
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) mylen += __shfl_xor_sync(0xffffffffu, mylen, o);
-        if ((threadIdx.x & 31) == 0 && mylen) atomicAdd(scanned, mylen);
+        if ((threadIdx.x & 31) == 0 && mylen) atomicAdd(&blk, mylen);
+        __syncthreads();
+        if (threadIdx.x == 0 && blk) atomicAdd(scanned, blk);
     }
 }
 
 // Single CTA: exclusive scans of pairs-per-bucket and groups-per-bucket.
 __global__ void __launch_bounds__(1024)
-plan_scan_kernel(const int* __restrict__ bucket_cnt, int nb, int qn, int* bucket_off, int* group_off) {
+plan_scan_kernel(const int* __restrict__ bucket_cnt, int nb, int qn, int* bucket_off, int* group_off, int4* items) {
     __shared__ int s_p[1024], s_g[1024];
     const int t = threadIdx.x;
     const int per = (nb + 1023) / 1024;
@@ -64,6 +69,10 @@ plan_scan_kernel(const int* __restrict__ bucket_cnt, int nb, int qn, int* bucket
         const int c = bucket_cnt[b];
         bucket_off[b] = op;
         group_off[b] = og;
+        if (items) {  // work-item table of the tensor-core kernels: (cell, first pair slot, number of pairs, 0)
+            int g = og;
+            for (int p = op; p < op + c; p += qn, ++g) items[g] = make_int4(b, p, min(qn, op + c - p), 0);
+        }
         op += c;
         og += (c + qn - 1) / qn;
     }
@@ -87,14 +96,6 @@ __global__ void plan_scatter_kernel(const int32_t* __restrict__ cells, int64_t n
 }
 
 // Work-item table of the query-per-lane kernels: item -> (cell, first pair slot, number of pairs).
-__global__ void plan_items_kernel(const int* __restrict__ bucket_off, const int* __restrict__ group_off, int kc,
-                                  int qn, int4* __restrict__ items) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= kc) return;
-    const int p1 = bucket_off[c + 1];
-    int g = group_off[c];
-    for (int p = bucket_off[c]; p < p1; p += qn, ++g) items[g] = make_int4(c, p, min(qn, p1 - p), 0);
-}
 
 // ---------------------------------------------------------------------------------------------
 // Final merge, one warp per query: k-way merge of L sorted candidate lists (lane l owns lists
@@ -654,7 +655,9 @@ cudaError_t search_t(ivfadc_index* h, const void* dQ, int64_t nq, int k, int w, 
     const int split = qlane ? 0 : 1;
     plan_count_kernel<bits_t><<<pgrid, pthreads, 0, s>>>(d_cells, npairs, nq, w, kc, split, h->d_len, bucket_cnt,
                                                          thr, inf_bits, (unsigned long long*)d_scanned);
-    plan_scan_kernel<<<1, 1024, 0, s>>>(bucket_cnt, nb, qn, bucket_off, group_off);
+    const bool want_items = qlane && (use_scanu(h) || use_scant(h));  // nb = kc there: bucket = cell
+    plan_scan_kernel<<<1, 1024, 0, s>>>(bucket_cnt, nb, qn, bucket_off, group_off,
+                                        want_items ? h->ws_items.as<int4>() : nullptr);
     plan_scatter_kernel<<<pgrid, pthreads, 0, s>>>(d_cells, npairs, w, kc, split, h->d_len, bucket_off, cursor,
                                                    sorted_pairs);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
@@ -677,10 +680,6 @@ cudaError_t search_t(ivfadc_index* h, const void* dQ, int64_t nq, int k, int w, 
     // upper bound on the number of work items: every bucket adds at most one partial group
     int64_t max_items = std::min<int64_t>(npairs, npairs / qn + nb);
     if (max_items < 1) max_items = 1;
-    if (qlane && (use_scanu(h) || use_scant(h))) {
-        plan_items_kernel<<<(kc + 255) / 256, 256, 0, s>>>(bucket_off, group_off, kc, QG, h->ws_items.as<int4>());
-        *launches += 1;
-    }
     if (h->stats_timing) cudaEventRecord(h->ev[2], s);
     h->stats.last_scan_kernel = !qlane ? 1 : use_scanu(h) ? 4 : use_scant(h) ? 3 : 2;
     if (qlane) {
