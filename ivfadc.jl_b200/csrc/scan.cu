@@ -13,6 +13,8 @@ namespace {
 // from one pass over a list.  Two bucket classes per list: probe rank 0 (scheduled first: the
 // nearest cell gives each query a tight k-th-distance bound early) and ranks >= 1.
 // ---------------------------------------------------------------------------------------------
+constexpr int PLAN_PAD = 32;  // ints per bucket in the counter array: one 128-byte line each
+
 template <typename BitsT>
 __global__ void plan_count_kernel(const int32_t* __restrict__ cells, int64_t npairs, int64_t nq, int w,
                                   int kc, int split, const int64_t* __restrict__ list_len, int* bucket_cnt,
@@ -25,7 +27,7 @@ __global__ void plan_count_kernel(const int32_t* __restrict__ cells, int64_t npa
         const int64_t len = (cell >= 0 && cell < kc) ? list_len[cell] : 0;
         if (len > 0) {
             const int rank = (int)(p % w);
-            atomicAdd(&bucket_cnt[((split && rank) ? kc : 0) + cell], 1);
+            atomicAdd(&bucket_cnt[(size_t)(((split && rank) ? kc : 0) + cell) * PLAN_PAD], 1);
             mylen = (unsigned long long)len;
         }
     }
@@ -50,7 +52,7 @@ plan_scan_kernel(const int* __restrict__ bucket_cnt, int nb, int qn, int* bucket
     const int lo = min(nb, t * per), hi = min(nb, lo + per);
     int sp = 0, sg = 0;
     for (int b = lo; b < hi; ++b) {
-        const int c = bucket_cnt[b];
+        const int c = bucket_cnt[(size_t)b * PLAN_PAD];
         sp += c;
         sg += (c + qn - 1) / qn;
     }
@@ -66,7 +68,7 @@ plan_scan_kernel(const int* __restrict__ bucket_cnt, int nb, int qn, int* bucket
     }
     int op = s_p[t] - sp, og = s_g[t] - sg;
     for (int b = lo; b < hi; ++b) {
-        const int c = bucket_cnt[b];
+        const int c = bucket_cnt[(size_t)b * PLAN_PAD];
         bucket_off[b] = op;
         group_off[b] = og;
         if (items) {  // work-item table of the tensor-core kernels: (cell, first pair slot, number of pairs, 0)
@@ -82,6 +84,8 @@ plan_scan_kernel(const int* __restrict__ bucket_cnt, int nb, int qn, int* bucket
     }
 }
 
+// (PLAN_PAD: the per-bucket counter and cursor sit in a 128-byte line of their own -- 32 neighbouring counters in
+// one line serialise the atomics of a batch in the L2)
 __global__ void plan_scatter_kernel(const int32_t* __restrict__ cells, int64_t npairs, int w, int kc,
                                     int split, const int64_t* __restrict__ list_len,
                                     const int* __restrict__ bucket_off, int* cursor,
@@ -91,7 +95,7 @@ __global__ void plan_scatter_kernel(const int32_t* __restrict__ cells, int64_t n
     const int cell = cells[p];
     if (cell < 0 || cell >= kc || list_len[cell] <= 0) return;
     const int b = ((split && (p % w)) ? kc : 0) + cell;
-    const int slot = bucket_off[b] + atomicAdd(&cursor[b], 1);
+    const int slot = bucket_off[b] + atomicAdd(&cursor[(size_t)b * PLAN_PAD], 1);
     sorted_pairs[slot] = (int32_t)p;
 }
 
@@ -631,12 +635,13 @@ cudaError_t search_t(ivfadc_index* h, const void* dQ, int64_t nq, int k, int w, 
     cudaError_t e;
 
     // workspaces (sizes validated / reserved by the caller through scan_plan_sizes)
-    int* bucket_cnt = h->ws_bucket.as<int>();  // [2kc] counts | [2kc] cursor | [2kc+1] off | [2kc+1] groups | redo_cnt
-    int* cursor = bucket_cnt + 2 * kc;
-    int* bucket_off = cursor + 2 * kc;
-    int* group_off = bucket_off + 2 * kc + 1;
-    int* redo_cnt = group_off + 2 * kc + 1;
+    // [2kc][PLAN_PAD] (word 0 count, word 1 cursor) | redo_cnt | item_counter | [2kc+1] off | [2kc+1] groups
+    int* bucket_cnt = h->ws_bucket.as<int>();
+    int* cursor = bucket_cnt + 1;
+    int* redo_cnt = bucket_cnt + (size_t)2 * kc * PLAN_PAD;
     int* item_counter = redo_cnt + 1;
+    int* bucket_off = item_counter + 1;
+    int* group_off = bucket_off + 2 * kc + 1;
     int32_t* sorted_pairs = h->ws_sorted.as<int32_t>();
     int32_t* redo_pairs = sorted_pairs + npairs;
     T* pair_d = h->ws_pair_d.as<T>();
@@ -644,7 +649,8 @@ cudaError_t search_t(ivfadc_index* h, const void* dQ, int64_t nq, int k, int w, 
     int32_t* pair_cnt = h->ws_pair_cnt.as<int32_t>();
     bits_t* thr = h->ws_thr.as<bits_t>();
 
-    if ((e = cudaMemsetAsync(bucket_cnt, 0, sizeof(int) * (size_t)(8 * kc + 4), s)) != cudaSuccess) return e;
+    if ((e = cudaMemsetAsync(bucket_cnt, 0, sizeof(int) * (size_t)nb * PLAN_PAD, s)) != cudaSuccess) return e;
+    if ((e = cudaMemsetAsync(redo_cnt, 0, 2 * sizeof(int), s)) != cudaSuccess) return e;
     if ((e = cudaMemsetAsync(pair_cnt, 0, sizeof(int32_t) * npairs, s)) != cudaSuccess) return e;
 
     const int pthreads = 256;
@@ -876,7 +882,7 @@ ScanPlanSizes scan_plan_sizes(const ivfadc_index* h, int64_t nq, int w, int k) {
     ScanPlanSizes z;
     const int64_t npairs = nq * w;
     const int nb = 2 * h->cfg.kc;
-    z.bucket_bytes = sizeof(int) * (size_t)(4 * nb + 4);
+    z.bucket_bytes = sizeof(int) * ((size_t)nb * PLAN_PAD + 2 * (size_t)nb + 8);
     z.sorted_bytes = sizeof(int32_t) * (size_t)npairs * 2;  // sorted pairs | redo queue
     const int ps = pair_stride(h, npairs, k);
     z.pair_d_bytes = h->tsize * (size_t)npairs * ps;

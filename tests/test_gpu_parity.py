@@ -307,6 +307,29 @@ def test_search_qlane_bit_exact(D, m, ksub, kc, n, nq, k, w, identity):
         e.close()
 
 
+def test_scan_kernel_choice():
+    """The engine picks the scan kernel from a cost model ("which scan kernel"): many queries per list ->
+    the tensor-memory query-per-lane kernel (4), few queries per long list (config-D-like) -> vector per lane (1).
+    Both answers stay within the tolerance bar of the oracle."""
+    from ivfadc_jl_b200 import synth
+    for (D, m, kc, n, nq, w, want) in ((128, 16, 16, 16000, 600, 8, 4), (128, 8, 64, 64000, 100, 8, 1)):
+        X = synth.blobs(n, D, kc, seed=31)
+        cent, cb, codes = synth.random_quantizers(kc, D, m, 256, seed=7, data=X)
+        cent = synth.blob_centres(D, kc)   # balanced lists of n / kc vectors
+        qz = orc.Quantizers(cent, cb, codes)
+        cells, ocodes = orc.encode(qz, X, nthreads=8)
+        order = np.argsort(cells, kind="stable")
+        offsets = np.zeros(kc + 1, dtype=np.int64)
+        np.cumsum(np.bincount(cells, minlength=kc), out=offsets[1:])
+        Q = synth.blobs(nq, D, kc, seed=32)
+        oi, od, oc, _ = orc.search_csr(qz, offsets, ocodes[order], order.astype(np.uint64), Q, 10, w, nthreads=8)
+        e = engine_from(qz, np.uint32, X, flags=0)
+        gi, gd, gc = e.search_packed(Q, 10, w)
+        assert e.stats()["last_scan_kernel"] == want, (want, e.stats())
+        orc.compare_search(gi, gd, gc, oi, od, oc, rtol=RTOL)
+        e.close()
+
+
 @pytest.mark.parametrize("D,m,ksub,identity", [(128, 16, 256, True), (96, 12, 256, True), (40, 8, 100, False),
                                                (16, 4, 256, True)])
 def test_tcgen05_tables_against_fp64(D, m, ksub, identity):
