@@ -210,6 +210,9 @@ def main():
     dev = torch.device("cuda", local_rank)
     dist = None
     if world > 1:
+        # rank 0 prints ONE JSON line on stdout: keep NCCL's version banner (NCCL_DEBUG=VERSION in this image) off it
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
 
