@@ -50,6 +50,9 @@ def _dtype_code(dt):
     raise TypeError(f"IVFADCIndex needs an AbstractFloat element type (Float32/Float64), got {dt}")
 
 
+DEVICE_TRAINING_PAIRS = 1 << 22   # nvectors * kc from which the constructor trains on the GPU
+
+
 class IVFADCIndex:
     """IVFADCIndex{U,I,Dc,Dr,T,Q} (src/index.jl:39-48) with device-resident lists."""
 
@@ -79,9 +82,14 @@ class IVFADCIndex:
         if quantization_method != "pq":
             raise NotImplementedError("only quantization_method=:pq is on the hot path (SURVEY 8f-4)")
         X = np.ascontiguousarray(data.T)  # [nvectors, nrows]: the same bytes Julia holds
-        # training stays outside the engine (Clustering.jl / QuantizedArrays.jl in production)
-        centroids, assign, cb_vectors, cb_codes = training.train_quantizers(
-            X, kc, k, m, coarse_maxiter, quantization_maxiter, seed)
+        # training stays outside the engine's parity scope (Clustering.jl / QuantizedArrays.jl in production);
+        # beyond toy sizes the Lloyd iterations run on the GPU, their assignment step being the engine's K1
+        if nvectors * kc >= DEVICE_TRAINING_PAIRS:
+            centroids, assign, cb_vectors, cb_codes = training.train_quantizers_device(
+                X, kc, k, m, coarse_maxiter, quantization_maxiter, seed, device)
+        else:
+            centroids, assign, cb_vectors, cb_codes = training.train_quantizers(
+                X, kc, k, m, coarse_maxiter, quantization_maxiter, seed)
         self._init_from_quantizers(centroids, cb_vectors, cb_codes, index_type, coarse_quantizer,
                                    coarse_distance, quantization_distance, device, shard, flags)
         # _build_residuals + _build_inverted_index (src/index.jl:168-194): k-means' own

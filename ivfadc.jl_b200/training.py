@@ -106,3 +106,88 @@ def kmeans_torch(X, k: int, iters: int = 10, seed: int = 0, chunk: int = 1 << 18
         if (~nz).any():
             centers[~nz] = X[torch.randint(0, n, (int((~nz).sum()),), generator=g).to(X.device)].float()
     return centers
+
+
+# ---------------------------------------------------------------------------------------------
+# Device trainer: Lloyd iterations whose assignment step is the engine's own coarse
+# kernel (K1: exact nearest centre in the reference's direct form, tensor-core pruned where the
+# shape allows) -- what makes IVFADCIndex(data; ...) practical at 10^6+ vectors, where the host
+# trainer above would need an n x kc float64 distance matrix.  torch carries the device buffers and
+# the centre update (index_add); seeding is k-means++ on a sample.  Not parity-graded (the
+# reference's training is unseeded); graded by quantisation error against the host trainer
+# (tests/test_gpu_parity.py::test_device_trainer).
+# ---------------------------------------------------------------------------------------------
+def _dummy_codebook(d: int, dtype):
+    """The engine wants a product quantizer next to the centroids; training only uses the coarse step."""
+    m = max(x for x in range(1, min(d, 16) + 1) if d % x == 0)
+    return np.zeros((m, 2, d // m), dtype=dtype)
+
+
+def kmeans_device(X, k: int, maxiter: int = 25, seed: int = 0, device: int = 0, chunk: int = 1 << 20):
+    """Lloyd on the GPU.  X [n, d] (numpy, float32 / float64) -> (centers [k, d] in X.dtype, assignments
+    int64[n] 0-based, consistent with the returned centers)."""
+    import torch
+
+    from . import sharded
+    from .index import IVFADCIndex
+
+    X = np.ascontiguousarray(X)
+    n, d = X.shape
+    assert 1 <= k <= n
+    dev = torch.device("cuda", device)
+    dX = torch.from_numpy(X).to(dev)
+    rng = np.random.default_rng(seed)
+    gen = torch.Generator(device=dev).manual_seed(seed)
+    # k-means++ on a sample
+    ns = min(n, max(32768, 8 * k))
+    S = dX[torch.from_numpy(rng.choice(n, ns, replace=False)).to(dev)].double()
+    centers = torch.empty((k, d), dtype=torch.float64, device=dev)
+    centers[0] = S[int(rng.integers(ns))]
+    d2 = ((S - centers[0]) ** 2).sum(1)
+    for j in range(1, k):
+        tot = float(d2.sum())
+        idx = int(torch.multinomial(d2 / tot, 1, generator=gen)) if tot > 0 else int(rng.integers(ns))
+        centers[j] = S[idx]
+        d2 = torch.minimum(d2, ((S - centers[j]) ** 2).sum(1))
+    cb = _dummy_codebook(d, X.dtype)
+    assign = torch.zeros(n, dtype=torch.long, device=dev)
+    dist = torch.empty(n, dtype=dX.dtype, device=dev)
+    for it in range(maxiter + 1):
+        cnp = centers.to(dX.dtype).cpu().numpy()
+        eng = IVFADCIndex.from_quantizers(cnp, cb, None, device=device)
+        new_assign = torch.empty_like(assign)
+        for s in range(0, n, chunk):  # K1: nearest centre of every point (w = 1), the engine's coarse kernel
+            c, dc = sharded.coarse_device(eng, dX[s:s + chunk], 1)
+            new_assign[s:s + chunk] = c[:, 0].long()
+            dist[s:s + chunk] = dc[:, 0]
+        torch.cuda.synchronize(dev)
+        eng.close()
+        same = it > 0 and bool(torch.equal(new_assign, assign))
+        assign = new_assign
+        if it == maxiter or same:
+            break
+        counts = torch.bincount(assign, minlength=k)
+        sums = torch.zeros((k, d), dtype=torch.float64, device=dev).index_add_(0, assign, dX.double())
+        nz = counts > 0
+        centers[nz] = sums[nz] / counts[nz, None].double()
+        nempty = int((~nz).sum())
+        if nempty:  # re-seed empty clusters on the points farthest from their centre
+            far = torch.topk(dist.double(), nempty).indices
+            centers[~nz] = dX[far].double()
+    return centers.to(dX.dtype).cpu().numpy(), assign.cpu().numpy().astype(np.int64)
+
+
+def train_quantizers_device(data, kc: int, k: int, m: int, coarse_maxiter: int = 25,
+                            quantization_maxiter: int = 25, seed: int = 0, device: int = 0):
+    """train_quantizers with the Lloyd iterations on the GPU (same outputs, same layout)."""
+    data = np.ascontiguousarray(data)
+    n, D = data.shape
+    dsub = D // m
+    centroids, assign = kmeans_device(data, kc, coarse_maxiter, seed, device)
+    resid = data - centroids[assign]
+    cb_vectors = np.empty((m, k, dsub), dtype=data.dtype)
+    for i in range(m):
+        cb_vectors[i], _ = kmeans_device(np.ascontiguousarray(resid[:, i * dsub:(i + 1) * dsub]), k,
+                                         quantization_maxiter, seed + 1 + i, device)
+    cb_codes = np.tile(np.arange(k, dtype=np.uint8), (m, 1))
+    return centroids, assign, cb_vectors, cb_codes

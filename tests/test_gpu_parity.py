@@ -672,3 +672,30 @@ def test_config_b_full_size_properties():
     iv.delete_from_index(e, (dele + 1).tolist())       # 1-based, as the reference takes them
     assert len(e) == N - len(dele)
     e.close(); x.close(); y.close()
+
+
+# ------------------------------------------------------------------------------------------------
+# Device trainer (not parity-graded: the reference's training is unseeded)
+# ------------------------------------------------------------------------------------------------
+def test_device_trainer():
+    """Lloyd with the engine's coarse kernel as the assignment step: quantisation error on a par with the host
+    trainer, assignments consistent with the returned centres; the constructor uses it beyond toy sizes."""
+    from ivfadc_jl_b200 import synth, training
+    X = synth.blobs(40000, 32, 48, seed=41)
+    c_host, a_host = training.kmeans(X, 48, maxiter=15, seed=3)
+    c_dev, a_dev = training.kmeans_device(X, 48, maxiter=15, seed=3)
+    inertia = lambda c, a: float(((X.astype(np.float64) - c[a].astype(np.float64)) ** 2).sum())
+    assert inertia(c_dev, a_dev) <= 1.05 * inertia(c_host, a_host)
+    d = ((X[:2000, None, :].astype(np.float64) - c_dev[None].astype(np.float64)) ** 2).sum(2)
+    assert (d[np.arange(2000), a_dev[:2000]] <= d.min(1) * (1 + 1e-6)).all()   # nearest centre (up to fp32 ties)
+    # constructor beyond DEVICE_TRAINING_PAIRS: 150 000 vectors x 64 cells
+    n, D, kc = 150_000, 32, 64
+    Xb = synth.blobs(n, D, kc, seed=42)
+    idx = iv.IVFADCIndex(np.ascontiguousarray(Xb.T), kc=kc, k=256, m=8, coarse_maxiter=8, quantization_maxiter=8,
+                         index_type=np.uint32)
+    assert len(idx) == n
+    qs = np.arange(0, n, n // 200)[:200]
+    ids, dists, counts = idx.search_packed(Xb[qs], 10, 8)
+    hits = sum(int(q in ids[i, :counts[i]]) for i, q in enumerate(qs))
+    assert hits >= 150, hits   # a database point finds itself among its 10 nearest (PQ-approximate) neighbours
+    idx.close()
