@@ -80,7 +80,7 @@ def test_coarse_search_bit_exact(dtype, D, kc, nq, w):
 @pytest.mark.parametrize("data", ["uniform", "blobs", "large_norm", "ties"])
 @pytest.mark.parametrize("D,kc,nq,w", [(128, 1024, 1000, 16), (128, 1024, 129, 1), (96, 4096, 300, 16),
                                        (64, 300, 500, 8), (128, 256, 128, 32), (16, 700, 260, 5),
-                                       (128, 2048, 4000, 16)])
+                                       (128, 2048, 4000, 16), (128, 1024, 1, 16), (32, 512, 7, 32)])
 def test_coarse_tensor_core_bit_exact(data, D, kc, nq, w):
     """coarse_tc.cuh: TF32 tensor-core scores only prune; cells and distances must be bit-identical to the
     oracle's direct form (src/coarsequantizers.jl:33-37), stable ties included.  COARSE_REDO sends every
