@@ -556,11 +556,13 @@ bool use_scanq(const ivfadc_index* h, int64_t npairs, int k) {
     // same whether 5 or 32 queries share it -- kc (n/32 + 1/2) items of ceil(L / 1024) passes of `tables` table
     // builds + scans at ~0.0099 us of GPU time each -- while the vector-per-lane kernel streams the pairs' code
     // bytes at ~1.3 TB/s.  Few queries per (long) list, as in config D (10 per list of 6100), favour the latter.
-    const double kc = (double)h->cfg.kc, nbar = (double)npairs / kc;
+    // (a shard owns every world-th cell: its share of the cells and of the pairs, its own vectors)
+    const int world = std::max(1, h->cfg.shard_world);
+    const double kc = std::max(1.0, (double)h->cfg.kc / world), np_loc = (double)npairs / world, nbar = np_loc / kc;
     const double lbar = std::max(1.0, (double)h->n_local / kc);
     const int tables = h->cfg.m * ((h->dsub <= 8 || h->dsub == 16) ? scanu_dup(h) : 1);
     const double est_q = kc * (nbar / 32.0 + 0.5) * std::ceil(lbar / 1024.0) * tables * 0.0099;
-    const double est_v = (double)npairs * lbar * h->cfg.m / 1.3e6;
+    const double est_v = np_loc * lbar * h->cfg.m / 1.3e6;
     return est_q < est_v;
 }
 

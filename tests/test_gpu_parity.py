@@ -328,6 +328,19 @@ def test_scan_kernel_choice():
         assert e.stats()["last_scan_kernel"] == want, (want, e.stats())
         orc.compare_search(gi, gd, gc, oi, od, oc, rtol=RTOL)
         e.close()
+    # a shard owns every fourth cell: the model has to count ITS cells, pairs and vectors (a quarter of each),
+    # or a config-B-like shard falls to the vector-per-lane kernel (seen at N = 4: scan 0.64 ms instead of 0.26)
+    import torch
+    from ivfadc_jl_b200 import sharded
+    D, m, kc, n, nq, w = 128, 16, 64, 64000, 2400, 8
+    X = synth.blobs(n, D, kc, seed=33)
+    _, cb, codes = synth.random_quantizers(kc, D, m, 256, seed=8, data=X)
+    qz = orc.Quantizers(synth.blob_centres(D, kc), cb, codes)
+    e = engine_from(qz, np.uint32, X, shard=(1, 4), flags=0)
+    sharded.search_local(e, torch.from_numpy(synth.blobs(nq, D, kc, seed=34)).cuda(), 10, w)
+    torch.cuda.synchronize()
+    assert e.stats()["last_scan_kernel"] == 4, e.stats()
+    e.close()
 
 
 @pytest.mark.parametrize("D,m,ksub,identity", [(128, 16, 256, True), (96, 12, 256, True), (40, 8, 100, False),
