@@ -21,8 +21,9 @@
 //      centroids with s <= B would all have a strictly smaller exact distance -- so the candidates
 //      are a superset of the exact top-w, ties included.  The tile is read twice from tensor
 //      memory (minima, then filter): re-reading costs no shared-memory or HBM traffic.
-//   4. exact re-rank: one warp per query, lane = candidate: the oracle's fma chain over the fp32
-//      centroid row, then w rounds of warp arg-min by (distance, cell) -- sortperm's stable order.
+//   4. exact re-rank (coarse3_rerank_kernel, persistent warps, one query at a time): the surviving centroid rows
+//      are fetched coalesced into a shared tile, lane = candidate runs the oracle's fma chain over its row, the
+//      ranks by (distance, cell) -- sortperm's stable order -- come from counting, lanes of rank < w write.
 //   5. a query with more candidates than slots (heavy ties, duplicate centroids) is flagged and
 //      redone by the packed-FP32 kernel (coarse2_kernel with a redo mask, launched right after).
 //
@@ -49,20 +50,16 @@ constexpr uint32_t SPIN = 1u << 22;     // bound on every mbarrier wait (error f
 constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((256u >> 3) << 17) | ((128u >> 4) << 24);
 
 struct Smem {
-    uint32_t a, b, cand_s, cand_c, norms, qn, thr, cnt, scratch, bars, total;
+    uint32_t a, b, cand_s, cand_c, stage, bars, total;
 };
 __host__ __device__ inline Smem smem_layout(int ksteps) {
     Smem s;
     uint32_t o = 0;
     s.a = o;       o += (uint32_t)(ksteps + 1) * ABLK;   // + the ones block that selects the norm k-step
     s.b = o;       o += NSLOT * BBLK;
-    s.cand_s = o;  o += (CAP + 1) * CSTR * 4;   // + a dummy slot
-    s.cand_c = o;  o += (CAP + 1) * CSTR * 4;
-    s.norms = o;   o += 4 * 32 * 32 * 4;     // per epilogue warp: the 32 x 32 scores of the chunk being filtered
-    s.qn = o;      o += MQ * 4;
-    s.thr = o;     o += MQ * 4;
-    s.cnt = o;     o += MQ * 4;
-    s.scratch = o; o += (THREADS / 32) * CAP * 4;
+    s.cand_s = o;  o += CAP * CSTR * 4;      // candidate scores  [slot][query row]
+    s.cand_c = o;  o += CAP * CSTR * 4;      // candidate cells
+    s.stage = o;   o += 4 * 32 * 32 * 4;     // per epilogue warp: the 32 x 32 scores of the chunk being filtered
     s.bars = o;    o += 256;
     s.total = o;
     return s;
@@ -340,7 +337,7 @@ __global__ void __launch_bounds__(THREADS, 1) coarse3_kernel(const Args a) {
         int cnt = 0;
         const uint32_t trow = tmem_base + ((uint32_t)(32 * wid) << 16);
         // one group of 8 scores: minimum -> sorted list of the WL smallest group minima (branch-free insertion)
-        float* stage = reinterpret_cast<float*>(smem_c3 + L.norms) + wid * (32 * 32);  // [column of the chunk][lane]
+        float* stage = reinterpret_cast<float*>(smem_c3 + L.stage) + wid * (32 * 32);  // [column of the chunk][lane]
         for (int t = 0; t < ntiles; ++t) {
             const int buf = t & 1;
             C3S();
