@@ -78,3 +78,35 @@ def test_constructor_asserts_fire_before_any_device_use():
         iv.IVFADCIndex(data, index_type=np.uint8)
     with pytest.raises(AssertionError):
         iv.IVFADCIndex(data, kc=2, k=2, m=1, coarse_quantizer="kdtree")
+
+
+def test_delete_from_index_id_conversion_without_a_device():
+    """delete_from_index! takes 1-based integers and converts them with I.(points .- 1) (src/utils.jl:93): 0 or
+    negative -> InexactError, ids beyond the id type -> InexactError; duplicates and unknown ids pass through (the
+    engine ignores them).  Host logic only: the C-ABI call is captured by a stub, the integer-array path and the
+    generic path must hand over the same ids."""
+    import ctypes
+    import ivfadc_jl_b200 as iv
+
+    class StubLib:
+        def __init__(self):
+            self.calls = []
+
+        def ivfadc_delete(self, h, ptr, n):
+            self.calls.append(np.ctypeslib.as_array(ctypes.cast(ptr, ctypes.POINTER(ctypes.c_uint64)), shape=(n,)).copy())
+            return 0
+
+    for id_type, maxid in ((np.uint8, 255), (np.uint32, 2 ** 32 - 1)):
+        idx = iv.IVFADCIndex.__new__(iv.IVFADCIndex)
+        idx.I, idx._h, idx._lib = np.dtype(id_type), ctypes.c_void_p(1), StubLib()
+        iv.delete_from_index(idx, np.array([5, 1, 5, 200], dtype=np.int64))       # vectorised path
+        iv.delete_from_index(idx, [5, 1, 5, 200])                                  # generic path
+        assert [c.tolist() for c in idx._lib.calls] == [[4, 0, 4, 199]] * 2
+        for bad in (0, -3, maxid + 2):
+            with pytest.raises(OverflowError):
+                iv.delete_from_index(idx, np.array([1, bad], dtype=np.int64))
+            with pytest.raises(OverflowError):
+                iv.delete_from_index(idx, [1, bad])
+        iv.delete_from_index(idx, np.array([], dtype=np.int64))
+        assert len(idx._lib.calls) == 2
+        idx._h = None   # nothing to destroy
