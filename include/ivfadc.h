@@ -79,10 +79,12 @@ extern "C" {
 #define IVFADC_FLAG_LUT_MMASYNC 8
 /*
  * The default query-per-lane kernel keeps the lookup tables in tensor memory and looks them up with
- * tcgen05.ld at column = code byte (persistent CTAs).  This flag selects the previous generation,
- * which copies every table from tensor memory to shared memory and gathers with LDS.
+ * tcgen05.ld at column = code byte; its persistent CTAs are warp-specialised (12 scanning warps, a
+ * tensor-core producer warp, two loader warps, a finalizer; mbarriers only).  This flag selects the
+ * previous generation of the same arithmetic (16 scanning warps that also issue the tensor-core work, one
+ * CTA-wide barrier per table) -- kept for back-to-back measurements.
  */
-#define IVFADC_FLAG_SCAN_SMEMLUT 16
+#define IVFADC_FLAG_SCAN_TMEM_V1 16
 /*
  * The fp32 coarse step (D <= 128) uses packed FP32 instructions on transposed centroids; this flag
  * selects the scalar FFMA kernel instead (identical results, both bit-exact against the reference form).
@@ -133,7 +135,7 @@ typedef struct ivfadc_stats {
     double   merge_ms;
     double   encode_ms;
     uint64_t scan_launches;
-    uint64_t last_scan_kernel;  /* kernel of the last search: 1 vector-per-lane, 2 query-per-lane (scanq), 3 scant, 4 scanu */
+    uint64_t last_scan_kernel;  /* kernel of the last search: 1 vector-per-lane, 2 scanq, 4 scanu (v1), 5 scanw */
     uint64_t reserved[3];
 } ivfadc_stats;
 

@@ -18,7 +18,7 @@ ERR_BAD_ARG, ERR_CAPACITY, ERR_CUDA, ERR_OOM, ERR_UNSUPPORTED, ERR_EMPTY = -1, -
 F32, F64 = 0, 1
 SQEUCLIDEAN = 0
 LAST, FIRST = 0, 1
-FLAG_SCAN_LEGACY, FLAG_SCAN_QLANE, FLAG_LUT_EXACT, FLAG_LUT_MMASYNC, FLAG_SCAN_SMEMLUT, FLAG_COARSE_SCALAR = 1, 2, 4, 8, 16, 32
+FLAG_SCAN_LEGACY, FLAG_SCAN_QLANE, FLAG_LUT_EXACT, FLAG_LUT_MMASYNC, FLAG_SCAN_TMEM_V1, FLAG_COARSE_SCALAR = 1, 2, 4, 8, 16, 32
 FLAG_TEST_MERGE_SWEEP = 64
 FLAG_COARSE_FFMA, FLAG_TEST_COARSE_REDO = 128, 256
 

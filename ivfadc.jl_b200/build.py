@@ -10,8 +10,8 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 OBJDIR = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libivfadc_cuda.so")
-SOURCES = ["api.cu", "coarse.cu", "scan.cu", "encode.cu", "lists.cu"]
-HEADERS = ["common.cuh", "warp_topk.cuh", "scan_impl.cuh", "scanq_impl.cuh", "scant_impl.cuh", "scanu_impl.cuh", "coarse_tc.cuh"]
+SOURCES = ["api.cu", "coarse.cu", "scan.cu", "encode.cu", "lists.cu", "shard.cu"]
+HEADERS = ["common.cuh", "warp_topk.cuh", "scan_impl.cuh", "scanq_impl.cuh", "tc_common.cuh", "scanu_impl.cuh", "scanw_impl.cuh", "coarse_tc.cuh"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "-I" + os.path.join(ROOT, "include"), "-I" + CSRC,
@@ -50,7 +50,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     with ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
         objs = list(ex.map(compile_one, SOURCES))
     if force or _stale(LIB, objs):
-        cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"]
+        cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-ldl"]
         if verbose:
             print(" ".join(cmd))
         subprocess.check_call(cmd)

@@ -28,7 +28,7 @@ struct Extra {
     uint64_t scanned_flushed = 0;
 };
 
-Extra* extra(ivfadc_index* h) { return reinterpret_cast<Extra*>(h->stats.reserved[2]); }
+Extra* extra(ivfadc_index* h) { return static_cast<Extra*>(h->extra); }
 
 int fail(ivfadc_index* h, int code, const char* msg, cudaError_t e = cudaSuccess) {
     if (h) {
@@ -67,6 +67,7 @@ void flush_set(ivfadc_index* h, int i) {
 
 void flush_all(ivfadc_index* h) {
     for (int i = 0; i < kEventSets; ++i) flush_set(h, i);
+    shard_flush_timing(h);
     cudaGetLastError();
 }
 
@@ -134,8 +135,9 @@ int search_core(ivfadc_index* h, const void* dQ, int64_t nq, int k, int w, uint6
     if (w > coarse_max_w()) return fail(h, IVFADC_ERR_UNSUPPORTED, "w > 128 is not supported by the coarse kernel yet");
     if (nq == 0) return IVFADC_OK;
     h->stats.searches += 1;
-    // bound the per-pair candidate workspace (~512 MB)
-    const size_t per_query = (size_t)w * k * (h->tsize + 4) + 64;
+    // bound the per-pair candidate workspace (~512 MB): a pair's row holds k sorted entries, or 64 candidates
+    // (distance + position) when the tensor-memory kernels serve the batch (pair_stride in scan.cu)
+    const size_t per_query = (size_t)w * std::max(k, 64) * (h->tsize + 4) + 64;
     int64_t chunk = (int64_t)std::max<size_t>(1, ((size_t)512 << 20) / per_query);
     chunk = std::min<int64_t>(chunk, (int64_t)1 << 20);
     for (int64_t q0 = 0; q0 < nq; q0 += chunk) {
@@ -149,6 +151,31 @@ int search_core(ivfadc_index* h, const void* dQ, int64_t nq, int k, int w, uint6
     }
     return IVFADC_OK;
 }
+
+}  // namespace
+
+namespace ivf {
+int api_fail(ivfadc_index* h, int code, const char* msg, cudaError_t e) { return fail(h, code, msg, e); }
+int api_search_core(ivfadc_index* h, const void* dQ, int64_t nq, int k, int w, uint64_t* d_ids, void* d_dists,
+                    uint64_t* d_keys, int32_t* d_counts, cudaStream_t s, const int32_t* ext_cells, const void* ext_dc) {
+    return search_core(h, dQ, nq, k, w, d_ids, d_dists, d_keys, d_counts, s, ext_cells, ext_dc);
+}
+int api_check_pipeline_flag(ivfadc_index* h, int flag) {
+    if (!flag) return IVFADC_OK;
+    if (h->d_err) cudaMemset(h->d_err, 0, sizeof(int));
+    const char* what = flag >= 20 ? "tensor-memory scan kernel: a role's mbarrier wait timed out (staging / table release / candidates)"
+                     : flag >= 11 ? "tensor-core coarse kernel: pipeline wait timed out (TMA / MMA / accumulator tile)"
+                     : flag == 1 ? "tensor-core table builder: TMA operand never arrived"
+                     : flag == 2 ? "tensor-core table builder: MMA never completed"
+                     : flag == 3 ? "tensor-core table builder: shared-memory plan does not fit"
+                     : flag == 4 ? "tensor-core table builder: first A operands of a work item never written"
+                     : flag == 5 ? "tensor-core table builder: codebook ring did not drain"
+                                 : "tensor-core table builder: table buffer never released";
+    return fail(h, IVFADC_ERR_CUDA, what);
+}
+}  // namespace ivf
+
+namespace {
 
 // cells (+ optional codes) of a device-resident batch
 int cells_and_codes(ivfadc_index* h, const void* dX, int64_t n, const int64_t* d_assign, int base,
@@ -213,7 +240,8 @@ int ivfadc_create(ivfadc_index** out, const ivfadc_config* cfg, const void* cent
     h->dsub = cfg->dim / cfg->m;  // QuantizedArrays.rowrange: floor(D / m)
     h->tsize = cfg->dtype == IVFADC_F32 ? 4 : 8;
     h->id_dev_bytes = cfg->id_bytes <= 4 ? 4 : 8;
-    h->stats.reserved[2] = reinterpret_cast<uint64_t>(x);
+    h->extra = x;
+    if (cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, cfg->device) != cudaSuccess) h->num_sms = 0;
 
     const size_t cbytes = (size_t)cfg->kc * cfg->dim * h->tsize;
     const size_t vbytes = (size_t)cfg->m * cfg->ksub * h->dsub * h->tsize;
@@ -269,6 +297,8 @@ int ivfadc_destroy(ivfadc_index* h) {
     if (!h) return IVFADC_OK;
     cudaSetDevice(h->cfg.device);
     cudaDeviceSynchronize();
+    shard_destroy_ctx(h);
+    if (h->d_owner) cudaFree(h->d_owner);
     Extra* x = extra(h);
     if (x) {
         if (x->tm.ok)
@@ -288,7 +318,6 @@ int ivfadc_destroy(ivfadc_index* h) {
     if (h->d_cb_norms) cudaFree(h->d_cb_norms);
     if (h->d_afrag) cudaFree(h->d_afrag);
     if (h->d_wnfrag) cudaFree(h->d_wnfrag);
-    if (h->d_tcB) cudaFree(h->d_tcB);
     if (h->d_tcU) cudaFree(h->d_tcU);
     if (h->d_err) cudaFree(h->d_err);
     if (h->h_err) cudaFreeHost(h->h_err);
@@ -448,17 +477,7 @@ int ivfadc_search(ivfadc_index* h, const void* Q, int64_t nq, int32_t k, int32_t
         int flag = 0;
         if (h->h_err) flag = *h->h_err;
         else CUDA_OR_FAIL(h, cudaMemcpy(&flag, h->d_err, sizeof(int), cudaMemcpyDeviceToHost), "D2H");
-        if (flag) {
-            cudaMemset(h->d_err, 0, sizeof(int));
-            const char* what = flag >= 11 ? "tensor-core coarse kernel: pipeline wait timed out (TMA / MMA / accumulator tile)"
-                             : flag == 1 ? "tensor-core table builder: TMA operand never arrived"
-                             : flag == 2 ? "tensor-core table builder: MMA never completed"
-                             : flag == 3 ? "tensor-core table builder: shared-memory plan does not fit"
-                             : flag == 4 ? "tensor-core table builder: first A operands of a work item never written"
-                             : flag == 5 ? "tensor-core table builder: codebook ring did not drain"
-                                         : "tensor-core table builder: table buffer never released";
-            return fail(h, IVFADC_ERR_CUDA, what);
-        }
+        if (flag) return api_check_pipeline_flag(h, flag);
     }
     return IVFADC_OK;
 }
@@ -625,6 +644,29 @@ int ivfadc_set_length(ivfadc_index* h, int64_t n_total) {
     return IVFADC_OK;
 }
 
+int ivfadc_set_cell_owners(ivfadc_index* h, const int32_t* owners) {
+    if (check_handle(h) || !owners) return IVFADC_ERR_BAD_ARG;
+    if (h->n_local != 0 || h->n_total != 0) return fail(h, IVFADC_ERR_BAD_ARG, "cell owners must be set on an empty index");
+    const int kc = h->cfg.kc, world = h->cfg.shard_world;
+    for (int c = 0; c < kc; ++c)
+        if (owners[c] < 0 || owners[c] >= world) return fail(h, IVFADC_ERR_BAD_ARG, "cell owner outside [0, shard_world)");
+    cudaSetDevice(h->cfg.device);
+    if (!h->d_owner) CUDA_OR_FAIL(h, cudaMalloc(reinterpret_cast<void**>(&h->d_owner), sizeof(int32_t) * (size_t)kc), "owner map");
+    CUDA_OR_FAIL(h, cudaMemcpy(h->d_owner, owners, sizeof(int32_t) * (size_t)kc, cudaMemcpyHostToDevice), "H2D");
+    h->h_owner.assign(owners, owners + kc);
+    return IVFADC_OK;
+}
+
+int ivfadc_check_async(ivfadc_index* h, void* stream) {
+    if (check_handle(h)) return IVFADC_ERR_BAD_ARG;
+    cudaSetDevice(h->cfg.device);
+    CUDA_OR_FAIL(h, cudaStreamSynchronize(static_cast<cudaStream_t>(stream)), "sync");
+    if (!h->d_err) return IVFADC_OK;
+    int flag = 0;
+    CUDA_OR_FAIL(h, cudaMemcpy(&flag, h->d_err, sizeof(int), cudaMemcpyDeviceToHost), "D2H");
+    return api_check_pipeline_flag(h, flag);
+}
+
 int ivfadc_debug_tables(ivfadc_index* h, void* out) {
     if (check_handle(h)) return IVFADC_ERR_BAD_ARG;
     cudaSetDevice(h->cfg.device);
@@ -659,7 +701,6 @@ int ivfadc_get_stats(ivfadc_index* h, ivfadc_stats* out) {
         h->stats.scan_code_bytes = scanned * (uint64_t)h->cfg.m;
     }
     *out = h->stats;
-    out->reserved[2] = 0;
     return IVFADC_OK;
 }
 
@@ -667,9 +708,7 @@ int ivfadc_reset_stats(ivfadc_index* h) {
     if (check_handle(h)) return IVFADC_ERR_BAD_ARG;
     cudaSetDevice(h->cfg.device);
     flush_all(h);
-    const uint64_t keep = h->stats.reserved[2];
     h->stats = ivfadc_stats{};
-    h->stats.reserved[2] = keep;
     cudaMemset(extra(h)->d_scanned, 0, sizeof(uint64_t));
     return IVFADC_OK;
 }

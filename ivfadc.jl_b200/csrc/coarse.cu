@@ -336,25 +336,21 @@ __global__ void transpose_centroids_kernel(const float* __restrict__ C, int kc, 
 }
 
 template <int NTY, int R>
-cudaError_t launch_coarse2_inst(const float* Q, const float* Ct, int64_t nq, int kc, int kcp, int D, int w,
+cudaError_t launch_coarse2_inst(const ivfadc_index* h, const float* Q, const float* Ct, int64_t nq, int kc, int kcp, int D, int w,
                                 int32_t* cells, float* dc, cudaStream_t s, const uint8_t* redo) {
     constexpr int TQ2 = 4 * NTY;
     const size_t smem = ((size_t)D * (2 * TQ2 + 4) + 2 * (size_t)PDK * PLDC + (size_t)TQ2 * (PC + 1)) * sizeof(float);
-    static size_t configured = 0;
-    if (smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(coarse2_kernel<NTY, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        configured = smem;
-    }
+    cudaError_t e = ensure_smem(h, reinterpret_cast<const void*>(&coarse2_kernel<NTY, R>), smem);
+    if (e != cudaSuccess) return e;
     coarse2_kernel<NTY, R><<<(unsigned)((nq + TQ2 - 1) / TQ2), 16 * NTY, smem, s>>>(Q, Ct, nq, kc, kcp, D, w, cells, dc, redo);
     return cudaGetLastError();
 }
 template <int R>
-cudaError_t launch_coarse2_r(int nty, const float* Q, const float* Ct, int64_t nq, int kc, int kcp, int D, int w,
+cudaError_t launch_coarse2_r(const ivfadc_index* h, int nty, const float* Q, const float* Ct, int64_t nq, int kc, int kcp, int D, int w,
                              int32_t* cells, float* dc, cudaStream_t s, const uint8_t* redo = nullptr) {
-    if (nty == 4) return launch_coarse2_inst<4, R>(Q, Ct, nq, kc, kcp, D, w, cells, dc, s, redo);
-    if (nty == 6) return launch_coarse2_inst<6, R>(Q, Ct, nq, kc, kcp, D, w, cells, dc, s, redo);
-    return launch_coarse2_inst<8, R>(Q, Ct, nq, kc, kcp, D, w, cells, dc, s, redo);
+    if (nty == 4) return launch_coarse2_inst<4, R>(h, Q, Ct, nq, kc, kcp, D, w, cells, dc, s, redo);
+    if (nty == 6) return launch_coarse2_inst<6, R>(h, Q, Ct, nq, kc, kcp, D, w, cells, dc, s, redo);
+    return launch_coarse2_inst<8, R>(h, Q, Ct, nq, kc, kcp, D, w, cells, dc, s, redo);
 }
 
 template <typename T>
@@ -418,13 +414,9 @@ cudaError_t coarse_prepare(ivfadc_index* h, cudaStream_t s, int* launches) {
 
 namespace {
 template <int WL>
-cudaError_t launch_coarse3_inst(const ctc::Args& a, unsigned grid, size_t smem, cudaStream_t s) {
-    static size_t configured = 0;
-    if (smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(ctc::coarse3_kernel<WL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        configured = smem;
-    }
+cudaError_t launch_coarse3_inst(const ivfadc_index* h, const ctc::Args& a, unsigned grid, size_t smem, cudaStream_t s) {
+    cudaError_t e = ensure_smem(h, reinterpret_cast<const void*>(&ctc::coarse3_kernel<WL>), smem);
+    if (e != cudaSuccess) return e;
     ctc::coarse3_kernel<WL><<<grid, ctc::THREADS, smem, s>>>(a);
     return cudaGetLastError();
 }
@@ -437,12 +429,7 @@ cudaError_t launch_coarse(const ivfadc_index* h, const void* dQ, int64_t nq, int
     if (h->cfg.dtype == IVFADC_F32 && h->d_centroids_t && h->cfg.dim <= PMAXD && (h->cfg.dim & 3) == 0 &&
         !(h->cfg.flags & IVFADC_FLAG_COARSE_SCALAR)) {
         // queries per CTA: the block count that fills the resident-CTA slots of the SMs most evenly
-        static int num_sms = 0;
-        if (!num_sms) {
-            int dev = 0;
-            cudaGetDevice(&dev);
-            cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-        }
+        const int num_sms = h->num_sms > 0 ? h->num_sms : 148;
         const int D = h->cfg.dim;
         int best = 8;
         double best_eff = -1.0;
@@ -479,28 +466,23 @@ cudaError_t launch_coarse(const ivfadc_index* h, const void* dQ, int64_t nq, int
             ca.force_redo = (h->cfg.flags & IVFADC_FLAG_TEST_COARSE_REDO) ? 1 : 0;
             const unsigned grid = (unsigned)((nq + ctc::MQ - 1) / ctc::MQ);
             const size_t smem = ctc::smem_layout(D / 8).total;
-            if (w <= 1) e = launch_coarse3_inst<1>(ca, grid, smem, s);
-            else if (w <= 8) e = launch_coarse3_inst<8>(ca, grid, smem, s);
-            else if (w <= 16) e = launch_coarse3_inst<16>(ca, grid, smem, s);
-            else e = launch_coarse3_inst<32>(ca, grid, smem, s);
+            if (w <= 1) e = launch_coarse3_inst<1>(h, ca, grid, smem, s);
+            else if (w <= 8) e = launch_coarse3_inst<8>(h, ca, grid, smem, s);
+            else if (w <= 16) e = launch_coarse3_inst<16>(h, ca, grid, smem, s);
+            else e = launch_coarse3_inst<32>(h, ca, grid, smem, s);
             if (e != cudaSuccess) return e;
             const size_t rsmem = ctc::RR_WARPS * ctc::rr_warp_floats(D) * sizeof(float);
-            static size_t rr_configured = 0;
-            if (rsmem > rr_configured) {
-                e = cudaFuncSetAttribute(ctc::coarse3_rerank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem);
-                if (e != cudaSuccess) return e;
-                rr_configured = rsmem;
-            }
+            if ((e = ensure_smem(h, reinterpret_cast<const void*>(&ctc::coarse3_rerank_kernel), rsmem)) != cudaSuccess) return e;
             const unsigned rr_need = (unsigned)((nq + ctc::RR_WARPS - 1) / ctc::RR_WARPS);
             const unsigned rr_slots = (unsigned)num_sms * (unsigned)std::max<size_t>(1, (size_t)(227 * 1024) / (rsmem + 1024));
             ctc::coarse3_rerank_kernel<<<std::min(rr_need, rr_slots), ctc::RR_WARPS * 32, rsmem, s>>>(ca);
             if ((e = cudaGetLastError()) != cudaSuccess) return e;
             if (launches) *launches += 2;
-            return launch_coarse2_r<1>(best, Q, Ct, nq, h->cfg.kc, h->kc_pad, D, w, d_cells, dc, s, ca.redo);
+            return launch_coarse2_r<1>(h, best, Q, Ct, nq, h->cfg.kc, h->kc_pad, D, w, d_cells, dc, s, ca.redo);
         }
-        if (w <= 32) return launch_coarse2_r<1>(best, Q, Ct, nq, h->cfg.kc, h->kc_pad, D, w, d_cells, dc, s);
-        if (w <= 64) return launch_coarse2_r<2>(best, Q, Ct, nq, h->cfg.kc, h->kc_pad, D, w, d_cells, dc, s);
-        return launch_coarse2_r<4>(best, Q, Ct, nq, h->cfg.kc, h->kc_pad, D, w, d_cells, dc, s);
+        if (w <= 32) return launch_coarse2_r<1>(h, best, Q, Ct, nq, h->cfg.kc, h->kc_pad, D, w, d_cells, dc, s);
+        if (w <= 64) return launch_coarse2_r<2>(h, best, Q, Ct, nq, h->cfg.kc, h->kc_pad, D, w, d_cells, dc, s);
+        return launch_coarse2_r<4>(h, best, Q, Ct, nq, h->cfg.kc, h->kc_pad, D, w, d_cells, dc, s);
     }
     if (h->cfg.dtype == IVFADC_F32) return launch_coarse_t<float>(h, dQ, nq, w, d_cells, d_dc, s);
     return launch_coarse_t<double>(h, dQ, nq, w, d_cells, d_dc, s);

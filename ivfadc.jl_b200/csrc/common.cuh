@@ -5,6 +5,7 @@
 #include <stdint.h>
 
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "ivfadc.h"
@@ -116,7 +117,6 @@ struct ivfadc_index {
     void* d_afrag = nullptr;        // codebook as mma A fragments (scanq FAST table builder)
     void* d_wnfrag = nullptr;
     int frag_ntiles = 0, frag_ksteps = 0;
-    void* d_tcB = nullptr;          // codebook as tcgen05 B-operand blocks (scant table builder)
     void* d_tcU = nullptr;          // codebook as per-subspace B-operand blocks, rows = code values (scanu)
     int* h_err = nullptr;           // pinned host copy of d_err (read back with the results)
     int* d_err = nullptr;           // device error flag of the tcgen05 pipeline (mbarrier timeout)
@@ -134,19 +134,43 @@ struct ivfadc_index {
     int64_t* d_len = nullptr;                  // int64[kc]
     int64_t n_total = 0;                       // length(ivfadc) over all shards
     int64_t n_local = 0;                       // vectors stored in this handle
+    // which shard owns a cell: owner[c] (ivfadc_set_cell_owners: balanced by list length), or c % shard_world
+    std::vector<int32_t> h_owner;              // empty = modulo
+    int32_t* d_owner = nullptr;                // int32[kc] or null
+    bool owns(int c) const {
+        if (cfg.shard_world <= 1) return true;
+        return (h_owner.empty() ? c % cfg.shard_world : h_owner[c]) == cfg.shard_rank;
+    }
 
     // search / mutation workspaces (grow-only)
     ivf::DevBuf ws_q, ws_cells, ws_dc, ws_bucket, ws_sorted, ws_pair_d, ws_pair_pos, ws_pair_cnt,
         ws_thr, ws_out_ids, ws_out_d, ws_out_cnt, ws_out_keys, ws_misc, ws_x, ws_codes, ws_assign,
         ws_sort_tmp, ws_sort_keys, ws_sort_vals, ws_del, ws_items;
 
+    // Per-handle (hence per-device) launch state: the dynamic shared-memory limit configured for each kernel
+    // (function attributes are per device) and the SM count of the handle's device.
+    mutable std::unordered_map<const void*, size_t> func_smem;
+    int num_sms = 0;
+
     cudaEvent_t ev[10] = {};
     bool stats_timing = true;
     ivfadc_stats stats{};
     std::string err;
+    void* extra = nullptr;      // api.cu: event ring, scanned-vector counter
+    void* shard_ctx = nullptr;  // shard.cu: NCCL communicator, gathered buffers, CUDA graphs
 };
 
 namespace ivf {
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize of `func` on the handle's device, raised once per (handle, kernel).
+inline cudaError_t ensure_smem(const ivfadc_index* h, const void* func, size_t smem) {
+    if (smem <= 48 * 1024) return cudaSuccess;
+    size_t& cur = h->func_smem[func];
+    if (smem <= cur) return cudaSuccess;
+    cudaError_t e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) cur = smem;
+    return e;
+}
 
 // ---- coarse.cu --------------------------------------------------------------------------------
 // K1: w nearest centroids of every query, ascending (distance, cell); direct-form distances.
@@ -173,6 +197,20 @@ cudaError_t launch_merge_parts(const ivfadc_index* h, int parts, int64_t nq, int
                                const uint64_t* d_ids_in, const void* d_dists_in,
                                const uint64_t* d_keys_in, uint64_t* d_ids, void* d_dists,
                                int32_t* d_counts, cudaStream_t s, int* launches);
+
+// ---- api.cu (shared with shard.cu) ---------------------------------------------------------------
+int api_fail(ivfadc_index* h, int code, const char* msg, cudaError_t e = cudaSuccess);
+// Batched search with every pointer on the device, asynchronous on `s`; ext_cells / ext_dc: probe lists supplied by
+// the caller (coarse step done elsewhere) or null.
+int api_search_core(ivfadc_index* h, const void* dQ, int64_t nq, int k, int w, uint64_t* d_ids, void* d_dists,
+                    uint64_t* d_keys, int32_t* d_counts, cudaStream_t s, const int32_t* ext_cells = nullptr,
+                    const void* ext_dc = nullptr);
+// Reads (and clears) the device error flag of the tensor-core pipelines; IVFADC_OK or IVFADC_ERR_CUDA with a message.
+int api_check_pipeline_flag(ivfadc_index* h, int flag);
+
+// ---- shard.cu ------------------------------------------------------------------------------------
+void shard_destroy_ctx(ivfadc_index* h);
+void shard_flush_timing(ivfadc_index* h);
 
 // ---- encode.cu --------------------------------------------------------------------------------
 cudaError_t launch_codebook_norms(const ivfadc_index* h, cudaStream_t s, int* launches);

@@ -56,12 +56,12 @@ __global__ void scatter_append_kernel(const int32_t* __restrict__ sorted_cells,
                                       const int64_t* __restrict__ list_len,  // lengths BEFORE the append
                                       const uint8_t* __restrict__ codes_in, int m, uint8_t* codes,
                                       IdT* ids, uint64_t first_id, int step, int shard_rank,
-                                      int shard_world) {
+                                      int shard_world, const int32_t* __restrict__ owner) {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n) return;
     const int c = sorted_cells[t];
     if (c < 0 || c >= kc) return;
-    if (shard_world > 1 && (c % shard_world) != shard_rank) return;
+    if (shard_world > 1 && (owner ? owner[c] : c % shard_world) != shard_rank) return;
     const int64_t j = perm[t];
     const int64_t dst = list_off[c] + list_len[c] + (t - run_start[c]);
     const uint8_t* s = codes_in + (size_t)j * m;
@@ -313,7 +313,7 @@ cudaError_t lists_append(ivfadc_index* h, const int32_t* d_cells, const uint8_t*
     const int world = h->cfg.shard_world, rank = h->cfg.shard_rank;
     for (int c = 0; c < kc; ++c) {
         int64_t cnt = hs[kc + c] > 0 ? hs[kc + c] - hs[c] : 0;
-        if (world > 1 && (c % world) != rank) cnt = 0;
+        if (!h->owns(c)) cnt = 0;
         need[c] = h->h_len[c] + cnt;
         added += cnt;
     }
@@ -323,12 +323,12 @@ cudaError_t lists_append(ivfadc_index* h, const int32_t* d_cells, const uint8_t*
         scatter_append_kernel<uint32_t><<<grid, 256, 0, s>>>(keys_out, vals_out, n, kc, d_run_start, h->d_off,
                                                              h->d_len, d_codes, m, h->d_codes,
                                                              static_cast<uint32_t*>(h->d_ids), first_id, step,
-                                                             rank, world);
+                                                             rank, world, h->d_owner);
     else
         scatter_append_kernel<uint64_t><<<grid, 256, 0, s>>>(keys_out, vals_out, n, kc, d_run_start, h->d_off,
                                                              h->d_len, d_codes, m, h->d_codes,
                                                              static_cast<uint64_t*>(h->d_ids), first_id, step,
-                                                             rank, world);
+                                                             rank, world, h->d_owner);
     CK(cudaGetLastError());
     if (launches) *launches += 1;
     h->h_len = need;

@@ -1,8 +1,8 @@
 // Search planning, the scan launcher, and the final merges.  See scan_impl.cuh for K2/K3.
 #include "scan_impl.cuh"
 #include "scanq_impl.cuh"
-#include "scant_impl.cuh"
 #include "scanu_impl.cuh"
+#include "scanw_impl.cuh"
 
 namespace ivf {
 
@@ -207,7 +207,7 @@ __device__ __forceinline__ bool key_less(float da, uint64_t ka, float db, uint64
 
 template <typename IdT>
 __global__ void __launch_bounds__(128)
-merge_cands_kernel(int64_t nq, int w, int k, int ps, int cap, const int32_t* __restrict__ cells,
+merge_cands_kernel(int64_t nq, int w, int k, int ps, int rs, int cap, const int32_t* __restrict__ cells,
                    const float* __restrict__ pair_d, const uint32_t* __restrict__ pair_pos,
                    const int32_t* __restrict__ pair_cnt, const int64_t* __restrict__ list_off,
                    const IdT* __restrict__ ids_arena, uint64_t* __restrict__ out_ids,
@@ -240,11 +240,11 @@ merge_cands_kernel(int64_t nq, int w, int k, int ps, int cap, const int32_t* __r
 #pragma unroll
         for (int i = 0; i < 4; ++i) c[i] = r0 + i < w ? count_of(r0 + i) : 0;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) v[i] = lane < c[i] ? pair_d[(size_t)(q * w + r0 + i) * ps + lane] : inf;
+        for (int i = 0; i < 4; ++i) v[i] = lane < c[i] ? pair_d[(size_t)(q * w + r0 + i) * rs + lane] : inf;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             lmin = fminf(lmin, v[i]);
-            for (int e = lane + 32; e < c[i]; e += 32) lmin = fminf(lmin, pair_d[(size_t)(q * w + r0 + i) * ps + e]);
+            for (int e = lane + 32; e < c[i]; e += 32) lmin = fminf(lmin, pair_d[(size_t)(q * w + r0 + i) * rs + e]);
         }
     }
     int rank = 0;
@@ -277,7 +277,7 @@ merge_cands_kernel(int64_t nq, int w, int k, int ps, int cap, const int32_t* __r
         for (int i = 0; i < 4; ++i) c[i] = r0 + i < w ? count_of(r0 + i) : 0;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            const size_t o = (size_t)(q * w + r0 + i) * ps + lane;
+            const size_t o = (size_t)(q * w + r0 + i) * rs + lane;
             v[i] = lane < c[i] ? pair_d[o] : inf;
             pp[i] = lane < c[i] ? pair_pos[o] : 0u;
         }
@@ -287,7 +287,7 @@ merge_cands_kernel(int64_t nq, int w, int k, int ps, int cap, const int32_t* __r
             offer(r0 + i, lane, c[i], v[i], pp[i]);
             for (int e0 = 32; e0 < c[i]; e0 += 32) {
                 const int e = e0 + lane;
-                const size_t o = (size_t)(q * w + r0 + i) * ps + e;
+                const size_t o = (size_t)(q * w + r0 + i) * rs + e;
                 offer(r0 + i, e, c[i], e < c[i] ? pair_d[o] : inf, e < c[i] ? pair_pos[o] : 0u);
             }
         }
@@ -365,7 +365,7 @@ merge_cands_kernel(int64_t nq, int w, int k, int ps, int cap, const int32_t* __r
             uint64_t bk = ~0ull;
             for (int r = 0; r < w; ++r) {
                 const int c = count_of(r);
-                const size_t rb = (size_t)(q * w + r) * ps;
+                const size_t rb = (size_t)(q * w + r) * rs;
                 for (int i = lane; i < c; i += 32) {
                     const float dd = pair_d[rb + i];
                     const uint64_t kk = ((uint64_t)r << 32) | pair_pos[rb + i];
@@ -480,31 +480,27 @@ merge_parts_kernel(int parts, int64_t nq, int k, const uint64_t* __restrict__ in
 // Scan dispatch
 // ---------------------------------------------------------------------------------------------
 template <typename T, int QN, int MC, int R>
-cudaError_t launch_scan_inst(const ScanArgs<T>& a, int grid, size_t smem, cudaStream_t s) {
+cudaError_t launch_scan_inst(const ivfadc_index* h, const ScanArgs<T>& a, int grid, size_t smem, cudaStream_t s) {
     auto kern = scan_kernel<T, QN, MC, R>;
-    static size_t configured = 0;  // per instantiation
-    if (smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        configured = smem;
-    }
+    cudaError_t e = ensure_smem(h, reinterpret_cast<const void*>(kern), smem);
+    if (e != cudaSuccess) return e;
     kern<<<grid, STHREADS, smem, s>>>(a);
     return cudaGetLastError();
 }
 
 template <typename T, int QN, int MC>
-cudaError_t launch_scan_r(const ScanArgs<T>& a, int grid, size_t smem, cudaStream_t s) {
-    if (a.k <= 32) return launch_scan_inst<T, QN, MC, 1>(a, grid, smem, s);
-    return launch_scan_inst<T, QN, MC, 4>(a, grid, smem, s);
+cudaError_t launch_scan_r(const ivfadc_index* h, const ScanArgs<T>& a, int grid, size_t smem, cudaStream_t s) {
+    if (a.k <= 32) return launch_scan_inst<T, QN, MC, 1>(h, a, grid, smem, s);
+    return launch_scan_inst<T, QN, MC, 4>(h, a, grid, smem, s);
 }
 
 template <typename T, int QN>
-cudaError_t launch_scan_m(const ScanArgs<T>& a, int grid, size_t smem, cudaStream_t s) {
+cudaError_t launch_scan_m(const ivfadc_index* h, const ScanArgs<T>& a, int grid, size_t smem, cudaStream_t s) {
     switch (a.m) {
-        case 8: return launch_scan_r<T, QN, 8>(a, grid, smem, s);
-        case 12: return launch_scan_r<T, QN, 12>(a, grid, smem, s);
-        case 16: return launch_scan_r<T, QN, 16>(a, grid, smem, s);
-        default: return launch_scan_r<T, QN, 0>(a, grid, smem, s);
+        case 8: return launch_scan_r<T, QN, 8>(h, a, grid, smem, s);
+        case 12: return launch_scan_r<T, QN, 12>(h, a, grid, smem, s);
+        case 16: return launch_scan_r<T, QN, 16>(h, a, grid, smem, s);
+        default: return launch_scan_r<T, QN, 0>(h, a, grid, smem, s);
     }
 }
 
@@ -574,34 +570,37 @@ bool scanu_shape_ok(const ivfadc_index* h) {
     return (h->dsub <= 8 || h->dsub == 16) && h->cfg.m % 4 == 0 && mt <= 16 && scanu_smem_layout(mt).total + 1024 <= kSmemMax;
 }
 bool use_scanu(const ivfadc_index* h) {
-    if (h->cfg.flags & (IVFADC_FLAG_LUT_EXACT | IVFADC_FLAG_LUT_MMASYNC | IVFADC_FLAG_SCAN_SMEMLUT)) return false;
+    if (h->cfg.flags & (IVFADC_FLAG_LUT_EXACT | IVFADC_FLAG_LUT_MMASYNC)) return false;
     return h->d_tcU != nullptr && scanu_shape_ok(h);
+}
+// warp-specialised version (scanw_impl.cuh), the default; IVFADC_FLAG_SCAN_TMEM_V1 keeps the round-1 kernel
+bool use_scanw(const ivfadc_index* h) {
+    if (h->cfg.flags & IVFADC_FLAG_SCAN_TMEM_V1) return false;
+    return scanw_smem_layout(h->cfg.m * scanu_dup(h), h->cfg.m).total + 1024 <= kSmemMax;
 }
 
 template <int NP, bool DBG, int DUP>
-cudaError_t launch_scanu_inst(const ScanUArgs& ua, unsigned grid, size_t smem, cudaStream_t s) {
-    static size_t configured = 0;
-    if (smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(scanu_kernel<NP, DBG, DUP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        configured = smem;
+cudaError_t launch_scanu_inst(const ivfadc_index* h, bool v1, const ScanUArgs& ua, unsigned grid, cudaStream_t s) {
+    // v1 = the round-1 kernel (every warp scans, per-table CTA barrier; IVFADC_FLAG_SCAN_TMEM_V1), else the
+    // warp-specialised kernel of scanw_impl.cuh
+    cudaError_t e;
+    if (v1) {
+        const size_t smem = scanu_smem_layout(4 * NP * DUP).total;
+        if ((e = ensure_smem(h, reinterpret_cast<const void*>(&scanu_kernel<NP, DBG, DUP>), smem)) != cudaSuccess) return e;
+        scanu_kernel<NP, DBG, DUP><<<grid, QTHREADS, smem, s>>>(ua);
+    } else {
+        const size_t smem = scanw_smem_layout(4 * NP * DUP, 4 * NP).total;
+        if ((e = ensure_smem(h, reinterpret_cast<const void*>(&scanw_kernel<NP, DBG, DUP>), smem)) != cudaSuccess) return e;
+        scanw_kernel<NP, DBG, DUP><<<grid, W_THREADS, smem, s>>>(ua);
     }
-    scanu_kernel<NP, DBG, DUP><<<grid, QTHREADS, smem, s>>>(ua);
     return cudaGetLastError();
 }
 template <int NP, int DUP = 1>
-cudaError_t launch_scanu_np(const ScanUArgs& ua, unsigned grid, size_t smem, cudaStream_t s) {
+cudaError_t launch_scanu_np(const ivfadc_index* h, bool v1, const ScanUArgs& ua, unsigned grid, cudaStream_t s) {
     if constexpr (DUP == 1) {
-        if (ua.dbg) return launch_scanu_inst<NP, true, 1>(ua, grid, smem, s);  // table dump / timeline (bring-up, dsub <= 8)
+        if (ua.dbg) return launch_scanu_inst<NP, true, 1>(h, v1, ua, grid, s);  // table dump / timeline (bring-up, dsub <= 8)
     }
-    return launch_scanu_inst<NP, false, DUP>(ua, grid, smem, s);
-}
-
-// tcgen05 table builder with shared-memory tables (scant_impl.cuh): fp32, k <= 16, m in {4, 8, 12, 16}, dsub <= 8
-bool use_scant(const ivfadc_index* h) {
-    if (h->cfg.flags & (IVFADC_FLAG_LUT_EXACT | IVFADC_FLAG_LUT_MMASYNC)) return false;
-    return h->d_tcB != nullptr && h->dsub <= 8 &&
-           scant_smem_layout(h->cfg.m, T_DYN_BASE_GUESS).total + T_DYN_BASE_GUESS <= kSmemMax;
+    return launch_scanu_inst<NP, false, DUP>(h, v1, ua, grid, s);
 }
 
 // Row stride of the per-pair candidate arrays: k sorted entries, or U_CAP unsorted candidates when
@@ -611,15 +610,11 @@ int pair_stride(const ivfadc_index* h, int64_t npairs, int k) {
 }
 
 template <typename T, int MC>
-cudaError_t launch_redo_r(const ScanArgs<T>& a, const int32_t* redo_pairs, const int* redo_cnt, int grid,
+cudaError_t launch_redo_r(const ivfadc_index* h, const ScanArgs<T>& a, const int32_t* redo_pairs, const int* redo_cnt, int grid,
                           size_t smem, cudaStream_t s) {
     auto kern = scan_redo_kernel<T, MC, 1>;
-    static size_t configured = 0;
-    if (smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        configured = smem;
-    }
+    cudaError_t e = ensure_smem(h, reinterpret_cast<const void*>(kern), smem);
+    if (e != cudaSuccess) return e;
     kern<<<grid, STHREADS, smem, s>>>(a, redo_pairs, redo_cnt);
     return cudaGetLastError();
 }
@@ -663,7 +658,7 @@ cudaError_t search_t(ivfadc_index* h, const void* dQ, int64_t nq, int k, int w, 
     const int split = qlane ? 0 : 1;
     plan_count_kernel<bits_t><<<pgrid, pthreads, 0, s>>>(d_cells, npairs, nq, w, kc, split, h->d_len, bucket_cnt,
                                                          thr, inf_bits, (unsigned long long*)d_scanned);
-    const bool want_items = qlane && (use_scanu(h) || use_scant(h));  // nb = kc there: bucket = cell
+    const bool want_items = qlane && use_scanu(h);  // nb = kc there: bucket = cell
     plan_scan_kernel<<<1, 1024, 0, s>>>(bucket_cnt, nb, qn, bucket_off, group_off,
                                         want_items ? h->ws_items.as<int4>() : nullptr);
     plan_scatter_kernel<<<pgrid, pthreads, 0, s>>>(d_cells, npairs, w, kc, split, h->d_len, bucket_off, cursor,
@@ -682,14 +677,20 @@ cudaError_t search_t(ivfadc_index* h, const void* dQ, int64_t nq, int k, int w, 
     a.cells = d_cells; a.dc = static_cast<const T*>(d_dc);
     a.bucket_off = bucket_off; a.group_off = group_off; a.nb = nb; a.sorted_pairs = sorted_pairs;
     a.pair_d = pair_d; a.pair_pos = pair_pos; a.pair_cnt = pair_cnt; a.thr = thr;
+    // ps = capacity of a pair's row; rs = row stride.  Candidate rows (ps != k) keep the distances and the positions
+    // of a pair next to each other -- row = [ps distances][ps positions] of ONE array -- so that the scan kernel
+    // addresses both with one pointer and the merge finds them in neighbouring cache lines.
     const int ps = pair_stride(h, npairs, k);
-    a.pstride = ps;
+    const int rs = ps != k ? 2 * ps : ps;
+    if (ps != k) pair_pos = reinterpret_cast<uint32_t*>(pair_d) + ps;
+    a.pair_pos = pair_pos;
+    a.pstride = rs;
 
     // upper bound on the number of work items: every bucket adds at most one partial group
     int64_t max_items = std::min<int64_t>(npairs, npairs / qn + nb);
     if (max_items < 1) max_items = 1;
     if (h->stats_timing) cudaEventRecord(h->ev[2], s);
-    h->stats.last_scan_kernel = !qlane ? 1 : use_scanu(h) ? 4 : use_scant(h) ? 3 : 2;
+    h->stats.last_scan_kernel = !qlane ? 1 : use_scanu(h) ? (use_scanw(h) ? 5 : 4) : 2;
     if (qlane) {
         if constexpr (sizeof(T) == 4) {
             ScanQArgs qa;
@@ -706,50 +707,26 @@ cudaError_t search_t(ivfadc_index* h, const void* dQ, int64_t nq, int k, int w, 
                 uq.items = h->ws_items.as<int4>();
                 uq.item_counter = item_counter;
                 uq.pstride = ps;
+                uq.rstride = rs;
                 uq.err = h->d_err;
                 uq.dbg = static_cast<float*>(h->d_dbg_lut);
-                static int num_sms = 0;
-                if (!num_sms) {
-                    int dev = 0;
-                    cudaGetDevice(&dev);
-                    if ((e = cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
-                }
+                const int num_sms = h->num_sms > 0 ? h->num_sms : 148;
                 const int dup = scanu_dup(h);
-                const size_t usmem = scanu_smem_layout(a.m * dup).total;
+                const bool v1 = !use_scanw(h);
                 const unsigned ugrid = (unsigned)std::min<int64_t>(max_items, num_sms);  // persistent: one CTA per SM
                 if (dup == 2) {  // dsub = 16: two 8-dim tables per code byte
                     uq.q.dsub = 8;
-                    if (a.m == 4) e = launch_scanu_np<1, 2>(uq, ugrid, usmem, s);
-                    else e = launch_scanu_np<2, 2>(uq, ugrid, usmem, s);
+                    if (a.m == 4) e = launch_scanu_np<1, 2>(h, v1, uq, ugrid, s);
+                    else e = launch_scanu_np<2, 2>(h, v1, uq, ugrid, s);
                 } else {
                     switch (a.m) {
-                        case 4: e = launch_scanu_np<1>(uq, ugrid, usmem, s); break;
-                        case 8: e = launch_scanu_np<2>(uq, ugrid, usmem, s); break;
-                        case 12: e = launch_scanu_np<3>(uq, ugrid, usmem, s); break;
-                        default: e = launch_scanu_np<4>(uq, ugrid, usmem, s); break;
+                        case 4: e = launch_scanu_np<1>(h, v1, uq, ugrid, s); break;
+                        case 8: e = launch_scanu_np<2>(h, v1, uq, ugrid, s); break;
+                        case 12: e = launch_scanu_np<3>(h, v1, uq, ugrid, s); break;
+                        default: e = launch_scanu_np<4>(h, v1, uq, ugrid, s); break;
                     }
                 }
                 if (e != cudaSuccess) return e;
-                *launches += 1;
-            } else if (use_scant(h)) {
-                ScanTArgs tq;
-                tq.q = qa;
-                tq.tcB = static_cast<const float*>(h->d_tcB);
-                tq.items = h->ws_items.as<int4>();
-                tq.err = h->d_err;
-                tq.dbg_lut = static_cast<float*>(h->d_dbg_lut);
-                const size_t tsmem = kSmemMax;  // the kernel places its 64 KB table at a 64 KB-aligned absolute address
-                static size_t tconfigured[2] = {0, 0};
-                const int ident = a.cb_identity ? 1 : 0;
-                if (tsmem > tconfigured[ident]) {
-                    e = ident ? cudaFuncSetAttribute(scant_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsmem)
-                              : cudaFuncSetAttribute(scant_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsmem);
-                    if (e != cudaSuccess) return e;
-                    tconfigured[ident] = tsmem;
-                }
-                if (ident) scant_kernel<true><<<(unsigned)max_items, QTHREADS, tsmem, s>>>(tq);
-                else scant_kernel<false><<<(unsigned)max_items, QTHREADS, tsmem, s>>>(tq);
-                if ((e = cudaGetLastError()) != cudaSuccess) return e;
                 *launches += 1;
             } else {
             const bool fast = scanq_fast(h);
@@ -757,13 +734,9 @@ cudaError_t search_t(ivfadc_index* h, const void* dQ, int64_t nq, int k, int w, 
             qa.wnfrag = static_cast<const float2*>(h->d_wnfrag);
             qa.ntiles = h->frag_ntiles; qa.ksteps = h->frag_ksteps;
             const size_t qsmem = scanq_smem_layout(a.m, a.dsub, fast).total;
-            static size_t configured[2] = {0, 0};
-            if (qsmem > configured[fast]) {
-                e = fast ? cudaFuncSetAttribute(scanq_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)qsmem)
-                         : cudaFuncSetAttribute(scanq_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)qsmem);
-                if (e != cudaSuccess) return e;
-                configured[fast] = qsmem;
-            }
+            e = fast ? ensure_smem(h, reinterpret_cast<const void*>(&scanq_kernel<true>), qsmem)
+                     : ensure_smem(h, reinterpret_cast<const void*>(&scanq_kernel<false>), qsmem);
+            if (e != cudaSuccess) return e;
             if (fast) scanq_kernel<true><<<(unsigned)max_items, QTHREADS, qsmem, s>>>(qa);
             else scanq_kernel<false><<<(unsigned)max_items, QTHREADS, qsmem, s>>>(qa);
             if ((e = cudaGetLastError()) != cudaSuccess) return e;
@@ -773,19 +746,19 @@ cudaError_t search_t(ivfadc_index* h, const void* dQ, int64_t nq, int k, int w, 
             const size_t rsmem = smem_for<T>(1, h->cfg.m, h->dsub, k);
             const int rgrid = 2 * 148;
             switch (a.m) {
-                case 8: e = launch_redo_r<T, 8>(a, redo_pairs, redo_cnt, rgrid, rsmem, s); break;
-                case 12: e = launch_redo_r<T, 12>(a, redo_pairs, redo_cnt, rgrid, rsmem, s); break;
-                case 16: e = launch_redo_r<T, 16>(a, redo_pairs, redo_cnt, rgrid, rsmem, s); break;
-                default: e = launch_redo_r<T, 0>(a, redo_pairs, redo_cnt, rgrid, rsmem, s); break;
+                case 8: e = launch_redo_r<T, 8>(h, a, redo_pairs, redo_cnt, rgrid, rsmem, s); break;
+                case 12: e = launch_redo_r<T, 12>(h, a, redo_pairs, redo_cnt, rgrid, rsmem, s); break;
+                case 16: e = launch_redo_r<T, 16>(h, a, redo_pairs, redo_cnt, rgrid, rsmem, s); break;
+                default: e = launch_redo_r<T, 0>(h, a, redo_pairs, redo_cnt, rgrid, rsmem, s); break;
             }
             if (e != cudaSuccess) return e;
             *launches += 1;
         }
     } else {
         const size_t smem = smem_for<T>(qn, h->cfg.m, h->dsub, k);
-        if (qn == 4) e = launch_scan_m<T, 4>(a, (int)max_items, smem, s);
-        else if (qn == 2) e = launch_scan_m<T, 2>(a, (int)max_items, smem, s);
-        else e = launch_scan_m<T, 1>(a, (int)max_items, smem, s);
+        if (qn == 4) e = launch_scan_m<T, 4>(h, a, (int)max_items, smem, s);
+        else if (qn == 2) e = launch_scan_m<T, 2>(h, a, (int)max_items, smem, s);
+        else e = launch_scan_m<T, 1>(h, a, (int)max_items, smem, s);
         if (e != cudaSuccess) return e;
         *launches += 1;
     }
@@ -797,11 +770,11 @@ cudaError_t search_t(ivfadc_index* h, const void* dQ, int64_t nq, int k, int w, 
         if constexpr (sizeof(T) == 4) {
             if (h->id_dev_bytes == 4)
                 merge_cands_kernel<uint32_t><<<mgrid, 128, 0, s>>>(
-                    nq, w, k, ps, mcap, d_cells, pair_d, pair_pos, pair_cnt, h->d_off, static_cast<const uint32_t*>(h->d_ids),
+                    nq, w, k, ps, rs, mcap, d_cells, pair_d, pair_pos, pair_cnt, h->d_off, static_cast<const uint32_t*>(h->d_ids),
                     d_ids, static_cast<float*>(d_dists), d_keys, d_counts);
             else
                 merge_cands_kernel<uint64_t><<<mgrid, 128, 0, s>>>(
-                    nq, w, k, ps, mcap, d_cells, pair_d, pair_pos, pair_cnt, h->d_off, static_cast<const uint64_t*>(h->d_ids),
+                    nq, w, k, ps, rs, mcap, d_cells, pair_d, pair_pos, pair_cnt, h->d_off, static_cast<const uint64_t*>(h->d_ids),
                     d_ids, static_cast<float*>(d_dists), d_keys, d_counts);
         }
     } else if (h->id_dev_bytes == 4)
@@ -838,17 +811,6 @@ cudaError_t scanq_prepare(ivfadc_index* h, cudaStream_t s, int* launches) {
                                                      static_cast<float2*>(h->d_wnfrag));
     if (launches) *launches += 1;
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
-    // operand blocks of the tcgen05 builder
-    if (h->dsub <= 8 && m % 2 == 0) {
-        const size_t words = (size_t)(m / 2) * TB_NBLK * 2048;
-        if ((e = cudaMalloc(&h->d_tcB, words * sizeof(float))) != cudaSuccess) return e;
-        if ((e = cudaMalloc(&h->d_err, sizeof(int))) != cudaSuccess) return e;
-        if ((e = cudaMemsetAsync(h->d_err, 0, sizeof(int), s)) != cudaSuccess) return e;
-        prep_tc_kernel<<<(unsigned)((words + 255) / 256), 256, 0, s>>>(static_cast<const float*>(h->d_cb), m,
-                                                                      h->cfg.ksub, h->dsub,
-                                                                      static_cast<float*>(h->d_tcB));
-        if (launches) *launches += 1;
-    }
     // operand blocks of the tensor-memory lookup kernel (rows = code values)
     if (scanu_shape_ok(h)) {
         const int dup = scanu_dup(h);
@@ -887,8 +849,8 @@ ScanPlanSizes scan_plan_sizes(const ivfadc_index* h, int64_t nq, int w, int k) {
     z.bucket_bytes = sizeof(int) * ((size_t)nb * PLAN_PAD + 2 * (size_t)nb + 8);
     z.sorted_bytes = sizeof(int32_t) * (size_t)npairs * 2;  // sorted pairs | redo queue
     const int ps = pair_stride(h, npairs, k);
-    z.pair_d_bytes = h->tsize * (size_t)npairs * ps;
-    z.pair_pos_bytes = sizeof(uint32_t) * (size_t)npairs * ps;
+    z.pair_d_bytes = h->tsize * (size_t)npairs * ps * (ps != k ? 2 : 1);  // candidate rows: [ps distances][ps positions]
+    z.pair_pos_bytes = ps != k ? 16 : sizeof(uint32_t) * (size_t)npairs * ps;
     z.pair_cnt_bytes = sizeof(int32_t) * (size_t)npairs;
     z.thr_bytes = 8 * (size_t)nq;
     z.items_bytes = sizeof(int4) * (size_t)(std::min<int64_t>(npairs, npairs / QG + h->cfg.kc) + 1);

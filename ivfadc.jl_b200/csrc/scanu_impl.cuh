@@ -40,7 +40,7 @@
 // distance (bound 1e-5).
 #pragma once
 
-#include "scant_impl.cuh"
+#include "tc_common.cuh"
 
 namespace ivf {
 
@@ -66,7 +66,8 @@ struct ScanUArgs {
     const float* tcU;     // [m][3][2048] tf32 words: -2w hi / lo, split norms; rows = code values
     const int4* items;    // [nitems] (cell, first pair slot, number of pairs, 0)
     int* item_counter;    // work distribution (zeroed per launch)
-    int pstride;          // row stride of pair_d / pair_pos (candidate capacity per pair)
+    int pstride;          // candidate capacity of a pair's row
+    int rstride;          // row stride of pair_d / pair_pos (words)
     int* err;             // device error flag (mbarrier timeout)
     float* dbg;           // optional: tables of the first item [m][256][32], then int pair[32], cell
 };
@@ -746,7 +747,7 @@ scanu_kernel(const ScanUArgs ua) {
             const int pair = (int)lds_u(pair_u + q * 4);
             if (!bad) {
                 const uint32_t src = cand_u + ((q * QWARPS + w2) * U_CW + half * (U_CW / 2)) * 8;
-                const size_t dst = (size_t)pair * ps + cf + (incl - nl);
+                const size_t dst = (size_t)pair * ua.rstride + cf + (incl - nl);
                 const uint32_t pbase = (uint32_t)pass * U_VP + 16 * (w2 < U_SW ? w2 : 4 * U_SW);  // position of register slot 0 of warp w2
                 const uint32_t pstep = 16 * (w2 < U_SW ? U_SW : 1);
                 for (int i = 0; i < nl; ++i) {

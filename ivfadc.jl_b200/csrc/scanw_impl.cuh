@@ -1,0 +1,638 @@
+// K2 + K3, warp-specialised "tensor-memory lookup" scan -- the default batched search kernel on sm_100a
+// (fp32, k <= 16, dsub <= 8 or dsub = 16, m in {4, 8, 12, 16}).
+//
+// Same arithmetic and the same work decomposition as scanu_impl.cuh (work item = one inverted list x up to 32
+// queries that probe it, lane = query, the lookup table of one subspace is an accumulator tile
+// D[128 lanes][256 columns] in tensor memory built by four tcgen05.mma kind::tf32, a lookup is
+// tcgen05.ld.32x32b.x1 at column = code byte; reference: the LUT of src/index.jl:232-236 and the scan of
+// src/index.jl:240-246), but the CTA is split into ROLES that only meet on mbarriers -- no CTA-wide barrier
+// anywhere between the prologue and the epilogue of the persistent kernel:
+//
+//   * warps 0..11  SCANNERS  (152 registers via setmaxnreg): 96 partial distances per lane, so a pass covers
+//     12 x 96 = 1152 vectors of the list.  Per table: wait for the build (mbarrier of tcgen05.commit), 96 lookups,
+//     arrive on the table buffer's "free" mbarrier -- and straight on to the next table.  At the end of a pass:
+//     two group minima per warp -> the k-th smallest of the 24 minima bounds the list's k-th distance (two
+//     named barriers among the 384 scanner threads) -> every vector within the bound is appended to the
+//     pair's candidate row in HBM (slot from a per-query shared-memory counter), no staging through shared memory.
+//   * warp 12      PRODUCER  (40 registers): the stream of table builds t = 0, 1, 2, ... runs across segment and
+//     item boundaries.  Per build: A operand (TF32 hi / lo of the residuals, four row copies) into its ring slot
+//     as soon as build t - 2 has completed, wait until the 12 scanners have released table t - 2, four MMAs +
+//     commit, refill of the codebook ring (cp.async.bulk, three slots).
+//   * warps 13, 14 LOADERS: next segment (item, pass) while the scanners work on the current one -- item
+//     descriptor, query rows / centroid slices / code bytes by cp.async, byte-plane transposes of the codes
+//     (double-buffered planes), residuals r = q - c with their norms (double-buffered per item).
+//   * warp 15      FINALIZER: after the scanners' last append of a list, publishes the candidate counts of the
+//     item's pairs (or queues the pair for the exact redo kernel on overflow) and hands the buffers back to
+//     the loaders.
+//
+// Candidate rows, merge_cands_kernel and the redo queue are those of scanu (scan.cu).
+#pragma once
+
+#include "scanu_impl.cuh"
+
+namespace ivf {
+
+constexpr int W_SCAN = 12;                   // scanning warps
+constexpr int W_THREADS = 512;               // + producer, two loaders, finalizer
+constexpr int W_PROD = 12, W_LOAD = 13, W_FIN = 15;
+constexpr int W_NLOAD = 64;                  // loader threads
+constexpr int W_NV = 96;                     // partial distances per lane
+constexpr int W_NCH = W_NV / 16;             // chunks of 16 vectors per scanner and pass
+constexpr int W_VP = W_SCAN * W_NV;          // 1152 vectors per pass
+constexpr int W_CSTEP = 16 * W_SCAN;         // byte distance of a scanner's consecutive chunks in a plane
+constexpr int W_NMIN = 2 * W_SCAN;           // group minima per query and pass
+constexpr int W_STATE = 5 * QG * 4;          // per item: pair | dc -> base | run | cnt | flag
+constexpr int W_SEG = 32;                    // per segment: valid, nv, pass, ipar, nj, last
+constexpr uint32_t W_SPIN = 1u << 20;
+#ifndef W_DEPTH
+#define W_DEPTH 16                           // lookups in flight per tcgen05.wait::ld (16 or 32)
+#endif
+
+struct ScanWSmem {
+    uint32_t aone, aring, bring, planes, raw, resid, rawq, smin, thr, rnorm, state, seg, ldesc, cbuf, bars, total;
+};
+
+// m = tables per item (8 dims each), mc = code bytes per vector
+__host__ __device__ inline ScanWSmem scanw_smem_layout(int m, int mc) {
+    ScanWSmem s;
+    uint32_t o = 0;
+    s.aone = o;    o += U_ABLK;
+    s.aring = o;   o += 2 * U_ASUB;
+    s.bring = o;   o += U_NB * U_BSUB;
+    s.planes = o;  o += 2u * (uint32_t)mc * W_VP;
+    s.raw = o;     o += (uint32_t)mc * W_VP + 16;
+    s.rawq = o;    o += (uint32_t)QG * m * 32;
+    s.resid = o;   o += 2u * (uint32_t)m * 8 * T_RS * 4;
+    o = (o + 15) & ~15u;
+    s.smin = o;    o += W_NMIN * QG * 4;
+    s.thr = o;     o += QG * 4;
+    s.rnorm = o;   o += (uint32_t)m * QG * 4;
+    s.state = o;   o += 2 * W_STATE;
+    s.seg = o;     o += 2 * W_SEG;
+    s.ldesc = o;   o += 64;
+    s.cbuf = o;    o += (uint32_t)m * 32;
+    s.bars = o;    o += 144;
+    s.total = o;
+    return s;
+}
+
+__device__ __forceinline__ void named_bar(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// Bounded wait that gives up at once when another wait of this CTA has already timed out (`dead` flag in shared
+// memory): a broken pipeline ends in an error code within about a second, not in a hang.
+__device__ __forceinline__ void mbar_wait_w(uint32_t bar, uint32_t parity, uint32_t dead_u, int* err, int code) {
+#pragma unroll 1
+    for (uint32_t i = 0; i < W_SPIN; ++i) {
+        if (mbar_try_wait(bar, parity)) return;
+        if ((i & 255u) == 255u && lds_u(dead_u) != 0u) return;
+    }
+    sts_u(dead_u, 1u);
+    atomicExch(err, code);
+}
+
+template <bool FULL>
+__device__ __forceinline__ void scanw_sub(uint32_t tb, uint32_t plane_w, int nch, float (&acc)[W_NV]) {
+    if constexpr (FULL && W_DEPTH == 32) {
+#pragma unroll
+        for (int j2 = 0; j2 < W_NCH / 2; ++j2) {
+            const uint4 x0 = lds_v4(plane_w + (2 * j2) * W_CSTEP), x1 = lds_v4(plane_w + (2 * j2 + 1) * W_CSTEP);
+            float t[32];
+            scanu_issue<0>(tb, x0, t);
+            scanu_issue<0>(tb, x1, t + 16);
+            tc_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) add_pair(acc[32 * j2 + i], acc[32 * j2 + i + 1], t[i], t[i + 1]);
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < W_NCH; ++j) {
+            if (FULL || j < nch) {  // warp-uniform; slots beyond the list are masked after the last table
+                const uint4 x = lds_v4(plane_w + j * W_CSTEP);
+                float t[16];
+                scanu_issue<0>(tb, x, t);
+                tc_wait_ld();
+#pragma unroll
+                for (int i = 0; i < 16; i += 2) add_pair(acc[16 * j + i], acc[16 * j + i + 1], t[i], t[i + 1]);
+            }
+        }
+    }
+}
+
+// NP = (code bytes per vector) / 4; DUP = 2 serves dsub = 16 (two 8-dim tables share a code byte, see scanu_kernel).
+// Debug buffer (DBG instantiation, CTA 0): tables of the first segment [m][256][32], int pair[32], cell, then
+// clock64 stamps of segment W_DBG_SEG: scanner w at [16 w ..], producer at [192 ..], loaders [256 ..], finalizer [272 ..].
+constexpr int W_DBG_SEG = 3;
+
+template <int NP, bool DBG, int DUP = 1>
+__global__ void __launch_bounds__(W_THREADS, 1)
+scanw_kernel(const ScanUArgs ua) {
+    const ScanQArgs& a = ua.q;
+    extern __shared__ __align__(1024) unsigned char smem_w[];
+    constexpr int mc = 4 * NP;      // code bytes per vector
+    constexpr int m = mc * DUP;     // tables per segment
+    constexpr uint32_t RESID_BYTES = (uint32_t)m * 8 * T_RS * 4;
+    constexpr uint32_t PLANES_BYTES = (uint32_t)mc * W_VP;
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int wid = __shfl_sync(0xffffffffu, tid >> 5, 0);  // provably warp-uniform for ptxas
+    const int k = a.k;
+    const int ps = ua.pstride;
+    const bool fastq = a.dsub == 8 && (a.D & 3) == 0;  // 16-byte aligned query / centroid slices
+    const int nitems = a.group_off[a.kc];
+    if ((int)blockIdx.x >= nitems) return;  // before any allocation
+
+    uint32_t sb;
+    asm volatile("mov.u32 %0, %1;" : "=r"(sb) : "r"(smem_u32(smem_w)));
+    const ScanWSmem L = scanw_smem_layout(m, mc);
+    const uint32_t aone_u = sb + L.aone, aring_u = sb + L.aring, bring_u = sb + L.bring, planes_u = sb + L.planes,
+                   raw_u = sb + L.raw, resid_u = sb + L.resid, rawq_u = sb + L.rawq, smin_u = sb + L.smin,
+                   thr_u = sb + L.thr, rnorm_u = sb + L.rnorm, state_u = sb + L.state, seg_u = sb + L.seg,
+                   ldesc_u = sb + L.ldesc, cbuf_u = sb + L.cbuf;
+    const uint32_t bar_full = sb + L.bars;          // 3: codebook operand landed in ring slot
+    const uint32_t bar_mma = bar_full + 24;         // 2: table build complete (tcgen05.commit)
+    const uint32_t bar_free = bar_full + 40;        // 2: the 12 scanners are done with the table buffer
+    const uint32_t bar_staged = bar_full + 56;      // 2: segment staged by the loaders
+    const uint32_t bar_extract = bar_full + 72;     // 2: the 12 scanners have appended their candidates
+    const uint32_t bar_segfree = bar_full + 88;     // 2: finalizer is done with the segment's buffers
+    const uint32_t tmem_slot = bar_full + 104, dead_u = bar_full + 108;
+
+    // ---- one-time setup ----
+    if (tid == 0) {
+        for (int i = 0; i < U_NB; ++i) mbar_init(bar_full + 8 * i, 1);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(bar_mma + 8 * i, 1);
+            mbar_init(bar_free + 8 * i, W_SCAN);
+            mbar_init(bar_staged + 8 * i, 1);
+            mbar_init(bar_extract + 8 * i, W_SCAN);
+            mbar_init(bar_segfree + 8 * i, 1);
+        }
+        sts_u(dead_u, 0u);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        for (int i = 0; i < U_NB; ++i) {
+            mbar_expect_tx(bar_full + 8 * i, U_BSUB);
+            tma_bulk_g2s(bring_u + i * U_BSUB, ua.tcU + (size_t)(i % m) * (U_BSUB / 4), U_BSUB, bar_full + 8 * i);
+        }
+    }
+    if (wid == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot),
+                     "r"(U_TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    // ones block of the A operand: every row selects the split norm (k slots 0, 1)
+    for (int i = tid; i < 256; i += W_THREADS) {
+        const int r = i >> 1, half = i & 1;
+        const float one = half == 0 ? 1.f : 0.f;
+        sts_v4f(aone_u + (r >> 3) * 256 + half * 128 + (r & 7) * 16, one, one, 0.f, 0.f);
+    }
+    fence_proxy_async();  // ones block: generic-proxy writes -> async proxy (tensor core)
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = lds_u(tmem_slot);
+
+    auto warp_wait = [&](uint32_t bar, uint32_t parity, int code) {
+        if (lane == 0) mbar_wait_w(bar, parity, dead_u, ua.err, code);
+        __syncwarp();
+    };
+    long long* const stamps = (DBG && blockIdx.x == 0 && ua.dbg != nullptr)
+                                  ? reinterpret_cast<long long*>(ua.dbg + (size_t)m * 256 * 32 + 64) : nullptr;
+
+    if (wid < W_SCAN) {
+        // =========================================== SCANNERS ===========================================
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 152;");
+        const uint32_t tq = tmem_base + ((uint32_t)((wid & 3) * 32) << 16);
+        const uint32_t plane_w0 = planes_u + 16 * wid;
+        long long* const st = (stamps && lane == 0) ? stamps + 16 * wid : nullptr;
+        uint32_t tg = 0;
+        float acc[W_NV];
+#pragma unroll 1
+        for (uint32_t g = 0;; ++g) {
+            const uint32_t spar = g & 1;
+            warp_wait(bar_staged + 8 * spar, (g >> 1) & 1, 20);
+            const uint32_t sg = seg_u + spar * W_SEG;
+            if (lds_u(sg) == 0u) break;
+            const int nv = (int)lds_u(sg + 4), pass = (int)lds_u(sg + 8);
+            const uint32_t stt = state_u + lds_u(sg + 12) * W_STATE;  // pair | base | run | cnt | flag of the item
+            const bool stamp_on = DBG && st && g == W_DBG_SEG;
+            if (stamp_on) st[0] = clock64();
+            const float base = lds_f(stt + QG * 4 + lane * 4);
+            const int nch = min(W_NCH, max(0, (nv - 16 * wid + W_CSTEP - 1) / W_CSTEP));  // chunks j with 16 (wid + 12 j) < nv
+#pragma unroll
+            for (int j = 0; j < W_NV; ++j) acc[j] = base;  // dc + |r|^2, then the table entries in subspace order
+#pragma unroll 1
+            for (int s = 0; s < m; ++s) {
+                const uint32_t t = tg + s;
+                if (stamp_on && (s == 5 || s == 6)) st[6 + (s - 5) * 3] = clock64();
+                warp_wait(bar_mma + 8 * (t & 1), (t >> 1) & 1, 2);
+                tc_fence_after();
+                if (stamp_on && (s == 5 || s == 6)) st[7 + (s - 5) * 3] = clock64();
+                // s and t are warp-uniform, but ptxas keeps the loop counter in a vector register unless told
+                const uint32_t tb = tq + (__shfl_sync(0xffffffffu, t, 0) & 1) * 256;
+                const uint32_t plane_w = plane_w0 + spar * PLANES_BYTES + (__shfl_sync(0xffffffffu, s, 0) / DUP) * W_VP;
+                if (nch == W_NCH) scanw_sub<true>(tb, plane_w, nch, acc);
+                else scanw_sub<false>(tb, plane_w, nch, acc);
+                if (DBG && g == 0 && blockIdx.x == 0 && ua.dbg != nullptr) {  // bring-up: dump the tables of the first segment
+                    if (wid < 4) {
+                        for (int c = wid; c < 256; c += 4) {
+                            const float v = tc_ld1(tb + c);
+                            tc_wait_ld();
+                            ua.dbg[((size_t)s * 256 + c) * 32 + lane] = v;
+                        }
+                    }
+                    if (s == 0 && wid == 0) {
+                        reinterpret_cast<int*>(ua.dbg + (size_t)m * 256 * 32)[lane] = (int)lds_u(stt + lane * 4);
+                        if (lane == 0) reinterpret_cast<int*>(ua.dbg + (size_t)m * 256 * 32)[QG] = (int)lds_u(sg + 24);
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_free + 8 * (t & 1));
+                if (stamp_on && (s == 5 || s == 6)) st[8 + (s - 5) * 3] = clock64();
+            }
+            tg += m;
+            if (stamp_on) st[1] = clock64();
+
+            // ---- end of the pass: bound, candidates ----
+            {   // slot 16 j + i holds vector 16 (wid + 12 j) + i of the pass: mask the slots beyond the list
+                const int lim = nv - 16 * wid;
+#pragma unroll
+                for (int j = 0; j < W_NCH; ++j) {
+                    if (W_CSTEP * j + 16 > lim) {  // warp-uniform
+#pragma unroll
+                        for (int i = 0; i < 16; ++i)
+                            if (W_CSTEP * j + i >= lim) acc[16 * j + i] = Limits<float>::inf();
+                    }
+                }
+            }
+            float mn0 = Limits<float>::inf(), mn1 = Limits<float>::inf();
+#pragma unroll
+            for (int j = 0; j < W_NV / 2; ++j) {
+                mn0 = fminf(mn0, acc[j]);
+                mn1 = fminf(mn1, acc[W_NV / 2 + j]);
+            }
+            sts_f(smin_u + ((2 * wid) * QG + lane) * 4, mn0);
+            sts_f(smin_u + ((2 * wid + 1) * QG + lane) * 4, mn1);
+            named_bar(1, W_SCAN * 32);
+            if (stamp_on) st[2] = clock64();
+            {
+                int r0 = 0, r1 = 0;
+#pragma unroll
+                for (int i = 0; i < W_NMIN; ++i) {
+                    const float o = lds_f(smin_u + (i * QG + lane) * 4);
+                    r0 += (o < mn0 || (o == mn0 && i < 2 * wid)) ? 1 : 0;
+                    r1 += (o < mn1 || (o == mn1 && i < 2 * wid + 1)) ? 1 : 0;
+                }
+                // the k-th smallest of 24 disjoint group minima bounds the k-th smallest of all; the bound of the
+                // previous passes of this list stays valid
+                const int kk = min(k, W_NMIN) - 1;
+                if (r0 == kk || r1 == kk) {
+                    const float thr = fminf(r0 == kk ? mn0 : mn1, lds_f(stt + 2 * QG * 4 + lane * 4));
+                    sts_f(thr_u + lane * 4, thr);
+                    sts_f(stt + 2 * QG * 4 + lane * 4, thr);
+                }
+            }
+            named_bar(1, W_SCAN * 32);
+            if (stamp_on) st[3] = clock64();
+            {
+                const float thr = lds_f(thr_u + lane * 4);
+                // keep d <= bound; while fewer than k vectors have been seen (bound = +inf) keep every real slot
+                const float cut = thr < Limits<float>::inf() ? thr : 3.402823466e+38f;
+                const int pair = (int)lds_u(stt + lane * 4);
+                int c = 0;
+#pragma unroll
+                for (int j = 0; j < W_NV; ++j) c += acc[j] <= cut ? 1 : 0;
+                if (pair < 0) c = 0;
+                int old = 0;
+                if (c > 0) old = atoms_add(stt + 3 * QG * 4 + lane * 4, c);
+                const bool ok = c > 0 && old + c <= ps;
+                if (c > 0 && !ok) sts_u(stt + 4 * QG * 4 + lane * 4, 1u);  // row overflow: the pair goes to the redo queue
+                if (ok) {
+                    // row of the pair = [U_CAP distances][U_CAP positions]: one pointer serves both stores
+                    uint32_t* pd = reinterpret_cast<uint32_t*>(a.pair_d) + (size_t)pair * (2 * U_CAP) + old;
+                    const uint32_t p0 = (uint32_t)pass * W_VP + 16u * wid;
+#pragma unroll
+                    for (int j = 0; j < W_NV; ++j) {
+                        if (acc[j] <= cut) {
+                            pd[0] = __float_as_uint(acc[j]);
+                            pd[U_CAP] = p0 + (uint32_t)((j >> 4) * W_CSTEP + (j & 15));
+                            ++pd;
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_extract + 8 * spar);
+            if (stamp_on) st[4] = clock64();
+        }
+    } else {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+        if (wid == W_PROD) {
+            // =========================================== PRODUCER ===========================================
+            const uint64_t descA0 = tc_smem_desc(aring_u), descB0 = tc_smem_desc(bring_u), desc1 = tc_smem_desc(aone_u);
+            uint32_t t = 0;
+            uint32_t bslot = 0, bphase = 0;            // ring slot / phase of build t
+            uint32_t fslot = 0, fsub = U_NB % m;       // next refill: slot (= slot of build t - 2), subspace of build t + 1
+            uint32_t nfill = U_NB;                     // fills issued so far
+            long long* const st = (stamps && lane == 0) ? stamps + 192 : nullptr;
+#pragma unroll 1
+            for (uint32_t g = 0;; ++g) {
+                const uint32_t spar = g & 1;
+                warp_wait(bar_staged + 8 * spar, (g >> 1) & 1, 21);
+                const uint32_t sg = seg_u + spar * W_SEG;
+                if (lds_u(sg) == 0u) break;
+                const uint32_t res_i = resid_u + lds_u(sg + 12) * RESID_BYTES;
+                const bool stamp_on = DBG && st && g == W_DBG_SEG;
+#pragma unroll 1
+                for (int s = 0; s < m; ++s, ++t) {
+                    const uint32_t buf = t & 1;
+                    if (t >= 2) {
+                        // build t - 2 has completed: its A slot (= the one of build t) and its codebook ring slot are free
+                        warp_wait(bar_mma + 8 * buf, ((t - 2) >> 1) & 1, 22);
+                        if (lane == 0) {
+                            const uint32_t bar = bar_full + 8 * fslot;
+                            mbar_expect_tx(bar, U_BSUB);
+                            tma_bulk_g2s(bring_u + fslot * U_BSUB, ua.tcU + (size_t)fsub * (U_BSUB / 4), U_BSUB, bar);
+                        }
+                        if (++fslot == U_NB) fslot = 0;
+                        if (++fsub == (uint32_t)m) fsub = 0;
+                        ++nfill;
+                    }
+                    if (stamp_on) st[4 * s] = clock64();
+                    {   // A operand of table s: rows (copy, q) = TF32 hi / lo of r[s][q][0..7]; lane = query
+                        float hi[8], lo[8];
+#pragma unroll
+                        for (int d = 0; d < 8; ++d) {
+                            const float r = lds_f(res_i + ((s * 8 + d) * T_RS + lane) * 4);
+                            hi[d] = __uint_as_float(to_tf32(r));
+                            lo[d] = __uint_as_float(to_tf32(r - hi[d]));
+                        }
+                        const uint32_t ph0 = aring_u + buf * U_ASUB + (lane >> 3) * 256 + (lane & 7) * 16;
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) {  // row = 32 c + lane
+                            const uint32_t ph = ph0 + c * 1024;
+                            sts_v4f(ph, hi[0], hi[1], hi[2], hi[3]);
+                            sts_v4f(ph + 128, hi[4], hi[5], hi[6], hi[7]);
+                            sts_v4f(ph + U_ABLK, lo[0], lo[1], lo[2], lo[3]);
+                            sts_v4f(ph + U_ABLK + 128, lo[4], lo[5], lo[6], lo[7]);
+                        }
+                        fence_proxy_async();  // generic-proxy writes of this lane -> async proxy
+                        __syncwarp();
+                    }
+                    if (stamp_on) st[4 * s + 1] = clock64();
+                    if (t >= 2) warp_wait(bar_free + 8 * buf, ((t - 2) >> 1) & 1, 23);  // scanners released table t - 2
+                    warp_wait(bar_full + 8 * bslot, bphase, 1);
+                    if (stamp_on) st[4 * s + 2] = clock64();
+                    tc_fence_after();
+                    const uint32_t slot_u = __shfl_sync(0xffffffffu, bslot, 0), buf_u = __shfl_sync(0xffffffffu, buf, 0);
+                    const uint64_t Ah = descA0 + (uint64_t)(buf_u * (U_ASUB >> 4)), Al = Ah + (U_ABLK >> 4);
+                    const uint64_t Bh = descB0 + (uint64_t)(slot_u * (U_BSUB >> 4)), Bl = Bh + (U_BBLK >> 4), Bn = Bl + (U_BBLK >> 4);
+                    const uint32_t d = tmem_base + buf_u * 256;
+                    tc_mma_elect(d, Ah, Bh, 0);
+                    tc_mma_elect(d, Al, Bh, 1);
+                    tc_mma_elect(d, Ah, Bl, 1);
+                    tc_mma_elect(d, desc1, Bn, 1);
+                    tc_commit_elect(bar_mma + 8 * buf_u);
+                    if (++bslot == U_NB) { bslot = 0; bphase ^= 1; }
+                    if (stamp_on) st[4 * s + 3] = clock64();
+                }
+            }
+            // drain: codebook operands fetched for builds that never ran
+            if (lane == 0) {
+                for (uint32_t f = t; f < nfill; ++f) mbar_wait_w(bar_full + 8 * (f % U_NB), (f / U_NB) & 1, dead_u, ua.err, 5);
+            }
+            __syncwarp();
+        } else if (wid == W_FIN) {
+            // =========================================== FINALIZER ===========================================
+            long long* const st = (stamps && lane == 0) ? stamps + 272 : nullptr;
+#pragma unroll 1
+            for (uint32_t g = 0;; ++g) {
+                const uint32_t spar = g & 1;
+                warp_wait(bar_staged + 8 * spar, (g >> 1) & 1, 24);
+                const uint32_t sg = seg_u + spar * W_SEG;
+                if (lds_u(sg) == 0u) break;
+                const uint32_t stt = state_u + lds_u(sg + 12) * W_STATE;
+                const int nj = (int)lds_u(sg + 16);
+                const bool last = lds_u(sg + 20) != 0u;
+                warp_wait(bar_extract + 8 * spar, (g >> 1) & 1, 25);
+                if (DBG && st && g == W_DBG_SEG) st[0] = clock64();
+                if (last && lane < nj) {  // last pass of the list: publish the pair
+                    const int pair = (int)lds_u(stt + lane * 4);
+                    const int c = (int)lds_u(stt + 3 * QG * 4 + lane * 4);
+                    const bool bad = lds_u(stt + 4 * QG * 4 + lane * 4) != 0u || c > ps;
+                    if (pair >= 0) {
+                        if (bad) {
+                            a.pair_cnt[pair] = 0;
+                            a.redo_pairs[atomicAdd(a.redo_cnt, 1)] = pair;
+                        } else {
+                            a.pair_cnt[pair] = c;
+                        }
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_segfree + 8 * spar);
+                if (DBG && st && g == W_DBG_SEG) st[1] = clock64();
+            }
+        } else {
+            // =========================================== LOADERS ===========================================
+            const int lt = tid - W_LOAD * 32;  // 0..63
+            const int lw = wid - W_LOAD;       // 0, 1
+            auto cp_async = [&](uint32_t dst, const void* src, int bytes) {
+                if (bytes == 16) asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+                else if (bytes == 8) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+                else asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+            };
+            auto cp_wait = [&]() { asm volatile("cp.async.wait_all;" ::: "memory"); };
+            long long* const st = (stamps && lt == 0) ? stamps + 256 : nullptr;
+            int item = blockIdx.x, pass = 0, npass = 1, ipar = 0, nj = 0, cell = 0;
+            int64_t len = 0, off = 0;
+            bool new_item = true;
+#pragma unroll 1
+            for (uint32_t g = 0;; ++g) {
+                const uint32_t spar = g & 1;
+                const uint32_t sg = seg_u + spar * W_SEG;
+                if (g >= 2) warp_wait(bar_segfree + 8 * spar, ((g - 2) >> 1) & 1, 26);
+                const bool stamp_on = DBG && st && g == W_DBG_SEG + 1;   // the segment staged WHILE segment W_DBG_SEG is scanned
+                if (stamp_on) st[0] = clock64();
+                if (item >= nitems) {
+                    named_bar(2, W_NLOAD);
+                    if (lt == 0) {
+                        sts_u(sg, 0u);
+                        mbar_arrive(bar_staged + 8 * spar);
+                    }
+                    break;
+                }
+                const uint32_t stt = state_u + ipar * W_STATE;
+                const uint32_t res_i = resid_u + ipar * RESID_BYTES;
+                if (new_item) {
+                    if (lw == 0) {
+                        // descriptor: (cell, first pair slot, number of pairs) -> list length / offset, the pairs
+                        if (lane == 0) cp_async(ldesc_u, ua.items + item, 16);
+                        cp_wait();
+                        __syncwarp();
+                        const int dcell = (int)lds_u(ldesc_u), dfirst = (int)lds_u(ldesc_u + 4), dnj = (int)lds_u(ldesc_u + 8);
+                        if (lane == 0) {
+                            cp_async(ldesc_u + 16, a.list_len + dcell, 8);
+                            cp_async(ldesc_u + 24, a.list_off + dcell, 8);
+                        }
+                        if (lane < dnj) cp_async(stt + lane * 4, a.sorted_pairs + dfirst + lane, 4);
+                        else sts_u(stt + lane * 4, 0xFFFFFFFFu);
+                        cp_wait();
+                    } else {
+                        // the item after this one (work distribution by an atomic counter), and the item's running state
+                        if (lane == 0) sts_u(ldesc_u + 32, (uint32_t)(gridDim.x + atomicAdd(ua.item_counter, 1)));
+                        sts_f(stt + 2 * QG * 4 + lane * 4, Limits<float>::inf());
+                        sts_u(stt + 3 * QG * 4 + lane * 4, 0u);
+                        sts_u(stt + 4 * QG * 4 + lane * 4, 0u);
+                    }
+                    named_bar(2, W_NLOAD);
+                    cell = (int)lds_u(ldesc_u);
+                    nj = (int)lds_u(ldesc_u + 8);
+                    { const uint2 v = lds_v2u(ldesc_u + 16); len = (int64_t)(((uint64_t)v.y << 32) | v.x); }
+                    { const uint2 v = lds_v2u(ldesc_u + 24); off = (int64_t)(((uint64_t)v.y << 32) | v.x); }
+                    npass = (int)((len + W_VP - 1) / W_VP);
+                    if (stamp_on) st[1] = clock64();
+                    if (fastq) {
+                        // Query rows, coalesced: row q = m * 32 contiguous bytes = 2 m chunks of 16, stored at
+                        // chunk ^ (q & 7) (keeps the transposing reads below at 4-way bank conflicts)
+                        for (int idx = lt; idx < QG * 2 * m; idx += W_NLOAD) {
+                            const int q = idx / (2 * m), ch = idx - q * (2 * m);
+                            const int pq = (int)lds_u(stt + q * 4);
+                            const uint32_t dst = rawq_u + q * (m * 32) + ((ch ^ (q & 7)) * 16);
+                            if (pq >= 0) cp_async(dst, a.Q + (size_t)(pq / a.w) * a.D + ch * 4, 16);
+                            else sts_v4f(dst, 0.f, 0.f, 0.f, 0.f);
+                        }
+                        if (lt < 2 * m) cp_async(cbuf_u + lt * 16, a.C + (size_t)cell * a.D + lt * 4, 16);
+                    } else {
+                        for (int x = lt; x < m * QG; x += W_NLOAD) {
+                            const int s = x >> 5, q = x & 31;
+                            const int pq = (int)lds_u(stt + q * 4);
+                            const float* qv = a.Q + (size_t)(pq >= 0 ? pq / a.w : 0) * a.D + s * a.dsub;
+#pragma unroll
+                            for (int d = 0; d < 8; ++d) {
+                                const uint32_t dst = res_i + ((s * 8 + d) * T_RS + q) * 4;
+                                if (pq >= 0 && d < a.dsub) cp_async(dst, qv + d, 4);
+                                else sts_f(dst, 0.f);
+                            }
+                        }
+                        for (int x = lt; x < m * 8; x += W_NLOAD) {
+                            const int s = x >> 3, d = x & 7;
+                            if (d < a.dsub) cp_async(cbuf_u + x * 4, a.C + (size_t)cell * a.D + s * a.dsub + d, 4);
+                            else sts_f(cbuf_u + x * 4, 0.f);
+                        }
+                    }
+                    if (lw == 0) {  // dc lands in the `base` slot; |r|^2 is added below
+                        const int pq = (int)lds_u(stt + lane * 4);
+                        if (pq >= 0) cp_async(stt + QG * 4 + lane * 4, a.dc + pq, 4);
+                        else sts_f(stt + QG * 4 + lane * 4, 0.f);
+                    }
+                }
+                // code bytes of the pass as they lie in the list (16-byte pieces; the list starts 16-byte aligned, a pass
+                // is a multiple of 16 bytes, and the arena keeps slack behind every list)
+                const int64_t vb = (int64_t)pass * W_VP;
+                const int nvn = (int)min((int64_t)W_VP, len - vb);
+                {
+                    const uint8_t* src = a.codes + (size_t)(off + vb) * mc;
+                    const int n16 = (nvn * mc + 15) >> 4;
+                    for (int idx = lt; idx < n16; idx += W_NLOAD) cp_async(raw_u + idx * 16, src + (size_t)idx * 16, 16);
+                }
+                cp_wait();
+                named_bar(2, W_NLOAD);
+                if (stamp_on) st[2] = clock64();
+                // byte planes: plane p = code byte p of the pass's vectors (4 x 4 byte transposes)
+                for (int task = lt; 4 * task < nvn; task += W_NLOAD) {
+                    const int v0 = 4 * task;
+                    uint32_t cw[4][NP];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        if constexpr (NP == 4) {
+                            const uint4 r = lds_v4(raw_u + (v0 + i) * 16);
+                            cw[i][0] = r.x; cw[i][1] = r.y; cw[i][2] = r.z; cw[i][3] = r.w;
+                        } else {
+#pragma unroll
+                            for (int c = 0; c < NP; ++c) cw[i][c] = lds_u(raw_u + ((v0 + i) * NP + c) * 4);
+                        }
+                    }
+#pragma unroll
+                    for (int c = 0; c < NP; ++c) {
+                        const uint32_t w0 = cw[0][c], w1 = cw[1][c], w2 = cw[2][c], w3 = cw[3][c];
+                        const uint32_t t01l = __byte_perm(w0, w1, 0x5140), t23l = __byte_perm(w2, w3, 0x5140);
+                        const uint32_t t01h = __byte_perm(w0, w1, 0x7362), t23h = __byte_perm(w2, w3, 0x7362);
+                        const uint32_t pb = planes_u + spar * PLANES_BYTES + (4 * c) * W_VP + v0;
+                        sts_u(pb, __byte_perm(t01l, t23l, 0x5410));
+                        sts_u(pb + W_VP, __byte_perm(t01l, t23l, 0x7632));
+                        sts_u(pb + 2 * W_VP, __byte_perm(t01h, t23h, 0x5410));
+                        sts_u(pb + 3 * W_VP, __byte_perm(t01h, t23h, 0x7632));
+                    }
+                }
+                if (stamp_on) st[3] = clock64();
+                if (new_item) {
+                    // residuals r = q - c (reference _closest_cluster_residuals, src/coarsequantizers.jl:40-45) and
+                    // their squared norms per table; a loader warp handles one table per round, lane = query
+                    for (int x = lt; x < m * QG; x += W_NLOAD) {
+                        const int s = x >> 5;
+                        float qd[8];
+                        if (fastq) {
+                            const uint32_t rq = rawq_u + lane * (m * 32);
+                            const uint4 u0 = lds_v4(rq + (((2 * s) ^ (lane & 7)) * 16)), u1 = lds_v4(rq + (((2 * s + 1) ^ (lane & 7)) * 16));
+                            qd[0] = __uint_as_float(u0.x); qd[1] = __uint_as_float(u0.y); qd[2] = __uint_as_float(u0.z); qd[3] = __uint_as_float(u0.w);
+                            qd[4] = __uint_as_float(u1.x); qd[5] = __uint_as_float(u1.y); qd[6] = __uint_as_float(u1.z); qd[7] = __uint_as_float(u1.w);
+                        } else {
+#pragma unroll
+                            for (int d = 0; d < 8; ++d) qd[d] = lds_f(res_i + ((s * 8 + d) * T_RS + lane) * 4);
+                        }
+                        float part = 0.f;
+#pragma unroll
+                        for (int d = 0; d < 8; ++d) {
+                            const float r = sub_rn(qd[d], lds_f(cbuf_u + (s * 8 + d) * 4));
+                            sts_f(res_i + ((s * 8 + d) * T_RS + lane) * 4, r);
+                            part = fma_rn(r, r, part);
+                        }
+                        sts_f(rnorm_u + (s * QG + lane) * 4, part);
+                    }
+                    named_bar(2, W_NLOAD);
+                    if (lw == 0) {
+                        float rn = 0.f;
+                        for (int s = 0; s < m; ++s) rn = add_rn(rn, lds_f(rnorm_u + (s * QG + lane) * 4));  // fixed order
+                        const uint32_t bu = stt + QG * 4 + lane * 4;
+                        sts_f(bu, add_rn(lds_f(bu), rn));  // dc + |r|^2 over the PQ dims
+                    }
+                }
+                if (lt == 0) {
+                    sts_u(sg + 4, (uint32_t)nvn);
+                    sts_u(sg + 8, (uint32_t)pass);
+                    sts_u(sg + 12, (uint32_t)ipar);
+                    sts_u(sg + 16, (uint32_t)nj);
+                    sts_u(sg + 20, pass + 1 == npass ? 1u : 0u);
+                    sts_u(sg + 24, (uint32_t)cell);
+                    sts_u(sg, 1u);
+                }
+                named_bar(2, W_NLOAD);
+                if (lt == 0) mbar_arrive(bar_staged + 8 * spar);
+                if (stamp_on) st[4] = clock64();
+                if (pass + 1 < npass) {
+                    ++pass;
+                    new_item = false;
+                } else {
+                    item = (int)lds_u(ldesc_u + 32);
+                    pass = 0;
+                    ipar ^= 1;
+                    new_item = true;
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (wid == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(U_TMEM_COLS)
+                     : "memory");
+    }
+}
+
+}  // namespace ivf

@@ -16,7 +16,7 @@ pytestmark = pytest.mark.gpu
 RTOL = 1e-5  # the tolerance north_star states for ADC distances (we assert exact equality too)
 
 
-LEGACY, QLANE, LUT_EXACT, LUT_MMASYNC, SMEMLUT, COARSE_SCALAR, MERGE_SWEEP = 1, 2, 4, 8, 16, 32, 64  # ivfadc_config.flags (include/ivfadc.h)
+LEGACY, QLANE, LUT_EXACT, LUT_MMASYNC, TMEM_V1, COARSE_SCALAR, MERGE_SWEEP = 1, 2, 4, 8, 16, 32, 64  # ivfadc_config.flags (include/ivfadc.h)
 COARSE_FFMA, COARSE_REDO = 128, 256
 # Default flags for the bit-exact tests: whichever scan kernel the engine picks, tables in the
 # reference's direct form.  The tensor-core (3xTF32) tables are tested at the stated tolerance in
@@ -287,14 +287,16 @@ def test_search_qlane_bit_exact(D, m, ksub, kc, n, nq, k, w, identity):
         np.testing.assert_array_equal(gi, oi, err_msg=f"flags={flags}")
         e.close()
     # tensor-core tables (the default for large batches): the north_star's tolerance bar.
-    # QLANE alone = tensor-memory lookup kernel (tcgen05.mma tables looked up with tcgen05.ld) where the
-    # shape allows it (dsub <= 8), QLANE | SMEMLUT = tcgen05 tables copied to shared memory,
-    # QLANE | LUT_MMASYNC = the warp-level mma.sync builder.
+    # QLANE alone = warp-specialised tensor-memory lookup kernel (tcgen05.mma tables looked up with tcgen05.ld)
+    # where the shape allows it (dsub <= 8 or 16), QLANE | TMEM_V1 = the round-1 version of the same arithmetic
+    # (identical bits), QLANE | LUT_MMASYNC = the warp-level mma.sync builder.
     # QLANE | MERGE_SWEEP: the heavy-tie fallback of the final selection on ordinary data.
     first = None
-    for flags in (QLANE, QLANE | MERGE_SWEEP, QLANE | SMEMLUT, QLANE | LUT_MMASYNC):
+    for flags in (QLANE, QLANE | MERGE_SWEEP, QLANE | TMEM_V1, QLANE | LUT_MMASYNC):
         e = engine_from(qz, np.uint32, X, flags=flags)
         gi, gd, gc = e.search_packed(Q, k, w)
+        if flags in (QLANE, QLANE | MERGE_SWEEP) and scanu_shape(D, m):
+            assert e.stats()["last_scan_kernel"] == 5, e.stats()
         rep = orc.compare_search(gi, gd, gc, oi, od, oc, rtol=RTOL)
         assert rep["near_tie_id_mismatches"] <= max(2, rep["results"] // 200), (flags, rep)
         assert rep["max_rel_err"] < 3e-6, (flags, rep)   # measured error budget of 3xTF32
@@ -307,12 +309,18 @@ def test_search_qlane_bit_exact(D, m, ksub, kc, n, nq, k, w, identity):
         e.close()
 
 
+def scanu_shape(D, m):
+    """Shapes served by the tensor-memory lookup kernels (scan.cu, scanu_shape_ok)."""
+    dsub = D // m
+    return (dsub <= 8 or dsub == 16) and m % 4 == 0 and m * (2 if dsub == 16 else 1) <= 16
+
+
 def test_scan_kernel_choice():
     """The engine picks the scan kernel from a cost model ("which scan kernel"): many queries per list ->
     the tensor-memory query-per-lane kernel (4), few queries per long list (config-D-like) -> vector per lane (1).
     Both answers stay within the tolerance bar of the oracle."""
     from ivfadc_jl_b200 import synth
-    for (D, m, kc, n, nq, w, want) in ((128, 16, 16, 16000, 600, 8, 4), (128, 8, 64, 64000, 100, 8, 1)):
+    for (D, m, kc, n, nq, w, want) in ((128, 16, 16, 16000, 600, 8, 5), (128, 8, 64, 64000, 100, 8, 1)):
         X = synth.blobs(n, D, kc, seed=31)
         cent, cb, codes = synth.random_quantizers(kc, D, m, 256, seed=7, data=X)
         cent = synth.blob_centres(D, kc)   # balanced lists of n / kc vectors
@@ -339,7 +347,7 @@ def test_scan_kernel_choice():
     e = engine_from(qz, np.uint32, X, shard=(1, 4), flags=0)
     sharded.search_local(e, torch.from_numpy(synth.blobs(nq, D, kc, seed=34)).cuda(), 10, w)
     torch.cuda.synchronize()
-    assert e.stats()["last_scan_kernel"] == 4, e.stats()
+    assert e.stats()["last_scan_kernel"] == 5, e.stats()
     e.close()
 
 
@@ -403,7 +411,7 @@ def test_search_qlane_ties_overflow_redo():
         for k, w in ((10, 2), (16, 4), (1, 1)):
             assert_search_equal(e, oidx, Q, k, w)
         e.close()
-    for flags in (QLANE, QLANE | MERGE_SWEEP, QLANE | SMEMLUT):
+    for flags in (QLANE, QLANE | MERGE_SWEEP, QLANE | TMEM_V1):
         e = engine_from(qz, np.uint32, Xc, assign, flags=flags)
         for k, w in ((10, 2), (16, 4), (1, 1)):
             gi, gd, gc = e.search_packed(Q, k, w)
