@@ -18,7 +18,8 @@
  *     that carries cells (`assign`) has an explicit base so Julia's 1-based
  *     `KmeansResult.assignments` can be passed untouched;
  *   - a handle is bound to ONE CUDA device and is not thread-safe; host-buffer calls are
- *     synchronous, `_device` calls are asynchronous on the stream given;
+ *     synchronous, `_device` calls are asynchronous on the stream given; several GPUs are driven either by one
+ *     handle per process joined by ivfadc_comm_init_rank, or by an ivfadc_group inside one process;
  *   - there is no CPU fallback: every entry point fails with IVFADC_ERR_CUDA when no device
  *     is present.
  */
@@ -32,7 +33,7 @@
 extern "C" {
 #endif
 
-#define IVFADC_ABI_VERSION 1
+#define IVFADC_ABI_VERSION 2
 
 /* status codes */
 #define IVFADC_OK               0
@@ -42,6 +43,7 @@ extern "C" {
 #define IVFADC_ERR_OOM         -4
 #define IVFADC_ERR_UNSUPPORTED -5   /* metric / code width outside the hot-path scope            */
 #define IVFADC_ERR_EMPTY       -6   /* pop from an empty index (src/utils.jl:44)                 */
+#define IVFADC_ERR_NCCL        -7   /* NCCL could not be loaded, or a collective failed          */
 
 /* element type T of data, centroids, codebooks and returned distances */
 #define IVFADC_F32 0
@@ -136,7 +138,8 @@ typedef struct ivfadc_stats {
     double   encode_ms;
     uint64_t scan_launches;
     uint64_t last_scan_kernel;  /* kernel of the last search: 1 vector-per-lane, 2 scanq, 4 scanu (v1), 5 scanw */
-    uint64_t reserved[3];
+    double   comm_ms;           /* sharded search: device time of the two grouped all-gathers (eager steps)  */
+    uint64_t reserved[2];
 } ivfadc_stats;
 
 int ivfadc_abi_version(void);
@@ -241,6 +244,71 @@ int ivfadc_merge_device(ivfadc_index* h, int32_t parts, int64_t nq, int32_t k,
                         const uint64_t* d_ids_in, const void* d_dists_in,
                         const uint64_t* d_keys_in, uint64_t* d_ids, void* d_dists,
                         int32_t* d_counts, void* stream);
+
+/*
+ * ---- cell-sharded search inside the library (NCCL over NVLink / NVSwitch) -----------------------------------
+ * The one batched knn_search call of the reference (src/index.jl:261-273) fans out over the GPUs by itself:
+ * every rank (handle with shard_rank / shard_world) runs coarse_search on its slice of the queries, ONE grouped
+ * in-place all-gather distributes the probe lists (and the query slices, when they came from the host), every rank
+ * scans the probed cells it owns, ONE grouped in-place all-gather brings the per-rank candidates (id, distance,
+ * probe rank << 32 | position) together, and a merge kernel keeps the k smallest in the reference's order
+ * (src/index.jl:247-257): bit-identical to the unsharded result.  The whole step is enqueued on one stream without
+ * host synchronisation and replayed from a CUDA graph from the third call with the same shape on.
+ *
+ * One process per GPU: rank 0 calls ivfadc_nccl_unique_id, the IVFADC_NCCL_ID_BYTES travel over the caller's own
+ * channel (torch.distributed / MPI / a file), every rank calls ivfadc_comm_init_rank on its handle.
+ */
+#define IVFADC_NCCL_ID_BYTES 128
+int ivfadc_nccl_unique_id(void* id_out);
+int ivfadc_comm_init_rank(ivfadc_index* h, const void* id, int32_t world, int32_t rank);
+int ivfadc_comm_destroy(ivfadc_index* h);
+/* CUDA-graph replay of the sharded step on / off (default on; per-kernel stats timing needs eager steps). */
+int ivfadc_set_graph_replay(ivfadc_index* h, int32_t enable);
+/*
+ * Collective call: every rank passes the same batch.  Host variant: Q[nq][D] replicated on every rank, each rank
+ * uploads only ITS slice (the all-gather completes the batch over NVLink) and receives the full result.
+ * Device variant: dQ is the full batch on every rank's device; asynchronous on `stream`.
+ */
+int ivfadc_search_sharded(ivfadc_index* h, const void* Q, int64_t nq, int32_t k, int32_t w, uint64_t* ids_out,
+                          void* dists_out, int32_t* counts_out);
+int ivfadc_search_sharded_device(ivfadc_index* h, const void* dQ, int64_t nq, int32_t k, int32_t w, uint64_t* d_ids,
+                                 void* d_dists, int32_t* d_counts, void* stream);
+/* Bytes one ivfadc_search_sharded step moves on this rank: host->device, device->host, received over NVLink. */
+int ivfadc_sharded_step_bytes(ivfadc_index* h, int64_t nq, int32_t k, int32_t w, int64_t* h2d_out, int64_t* d2h_out,
+                              int64_t* nvlink_out);
+/*
+ * Which shard owns a cell: owners int32[kc] with values in [0, shard_world) (e.g. greedy bin-packing on the
+ * list lengths known from the k-means assignments); default cell % shard_world.  Must be called on every shard
+ * with the same map, before any vector is added.
+ */
+int ivfadc_set_cell_owners(ivfadc_index* h, const int32_t* owners);
+/*
+ * The *_device entry points are asynchronous and do not read the error flag of the tensor-core pipelines
+ * (mbarrier time-outs); this call synchronises `stream` and reports (and clears) it.
+ */
+int ivfadc_check_async(ivfadc_index* h, void* stream);
+
+/*
+ * One process, several GPUs (what the Julia glue binds when IVFADC_DEVICES names more than one device): n handles
+ * with shard_rank = i, a communicator from ncclCommInitAll, and the calls of the single-GPU API fanned out.
+ * device_ids == NULL means devices 0..n_devices-1.  ivfadc_group_handle gives access to a shard for everything else
+ * (list export / import, statistics).
+ */
+typedef struct ivfadc_group ivfadc_group;
+int ivfadc_group_create(ivfadc_group** out, const ivfadc_config* cfg, int32_t n_devices, const int32_t* device_ids,
+                        const void* centroids, const void* codebook_vectors, const uint8_t* codebook_codes);
+int ivfadc_group_destroy(ivfadc_group* g);
+int ivfadc_group_size(const ivfadc_group* g);
+int ivfadc_group_handle(ivfadc_group* g, int32_t i, ivfadc_index** out);
+const char* ivfadc_group_last_error(const ivfadc_group* g);
+int ivfadc_group_set_cell_owners(ivfadc_group* g, const int32_t* owners);
+int ivfadc_group_add(ivfadc_group* g, const void* X, int64_t n, int32_t position, const int64_t* assign,
+                     int32_t assign_base, int32_t* cells_out);
+int ivfadc_group_search(ivfadc_group* g, const void* Q, int64_t nq, int32_t k, int32_t w, uint64_t* ids_out,
+                        void* dists_out, int32_t* counts_out);
+int ivfadc_group_delete(ivfadc_group* g, const uint64_t* ids, int64_t n);
+int ivfadc_group_pop(ivfadc_group* g, int32_t position, void* vec_out);
+int ivfadc_group_length(const ivfadc_group* g, int64_t* n_out);
 
 /*
  * delete_from_index! (src/utils.jl:90-105): ids are the STORED 0-based ids (the Julia glue

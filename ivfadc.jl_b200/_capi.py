@@ -30,7 +30,13 @@ SYMBOLS = [
     "ivfadc_merge_device", "ivfadc_delete", "ivfadc_pop", "ivfadc_length",
     "ivfadc_list_sizes", "ivfadc_export_list", "ivfadc_import_list", "ivfadc_export_quantizers",
     "ivfadc_set_length", "ivfadc_get_stats", "ivfadc_reset_stats", "ivfadc_debug_tables", "ivfadc_set_stats_timing",
+    "ivfadc_nccl_unique_id", "ivfadc_comm_init_rank", "ivfadc_comm_destroy", "ivfadc_set_graph_replay",
+    "ivfadc_search_sharded", "ivfadc_search_sharded_device", "ivfadc_sharded_step_bytes", "ivfadc_set_cell_owners",
+    "ivfadc_check_async", "ivfadc_group_create", "ivfadc_group_destroy", "ivfadc_group_size", "ivfadc_group_handle",
+    "ivfadc_group_last_error", "ivfadc_group_set_cell_owners", "ivfadc_group_add", "ivfadc_group_search",
+    "ivfadc_group_delete", "ivfadc_group_pop", "ivfadc_group_length",
 ]
+NCCL_ID_BYTES = 128
 
 
 class Config(ctypes.Structure):
@@ -44,7 +50,7 @@ class Stats(ctypes.Structure):
         ("searches", c_uint64), ("queries", c_uint64), ("scanned_vectors", c_uint64),
         ("scan_code_bytes", c_uint64), ("gpu_launches", c_uint64), ("coarse_ms", c_double),
         ("plan_ms", c_double), ("scan_ms", c_double), ("merge_ms", c_double), ("encode_ms", c_double),
-        ("scan_launches", c_uint64), ("last_scan_kernel", c_uint64), ("reserved", c_uint64 * 3),
+        ("scan_launches", c_uint64), ("last_scan_kernel", c_uint64), ("comm_ms", c_double), ("reserved", c_uint64 * 2),
     ]
 
     def as_dict(self):
@@ -103,9 +109,32 @@ def load(build_if_missing: bool = True):
     lib.ivfadc_reset_stats.argtypes = [H]
     lib.ivfadc_debug_tables.argtypes = [H, c_void_p]
     lib.ivfadc_set_stats_timing.argtypes = [H, c_int32]
+    lib.ivfadc_nccl_unique_id.argtypes = [c_void_p]
+    lib.ivfadc_comm_init_rank.argtypes = [H, c_void_p, c_int32, c_int32]
+    lib.ivfadc_comm_destroy.argtypes = [H]
+    lib.ivfadc_set_graph_replay.argtypes = [H, c_int32]
+    lib.ivfadc_search_sharded.argtypes = [H, c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p, c_void_p]
+    lib.ivfadc_search_sharded_device.argtypes = [H, c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p,
+                                                 c_void_p, c_void_p]
+    lib.ivfadc_sharded_step_bytes.argtypes = [H, c_int64, c_int32, c_int32, POINTER(c_int64), POINTER(c_int64),
+                                              POINTER(c_int64)]
+    lib.ivfadc_set_cell_owners.argtypes = [H, c_void_p]
+    lib.ivfadc_check_async.argtypes = [H, c_void_p]
+    lib.ivfadc_group_create.argtypes = [POINTER(H), POINTER(Config), c_int32, c_void_p, c_void_p, c_void_p, c_void_p]
+    lib.ivfadc_group_destroy.argtypes = [H]
+    lib.ivfadc_group_size.argtypes = [H]
+    lib.ivfadc_group_handle.argtypes = [H, c_int32, POINTER(H)]
+    lib.ivfadc_group_last_error.argtypes = [H]
+    lib.ivfadc_group_last_error.restype = c_char_p
+    lib.ivfadc_group_set_cell_owners.argtypes = [H, c_void_p]
+    lib.ivfadc_group_add.argtypes = [H, c_void_p, c_int64, c_int32, c_void_p, c_int32, c_void_p]
+    lib.ivfadc_group_search.argtypes = [H, c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p, c_void_p]
+    lib.ivfadc_group_delete.argtypes = [H, c_void_p, c_int64]
+    lib.ivfadc_group_pop.argtypes = [H, c_int32, c_void_p]
+    lib.ivfadc_group_length.argtypes = [H, POINTER(c_int64)]
     for name in SYMBOLS:
         fn = getattr(lib, name)
-        if name not in ("ivfadc_last_error",):
+        if name not in ("ivfadc_last_error", "ivfadc_group_last_error"):
             fn.restype = c_int32
     _lib = lib
     return lib

@@ -93,6 +93,7 @@ struct ShardCtx {
     GraphKey key;
     int seen = 0;                 // eager runs with this key so far
     cudaGraphExec_t exec = nullptr;
+    uint64_t graph_launches = 0;  // kernels of this library inside one replay
     // timing of the eager path: coarse slice, the two collectives
     cudaEvent_t ev[6] = {};
     bool ev_ok = false, ev_pending = false;
@@ -243,6 +244,7 @@ int run_step(ivfadc_index* h, ShardCtx* c, const void* dQ, int64_t nq, int k, in
         CUDA_OR_FAIL(h, cudaGraphLaunch(c->exec, s), "graph launch");
         h->stats.searches += 1;
         h->stats.queries += nq;
+        h->stats.gpu_launches += c->graph_launches;
         return IVFADC_OK;
     }
     if (!graph_ok || c->seen < 2) {

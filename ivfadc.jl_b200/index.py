@@ -183,6 +183,16 @@ class IVFADCIndex:
             raise TypeError(f"expected a vector of {_JULIA_FLOAT[np.dtype(self.T)]}, got {point.dtype}")
         return point
 
+    def set_cell_owners(self, owners):
+        """Which shard owns each cell (int32 [kc], values in [0, world)); before any vector is added."""
+        owners = np.ascontiguousarray(owners, dtype=np.int32)
+        assert owners.shape == (self.kc,)
+        _capi.check(self._h, self._lib.ivfadc_set_cell_owners(self._h, _capi.ptr(owners)))
+
+    def check_async(self, stream=None):
+        """Synchronise `stream` and raise if a tensor-core pipeline of an asynchronous call timed out."""
+        _capi.check(self._h, self._lib.ivfadc_check_async(self._h, ctypes.c_void_p(stream or 0)))
+
     def list_sizes(self):
         out = np.empty(self.kc, dtype=np.int64)
         _capi.check(self._h, self._lib.ivfadc_list_sizes(self._h, _capi.ptr(out)))

@@ -114,6 +114,67 @@ def merge_parts(engine, parts, k: int):
     return merge_gathered(engine, ids_all, dists_all, keys_all, k)
 
 
+# ---- the sharded step INSIDE the library (csrc/shard.cu): NCCL communicator owned by the handle ----------------
+def balanced_owners(list_sizes, world: int) -> np.ndarray:
+    """Cell -> shard by greedy bin-packing on the list lengths (longest list first onto the lightest shard):
+    every GPU scans about the same number of code bytes.  Ties keep cell order, so every rank computes the same map."""
+    sizes = np.asarray(list_sizes, dtype=np.int64)
+    owners = np.empty(len(sizes), dtype=np.int32)
+    load = np.zeros(world, dtype=np.int64)
+    count = np.zeros(world, dtype=np.int64)
+    for c in np.argsort(-sizes, kind="stable"):
+        r = int(np.lexsort((count, load))[0])   # lightest shard, then fewest cells
+        owners[c] = r
+        load[r] += sizes[c]
+        count[r] += 1
+    return owners
+
+
+def init_comm(index, group=None):
+    """Rank 0 draws the NCCL unique id, torch.distributed carries its 128 bytes (plumbing), every rank joins:
+    afterwards `search_sharded*` run without Python in the loop."""
+    import torch.distributed as dist
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    buf = (ctypes.c_ubyte * _capi.NCCL_ID_BYTES)()
+    if rank == 0:
+        rc = index._lib.ivfadc_nccl_unique_id(buf)
+        if rc != 0:
+            raise _capi.IvfadcError(rc, "ivfadc_nccl_unique_id failed (libnccl.so.2 not loadable?)")
+    box = [bytes(buf)]
+    dist.broadcast_object_list(box, src=0, group=group)
+    idb = (ctypes.c_ubyte * _capi.NCCL_ID_BYTES).from_buffer_copy(box[0])
+    _capi.check(index._h, index._lib.ivfadc_comm_init_rank(index._h, idb, world, rank))
+
+
+def search_sharded_device(index, dQ: torch.Tensor, k: int, w: int = 1, out=None):
+    """ivfadc_search_sharded_device on torch's current stream (collective: every rank, same batch)."""
+    assert dQ.is_cuda and dQ.is_contiguous() and dQ.dtype == _tdtype(index)
+    nq = dQ.shape[0]
+    if out is None:
+        out = (torch.empty((nq, k), dtype=torch.int64, device=dQ.device),
+               torch.empty((nq, k), dtype=dQ.dtype, device=dQ.device),
+               torch.empty((nq,), dtype=torch.int32, device=dQ.device))
+    ids, dists, counts = out
+    rc = index._lib.ivfadc_search_sharded_device(index._h, ctypes.c_void_p(dQ.data_ptr()), nq, k, w,
+                                                 ctypes.c_void_p(ids.data_ptr()), ctypes.c_void_p(dists.data_ptr()),
+                                                 ctypes.c_void_p(counts.data_ptr()), _stream_ptr())
+    _capi.check(index._h, rc)
+    return ids, dists, counts
+
+
+def search_sharded_host(index, Q: np.ndarray, k: int, w: int = 1, out=None):
+    """ivfadc_search_sharded: host buffers in and out (this rank uploads only its slice of Q)."""
+    Q = np.ascontiguousarray(Q, dtype=index.T)
+    nq = Q.shape[0]
+    if out is None:
+        out = (np.empty((nq, k), dtype=np.uint64), np.empty((nq, k), dtype=index.T), np.empty(nq, dtype=np.int32))
+    ids, dists, counts = out
+    rc = index._lib.ivfadc_search_sharded(index._h, _capi.ptr(Q), nq, k, w, _capi.ptr(ids), _capi.ptr(dists),
+                                          _capi.ptr(counts))
+    _capi.check(index._h, rc)
+    return ids, dists, counts
+
+
 class CudaShardEngine:
     """Adapter: the two device entry points the distributed searcher needs."""
 

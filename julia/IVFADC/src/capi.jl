@@ -5,7 +5,7 @@ const LIBIVFADC = Ref{String}("libivfadc_cuda")
 function __init__()
     LIBIVFADC[] = get(ENV, "LIBIVFADC_CUDA", "libivfadc_cuda")
     ver = ccall((:ivfadc_abi_version, LIBIVFADC[]), Cint, ())
-    ver == 1 || error("libivfadc_cuda ABI $ver, this package binds ABI 1")
+    ver == 2 || error("libivfadc_cuda ABI $ver, this package binds ABI 2")
     # no CPU fallback: fail at load time if there is no device
     ccall((:ivfadc_device_count, LIBIVFADC[]), Cint, ()) > 0 ||
         error("libivfadc_cuda found no CUDA device (the engine has no CPU fallback)")
