@@ -161,5 +161,11 @@ int main() {
     run<16, 0>("lookups x16 + tf32 MMA back to back (4)", d_codes, d_out, d_cyc, nsm, 4);
     run<32, 0>("lookups x32 + tf32 MMA back to back (4)", d_codes, d_out, d_cyc, nsm, 4);
     run<16, 1>("lookups x16 + f16 MMA back to back (4)", d_codes, d_out, d_cyc, nsm, 4);
+    run<16, 1>("lookups x16 + f16 MMA back to back (2)", d_codes, d_out, d_cyc, nsm, 2);
+    run<16, 1>("lookups x16 + f16 MMA back to back (1)", d_codes, d_out, d_cyc, nsm, 1);
+    run<16, 0>("lookups x16 + tf32 MMA back to back (2)", d_codes, d_out, d_cyc, nsm, 2);
+    run<16, 0>("lookups x16 + tf32 MMA back to back (1)", d_codes, d_out, d_cyc, nsm, 1);
+    run<0, 1>("MMA f16 only, 2 per build", d_codes, d_out, d_cyc, nsm, 2);
+    run<0, 1>("MMA f16 only, 1 per build", d_codes, d_out, d_cyc, nsm, 1);
     return 0;
 }
