@@ -12,18 +12,21 @@
 //     12 x 96 = 1152 vectors of the list.  Per table: wait for the build (mbarrier of tcgen05.commit), 96 lookups,
 //     arrive on the table buffer's "free" mbarrier -- and straight on to the next table.  At the end of a pass:
 //     two group minima per warp -> the k-th smallest of the 24 minima bounds the list's k-th distance (two
-//     named barriers among the 384 scanner threads) -> every vector within the bound is appended to the
-//     pair's candidate row in HBM (slot from a per-query shared-memory counter), no staging through shared memory.
-//   * warp 12      PRODUCER  (40 registers): the stream of table builds t = 0, 1, 2, ... runs across segment and
-//     item boundaries.  Per build: A operand (TF32 hi / lo of the residuals, four row copies) into its ring slot
-//     as soon as build t - 2 has completed, wait until the 12 scanners have released table t - 2, four MMAs +
-//     commit, refill of the codebook ring (cp.async.bulk, three slots).
+//     named barriers among the 384 scanner threads) -> every vector within the bound goes to the query's row of a
+//     shared-memory staging area (slot from a per-query shared-memory counter).
+//   * warp 12      ISSUER: the stream of table builds t = 0, 1, 2, ... runs across segment and item boundaries.
+//     Per build only: wait for the A operand, for the 12 scanners to have released table t - 2 and for the
+//     codebook operand, then four MMAs + commit and the refill of the codebook ring (cp.async.bulk, three slots).
+//     Nothing else is on the path from "table buffer released" to "next build issued" (with the operand writes in
+//     the same warp that path was 1.6 k cycles per table: the round's first timeline).
+//   * warp 15      OPERAND WRITER: A operand of build t (TF32 hi / lo of the residuals, four row copies) into its
+//     ring slot as soon as build t - 2 has completed.
 //   * warps 13, 14 LOADERS: next segment (item, pass) while the scanners work on the current one -- item
 //     descriptor, query rows / centroid slices / code bytes by cp.async, byte-plane transposes of the codes
-//     (double-buffered planes), residuals r = q - c with their norms (double-buffered per item).
-//   * warp 15      FINALIZER: after the scanners' last append of a list, publishes the candidate counts of the
-//     item's pairs (or queues the pair for the exact redo kernel on overflow) and hands the buffers back to
-//     the loaders.
+//     (double-buffered planes), residuals r = q - c with their norms (double-buffered per item).  Before a
+//     segment's buffers are reused they FINALIZE the segment that used them: staged candidates -> the pairs'
+//     candidate rows in HBM, and after the last pass of a list the candidate counts of the item's pairs (or the
+//     pair is queued for the exact redo kernel on overflow).
 //
 // Candidate rows, merge_cands_kernel and the redo queue are those of scanu (scan.cu).
 #pragma once
@@ -34,7 +37,7 @@ namespace ivf {
 
 constexpr int W_SCAN = 12;                   // scanning warps
 constexpr int W_THREADS = 512;               // + producer, two loaders, finalizer
-constexpr int W_PROD = 12, W_LOAD = 13, W_FIN = 15;
+constexpr int W_ISSUE = 12, W_LOAD = 13, W_OPER = 15;
 constexpr int W_NLOAD = 64;                  // loader threads
 constexpr int W_NV = 96;                     // partial distances per lane
 constexpr int W_NCH = W_NV / 16;             // chunks of 16 vectors per scanner and pass
@@ -43,13 +46,14 @@ constexpr int W_CSTEP = 16 * W_SCAN;         // byte distance of a scanner's con
 constexpr int W_NMIN = 2 * W_SCAN;           // group minima per query and pass
 constexpr int W_STATE = 5 * QG * 4;          // per item: pair | dc -> base | run | cnt | flag
 constexpr int W_SEG = 32;                    // per segment: valid, nv, pass, ipar, nj, last
+constexpr int W_CAND = QG * U_CAP * 4;       // one plane (distances or positions) of the staged candidates of a pass
 constexpr uint32_t W_SPIN = 1u << 20;
 #ifndef W_DEPTH
 #define W_DEPTH 16                           // lookups in flight per tcgen05.wait::ld (16 or 32)
 #endif
 
 struct ScanWSmem {
-    uint32_t aone, aring, bring, planes, raw, resid, rawq, smin, thr, rnorm, state, seg, ldesc, cbuf, bars, total;
+    uint32_t aone, aring, bring, planes, raw, resid, rawq, cand, smin, thr, rnorm, state, seg, segcnt, ldesc, cbuf, bars, total;
 };
 
 // m = tables per item (8 dims each), mc = code bytes per vector
@@ -64,14 +68,16 @@ __host__ __device__ inline ScanWSmem scanw_smem_layout(int m, int mc) {
     s.rawq = o;    o += (uint32_t)QG * m * 32;
     s.resid = o;   o += 2u * (uint32_t)m * 8 * T_RS * 4;
     o = (o + 15) & ~15u;
+    s.cand = o;    o += 2 * W_CAND;             // [distances | positions][query][U_CAP]
     s.smin = o;    o += W_NMIN * QG * 4;
     s.thr = o;     o += QG * 4;
     s.rnorm = o;   o += (uint32_t)m * QG * 4;
     s.state = o;   o += 2 * W_STATE;
     s.seg = o;     o += 2 * W_SEG;
+    s.segcnt = o;  o += 2 * QG * 4;            // candidates staged per query by the scanners of a segment
     s.ldesc = o;   o += 64;
     s.cbuf = o;    o += (uint32_t)m * 32;
-    s.bars = o;    o += 144;
+    s.bars = o;    o += 160;
     s.total = o;
     return s;
 }
@@ -151,14 +157,15 @@ scanw_kernel(const ScanUArgs ua) {
     const uint32_t aone_u = sb + L.aone, aring_u = sb + L.aring, bring_u = sb + L.bring, planes_u = sb + L.planes,
                    raw_u = sb + L.raw, resid_u = sb + L.resid, rawq_u = sb + L.rawq, smin_u = sb + L.smin,
                    thr_u = sb + L.thr, rnorm_u = sb + L.rnorm, state_u = sb + L.state, seg_u = sb + L.seg,
-                   ldesc_u = sb + L.ldesc, cbuf_u = sb + L.cbuf;
+                   ldesc_u = sb + L.ldesc, cbuf_u = sb + L.cbuf, cand_u = sb + L.cand, segcnt_u = sb + L.segcnt;
     const uint32_t bar_full = sb + L.bars;          // 3: codebook operand landed in ring slot
     const uint32_t bar_mma = bar_full + 24;         // 2: table build complete (tcgen05.commit)
     const uint32_t bar_free = bar_full + 40;        // 2: the 12 scanners are done with the table buffer
     const uint32_t bar_staged = bar_full + 56;      // 2: segment staged by the loaders
-    const uint32_t bar_extract = bar_full + 72;     // 2: the 12 scanners have appended their candidates
-    const uint32_t bar_segfree = bar_full + 88;     // 2: finalizer is done with the segment's buffers
-    const uint32_t tmem_slot = bar_full + 104, dead_u = bar_full + 108;
+    const uint32_t bar_extract = bar_full + 72;     // 2: the 12 scanners have staged their candidates
+    const uint32_t bar_a = bar_full + 88;           // 2: A operand of a build written
+    const uint32_t bar_candfree = bar_full + 104;   // 1: staged candidates of a segment copied out
+    const uint32_t tmem_slot = bar_full + 112, dead_u = bar_full + 116;
 
     // ---- one-time setup ----
     if (tid == 0) {
@@ -168,8 +175,9 @@ scanw_kernel(const ScanUArgs ua) {
             mbar_init(bar_free + 8 * i, W_SCAN);
             mbar_init(bar_staged + 8 * i, 1);
             mbar_init(bar_extract + 8 * i, W_SCAN);
-            mbar_init(bar_segfree + 8 * i, 1);
+            mbar_init(bar_a + 8 * i, 1);
         }
+        mbar_init(bar_candfree, 1);
         sts_u(dead_u, 0u);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         for (int i = 0; i < U_NB; ++i) {
@@ -224,16 +232,21 @@ scanw_kernel(const ScanUArgs ua) {
             const int nch = min(W_NCH, max(0, (nv - 16 * wid + W_CSTEP - 1) / W_CSTEP));  // chunks j with 16 (wid + 12 j) < nv
 #pragma unroll
             for (int j = 0; j < W_NV; ++j) acc[j] = base;  // dc + |r|^2, then the table entries in subspace order
+            // Everything that forms a lookup address must be PROVABLY warp-uniform for ptxas (shuffles from lane 0):
+            // only then the code words are moved to uniform registers once (R2UR) and a lookup is UPRMT + LDTM;
+            // otherwise every address is formed in a vector register and moved on its own (PRMT + R2UR + LDTM).
+            // tg is a multiple of m (even), so table t = tg + s lives in buffer s & 1 and its phase flips every two tables.
+            const uint32_t plane_seg = plane_w0 + spar * PLANES_BYTES;
+            uint32_t par = (tg >> 1) & 1;
 #pragma unroll 1
             for (int s = 0; s < m; ++s) {
-                const uint32_t t = tg + s;
+                const uint32_t b = (uint32_t)s & 1u;
                 if (stamp_on && (s == 5 || s == 6)) st[6 + (s - 5) * 3] = clock64();
-                warp_wait(bar_mma + 8 * (t & 1), (t >> 1) & 1, 2);
+                warp_wait(bar_mma + 8 * b, par, 2);
                 tc_fence_after();
                 if (stamp_on && (s == 5 || s == 6)) st[7 + (s - 5) * 3] = clock64();
-                // s and t are warp-uniform, but ptxas keeps the loop counter in a vector register unless told
-                const uint32_t tb = tq + (__shfl_sync(0xffffffffu, t, 0) & 1) * 256;
-                const uint32_t plane_w = plane_w0 + spar * PLANES_BYTES + (__shfl_sync(0xffffffffu, s, 0) / DUP) * W_VP;
+                const uint32_t tb = __shfl_sync(0xffffffffu, tq + b * 256, 0);
+                const uint32_t plane_w = __shfl_sync(0xffffffffu, plane_seg + (uint32_t)(s / DUP) * W_VP, 0);
                 if (nch == W_NCH) scanw_sub<true>(tb, plane_w, nch, acc);
                 else scanw_sub<false>(tb, plane_w, nch, acc);
                 if (DBG && g == 0 && blockIdx.x == 0 && ua.dbg != nullptr) {  // bring-up: dump the tables of the first segment
@@ -251,8 +264,9 @@ scanw_kernel(const ScanUArgs ua) {
                 }
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(bar_free + 8 * (t & 1));
+                if (lane == 0) mbar_arrive(bar_free + 8 * b);
                 if (stamp_on && (s == 5 || s == 6)) st[8 + (s - 5) * 3] = clock64();
+                par ^= b;
             }
             tg += m;
             if (stamp_on) st[1] = clock64();
@@ -307,20 +321,21 @@ scanw_kernel(const ScanUArgs ua) {
 #pragma unroll
                 for (int j = 0; j < W_NV; ++j) c += acc[j] <= cut ? 1 : 0;
                 if (pair < 0) c = 0;
+                // the staging area is single-buffered: the loaders have copied out the previous segment long ago
+                if (g > 0) warp_wait(bar_candfree, (g - 1) & 1, 27);
                 int old = 0;
-                if (c > 0) old = atoms_add(stt + 3 * QG * 4 + lane * 4, c);
-                const bool ok = c > 0 && old + c <= ps;
-                if (c > 0 && !ok) sts_u(stt + 4 * QG * 4 + lane * 4, 1u);  // row overflow: the pair goes to the redo queue
+                if (c > 0) old = atoms_add(segcnt_u + spar * (QG * 4) + lane * 4, c);
+                const bool ok = c > 0 && old + c <= U_CAP;
+                // more than a row can hold (the counter keeps the total): the loaders queue the pair for the redo kernel
                 if (ok) {
-                    // row of the pair = [U_CAP distances][U_CAP positions]: one pointer serves both stores
-                    uint32_t* pd = reinterpret_cast<uint32_t*>(a.pair_d) + (size_t)pair * (2 * U_CAP) + old;
-                    const uint32_t p0 = (uint32_t)pass * W_VP + 16u * wid;
+                    uint32_t pd = cand_u + (uint32_t)(lane * U_CAP + old) * 4;
+                    uint32_t pos = (uint32_t)pass * W_VP + 16u * wid;
 #pragma unroll
                     for (int j = 0; j < W_NV; ++j) {
                         if (acc[j] <= cut) {
-                            pd[0] = __float_as_uint(acc[j]);
-                            pd[U_CAP] = p0 + (uint32_t)((j >> 4) * W_CSTEP + (j & 15));
-                            ++pd;
+                            sts_f(pd, acc[j]);
+                            sts_u(pd + W_CAND, pos + (uint32_t)((j >> 4) * W_CSTEP + (j & 15)));
+                            pd += 4;
                         }
                     }
                 }
@@ -331,8 +346,8 @@ scanw_kernel(const ScanUArgs ua) {
         }
     } else {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
-        if (wid == W_PROD) {
-            // =========================================== PRODUCER ===========================================
+        if (wid == W_ISSUE) {
+            // =========================================== ISSUER ===========================================
             const uint64_t descA0 = tc_smem_desc(aring_u), descB0 = tc_smem_desc(bring_u), desc1 = tc_smem_desc(aone_u);
             uint32_t t = 0;
             uint32_t bslot = 0, bphase = 0;            // ring slot / phase of build t
@@ -343,16 +358,14 @@ scanw_kernel(const ScanUArgs ua) {
             for (uint32_t g = 0;; ++g) {
                 const uint32_t spar = g & 1;
                 warp_wait(bar_staged + 8 * spar, (g >> 1) & 1, 21);
-                const uint32_t sg = seg_u + spar * W_SEG;
-                if (lds_u(sg) == 0u) break;
-                const uint32_t res_i = resid_u + lds_u(sg + 12) * RESID_BYTES;
+                if (lds_u(seg_u + spar * W_SEG) == 0u) break;
                 const bool stamp_on = DBG && st && g == W_DBG_SEG;
 #pragma unroll 1
                 for (int s = 0; s < m; ++s, ++t) {
                     const uint32_t buf = t & 1;
+                    // A operand of build t written => build t - 2 has completed => its codebook ring slot is free
+                    warp_wait(bar_a + 8 * buf, (t >> 1) & 1, 22);
                     if (t >= 2) {
-                        // build t - 2 has completed: its A slot (= the one of build t) and its codebook ring slot are free
-                        warp_wait(bar_mma + 8 * buf, ((t - 2) >> 1) & 1, 22);
                         if (lane == 0) {
                             const uint32_t bar = bar_full + 8 * fslot;
                             mbar_expect_tx(bar, U_BSUB);
@@ -363,29 +376,9 @@ scanw_kernel(const ScanUArgs ua) {
                         ++nfill;
                     }
                     if (stamp_on) st[4 * s] = clock64();
-                    {   // A operand of table s: rows (copy, q) = TF32 hi / lo of r[s][q][0..7]; lane = query
-                        float hi[8], lo[8];
-#pragma unroll
-                        for (int d = 0; d < 8; ++d) {
-                            const float r = lds_f(res_i + ((s * 8 + d) * T_RS + lane) * 4);
-                            hi[d] = __uint_as_float(to_tf32(r));
-                            lo[d] = __uint_as_float(to_tf32(r - hi[d]));
-                        }
-                        const uint32_t ph0 = aring_u + buf * U_ASUB + (lane >> 3) * 256 + (lane & 7) * 16;
-#pragma unroll
-                        for (int c = 0; c < 4; ++c) {  // row = 32 c + lane
-                            const uint32_t ph = ph0 + c * 1024;
-                            sts_v4f(ph, hi[0], hi[1], hi[2], hi[3]);
-                            sts_v4f(ph + 128, hi[4], hi[5], hi[6], hi[7]);
-                            sts_v4f(ph + U_ABLK, lo[0], lo[1], lo[2], lo[3]);
-                            sts_v4f(ph + U_ABLK + 128, lo[4], lo[5], lo[6], lo[7]);
-                        }
-                        fence_proxy_async();  // generic-proxy writes of this lane -> async proxy
-                        __syncwarp();
-                    }
+                    warp_wait(bar_full + 8 * bslot, bphase, 1);
                     if (stamp_on) st[4 * s + 1] = clock64();
                     if (t >= 2) warp_wait(bar_free + 8 * buf, ((t - 2) >> 1) & 1, 23);  // scanners released table t - 2
-                    warp_wait(bar_full + 8 * bslot, bphase, 1);
                     if (stamp_on) st[4 * s + 2] = clock64();
                     tc_fence_after();
                     const uint32_t slot_u = __shfl_sync(0xffffffffu, bslot, 0), buf_u = __shfl_sync(0xffffffffu, buf, 0);
@@ -406,8 +399,9 @@ scanw_kernel(const ScanUArgs ua) {
                 for (uint32_t f = t; f < nfill; ++f) mbar_wait_w(bar_full + 8 * (f % U_NB), (f / U_NB) & 1, dead_u, ua.err, 5);
             }
             __syncwarp();
-        } else if (wid == W_FIN) {
-            // =========================================== FINALIZER ===========================================
+        } else if (wid == W_OPER) {
+            // =========================================== OPERAND WRITER ===========================================
+            uint32_t t = 0;
             long long* const st = (stamps && lane == 0) ? stamps + 272 : nullptr;
 #pragma unroll 1
             for (uint32_t g = 0;; ++g) {
@@ -415,27 +409,35 @@ scanw_kernel(const ScanUArgs ua) {
                 warp_wait(bar_staged + 8 * spar, (g >> 1) & 1, 24);
                 const uint32_t sg = seg_u + spar * W_SEG;
                 if (lds_u(sg) == 0u) break;
-                const uint32_t stt = state_u + lds_u(sg + 12) * W_STATE;
-                const int nj = (int)lds_u(sg + 16);
-                const bool last = lds_u(sg + 20) != 0u;
-                warp_wait(bar_extract + 8 * spar, (g >> 1) & 1, 25);
-                if (DBG && st && g == W_DBG_SEG) st[0] = clock64();
-                if (last && lane < nj) {  // last pass of the list: publish the pair
-                    const int pair = (int)lds_u(stt + lane * 4);
-                    const int c = (int)lds_u(stt + 3 * QG * 4 + lane * 4);
-                    const bool bad = lds_u(stt + 4 * QG * 4 + lane * 4) != 0u || c > ps;
-                    if (pair >= 0) {
-                        if (bad) {
-                            a.pair_cnt[pair] = 0;
-                            a.redo_pairs[atomicAdd(a.redo_cnt, 1)] = pair;
-                        } else {
-                            a.pair_cnt[pair] = c;
-                        }
+                const uint32_t res_i = resid_u + lds_u(sg + 12) * RESID_BYTES;
+                const bool stamp_on = DBG && st && g == W_DBG_SEG;
+#pragma unroll 1
+                for (int s = 0; s < m; ++s, ++t) {
+                    const uint32_t buf = t & 1;
+                    // rows (copy, q) = TF32 hi / lo of r[s][q][0..7]; lane = query
+                    float hi[8], lo[8];
+#pragma unroll
+                    for (int d = 0; d < 8; ++d) {
+                        const float r = lds_f(res_i + ((s * 8 + d) * T_RS + lane) * 4);
+                        hi[d] = __uint_as_float(to_tf32(r));
+                        lo[d] = __uint_as_float(to_tf32(r - hi[d]));
                     }
+                    if (t >= 2) warp_wait(bar_mma + 8 * buf, ((t - 2) >> 1) & 1, 25);  // build t - 2 has read this ring slot
+                    if (stamp_on) st[2 * s] = clock64();
+                    const uint32_t ph0 = aring_u + buf * U_ASUB + (lane >> 3) * 256 + (lane & 7) * 16;
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {  // row = 32 c + lane
+                        const uint32_t ph = ph0 + c * 1024;
+                        sts_v4f(ph, hi[0], hi[1], hi[2], hi[3]);
+                        sts_v4f(ph + 128, hi[4], hi[5], hi[6], hi[7]);
+                        sts_v4f(ph + U_ABLK, lo[0], lo[1], lo[2], lo[3]);
+                        sts_v4f(ph + U_ABLK + 128, lo[4], lo[5], lo[6], lo[7]);
+                    }
+                    fence_proxy_async();  // generic-proxy writes of this lane -> async proxy
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar_a + 8 * buf);
+                    if (stamp_on) st[2 * s + 1] = clock64();
                 }
-                __syncwarp();
-                if (lane == 0) mbar_arrive(bar_segfree + 8 * spar);
-                if (DBG && st && g == W_DBG_SEG) st[1] = clock64();
             }
         } else {
             // =========================================== LOADERS ===========================================
@@ -451,21 +453,62 @@ scanw_kernel(const ScanUArgs ua) {
             int item = blockIdx.x, pass = 0, npass = 1, ipar = 0, nj = 0, cell = 0;
             int64_t len = 0, off = 0;
             bool new_item = true;
+            // Segment x is over (its scanners have staged their candidates): copy them into the pairs' candidate rows
+            // -- row = [U_CAP distances][U_CAP positions], two loader threads per query -- and after the last pass of
+            // the list publish the pairs.  Runs before the buffers of segment x are staged again (x + 2).
+            auto finalize = [&](uint32_t x) {
+                const uint32_t sp = x & 1;
+                const uint32_t sgx = seg_u + sp * W_SEG;
+                warp_wait(bar_extract + 8 * sp, (x >> 1) & 1, 26);
+                const uint32_t stx = state_u + lds_u(sgx + 12) * W_STATE;
+                const int njx = (int)lds_u(sgx + 16);
+                const bool last = lds_u(sgx + 20) != 0u;
+                const int q = lt & 31, half = lt >> 5;
+                const int pair = (int)lds_u(stx + q * 4);
+                const int n = (int)lds_u(segcnt_u + sp * (QG * 4) + q * 4);
+                const int base = (int)lds_u(stx + 3 * QG * 4 + q * 4);
+                const bool bad = lds_u(stx + 4 * QG * 4 + q * 4) != 0u || base + n > ps;
+                if (pair >= 0 && !bad) {
+                    uint32_t* row = reinterpret_cast<uint32_t*>(a.pair_d) + (size_t)pair * (2 * U_CAP) + base;
+                    const uint32_t src = cand_u + (uint32_t)(q * U_CAP) * 4;
+                    for (int i = half; i < n; i += 2) {
+                        row[i] = lds_u(src + i * 4);
+                        row[U_CAP + i] = lds_u(src + W_CAND + i * 4);
+                    }
+                }
+                named_bar(2, W_NLOAD);  // both halves have read the running count
+                if (lt == 0) mbar_arrive(bar_candfree);
+                if (half == 0) {
+                    sts_u(stx + 3 * QG * 4 + q * 4, (uint32_t)(base + n));
+                    if (bad) sts_u(stx + 4 * QG * 4 + q * 4, 1u);
+                    if (last && q < njx && pair >= 0) {  // last pass of the list: publish the pair
+                        if (bad) {
+                            a.pair_cnt[pair] = 0;
+                            a.redo_pairs[atomicAdd(a.redo_cnt, 1)] = pair;
+                        } else {
+                            a.pair_cnt[pair] = base + n;
+                        }
+                    }
+                }
+                named_bar(2, W_NLOAD);  // state / counters of the segment are free for the next staging
+            };
 #pragma unroll 1
             for (uint32_t g = 0;; ++g) {
                 const uint32_t spar = g & 1;
                 const uint32_t sg = seg_u + spar * W_SEG;
-                if (g >= 2) warp_wait(bar_segfree + 8 * spar, ((g - 2) >> 1) & 1, 26);
                 const bool stamp_on = DBG && st && g == W_DBG_SEG + 1;   // the segment staged WHILE segment W_DBG_SEG is scanned
                 if (stamp_on) st[0] = clock64();
+                if (g >= 2) finalize(g - 2);
+                if (stamp_on) st[5] = clock64();
                 if (item >= nitems) {
-                    named_bar(2, W_NLOAD);
                     if (lt == 0) {
                         sts_u(sg, 0u);
                         mbar_arrive(bar_staged + 8 * spar);
                     }
+                    if (g >= 1) finalize(g - 1);
                     break;
                 }
+                if (lt < QG) sts_u(segcnt_u + spar * (QG * 4) + lt * 4, 0u);
                 const uint32_t stt = state_u + ipar * W_STATE;
                 const uint32_t res_i = resid_u + ipar * RESID_BYTES;
                 if (new_item) {

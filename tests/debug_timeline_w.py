@@ -26,9 +26,10 @@ for wv in range(12):
     r = sc[wv]
     print("  warp %2d" % wv, [int(x - t0) if x else None for x in r[:5]], [int(x - t0) if x else None for x in r[6:12]])
 pr = ts[192:256].reshape(16, 4)
-print("producer per table (after build t-2 done+refill, A written, free+operand waited, issued), relative:")
+ow = ts[272:304].reshape(16, 2)
+print("issuer per table (A operand seen + refill issued, codebook operand seen, table buffer released, MMAs issued) | operand writer (ring slot free, A written), relative:")
 for s in range(16):
-    print("  s=%2d" % s, [int(x - t0) if x else None for x in pr[s]])
-print("loader (segment after): start, desc, copies landed, planes, staged:", [int(x - t0) if x else None for x in ts[256:261]])
-print("finalizer: extract seen, done:", [int(x - t0) if x else None for x in ts[272:274]])
+    print("  s=%2d" % s, [int(x - t0) if x else None for x in pr[s]], [int(x - t0) if x else None for x in ow[s]])
+print("loader (segment after): start, finalize of the segment two back done, desc, copies landed, planes, staged:",
+      [int(x - t0) if x else None for x in (ts[256], ts[261], ts[257], ts[258], ts[259], ts[260])])
 e.close()
