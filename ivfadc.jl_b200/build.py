@@ -33,6 +33,11 @@ def _stale(target: str, deps) -> bool:
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
+    # bring-up: IVFADC_NVCC_EXTRA="-DX=1" IVFADC_LIB_OUT=/path/lib.so builds a variant beside the product library
+    extra = os.environ.get("IVFADC_NVCC_EXTRA", "").split()
+    out = os.environ.get("IVFADC_LIB_OUT")
+    if extra or out:
+        return _build_variant(extra, out or LIB + ".variant")
     os.makedirs(OBJDIR, exist_ok=True)
     common = [os.path.join(CSRC, h) for h in HEADERS] + [os.path.join(ROOT, "include", "ivfadc.h")]
     nvcc = _nvcc()
@@ -55,6 +60,20 @@ def build(force: bool = False, verbose: bool = False) -> str:
             print(" ".join(cmd))
         subprocess.check_call(cmd)
     return LIB
+
+
+def _build_variant(extra, out: str) -> str:
+    import tempfile
+    nvcc = _nvcc()
+    with tempfile.TemporaryDirectory() as tmp:
+        def one(src):
+            obj = os.path.join(tmp, src.replace(".cu", ".o"))
+            subprocess.check_call([nvcc] + NVCC_FLAGS + extra + ["-c", os.path.join(CSRC, src), "-o", obj])
+            return obj
+        with ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
+            objs = list(ex.map(one, SOURCES))
+        subprocess.check_call([nvcc, "-shared", "-o", out] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-ldl"])
+    return out
 
 
 if __name__ == "__main__":

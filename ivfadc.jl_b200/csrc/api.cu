@@ -2,6 +2,7 @@
 // All numerics live in coarse.cu / scan*.cu / encode.cu / lists.cu.
 #include <algorithm>
 #include <cmath>
+#include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <new>
@@ -267,6 +268,30 @@ int ivfadc_create(ivfadc_index** out, const ivfadc_config* cfg, const void* cent
         }
         ok = x->tm.ok;
     }
+    if (cfg->dtype == IVFADC_F32) {
+        // fp16 operand scales of the tensor-memory scan (scanw_impl.cuh): -2 w 2^ew and |w|^2 2^en (norm of an
+        // 8-dim piece of a codeword) just below 2^14
+        const float* cbv = static_cast<const float*>(codebook_vectors);
+        const int dsub = h->dsub;
+        double maxw = 0.0, maxn = 0.0;
+        for (size_t r = 0; r < (size_t)cfg->m * cfg->ksub; ++r)
+            for (int d0 = 0; d0 < dsub; d0 += 8) {
+                double nn = 0.0;
+                for (int d = d0; d < std::min(dsub, d0 + 8); ++d) {
+                    const double v = cbv[r * dsub + d];
+                    if (std::isfinite(v)) {
+                        maxw = std::max(maxw, std::fabs(v));
+                        nn += v * v;
+                    }
+                }
+                maxn = std::max(maxn, nn);
+            }
+        int e = 0;
+        if (maxw > 0.0) { std::frexp(2.0 * maxw, &e); h->tch_ew = 14 - e; }
+        if (maxn > 0.0) { std::frexp(maxn, &e); h->tch_en = 14 - e; }
+        h->tch_ew = std::max(-60, std::min(60, h->tch_ew));
+        h->tch_en = std::max(-60, std::min(60, h->tch_en));
+    }
     h->cb_identity = 1;
     for (int i = 0; i < cfg->m && h->cb_identity; ++i)
         for (int c = 0; c < cfg->ksub; ++c)
@@ -320,6 +345,7 @@ int ivfadc_destroy(ivfadc_index* h) {
     if (h->d_afrag) cudaFree(h->d_afrag);
     if (h->d_wnfrag) cudaFree(h->d_wnfrag);
     if (h->d_tcU) cudaFree(h->d_tcU);
+    if (h->d_tcH) cudaFree(h->d_tcH);
     if (h->d_err) cudaFree(h->d_err);
     if (h->h_err) cudaFreeHost(h->h_err);
     if (h->d_dbg_lut) cudaFree(h->d_dbg_lut);

@@ -118,6 +118,8 @@ struct ivfadc_index {
     void* d_wnfrag = nullptr;
     int frag_ntiles = 0, frag_ksteps = 0;
     void* d_tcU = nullptr;          // codebook as per-subspace B-operand blocks, rows = code values (scanu)
+    void* d_tcH = nullptr;          // the same as fp16 two-piece operand blocks (scanw): [tables][2][256 rows][16 k]
+    int tch_ew = 0, tch_en = 0;     // power-of-two scales of -2w and |w|^2 in d_tcH (fp16 range), fixed at create
     int* h_err = nullptr;           // pinned host copy of d_err (read back with the results)
     int* d_err = nullptr;           // device error flag of the tcgen05 pipeline (mbarrier timeout)
     void* d_dbg_lut = nullptr;      // optional table dump of work item 0 (tests), float[m][256][32]

@@ -704,6 +704,9 @@ cudaError_t search_t(ivfadc_index* h, const void* dQ, int64_t nq, int k, int w, 
                 ScanUArgs uq;
                 uq.q = qa;
                 uq.tcU = static_cast<const float*>(h->d_tcU);
+                uq.tcH = h->d_tcH;
+                uq.ew = h->tch_ew;
+                uq.en = h->tch_en;
                 uq.items = h->ws_items.as<int4>();
                 uq.item_counter = item_counter;
                 uq.pstride = ps;
@@ -825,6 +828,14 @@ cudaError_t scanq_prepare(ivfadc_index* h, cudaStream_t s, int* launches) {
         prep_tcu_kernel<<<(n + 255) / 256, 256, 0, s>>>(static_cast<const float*>(h->d_cb), h->d_cb_codes,
                                                         h->cb_identity ? 1 : 0, m, h->cfg.ksub, h->dsub, dup,
                                                         static_cast<float*>(h->d_tcU));
+        if (launches) *launches += 1;
+        // fp16 two-piece operand blocks of the warp-specialised kernel
+        const size_t hbytes = (size_t)m * dup * W_BSUB;
+        if ((e = cudaMalloc(&h->d_tcH, hbytes)) != cudaSuccess) return e;
+        if ((e = cudaMemsetAsync(h->d_tcH, 0, hbytes, s)) != cudaSuccess) return e;
+        prep_tch_kernel<<<(n + 255) / 256, 256, 0, s>>>(static_cast<const float*>(h->d_cb), h->d_cb_codes,
+                                                        h->cb_identity ? 1 : 0, m, h->cfg.ksub, h->dsub, dup,
+                                                        h->tch_ew, h->tch_en, static_cast<__half*>(h->d_tcH));
         if (launches) *launches += 1;
     }
     return cudaGetLastError();

@@ -64,6 +64,8 @@ constexpr int U_CAP = 64;                    // candidate row of a (query, list)
 struct ScanUArgs {
     ScanQArgs q;
     const float* tcU;     // [m][3][2048] tf32 words: -2w hi / lo, split norms; rows = code values
+    const void* tcH;      // scanw: [m][2][4096] fp16: (hi | hi), (lo | norm pieces) of -2w 2^ew, |w|^2 2^en
+    int ew, en;           // scanw: the two power-of-two scales
     const int4* items;    // [nitems] (cell, first pair slot, number of pairs, 0)
     int* item_counter;    // work distribution (zeroed per launch)
     int pstride;          // candidate capacity of a pair's row

@@ -31,6 +31,8 @@
 // Candidate rows, merge_cands_kernel and the redo queue are those of scanu (scan.cu).
 #pragma once
 
+#include <cuda_fp16.h>
+
 #include "scanu_impl.cuh"
 
 namespace ivf {
@@ -44,25 +46,28 @@ constexpr int W_NCH = W_NV / 16;             // chunks of 16 vectors per scanner
 constexpr int W_VP = W_SCAN * W_NV;          // 1152 vectors per pass
 constexpr int W_CSTEP = 16 * W_SCAN;         // byte distance of a scanner's consecutive chunks in a plane
 constexpr int W_NMIN = 2 * W_SCAN;           // group minima per query and pass
-constexpr int W_STATE = 5 * QG * 4;          // per item: pair | dc -> base | run | cnt | flag
+constexpr int W_STATE = 8 * QG * 4;          // per item: pair | dc -> base 2^s | run | cnt | flag | 2^sr | a | 2^-s
 constexpr int W_SEG = 32;                    // per segment: valid, nv, pass, ipar, nj, last
 constexpr int W_CAND = QG * U_CAP * 4;       // one plane (distances or positions) of the staged candidates of a pass
+constexpr int W_ABLK = 4096;                 // A block: 128 rows x 16 k (fp16)
+constexpr int W_ASUB = 2 * W_ABLK;           // (hi | lo), (hi | a a 0..) of one table
+constexpr int W_BBLK = 8192;                 // B block: 256 rows x 16 k (fp16)
+constexpr int W_BSUB = 2 * W_BBLK;           // (hi | hi), (lo | norm pieces) of one table
+constexpr int W_NB = 4;                      // B ring depth
+// Instruction descriptor of tcgen05.mma kind::f16: D fp32, A/B fp16 K-major, M = 128, N = 256 (K = 16).
+constexpr uint32_t W_IDESC = (1u << 4) | (0u << 7) | (0u << 10) | ((256u >> 3) << 17) | ((128u >> 4) << 24);
 constexpr uint32_t W_SPIN = 1u << 20;
-#ifndef W_DEPTH
-#define W_DEPTH 16                           // lookups in flight per tcgen05.wait::ld (16 or 32)
-#endif
 
 struct ScanWSmem {
-    uint32_t aone, aring, bring, planes, raw, resid, rawq, cand, smin, thr, rnorm, state, seg, segcnt, ldesc, cbuf, bars, total;
+    uint32_t aring, bring, planes, raw, resid, rawq, cand, smin, thr, rnorm, rmax, state, seg, segcnt, ldesc, cbuf, bars, total;
 };
 
 // m = tables per item (8 dims each), mc = code bytes per vector
 __host__ __device__ inline ScanWSmem scanw_smem_layout(int m, int mc) {
     ScanWSmem s;
     uint32_t o = 0;
-    s.aone = o;    o += U_ABLK;
-    s.aring = o;   o += 2 * U_ASUB;
-    s.bring = o;   o += U_NB * U_BSUB;
+    s.aring = o;   o += 2 * W_ASUB;
+    s.bring = o;   o += W_NB * W_BSUB;
     s.planes = o;  o += 2u * (uint32_t)mc * W_VP;
     s.raw = o;     o += (uint32_t)mc * W_VP + 16;
     s.rawq = o;    o += (uint32_t)QG * m * 32;
@@ -72,6 +77,7 @@ __host__ __device__ inline ScanWSmem scanw_smem_layout(int m, int mc) {
     s.smin = o;    o += W_NMIN * QG * 4;
     s.thr = o;     o += QG * 4;
     s.rnorm = o;   o += (uint32_t)m * QG * 4;
+    s.rmax = o;    o += (uint32_t)m * QG * 4;
     s.state = o;   o += 2 * W_STATE;
     s.seg = o;     o += 2 * W_SEG;
     s.segcnt = o;  o += 2 * QG * 4;            // candidates staged per query by the scanners of a segment
@@ -82,6 +88,11 @@ __host__ __device__ inline ScanWSmem scanw_smem_layout(int m, int mc) {
     return s;
 }
 
+__device__ __forceinline__ void sts_v4u(uint32_t a, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+}
+// 2^e as a float, e in [-126, 127]
+__device__ __forceinline__ float exp2i(int e) { return __uint_as_float((uint32_t)(e + 127) << 23); }
 __device__ __forceinline__ void named_bar(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
@@ -89,49 +100,104 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 // Bounded wait that gives up at once when another wait of this CTA has already timed out (`dead` flag in shared
-// memory): a broken pipeline ends in an error code within about a second, not in a hang.
+// memory): a broken pipeline ends in an error code within about a second, not in a hang.  A waiting thread must
+// not spin through issue slots the scanners need (the first version of this loop was 23% of the kernel's
+// instructions, ncu): mbarrier.try_wait gets a suspend-time hint, so the thread sleeps in hardware until the phase
+// completes (or the hint runs out), and the loop around it is four instructions.
+__device__ __forceinline__ uint32_t mbar_try_wait_hint(uint32_t bar, uint32_t parity, uint32_t ns) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity), "r"(ns)
+        : "memory");
+    return ok;
+}
 __device__ __forceinline__ void mbar_wait_w(uint32_t bar, uint32_t parity, uint32_t dead_u, int* err, int code) {
 #pragma unroll 1
-    for (uint32_t i = 0; i < W_SPIN; ++i) {
-        if (mbar_try_wait(bar, parity)) return;
-        if ((i & 255u) == 255u && lds_u(dead_u) != 0u) return;
+    for (uint32_t o = 0; o < (W_SPIN >> 8); ++o) {
+#pragma unroll 1
+        for (uint32_t i = 0; i < 256u; ++i)
+            if (mbar_try_wait_hint(bar, parity, 100000u)) return;
+        if (lds_u(dead_u) != 0u) return;
     }
     sts_u(dead_u, 1u);
     atomicExch(err, code);
 }
 
+// One table over the 96 slots of this warp.  tcgen05.wait::ld waits for ALL outstanding loads of the thread, so the
+// number of lookups between two waits is the warp's depth in flight.  Measured (phase profile of the DBG
+// instantiation + ncu): a lookup comes back after ~300 clocks under load, and with 16 in flight per warp the twelve
+// scanners keep only ~190 lookups in the tensor-memory pipe -- 0.5 per clock of the 1.0 it sustains.  Two chunks
+// (32 lookups) per wait.
 template <bool FULL>
 __device__ __forceinline__ void scanw_sub(uint32_t tb, uint32_t plane_w, int nch, float (&acc)[W_NV]) {
-    if constexpr (FULL && W_DEPTH == 32) {
 #pragma unroll
-        for (int j2 = 0; j2 < W_NCH / 2; ++j2) {
-            const uint4 x0 = lds_v4(plane_w + (2 * j2) * W_CSTEP), x1 = lds_v4(plane_w + (2 * j2 + 1) * W_CSTEP);
+    for (int jp = 0; jp < W_NCH / 2; ++jp) {
+        const int j0 = 2 * jp, j1 = 2 * jp + 1;
+        if (FULL || j1 < nch) {  // warp-uniform; slots beyond the list are masked after the last table
+            const uint4 xa = lds_v4(plane_w + j0 * W_CSTEP), xb = lds_v4(plane_w + j1 * W_CSTEP);
             float t[32];
-            scanu_issue<0>(tb, x0, t);
-            scanu_issue<0>(tb, x1, t + 16);
+            scanu_issue<0>(tb, xa, t);
+            scanu_issue<0>(tb, xb, t + 16);
             tc_wait_ld();
 #pragma unroll
-            for (int i = 0; i < 32; i += 2) add_pair(acc[32 * j2 + i], acc[32 * j2 + i + 1], t[i], t[i + 1]);
-        }
-    } else {
+            for (int i = 0; i < 32; i += 2) add_pair(acc[16 * j0 + i], acc[16 * j0 + i + 1], t[i], t[i + 1]);
+        } else if (j0 < nch) {
+            const uint4 xa = lds_v4(plane_w + j0 * W_CSTEP);
+            float t[16];
+            scanu_issue<0>(tb, xa, t);
+            tc_wait_ld();
 #pragma unroll
-        for (int j = 0; j < W_NCH; ++j) {
-            if (FULL || j < nch) {  // warp-uniform; slots beyond the list are masked after the last table
-                const uint4 x = lds_v4(plane_w + j * W_CSTEP);
-                float t[16];
-                scanu_issue<0>(tb, x, t);
-                tc_wait_ld();
-#pragma unroll
-                for (int i = 0; i < 16; i += 2) add_pair(acc[16 * j + i], acc[16 * j + i + 1], t[i], t[i + 1]);
-            }
+            for (int i = 0; i < 16; i += 2) add_pair(acc[16 * j0 + i], acc[16 * j0 + i + 1], t[i], t[i + 1]);
         }
     }
 }
 
 // NP = (code bytes per vector) / 4; DUP = 2 serves dsub = 16 (two 8-dim tables share a code byte, see scanu_kernel).
 // Debug buffer (DBG instantiation, CTA 0): tables of the first segment [m][256][32], int pair[32], cell, then
-// clock64 stamps of segment W_DBG_SEG: scanner w at [16 w ..], producer at [192 ..], loaders [256 ..], finalizer [272 ..].
-constexpr int W_DBG_SEG = 3;
+// the phase profile (WProf): 8 counters per warp.
+// One table build = two MMAs (kind::f16, K = 16) + commit, issued by one elected lane.
+__device__ __forceinline__ void tc_mma_f16_elect(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(W_IDESC), "r"(accumulate)
+        : "memory");
+}
+
+// Phase profile of the DBG instantiation: every role accumulates the SM clocks it spends per phase (registers only,
+// no memory traffic inside the loops); CTA 0 writes 8 counters per warp behind the table dump at the end.
+template <bool ON>
+struct WProf {
+    uint32_t last, a[8];
+    __device__ __forceinline__ void start() {
+        if constexpr (ON) {
+            last = (uint32_t)clock();
+#pragma unroll
+            for (int i = 0; i < 8; ++i) a[i] = 0;
+        }
+    }
+    __device__ __forceinline__ void tick(int i) {
+        if constexpr (ON) {
+            const uint32_t n = (uint32_t)clock();
+            a[i] += n - last;
+            last = n;
+        }
+    }
+    __device__ __forceinline__ void store(long long* dst) {
+        if constexpr (ON) {
+            if (dst) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) dst[i] = a[i];
+            }
+        }
+    }
+};
 
 template <int NP, bool DBG, int DUP = 1>
 __global__ void __launch_bounds__(W_THREADS, 1)
@@ -154,22 +220,23 @@ scanw_kernel(const ScanUArgs ua) {
     uint32_t sb;
     asm volatile("mov.u32 %0, %1;" : "=r"(sb) : "r"(smem_u32(smem_w)));
     const ScanWSmem L = scanw_smem_layout(m, mc);
-    const uint32_t aone_u = sb + L.aone, aring_u = sb + L.aring, bring_u = sb + L.bring, planes_u = sb + L.planes,
+    const uint32_t aring_u = sb + L.aring, bring_u = sb + L.bring, planes_u = sb + L.planes,
                    raw_u = sb + L.raw, resid_u = sb + L.resid, rawq_u = sb + L.rawq, smin_u = sb + L.smin,
-                   thr_u = sb + L.thr, rnorm_u = sb + L.rnorm, state_u = sb + L.state, seg_u = sb + L.seg,
+                   thr_u = sb + L.thr, rnorm_u = sb + L.rnorm, rmax_u = sb + L.rmax, state_u = sb + L.state, seg_u = sb + L.seg,
                    ldesc_u = sb + L.ldesc, cbuf_u = sb + L.cbuf, cand_u = sb + L.cand, segcnt_u = sb + L.segcnt;
-    const uint32_t bar_full = sb + L.bars;          // 3: codebook operand landed in ring slot
-    const uint32_t bar_mma = bar_full + 24;         // 2: table build complete (tcgen05.commit)
-    const uint32_t bar_free = bar_full + 40;        // 2: the 12 scanners are done with the table buffer
-    const uint32_t bar_staged = bar_full + 56;      // 2: segment staged by the loaders
-    const uint32_t bar_extract = bar_full + 72;     // 2: the 12 scanners have staged their candidates
-    const uint32_t bar_a = bar_full + 88;           // 2: A operand of a build written
-    const uint32_t bar_candfree = bar_full + 104;   // 1: staged candidates of a segment copied out
-    const uint32_t tmem_slot = bar_full + 112, dead_u = bar_full + 116;
+    const uint32_t bar_full = sb + L.bars;          // 4: codebook operand landed in ring slot
+    const uint32_t bar_mma = bar_full + 32;         // 2: table build complete (tcgen05.commit)
+    const uint32_t bar_free = bar_full + 48;        // 2: the 12 scanners are done with the table buffer
+    const uint32_t bar_staged = bar_full + 64;      // 2: segment staged by the loaders
+    const uint32_t bar_extract = bar_full + 80;     // 2: the 12 scanners have staged their candidates
+    const uint32_t bar_a = bar_full + 96;           // 2: A operand of a build written
+    const uint32_t bar_candfree = bar_full + 112;   // 1: staged candidates of a segment copied out
+    const uint32_t tmem_slot = bar_full + 120, dead_u = bar_full + 124;
+    const unsigned char* const tcH = static_cast<const unsigned char*>(ua.tcH);
 
     // ---- one-time setup ----
     if (tid == 0) {
-        for (int i = 0; i < U_NB; ++i) mbar_init(bar_full + 8 * i, 1);
+        for (int i = 0; i < W_NB; ++i) mbar_init(bar_full + 8 * i, 1);
         for (int i = 0; i < 2; ++i) {
             mbar_init(bar_mma + 8 * i, 1);
             mbar_init(bar_free + 8 * i, W_SCAN);
@@ -180,9 +247,9 @@ scanw_kernel(const ScanUArgs ua) {
         mbar_init(bar_candfree, 1);
         sts_u(dead_u, 0u);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        for (int i = 0; i < U_NB; ++i) {
-            mbar_expect_tx(bar_full + 8 * i, U_BSUB);
-            tma_bulk_g2s(bring_u + i * U_BSUB, ua.tcU + (size_t)(i % m) * (U_BSUB / 4), U_BSUB, bar_full + 8 * i);
+        for (int i = 0; i < W_NB; ++i) {
+            mbar_expect_tx(bar_full + 8 * i, W_BSUB);
+            tma_bulk_g2s(bring_u + i * W_BSUB, tcH + (size_t)(i % m) * W_BSUB, W_BSUB, bar_full + 8 * i);
         }
     }
     if (wid == 1) {
@@ -191,13 +258,6 @@ scanw_kernel(const ScanUArgs ua) {
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    // ones block of the A operand: every row selects the split norm (k slots 0, 1)
-    for (int i = tid; i < 256; i += W_THREADS) {
-        const int r = i >> 1, half = i & 1;
-        const float one = half == 0 ? 1.f : 0.f;
-        sts_v4f(aone_u + (r >> 3) * 256 + half * 128 + (r & 7) * 16, one, one, 0.f, 0.f);
-    }
-    fence_proxy_async();  // ones block: generic-proxy writes -> async proxy (tensor core)
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -215,7 +275,8 @@ scanw_kernel(const ScanUArgs ua) {
         asm volatile("setmaxnreg.inc.sync.aligned.u32 152;");
         const uint32_t tq = tmem_base + ((uint32_t)((wid & 3) * 32) << 16);
         const uint32_t plane_w0 = planes_u + 16 * wid;
-        long long* const st = (stamps && lane == 0) ? stamps + 16 * wid : nullptr;
+        WProf<DBG> pf;  // 0 wait staged, 1 wait table, 2 lookups, 3 release, 4 minima + barrier, 5 rank + barrier, 6 candidates
+        pf.start();
         uint32_t tg = 0;
         float acc[W_NV];
 #pragma unroll 1
@@ -226,10 +287,10 @@ scanw_kernel(const ScanUArgs ua) {
             if (lds_u(sg) == 0u) break;
             const int nv = (int)lds_u(sg + 4), pass = (int)lds_u(sg + 8);
             const uint32_t stt = state_u + lds_u(sg + 12) * W_STATE;  // pair | base | run | cnt | flag of the item
-            const bool stamp_on = DBG && st && g == W_DBG_SEG;
-            if (stamp_on) st[0] = clock64();
+            pf.tick(0);
             const float base = lds_f(stt + QG * 4 + lane * 4);
-            const int nch = min(W_NCH, max(0, (nv - 16 * wid + W_CSTEP - 1) / W_CSTEP));  // chunks j with 16 (wid + 12 j) < nv
+            // chunks j with 16 (wid + 12 j) < nv; provably warp-uniform (see below)
+            const int nch = __shfl_sync(0xffffffffu, min(W_NCH, max(0, (nv - 16 * wid + W_CSTEP - 1) / W_CSTEP)), 0);
 #pragma unroll
             for (int j = 0; j < W_NV; ++j) acc[j] = base;  // dc + |r|^2, then the table entries in subspace order
             // Everything that forms a lookup address must be PROVABLY warp-uniform for ptxas (shuffles from lane 0):
@@ -241,20 +302,22 @@ scanw_kernel(const ScanUArgs ua) {
 #pragma unroll 1
             for (int s = 0; s < m; ++s) {
                 const uint32_t b = (uint32_t)s & 1u;
-                if (stamp_on && (s == 5 || s == 6)) st[6 + (s - 5) * 3] = clock64();
-                warp_wait(bar_mma + 8 * b, par, 2);
+                pf.tick(3);
+                // every lane polls (no divergence on the common path); the bounded loop only when the build is late
+                if (!mbar_try_wait_hint(bar_mma + 8 * b, par, 100000u)) warp_wait(bar_mma + 8 * b, par, 2);
                 tc_fence_after();
-                if (stamp_on && (s == 5 || s == 6)) st[7 + (s - 5) * 3] = clock64();
+                pf.tick(1);
                 const uint32_t tb = __shfl_sync(0xffffffffu, tq + b * 256, 0);
                 const uint32_t plane_w = __shfl_sync(0xffffffffu, plane_seg + (uint32_t)(s / DUP) * W_VP, 0);
                 if (nch == W_NCH) scanw_sub<true>(tb, plane_w, nch, acc);
                 else scanw_sub<false>(tb, plane_w, nch, acc);
+                pf.tick(2);
                 if (DBG && g == 0 && blockIdx.x == 0 && ua.dbg != nullptr) {  // bring-up: dump the tables of the first segment
                     if (wid < 4) {
                         for (int c = wid; c < 256; c += 4) {
                             const float v = tc_ld1(tb + c);
                             tc_wait_ld();
-                            ua.dbg[((size_t)s * 256 + c) * 32 + lane] = v;
+                            ua.dbg[((size_t)s * 256 + c) * 32 + lane] = v * lds_f(stt + 7 * QG * 4 + lane * 4);
                         }
                     }
                     if (s == 0 && wid == 0) {
@@ -265,11 +328,10 @@ scanw_kernel(const ScanUArgs ua) {
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar_free + 8 * b);
-                if (stamp_on && (s == 5 || s == 6)) st[8 + (s - 5) * 3] = clock64();
                 par ^= b;
             }
             tg += m;
-            if (stamp_on) st[1] = clock64();
+            pf.tick(3);
 
             // ---- end of the pass: bound, candidates ----
             {   // slot 16 j + i holds vector 16 (wid + 12 j) + i of the pass: mask the slots beyond the list
@@ -292,7 +354,7 @@ scanw_kernel(const ScanUArgs ua) {
             sts_f(smin_u + ((2 * wid) * QG + lane) * 4, mn0);
             sts_f(smin_u + ((2 * wid + 1) * QG + lane) * 4, mn1);
             named_bar(1, W_SCAN * 32);
-            if (stamp_on) st[2] = clock64();
+            pf.tick(4);
             {
                 int r0 = 0, r1 = 0;
 #pragma unroll
@@ -311,16 +373,17 @@ scanw_kernel(const ScanUArgs ua) {
                 }
             }
             named_bar(1, W_SCAN * 32);
-            if (stamp_on) st[3] = clock64();
+            pf.tick(5);
             {
                 const float thr = lds_f(thr_u + lane * 4);
                 // keep d <= bound; while fewer than k vectors have been seen (bound = +inf) keep every real slot
                 const float cut = thr < Limits<float>::inf() ? thr : 3.402823466e+38f;
                 const int pair = (int)lds_u(stt + lane * 4);
+                const float unscale = lds_f(stt + 7 * QG * 4 + lane * 4);   // 2^-(ew + sr): exact
                 int c = 0;
 #pragma unroll
                 for (int j = 0; j < W_NV; ++j) c += acc[j] <= cut ? 1 : 0;
-                if (pair < 0) c = 0;
+                if (pair < 0 || lds_u(stt + 4 * QG * 4 + lane * 4) != 0u) c = 0;
                 // the staging area is single-buffered: the loaders have copied out the previous segment long ago
                 if (g > 0) warp_wait(bar_candfree, (g - 1) & 1, 27);
                 int old = 0;
@@ -333,7 +396,7 @@ scanw_kernel(const ScanUArgs ua) {
 #pragma unroll
                     for (int j = 0; j < W_NV; ++j) {
                         if (acc[j] <= cut) {
-                            sts_f(pd, acc[j]);
+                            sts_f(pd, acc[j] * unscale);
                             sts_u(pd + W_CAND, pos + (uint32_t)((j >> 4) * W_CSTEP + (j & 15)));
                             pd += 4;
                         }
@@ -342,24 +405,26 @@ scanw_kernel(const ScanUArgs ua) {
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_extract + 8 * spar);
-            if (stamp_on) st[4] = clock64();
+            pf.tick(6);
         }
+        pf.store(stamps && lane == 0 ? stamps + 8 * wid : nullptr);
     } else {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
         if (wid == W_ISSUE) {
             // =========================================== ISSUER ===========================================
-            const uint64_t descA0 = tc_smem_desc(aring_u), descB0 = tc_smem_desc(bring_u), desc1 = tc_smem_desc(aone_u);
+            const uint64_t descA0 = tc_smem_desc(aring_u), descB0 = tc_smem_desc(bring_u);
             uint32_t t = 0;
             uint32_t bslot = 0, bphase = 0;            // ring slot / phase of build t
-            uint32_t fslot = 0, fsub = U_NB % m;       // next refill: slot (= slot of build t - 2), subspace of build t + 1
-            uint32_t nfill = U_NB;                     // fills issued so far
-            long long* const st = (stamps && lane == 0) ? stamps + 192 : nullptr;
+            uint32_t fslot = 0, fsub = W_NB % m;       // next refill: slot (= slot of build t - 2), subspace of build t + 2
+            uint32_t nfill = W_NB;                     // fills issued so far
+            WProf<DBG> pf;  // 0 wait staged, 1 wait A operand (+ refill), 2 wait codebook operand, 3 wait release, 4 issue
+            pf.start();
 #pragma unroll 1
             for (uint32_t g = 0;; ++g) {
                 const uint32_t spar = g & 1;
                 warp_wait(bar_staged + 8 * spar, (g >> 1) & 1, 21);
                 if (lds_u(seg_u + spar * W_SEG) == 0u) break;
-                const bool stamp_on = DBG && st && g == W_DBG_SEG;
+                pf.tick(0);
 #pragma unroll 1
                 for (int s = 0; s < m; ++s, ++t) {
                     const uint32_t buf = t & 1;
@@ -368,41 +433,41 @@ scanw_kernel(const ScanUArgs ua) {
                     if (t >= 2) {
                         if (lane == 0) {
                             const uint32_t bar = bar_full + 8 * fslot;
-                            mbar_expect_tx(bar, U_BSUB);
-                            tma_bulk_g2s(bring_u + fslot * U_BSUB, ua.tcU + (size_t)fsub * (U_BSUB / 4), U_BSUB, bar);
+                            mbar_expect_tx(bar, W_BSUB);
+                            tma_bulk_g2s(bring_u + fslot * W_BSUB, tcH + (size_t)fsub * W_BSUB, W_BSUB, bar);
                         }
-                        if (++fslot == U_NB) fslot = 0;
+                        if (++fslot == W_NB) fslot = 0;
                         if (++fsub == (uint32_t)m) fsub = 0;
                         ++nfill;
                     }
-                    if (stamp_on) st[4 * s] = clock64();
-                    warp_wait(bar_full + 8 * bslot, bphase, 1);
-                    if (stamp_on) st[4 * s + 1] = clock64();
-                    if (t >= 2) warp_wait(bar_free + 8 * buf, ((t - 2) >> 1) & 1, 23);  // scanners released table t - 2
-                    if (stamp_on) st[4 * s + 2] = clock64();
-                    tc_fence_after();
                     const uint32_t slot_u = __shfl_sync(0xffffffffu, bslot, 0), buf_u = __shfl_sync(0xffffffffu, buf, 0);
-                    const uint64_t Ah = descA0 + (uint64_t)(buf_u * (U_ASUB >> 4)), Al = Ah + (U_ABLK >> 4);
-                    const uint64_t Bh = descB0 + (uint64_t)(slot_u * (U_BSUB >> 4)), Bl = Bh + (U_BBLK >> 4), Bn = Bl + (U_BBLK >> 4);
+                    const uint64_t A0 = descA0 + (uint64_t)(buf_u * (W_ASUB >> 4)), A1 = A0 + (W_ABLK >> 4);
+                    const uint64_t B0 = descB0 + (uint64_t)(slot_u * (W_BSUB >> 4)), B1 = B0 + (W_BBLK >> 4);
                     const uint32_t d = tmem_base + buf_u * 256;
-                    tc_mma_elect(d, Ah, Bh, 0);
-                    tc_mma_elect(d, Al, Bh, 1);
-                    tc_mma_elect(d, Ah, Bl, 1);
-                    tc_mma_elect(d, desc1, Bn, 1);
+                    pf.tick(1);
+                    warp_wait(bar_full + 8 * bslot, bphase, 1);
+                    pf.tick(2);
+                    if (t >= 2) warp_wait(bar_free + 8 * buf, ((t - 2) >> 1) & 1, 23);  // scanners released table t - 2
+                    pf.tick(3);
+                    tc_fence_after();
+                    tc_mma_f16_elect(d, A0, B0, 0);   // [rh | rl] . [wh | wh]
+                    tc_mma_f16_elect(d, A1, B1, 1);   // [rh | a a 0..] . [wl | n0 n1 0..]
                     tc_commit_elect(bar_mma + 8 * buf_u);
-                    if (++bslot == U_NB) { bslot = 0; bphase ^= 1; }
-                    if (stamp_on) st[4 * s + 3] = clock64();
+                    if (++bslot == W_NB) { bslot = 0; bphase ^= 1; }
+                    pf.tick(4);
                 }
             }
+            pf.store(stamps && lane == 0 ? stamps + 8 * wid : nullptr);
             // drain: codebook operands fetched for builds that never ran
             if (lane == 0) {
-                for (uint32_t f = t; f < nfill; ++f) mbar_wait_w(bar_full + 8 * (f % U_NB), (f / U_NB) & 1, dead_u, ua.err, 5);
+                for (uint32_t f = t; f < nfill; ++f) mbar_wait_w(bar_full + 8 * (f % W_NB), (f / W_NB) & 1, dead_u, ua.err, 5);
             }
             __syncwarp();
         } else if (wid == W_OPER) {
             // =========================================== OPERAND WRITER ===========================================
             uint32_t t = 0;
-            long long* const st = (stamps && lane == 0) ? stamps + 272 : nullptr;
+            WProf<DBG> pf;  // 0 wait staged, 1 convert, 2 wait ring slot, 3 write
+            pf.start();
 #pragma unroll 1
             for (uint32_t g = 0;; ++g) {
                 const uint32_t spar = g & 1;
@@ -410,35 +475,43 @@ scanw_kernel(const ScanUArgs ua) {
                 const uint32_t sg = seg_u + spar * W_SEG;
                 if (lds_u(sg) == 0u) break;
                 const uint32_t res_i = resid_u + lds_u(sg + 12) * RESID_BYTES;
-                const bool stamp_on = DBG && st && g == W_DBG_SEG;
+                const uint32_t stw = state_u + lds_u(sg + 12) * W_STATE;
+                const float sc = lds_f(stw + 5 * QG * 4 + lane * 4);     // 2^sr of this lane's query
+                const uint32_t aa = lds_u(stw + 6 * QG * 4 + lane * 4);  // (a, a) as two fp16
+                pf.tick(0);
 #pragma unroll 1
                 for (int s = 0; s < m; ++s, ++t) {
                     const uint32_t buf = t & 1;
-                    // rows (copy, q) = TF32 hi / lo of r[s][q][0..7]; lane = query
-                    float hi[8], lo[8];
+                    // rows (copy, q): block 0 = [rh | rl], block 1 = [rh | a a 0 ..] with r 2^sr = rh + rl in fp16; lane = query
+                    uint32_t hi[4], lo[4];
 #pragma unroll
-                    for (int d = 0; d < 8; ++d) {
-                        const float r = lds_f(res_i + ((s * 8 + d) * T_RS + lane) * 4);
-                        hi[d] = __uint_as_float(to_tf32(r));
-                        lo[d] = __uint_as_float(to_tf32(r - hi[d]));
+                    for (int d = 0; d < 8; d += 2) {
+                        const float r0 = lds_f(res_i + ((s * 8 + d) * T_RS + lane) * 4) * sc;
+                        const float r1 = lds_f(res_i + ((s * 8 + d + 1) * T_RS + lane) * 4) * sc;
+                        const __half h0 = __float2half_rn(r0), h1 = __float2half_rn(r1);
+                        const __half l0 = __float2half_rn(r0 - __half2float(h0)), l1 = __float2half_rn(r1 - __half2float(h1));
+                        hi[d >> 1] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+                        lo[d >> 1] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
                     }
+                    pf.tick(1);
                     if (t >= 2) warp_wait(bar_mma + 8 * buf, ((t - 2) >> 1) & 1, 25);  // build t - 2 has read this ring slot
-                    if (stamp_on) st[2 * s] = clock64();
-                    const uint32_t ph0 = aring_u + buf * U_ASUB + (lane >> 3) * 256 + (lane & 7) * 16;
+                    pf.tick(2);
+                    const uint32_t ph0 = aring_u + buf * W_ASUB + (lane >> 3) * 256 + (lane & 7) * 16;
 #pragma unroll
-                    for (int c = 0; c < 4; ++c) {  // row = 32 c + lane
+                    for (int c = 0; c < 4; ++c) {  // row = 32 c + lane: 8-row group stride 256, k halves 128 apart
                         const uint32_t ph = ph0 + c * 1024;
-                        sts_v4f(ph, hi[0], hi[1], hi[2], hi[3]);
-                        sts_v4f(ph + 128, hi[4], hi[5], hi[6], hi[7]);
-                        sts_v4f(ph + U_ABLK, lo[0], lo[1], lo[2], lo[3]);
-                        sts_v4f(ph + U_ABLK + 128, lo[4], lo[5], lo[6], lo[7]);
+                        sts_v4u(ph, hi[0], hi[1], hi[2], hi[3]);
+                        sts_v4u(ph + 128, lo[0], lo[1], lo[2], lo[3]);
+                        sts_v4u(ph + W_ABLK, hi[0], hi[1], hi[2], hi[3]);
+                        sts_v4u(ph + W_ABLK + 128, aa, 0u, 0u, 0u);
                     }
                     fence_proxy_async();  // generic-proxy writes of this lane -> async proxy
                     __syncwarp();
                     if (lane == 0) mbar_arrive(bar_a + 8 * buf);
-                    if (stamp_on) st[2 * s + 1] = clock64();
+                    pf.tick(3);
                 }
             }
+            pf.store(stamps && lane == 0 ? stamps + 8 * wid : nullptr);
         } else {
             // =========================================== LOADERS ===========================================
             const int lt = tid - W_LOAD * 32;  // 0..63
@@ -449,7 +522,8 @@ scanw_kernel(const ScanUArgs ua) {
                 else asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
             };
             auto cp_wait = [&]() { asm volatile("cp.async.wait_all;" ::: "memory"); };
-            long long* const st = (stamps && lt == 0) ? stamps + 256 : nullptr;
+            WProf<DBG> pf;  // 0 finalize (wait + copy-out), 1 descriptor, 2 copies, 3 byte planes, 4 residuals + post
+            pf.start();
             int item = blockIdx.x, pass = 0, npass = 1, ipar = 0, nj = 0, cell = 0;
             int64_t len = 0, off = 0;
             bool new_item = true;
@@ -496,10 +570,9 @@ scanw_kernel(const ScanUArgs ua) {
             for (uint32_t g = 0;; ++g) {
                 const uint32_t spar = g & 1;
                 const uint32_t sg = seg_u + spar * W_SEG;
-                const bool stamp_on = DBG && st && g == W_DBG_SEG + 1;   // the segment staged WHILE segment W_DBG_SEG is scanned
-                if (stamp_on) st[0] = clock64();
+                pf.tick(4);
                 if (g >= 2) finalize(g - 2);
-                if (stamp_on) st[5] = clock64();
+                pf.tick(0);
                 if (item >= nitems) {
                     if (lt == 0) {
                         sts_u(sg, 0u);
@@ -538,7 +611,7 @@ scanw_kernel(const ScanUArgs ua) {
                     { const uint2 v = lds_v2u(ldesc_u + 16); len = (int64_t)(((uint64_t)v.y << 32) | v.x); }
                     { const uint2 v = lds_v2u(ldesc_u + 24); off = (int64_t)(((uint64_t)v.y << 32) | v.x); }
                     npass = (int)((len + W_VP - 1) / W_VP);
-                    if (stamp_on) st[1] = clock64();
+                    pf.tick(1);
                     if (fastq) {
                         // Query rows, coalesced: row q = m * 32 contiguous bytes = 2 m chunks of 16, stored at
                         // chunk ^ (q & 7) (keeps the transposing reads below at 4-way bank conflicts)
@@ -585,7 +658,7 @@ scanw_kernel(const ScanUArgs ua) {
                 }
                 cp_wait();
                 named_bar(2, W_NLOAD);
-                if (stamp_on) st[2] = clock64();
+                pf.tick(2);
                 // byte planes: plane p = code byte p of the pass's vectors (4 x 4 byte transposes)
                 for (int task = lt; 4 * task < nvn; task += W_NLOAD) {
                     const int v0 = 4 * task;
@@ -612,7 +685,7 @@ scanw_kernel(const ScanUArgs ua) {
                         sts_u(pb + 3 * W_VP, __byte_perm(t01h, t23h, 0x7632));
                     }
                 }
-                if (stamp_on) st[3] = clock64();
+                pf.tick(3);
                 if (new_item) {
                     // residuals r = q - c (reference _closest_cluster_residuals, src/coarsequantizers.jl:40-45) and
                     // their squared norms per table; a loader warp handles one table per round, lane = query
@@ -628,21 +701,42 @@ scanw_kernel(const ScanUArgs ua) {
 #pragma unroll
                             for (int d = 0; d < 8; ++d) qd[d] = lds_f(res_i + ((s * 8 + d) * T_RS + lane) * 4);
                         }
-                        float part = 0.f;
+                        float part = 0.f, big = 0.f;
 #pragma unroll
                         for (int d = 0; d < 8; ++d) {
                             const float r = sub_rn(qd[d], lds_f(cbuf_u + (s * 8 + d) * 4));
                             sts_f(res_i + ((s * 8 + d) * T_RS + lane) * 4, r);
                             part = fma_rn(r, r, part);
+                            big = fmaxf(big, fabsf(r));
                         }
                         sts_f(rnorm_u + (s * QG + lane) * 4, part);
+                        sts_f(rmax_u + (s * QG + lane) * 4, big);
                     }
                     named_bar(2, W_NLOAD);
                     if (lw == 0) {
-                        float rn = 0.f;
-                        for (int s = 0; s < m; ++s) rn = add_rn(rn, lds_f(rnorm_u + (s * QG + lane) * 4));  // fixed order
+                        float rn = 0.f, big = 0.f;
+                        for (int s = 0; s < m; ++s) {
+                            rn = add_rn(rn, lds_f(rnorm_u + (s * QG + lane) * 4));  // fixed order
+                            big = fmaxf(big, lds_f(rmax_u + (s * QG + lane) * 4));
+                        }
                         const uint32_t bu = stt + QG * 4 + lane * 4;
-                        sts_f(bu, add_rn(lds_f(bu), rn));  // dc + |r|^2 over the PQ dims
+                        const float base = add_rn(lds_f(bu), rn);  // dc + |r|^2 over the PQ dims
+                        // Power-of-two scales of this query (header comment): r 2^sr below 2^14, a = 2^(ew + sr - en)
+                        // representable in fp16 (subnormals included), everything the scanners add scaled by 2^(ew + sr).
+                        // fmaxf drops NaNs, so a NaN residual shows up in the norm (base), an infinite one in `big`.
+                        const int eb = (int)((__float_as_uint(big) >> 23) & 0xffu) - 126;   // big < 2^eb
+                        int sr = min(14 - eb, 15 + ua.en - ua.ew);
+                        sr = max(-100, min(100, sr));
+                        const int sa = ua.ew + sr - ua.en, sall = ua.ew + sr;
+                        const int sallc = max(-126, min(126, sall));
+                        const float scaled = base * exp2i(sallc);
+                        const bool bad = !(fabsf(scaled) < 3.0e38f) || !(big < 3.0e38f) || sall > 120 || sall < -120;
+                        sts_f(bu, scaled);
+                        sts_f(stt + 5 * QG * 4 + lane * 4, exp2i(sr));
+                        const uint32_t ah = sa >= -24 ? (uint32_t)__half_as_ushort(__float2half_rn(exp2i(max(sa, -24)))) : 0u;
+                        sts_u(stt + 6 * QG * 4 + lane * 4, ah | (ah << 16));
+                        sts_f(stt + 7 * QG * 4 + lane * 4, exp2i(-sallc));
+                        if (bad) sts_u(stt + 4 * QG * 4 + lane * 4, 1u);   // the exact redo kernel serves this pair
                     }
                 }
                 if (lt == 0) {
@@ -656,7 +750,7 @@ scanw_kernel(const ScanUArgs ua) {
                 }
                 named_bar(2, W_NLOAD);
                 if (lt == 0) mbar_arrive(bar_staged + 8 * spar);
-                if (stamp_on) st[4] = clock64();
+                pf.tick(4);
                 if (pass + 1 < npass) {
                     ++pass;
                     new_item = false;
@@ -667,6 +761,7 @@ scanw_kernel(const ScanUArgs ua) {
                     new_item = true;
                 }
             }
+            pf.store(stamps && lane == 0 ? stamps + 8 * wid : nullptr);
         }
     }
 
@@ -676,6 +771,37 @@ scanw_kernel(const ScanUArgs ua) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(U_TMEM_COLS)
                      : "memory");
     }
+}
+
+// Codebook -> fp16 B operand blocks of the warp-specialised kernel, once at create.  Row n of a block is the codeword
+// whose code VALUE is n (as prep_tcu_kernel).  Per table two blocks of 256 rows x 16 k (K-major, no swizzle:
+// half(n, k) at byte (n >> 3) * 256 + (k >> 3) * 128 + (n & 7) * 16 + (k & 7) * 2):
+//   block 0 = [wh | wh], block 1 = [wl | n0 n1 0 ..]  with  -2 w 2^ew = wh + wl,  |w|^2 2^en = n0 + n1  (fp16 pieces).
+__global__ void prep_tch_kernel(const float* __restrict__ cb, const uint8_t* __restrict__ cb_codes, int identity,
+                                int m, int ksub, int dsub, int dup, int ew, int en, __half* __restrict__ out) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= m * dup * ksub) return;
+    const int t = idx / ksub, n = idx - t * ksub;
+    const int s = t / dup, d0 = (t - s * dup) * 8;
+    const int row = identity ? n : (int)cb_codes[(size_t)s * ksub + n];
+    __half* o = out + (size_t)t * (W_BSUB / 2);
+    const float sw = exp2i(ew), sn = exp2i(en);
+    const int rb = (row >> 3) * 128 + (row & 7) * 8;   // in halves
+    float nrm = 0.f;
+    for (int kk = 0; kk < 8; ++kk) {
+        const float w = d0 + kk < dsub ? cb[((size_t)s * ksub + n) * dsub + d0 + kk] : 0.f;
+        nrm = fma_rn(w, w, nrm);
+        const float v = -2.f * w * sw;
+        const __half hi = __float2half_rn(v);
+        const __half lo = __float2half_rn(v - __half2float(hi));
+        o[rb + kk] = hi;
+        o[rb + 64 + kk] = hi;
+        o[W_BBLK / 2 + rb + kk] = lo;
+    }
+    const float ns = nrm * sn;
+    const __half n0 = __float2half_rn(ns);
+    o[W_BBLK / 2 + rb + 64] = n0;
+    o[W_BBLK / 2 + rb + 65] = __float2half_rn(ns - __half2float(n0));
 }
 
 }  // namespace ivf

@@ -18,18 +18,17 @@ buf = np.zeros(m * 256 * 32 + 64 + 1024, dtype=np.float32)
 iv._capi.check(e._h, e._lib.ivfadc_debug_tables(e._h, buf.ctypes.data_as(ctypes.c_void_p)))
 ts = buf[m * 256 * 32 + 64:].view(np.int64)
 print("stats", e.stats())
-sc = ts[:192].reshape(12, 16)
-t0 = sc[:, 0][sc[:, 0] != 0].min() if (sc[:, 0] != 0).any() else 0
-names = ["start", "tables_done", "bar1", "bar2", "extract_done"]
-print("scanner stamps relative to the earliest segment start:", names, "| s=5: before wait, after wait, scan done | s=6: same")
-for wv in range(12):
-    r = sc[wv]
-    print("  warp %2d" % wv, [int(x - t0) if x else None for x in r[:5]], [int(x - t0) if x else None for x in r[6:12]])
-pr = ts[192:256].reshape(16, 4)
-ow = ts[272:304].reshape(16, 2)
-print("issuer per table (A operand seen + refill issued, codebook operand seen, table buffer released, MMAs issued) | operand writer (ring slot free, A written), relative:")
-for s in range(16):
-    print("  s=%2d" % s, [int(x - t0) if x else None for x in pr[s]], [int(x - t0) if x else None for x in ow[s]])
-print("loader (segment after): start, finalize of the segment two back done, desc, copies landed, planes, staged:",
-      [int(x - t0) if x else None for x in (ts[256], ts[261], ts[257], ts[258], ts[259], ts[260])])
+pr = ts[:128].reshape(16, 8)
+names = {
+    "scanner": ["wait staged", "wait table", "lookups", "release", "minima+bar", "rank+bar", "candidates", "-"],
+    "issuer": ["wait staged", "wait A (+refill)", "wait codebook", "wait release", "issue", "-", "-", "-"],
+    "loader": ["finalize", "descriptor", "copies", "byte planes", "residuals+post", "-", "-", "-"],
+    "writer": ["wait staged", "convert", "wait ring slot", "write", "-", "-", "-", "-"],
+}
+role = ["scanner"] * 12 + ["issuer", "loader", "loader", "writer"]
+print("phase profile of CTA 0 (SM clocks summed over the launch):")
+for wv in range(16):
+    tot = int(pr[wv].sum()) or 1
+    print("  warp %2d %-8s total %9d | " % (wv, role[wv], tot) + ", ".join(
+        "%s %4.1f%%" % (n, 100.0 * int(v) / tot) for n, v in zip(names[role[wv]], pr[wv]) if n != "-"))
 e.close()

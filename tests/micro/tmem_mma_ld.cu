@@ -7,7 +7,10 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 
-constexpr int WARPS = 16, THREADS = WARPS * 32;
+#ifndef NWARPS
+#define NWARPS 16
+#endif
+constexpr int WARPS = NWARPS, THREADS = WARPS * 32;
 constexpr int NCODES = 4096;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -132,8 +135,8 @@ void run(const char* name, const uint8_t* d_codes, float* d_out, long long* d_cy
     k<LOOK, KIND, SPIN><<<nsm, THREADS, smem>>>(d_codes, d_out, d_cyc, reps, nmma);
     cudaError_t err = cudaDeviceSynchronize();
     long long cyc[2] = {0, 0}; cudaMemcpy(cyc, d_cyc, 16, cudaMemcpyDeviceToHost);
-    printf("%-44s %s  lookup warps: %7.1f cycles per 64-lookup subspace (%.2f cyc/lookup/SM with 15 warps) | mma warp: %7.1f cycles per build of %d MMAs\n",
-           name, cudaGetErrorString(err), (double)cyc[0] / reps, (double)cyc[0] / reps / (64.0 * 15), (double)cyc[1] / reps, nmma);
+    printf("%-44s %s  lookup warps: %7.1f cycles per 64-lookup subspace (%.2f cyc/lookup/SM) | mma warp: %7.1f cycles per build of %d MMAs\n",
+           name, cudaGetErrorString(err), (double)cyc[0] / reps, (double)cyc[0] / reps / (64.0 * (WARPS - 1)), (double)cyc[1] / reps, nmma);
 }
 
 int main() {
