@@ -92,7 +92,10 @@ class ClockSampler(threading.Thread):
 
 def make_inputs(wl, seed=1002):
     from ivfadc_jl_b200 import synth
-    X = synth.blobs(wl["N"], wl["D"], wl["kc"], seed=seed)
+    per_list = int(os.environ.get("IVFADC_BENCH_PER_LIST", "0"))   # bring-up: exactly this many vectors per blob
+    if per_list:
+        wl["N"] = per_list * wl["kc"]
+    X = synth.blobs(wl["N"], wl["D"], wl["kc"], seed=seed, balanced=per_list > 0)
     Q = synth.blobs(wl["nq"], wl["D"], wl["kc"], seed=2001)
     return X, Q
 

@@ -270,6 +270,16 @@ scanw_kernel(const ScanUArgs ua) {
     long long* const stamps = (DBG && blockIdx.x == 0 && ua.dbg != nullptr)
                                   ? reinterpret_cast<long long*>(ua.dbg + (size_t)m * 256 * 32 + 64) : nullptr;
 
+    // DBG: clocks of a window of four consecutive table builds in the middle of the launch (CTA 0), 8 events per warp
+    // and table, as 32-bit words behind the 128 profile counters
+    constexpr uint32_t W_TR0 = 20 * m + 6;
+    uint32_t* const trace = stamps ? reinterpret_cast<uint32_t*>(stamps + 128) + wid * 32 : nullptr;
+    auto tr = [&](uint32_t t, int ev) {
+        if constexpr (DBG) {
+            if (trace && lane == 0 && t - W_TR0 < 4u) trace[(t - W_TR0) * 8 + ev] = (uint32_t)clock();
+        }
+    };
+
     if (wid < W_SCAN) {
         // =========================================== SCANNERS ===========================================
         asm volatile("setmaxnreg.inc.sync.aligned.u32 152;");
@@ -303,15 +313,18 @@ scanw_kernel(const ScanUArgs ua) {
             for (int s = 0; s < m; ++s) {
                 const uint32_t b = (uint32_t)s & 1u;
                 pf.tick(3);
+                tr(tg + s, 0);
                 // every lane polls (no divergence on the common path); the bounded loop only when the build is late
                 if (!mbar_try_wait_hint(bar_mma + 8 * b, par, 100000u)) warp_wait(bar_mma + 8 * b, par, 2);
                 tc_fence_after();
                 pf.tick(1);
+                tr(tg + s, 1);
                 const uint32_t tb = __shfl_sync(0xffffffffu, tq + b * 256, 0);
                 const uint32_t plane_w = __shfl_sync(0xffffffffu, plane_seg + (uint32_t)(s / DUP) * W_VP, 0);
                 if (nch == W_NCH) scanw_sub<true>(tb, plane_w, nch, acc);
                 else scanw_sub<false>(tb, plane_w, nch, acc);
                 pf.tick(2);
+                tr(tg + s, 2);
                 if (DBG && g == 0 && blockIdx.x == 0 && ua.dbg != nullptr) {  // bring-up: dump the tables of the first segment
                     if (wid < 4) {
                         for (int c = wid; c < 256; c += 4) {
@@ -328,6 +341,7 @@ scanw_kernel(const ScanUArgs ua) {
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar_free + 8 * b);
+                tr(tg + s, 3);
                 par ^= b;
             }
             tg += m;
@@ -428,8 +442,10 @@ scanw_kernel(const ScanUArgs ua) {
 #pragma unroll 1
                 for (int s = 0; s < m; ++s, ++t) {
                     const uint32_t buf = t & 1;
+                    tr(t, 0);
                     // A operand of build t written => build t - 2 has completed => its codebook ring slot is free
                     warp_wait(bar_a + 8 * buf, (t >> 1) & 1, 22);
+                    tr(t, 1);
                     if (t >= 2) {
                         if (lane == 0) {
                             const uint32_t bar = bar_full + 8 * fslot;
@@ -445,14 +461,18 @@ scanw_kernel(const ScanUArgs ua) {
                     const uint64_t B0 = descB0 + (uint64_t)(slot_u * (W_BSUB >> 4)), B1 = B0 + (W_BBLK >> 4);
                     const uint32_t d = tmem_base + buf_u * 256;
                     pf.tick(1);
+                    tr(t, 2);
                     warp_wait(bar_full + 8 * bslot, bphase, 1);
                     pf.tick(2);
+                    tr(t, 3);
                     if (t >= 2) warp_wait(bar_free + 8 * buf, ((t - 2) >> 1) & 1, 23);  // scanners released table t - 2
                     pf.tick(3);
+                    tr(t, 4);
                     tc_fence_after();
                     tc_mma_f16_elect(d, A0, B0, 0);   // [rh | rl] . [wh | wh]
                     tc_mma_f16_elect(d, A1, B1, 1);   // [rh | a a 0..] . [wl | n0 n1 0..]
                     tc_commit_elect(bar_mma + 8 * buf_u);
+                    tr(t, 5);
                     if (++bslot == W_NB) { bslot = 0; bphase ^= 1; }
                     pf.tick(4);
                 }
@@ -482,6 +502,7 @@ scanw_kernel(const ScanUArgs ua) {
 #pragma unroll 1
                 for (int s = 0; s < m; ++s, ++t) {
                     const uint32_t buf = t & 1;
+                    tr(t, 0);
                     // rows (copy, q): block 0 = [rh | rl], block 1 = [rh | a a 0 ..] with r 2^sr = rh + rl in fp16; lane = query
                     uint32_t hi[4], lo[4];
 #pragma unroll
@@ -494,8 +515,10 @@ scanw_kernel(const ScanUArgs ua) {
                         lo[d >> 1] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
                     }
                     pf.tick(1);
+                    tr(t, 1);
                     if (t >= 2) warp_wait(bar_mma + 8 * buf, ((t - 2) >> 1) & 1, 25);  // build t - 2 has read this ring slot
                     pf.tick(2);
+                    tr(t, 2);
                     const uint32_t ph0 = aring_u + buf * W_ASUB + (lane >> 3) * 256 + (lane & 7) * 16;
 #pragma unroll
                     for (int c = 0; c < 4; ++c) {  // row = 32 c + lane: 8-row group stride 256, k halves 128 apart
@@ -509,6 +532,7 @@ scanw_kernel(const ScanUArgs ua) {
                     __syncwarp();
                     if (lane == 0) mbar_arrive(bar_a + 8 * buf);
                     pf.tick(3);
+                    tr(t, 3);
                 }
             }
             pf.store(stamps && lane == 0 ? stamps + 8 * wid : nullptr);

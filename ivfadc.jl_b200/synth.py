@@ -10,10 +10,12 @@ import numpy as np
 
 
 def blobs(n: int, D: int, n_blobs: int, seed: int, dtype=np.float32, sigma: float = 0.05,
-          centre_seed: int = 1001):
+          centre_seed: int = 1001, balanced: bool = False):
     centres = np.random.default_rng(centre_seed).random((n_blobs, D))
     rng = np.random.default_rng(seed)
     which = rng.integers(0, n_blobs, size=n)
+    if balanced:  # bring-up experiments: every blob gets the same number of points
+        which = np.arange(n) % n_blobs
     out = np.empty((n, D), dtype=dtype)
     step = 1 << 18
     for s in range(0, n, step):
