@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define IVFADC_ABI_VERSION 2
+#define IVFADC_ABI_VERSION 3
 
 /* status codes */
 #define IVFADC_OK               0
@@ -176,6 +176,13 @@ const char* ivfadc_last_error(const ivfadc_index* h);
  */
 int ivfadc_add(ivfadc_index* h, const void* X, int64_t n, int32_t position,
                const int64_t* assign, int32_t assign_base, int32_t* cells_out);
+/*
+ * Same, with the batch (and the optional assignments / cells) already in device memory of the handle's device:
+ * the index build of the 10 M / 100 M-vector configurations never crosses PCIe (_build_inverted_index,
+ * src/index.jl:178-194).  Synchronous like ivfadc_add; out-of-range assignments fail with IVFADC_ERR_BAD_ARG.
+ */
+int ivfadc_add_device(ivfadc_index* h, const void* dX, int64_t n, int32_t position,
+                      const int64_t* d_assign, int32_t assign_base, int32_t* d_cells_out);
 
 /*
  * Encode without mutating: cells int32[n] (0-based), codes uint8[n][m].  If assign != NULL
@@ -340,6 +347,15 @@ int ivfadc_export_list(ivfadc_index* h, int32_t cell, uint64_t* ids_out, uint8_t
 int ivfadc_import_list(ivfadc_index* h, int32_t cell, const uint64_t* ids, const uint8_t* codes,
                        int64_t len);
 
+/*
+ * All lists at once (bulk persistency; the reference writes / reads element by element,
+ * src/persistency.jl:68-78,119-131): sizes come from ivfadc_list_sizes, the entries of all lists follow each other
+ * in ascending cell order -- ids uint64[sum sizes], codes uint8[sum sizes][m] -- gathered on the device and copied
+ * in one transfer per 16 M entries.  ivfadc_import_all REPLACES every list of the handle and adjusts the length.
+ */
+int ivfadc_export_all(ivfadc_index* h, uint64_t* ids_out, uint8_t* codes_out);
+int ivfadc_import_all(ivfadc_index* h, const int64_t* sizes, const uint64_t* ids, const uint8_t* codes);
+
 /* Copy the quantizers back out (same layouts as ivfadc_create). */
 int ivfadc_export_quantizers(ivfadc_index* h, void* centroids_out, void* codebook_vectors_out,
                              uint8_t* codebook_codes_out);
@@ -364,6 +380,20 @@ int ivfadc_set_stats_timing(ivfadc_index* h, int32_t enable);
 
 int ivfadc_get_stats(ivfadc_index* h, ivfadc_stats* out);
 int ivfadc_reset_stats(ivfadc_index* h);
+
+/*
+ * ---- synthetic inputs (harness utility) -------------------------------------------------
+ * Counter-based generator, Philox4x32-10 keyed by `seed`, counter = (vector lo, vector hi, dim, stream): every
+ * value depends only on (seed, vector index, dim), so a slice [first, first + n) of a data set of any size is
+ * produced directly in HBM.  oracle/ivfadc_oracle.c (oracle_synth_*) computes the same values bit for bit.
+ * fp32 only; the reference's README / tests draw `rand(Float32, D, N)` (README.md:32, test/index.jl:7).
+ *   uniform: X[n][D] in [0, 1) (24 bits)
+ *   blobs  : X = centres[blob(vector)] + t * scale, t = centred sum of four 22-bit uniforms (standard deviation
+ *            2^22 / sqrt(3)): pass scale = sigma * sqrt(3) / 2^22; d_blobs_out (optional) receives the blob ids
+ */
+int ivfadc_synth_uniform_device(void* dX, int64_t first, int64_t n, int32_t D, uint64_t seed, void* stream);
+int ivfadc_synth_blobs_device(void* dX, int32_t* d_blobs_out, int64_t first, int64_t n, int32_t D, int32_t n_blobs,
+                              uint64_t seed, float scale, const void* d_centres, void* stream);
 
 #ifdef __cplusplus
 }

@@ -193,6 +193,14 @@ int cells_and_codes(ivfadc_index* h, const void* dX, int64_t n, const int64_t* d
     return IVFADC_OK;
 }
 
+// caller-supplied assignments (reference: kmeans .assignments, src/index.jl:170-172) must name existing cells:
+// an out-of-range cell would index the centroid table and the append sort out of bounds
+bool assign_in_range(const int64_t* assign, int64_t n, int base, int kc) {
+    uint64_t bad = 0;
+    for (int64_t i = 0; i < n; ++i) bad |= (uint64_t)((uint64_t)(assign[i] - base) >= (uint64_t)kc);
+    return bad == 0;
+}
+
 constexpr int64_t kAddChunk = 1 << 20;
 
 }  // namespace
@@ -305,7 +313,7 @@ int ivfadc_create(ivfadc_index** out, const ivfadc_config* cfg, const void* cent
     ok = ok && coarse_prepare(h, h->stream, &launches) == cudaSuccess;
     ok = ok && cudaStreamSynchronize(h->stream) == cudaSuccess;
     std::string why;
-    if (ok && !scan_supported(h, &why)) {
+    if (ok && (!scan_supported(h, &why) || !encode_supported(h))) {
         ivfadc_destroy(h);
         return IVFADC_ERR_UNSUPPORTED;
     }
@@ -368,6 +376,8 @@ int ivfadc_add(ivfadc_index* h, const void* X, int64_t n, int32_t position, cons
     if (n < 0 || (n > 0 && !X)) return fail(h, IVFADC_ERR_BAD_ARG, "null data");
     if (position != IVFADC_LAST && position != IVFADC_FIRST) return fail(h, IVFADC_ERR_BAD_ARG, "bad position");
     if (n == 0) return IVFADC_OK;
+    if (assign && !assign_in_range(assign, n, assign_base, h->cfg.kc))
+        return fail(h, IVFADC_ERR_BAD_ARG, "assignment outside [assign_base, assign_base + kc)");
     cudaSetDevice(h->cfg.device);
     // reference src/utils.jl:134-135: bits(I) >= log2(N + 1) for every single push
     if (h->cfg.id_bytes < 8) {
@@ -410,10 +420,59 @@ int ivfadc_add(ivfadc_index* h, const void* X, int64_t n, int32_t position, cons
     return IVFADC_OK;
 }
 
+int ivfadc_add_device(ivfadc_index* h, const void* dX, int64_t n, int32_t position, const int64_t* d_assign,
+                      int32_t assign_base, int32_t* d_cells_out) {
+    if (check_handle(h)) return IVFADC_ERR_BAD_ARG;
+    if (n < 0 || (n > 0 && !dX)) return fail(h, IVFADC_ERR_BAD_ARG, "null data");
+    if (position != IVFADC_LAST && position != IVFADC_FIRST) return fail(h, IVFADC_ERR_BAD_ARG, "bad position");
+    if (n == 0) return IVFADC_OK;
+    cudaSetDevice(h->cfg.device);
+    if (h->cfg.id_bytes < 8) {   // reference src/utils.jl:134-135
+        const uint64_t capacity = 1ull << (8 * h->cfg.id_bytes);
+        if ((uint64_t)h->n_total + (uint64_t)n > capacity)
+            return fail(h, IVFADC_ERR_CAPACITY, "Cannot index, exceeding index capacity");
+    }
+    const int D = h->cfg.dim, m = h->cfg.m;
+    int launches = 0;
+    if (d_assign) {   // same contract as ivfadc_add: cells must exist (checked on the device, one flag back)
+        CUDA_OR_FAIL(h, h->ws_misc.reserve(sizeof(int)), "workspace");
+        CUDA_OR_FAIL(h, cudaMemsetAsync(h->ws_misc.p, 0, sizeof(int), h->stream), "memset");
+        CUDA_OR_FAIL(h, launch_assign_check(d_assign, n, assign_base, h->cfg.kc, h->ws_misc.as<int>(), h->stream,
+                                            &launches), "assign check");
+        int bad = 0;
+        CUDA_OR_FAIL(h, cudaMemcpyAsync(&bad, h->ws_misc.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream), "D2H");
+        CUDA_OR_FAIL(h, cudaStreamSynchronize(h->stream), "sync");
+        if (bad) return fail(h, IVFADC_ERR_BAD_ARG, "assignment outside [assign_base, assign_base + kc)");
+    }
+    if (position == IVFADC_FIRST) CUDA_OR_FAIL(h, lists_shift_ids(h, n, &launches), "shift ids");
+    for (int64_t j0 = 0; j0 < n; j0 += kAddChunk) {
+        const int64_t nb = std::min(kAddChunk, n - j0);
+        CUDA_OR_FAIL(h, h->ws_cells.reserve(sizeof(int32_t) * (size_t)nb), "workspace");
+        CUDA_OR_FAIL(h, h->ws_codes.reserve((size_t)nb * m), "workspace");
+        int32_t* d_cells = h->ws_cells.as<int32_t>();
+        int rc = cells_and_codes(h, static_cast<const char*>(dX) + (size_t)j0 * D * h->tsize, nb,
+                                 d_assign ? d_assign + j0 : nullptr, assign_base, d_cells, h->ws_codes.as<uint8_t>(),
+                                 &launches);
+        if (rc != IVFADC_OK) return rc;
+        if (d_cells_out)
+            CUDA_OR_FAIL(h, cudaMemcpyAsync(d_cells_out + j0, d_cells, sizeof(int32_t) * nb, cudaMemcpyDeviceToDevice,
+                                            h->stream), "D2D");
+        const uint64_t first_id = position == IVFADC_LAST ? (uint64_t)h->n_total + (uint64_t)j0
+                                                          : (uint64_t)(n - 1 - j0);
+        CUDA_OR_FAIL(h, lists_append(h, d_cells, h->ws_codes.as<uint8_t>(), nb, first_id,
+                                     position == IVFADC_LAST ? 1 : -1, &launches), "append");
+    }
+    h->n_total += n;
+    h->stats.gpu_launches += launches;
+    return IVFADC_OK;
+}
+
 int ivfadc_encode(ivfadc_index* h, const void* X, int64_t n, const int64_t* assign, int32_t assign_base,
                   int32_t* cells_out, uint8_t* codes_out) {
     if (check_handle(h)) return IVFADC_ERR_BAD_ARG;
     if (n < 0 || (n > 0 && (!X || !cells_out || !codes_out))) return fail(h, IVFADC_ERR_BAD_ARG, "null pointer");
+    if (assign && !assign_in_range(assign, n, assign_base, h->cfg.kc))
+        return fail(h, IVFADC_ERR_BAD_ARG, "assignment outside [assign_base, assign_base + kc)");
     cudaSetDevice(h->cfg.device);
     const int D = h->cfg.dim, m = h->cfg.m;
     int launches = 0;
@@ -644,6 +703,31 @@ int ivfadc_import_list(ivfadc_index* h, int32_t cell, const uint64_t* ids, const
     cudaSetDevice(h->cfg.device);
     int launches = 0;
     CUDA_OR_FAIL(h, lists_import(h, cell, ids, codes, len, &launches), "import");
+    h->stats.gpu_launches += launches;
+    return IVFADC_OK;
+}
+
+int ivfadc_export_all(ivfadc_index* h, uint64_t* ids_out, uint8_t* codes_out) {
+    if (check_handle(h)) return IVFADC_ERR_BAD_ARG;
+    if (h->n_local > 0 && (!ids_out || !codes_out)) return fail(h, IVFADC_ERR_BAD_ARG, "null pointer");
+    cudaSetDevice(h->cfg.device);
+    int launches = 0;
+    CUDA_OR_FAIL(h, lists_export_all(h, ids_out, codes_out, &launches), "export");
+    h->stats.gpu_launches += launches;
+    return IVFADC_OK;
+}
+
+int ivfadc_import_all(ivfadc_index* h, const int64_t* sizes, const uint64_t* ids, const uint8_t* codes) {
+    if (check_handle(h) || !sizes) return IVFADC_ERR_BAD_ARG;
+    int64_t total = 0;
+    for (int c = 0; c < h->cfg.kc; ++c) {
+        if (sizes[c] < 0) return fail(h, IVFADC_ERR_BAD_ARG, "negative list length");
+        total += sizes[c];
+    }
+    if (total > 0 && (!ids || !codes)) return fail(h, IVFADC_ERR_BAD_ARG, "null pointer");
+    cudaSetDevice(h->cfg.device);
+    int launches = 0;
+    CUDA_OR_FAIL(h, lists_import_all(h, sizes, ids, codes, &launches), "import");
     h->stats.gpu_launches += launches;
     return IVFADC_OK;
 }

@@ -164,6 +164,8 @@ struct ivfadc_index {
 
 namespace ivf {
 
+constexpr size_t kSmemMax = 227 * 1024;   // dynamic shared memory a CTA can opt in to on sm_100a
+
 // cudaFuncAttributeMaxDynamicSharedMemorySize of `func` on the handle's device, raised once per (handle, kernel).
 inline cudaError_t ensure_smem(const ivfadc_index* h, const void* func, size_t smem) {
     if (smem <= 48 * 1024) return cudaSuccess;
@@ -188,6 +190,7 @@ struct ScanPlanSizes {
 int scan_max_k();
 cudaError_t scanq_prepare(ivfadc_index* h, cudaStream_t s, int* launches);
 bool scan_supported(const ivfadc_index* h, std::string* why);
+bool encode_supported(const ivfadc_index* h);   // encode.cu: one codeword block + one residual slice fit a CTA
 ScanPlanSizes scan_plan_sizes(const ivfadc_index* h, int64_t nq, int w, int k);
 // K2+K3: plan, fused LUT build + list scan + per-pair top-k, then per-query merge.
 // Outputs (device): ids uint64[nq][k], dists T[nq][k], keys uint64[nq][k] (optional), counts.
@@ -219,6 +222,8 @@ cudaError_t launch_codebook_norms(const ivfadc_index* h, cudaStream_t s, int* la
 // K4: residual w.r.t. d_cells + per-subspace argmin (GEMM form).  codes uint8[n][m].
 cudaError_t launch_encode(const ivfadc_index* h, const void* dX, int64_t n, const int32_t* d_cells,
                           uint8_t* d_codes_out, cudaStream_t s, int* launches);
+cudaError_t launch_assign_check(const int64_t* d_assign, int64_t n, int base, int kc, int* d_bad, cudaStream_t s,
+                                int* launches);
 cudaError_t launch_assign_to_cells(const int64_t* d_assign, int64_t n, int base, int32_t* d_cells,
                                    cudaStream_t s, int* launches);
 
@@ -238,6 +243,9 @@ cudaError_t lists_delete(ivfadc_index* h, const uint64_t* d_sorted_ids, int64_t 
 cudaError_t lists_find(ivfadc_index* h, uint64_t id, int32_t* cell, int64_t* pos, int* launches);
 cudaError_t lists_decode(ivfadc_index* h, int32_t cell, int64_t pos, void* d_vec_out, int* launches);
 cudaError_t lists_export(ivfadc_index* h, int32_t cell, uint64_t* ids_out, uint8_t* codes_out);
+cudaError_t lists_export_all(ivfadc_index* h, uint64_t* ids_out, uint8_t* codes_out, int* launches);
+cudaError_t lists_import_all(ivfadc_index* h, const int64_t* sizes, const uint64_t* ids, const uint8_t* codes,
+                             int* launches);
 cudaError_t lists_import(ivfadc_index* h, int32_t cell, const uint64_t* ids, const uint8_t* codes,
                          int64_t len, int* launches);
 cudaError_t lists_sync_meta_to_device(ivfadc_index* h);

@@ -37,16 +37,24 @@ __global__ void assign_to_cells_kernel(const int64_t* __restrict__ assign, int64
     if (i < n) cells[i] = (int32_t)(assign[i] - base);
 }
 
+__global__ void assign_check_kernel(const int64_t* __restrict__ assign, int64_t n, int base, int kc,
+                                    int* __restrict__ bad) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && (uint64_t)(assign[i] - base) >= (uint64_t)kc) *bad = 1;
+}
+
 template <typename T, int DSUB>
 __global__ void __launch_bounds__(ETHREADS)
 encode_kernel(const T* __restrict__ X, int64_t n, const int32_t* __restrict__ cells,
               const T* __restrict__ C, const T* __restrict__ cb, const uint8_t* __restrict__ cb_codes,
               const T* __restrict__ cb_norms, int D, int m, int dsub_rt, int ksub,
-              uint8_t* __restrict__ codes_out) {
+              uint8_t* __restrict__ codes_out, int tiled) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int dsub = DSUB > 0 ? DSUB : dsub_rt;
     const int Dp = m * dsub;
-    const int LDR = Dp + 1;  // residual row stride (odd => conflict-free per-lane rows)
+    // residual row stride (odd => conflict-free per-lane rows).  Wide vectors (D of several hundred) do not fit
+    // 64 full residual rows in shared memory: `tiled` stages one subspace slice per codebook instead.
+    const int LDR = (tiled ? dsub : Dp) + 1;
     T* s_res = reinterpret_cast<T*>(smem_raw);                 // [EV][LDR]
     T* s_cw = s_res + (size_t)EV * LDR;                        // [ksub][dsub]
     T* s_nrm = s_cw + (size_t)ksub * dsub;                     // [ksub]
@@ -59,7 +67,7 @@ encode_kernel(const T* __restrict__ X, int64_t n, const int32_t* __restrict__ ce
     const int64_t v0 = (int64_t)blockIdx.x * EV;
 
     // residuals (reference src/utils.jl:157 / _build_residuals src/index.jl:168-175)
-    for (int idx = tid; idx < EV * Dp; idx += ETHREADS) {
+    for (int idx = tid; !tiled && idx < EV * Dp; idx += ETHREADS) {
         const int row = idx / Dp, d = idx - row * Dp;
         const int64_t gv = v0 + row;
         T r = (T)0;
@@ -75,9 +83,18 @@ encode_kernel(const T* __restrict__ X, int64_t n, const int32_t* __restrict__ ce
         for (int idx = tid; idx < ksub * dsub; idx += ETHREADS)
             s_cw[idx] = cb[(size_t)i * ksub * dsub + idx];
         for (int idx = tid; idx < ksub; idx += ETHREADS) s_nrm[idx] = cb_norms[i * ksub + idx];
+        if (tiled) {
+            for (int idx = tid; idx < EV * dsub; idx += ETHREADS) {
+                const int row = idx / dsub, d = idx - row * dsub;
+                const int64_t gv = v0 + row;
+                T r = (T)0;
+                if (gv < n) r = sub_rn(X[gv * D + i * dsub + d], C[(size_t)cells[gv] * D + i * dsub + d]);
+                s_res[row * LDR + d] = r;
+            }
+        }
         __syncthreads();
 
-        const T* xr = s_res + v * LDR + i * dsub;
+        const T* xr = s_res + v * LDR + (tiled ? 0 : i * dsub);
         T best = Limits<T>::inf();
         int besti = -1;
         if constexpr (DSUB > 0) {
@@ -135,12 +152,28 @@ encode_kernel(const T* __restrict__ X, int64_t n, const int32_t* __restrict__ ce
     }
 }
 
+}  // namespace
+
+// shared memory of encode_kernel: residual rows (all subspaces, or one slice when tiled), one codeword block,
+// its norms, the per-quarter partial minima
+size_t encode_smem_bytes(size_t elem, int m, int dsub, int ksub, bool tiled) {
+    return elem * ((size_t)EV * ((tiled ? dsub : m * dsub) + 1) + (size_t)ksub * dsub + ksub + 4 * EV) +
+           sizeof(int) * 4 * EV + 16;
+}
+
+bool encode_supported(const ivfadc_index* h) {
+    const size_t elem = h->cfg.dtype == IVFADC_F32 ? 4 : 8;
+    return encode_smem_bytes(elem, h->cfg.m, h->dsub, h->cfg.ksub, true) <= kSmemMax;
+}
+
+namespace {
+
 template <typename T>
 cudaError_t launch_encode_t(const ivfadc_index* h, const void* dX, int64_t n, const int32_t* d_cells,
                             uint8_t* d_codes_out, cudaStream_t s) {
     const int D = h->cfg.dim, m = h->cfg.m, dsub = h->dsub, ksub = h->cfg.ksub;
-    const size_t smem = sizeof(T) * ((size_t)EV * (m * dsub + 1) + (size_t)ksub * dsub + ksub + 4 * EV) +
-                        sizeof(int) * 4 * EV + 16;
+    const int tiled = encode_smem_bytes(sizeof(T), m, dsub, ksub, false) > kSmemMax ? 1 : 0;
+    const size_t smem = encode_smem_bytes(sizeof(T), m, dsub, ksub, tiled != 0);
     const unsigned grid = (unsigned)((n + EV - 1) / EV);
     const T* X = static_cast<const T*>(dX);
     const T* C = static_cast<const T*>(h->d_centroids);
@@ -149,11 +182,10 @@ cudaError_t launch_encode_t(const ivfadc_index* h, const void* dX, int64_t n, co
 #define IVF_LAUNCH_ENC(DS)                                                                          \
     do {                                                                                            \
         auto kern = encode_kernel<T, DS>;                                                           \
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
-                                             (int)smem);                                            \
+        cudaError_t e = ensure_smem(h, reinterpret_cast<const void*>(kern), smem);                 \
         if (e != cudaSuccess) return e;                                                             \
         kern<<<grid, ETHREADS, smem, s>>>(X, n, d_cells, C, cb, h->d_cb_codes, nrm, D, m, dsub,     \
-                                          ksub, d_codes_out);                                       \
+                                          ksub, d_codes_out, tiled);                                \
     } while (0)
     switch (dsub) {
         case 4: IVF_LAUNCH_ENC(4); break;
@@ -192,6 +224,14 @@ cudaError_t launch_assign_to_cells(const int64_t* d_assign, int64_t n, int base,
                                    cudaStream_t s, int* launches) {
     if (n <= 0) return cudaSuccess;
     assign_to_cells_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(d_assign, n, base, d_cells);
+    if (launches) *launches += 1;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_assign_check(const int64_t* d_assign, int64_t n, int base, int kc, int* d_bad, cudaStream_t s,
+                                int* launches) {
+    if (n <= 0) return cudaSuccess;
+    assign_check_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(d_assign, n, base, kc, d_bad);
     if (launches) *launches += 1;
     return cudaGetLastError();
 }

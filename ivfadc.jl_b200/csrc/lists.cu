@@ -185,6 +185,30 @@ __global__ void narrow_ids_kernel(const uint64_t* __restrict__ in, uint32_t* __r
     if (t < n) out[t] = (uint32_t)in[t];
 }
 
+// Bulk persistency: packed (cell-ascending, list order) <-> arena.  Packed entry p belongs to the cell with
+// pref[cell] <= p < pref[cell + 1] (binary search over the kc + 1 prefix sums); its arena slot is off[cell] + p - pref[cell].
+template <typename I, bool EXPORT>
+__global__ void pack_lists_kernel(uint8_t* __restrict__ arena_codes, I* __restrict__ arena_ids,
+                                  const int64_t* __restrict__ off, const int64_t* __restrict__ pref, int kc, int m,
+                                  int64_t p0, int64_t n, uint8_t* __restrict__ pk_codes, uint64_t* __restrict__ pk_ids) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const int64_t p = p0 + t;
+    int lo = 0, hi = kc;  // largest c with pref[c] <= p
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (pref[mid] <= p) lo = mid; else hi = mid;
+    }
+    const int64_t a = off[lo] + (p - pref[lo]);
+    if (EXPORT) {
+        pk_ids[t] = (uint64_t)arena_ids[a];
+        for (int j = 0; j < m; ++j) pk_codes[t * m + j] = arena_codes[a * m + j];
+    } else {
+        arena_ids[a] = (I)pk_ids[t];
+        for (int j = 0; j < m; ++j) arena_codes[a * m + j] = pk_codes[t * m + j];
+    }
+}
+
 #define CK(x)                                  \
     do {                                       \
         cudaError_t _e = (x);                  \
@@ -463,6 +487,75 @@ cudaError_t lists_import(ivfadc_index* h, int32_t cell, const uint64_t* ids, con
     h->n_local += len - h->h_len[cell];
     h->n_total += len - h->h_len[cell];
     h->h_len[cell] = len;
+    CK(cudaMemcpyAsync(h->d_len, h->h_len.data(), sizeof(int64_t) * kc, cudaMemcpyHostToDevice, h->stream));
+    return cudaStreamSynchronize(h->stream);
+}
+
+namespace {
+constexpr int64_t kPackChunk = 1 << 24;  // vectors per staging chunk (codes 16 m MB + ids 128 MB)
+
+template <bool EXPORT>
+cudaError_t pack_all(ivfadc_index* h, uint64_t* ids, uint8_t* codes, int* launches) {
+    const int kc = h->cfg.kc, m = h->cfg.m;
+    std::vector<int64_t> pref(kc + 1, 0);
+    for (int c = 0; c < kc; ++c) pref[c + 1] = pref[c] + h->h_len[c];
+    const int64_t total = pref[kc];
+    if (total == 0) return cudaSuccess;
+    CK(h->ws_sort_tmp.reserve(sizeof(int64_t) * (size_t)(kc + 1)));
+    int64_t* d_pref = h->ws_sort_tmp.as<int64_t>();
+    CK(cudaMemcpyAsync(d_pref, pref.data(), sizeof(int64_t) * (kc + 1), cudaMemcpyHostToDevice, h->stream));
+    const int64_t chunk = std::min(total, kPackChunk);
+    CK(h->ws_x.reserve((size_t)chunk * m));
+    CK(h->ws_misc.reserve(sizeof(uint64_t) * (size_t)chunk));
+    uint8_t* pk_codes = h->ws_x.as<uint8_t>();
+    uint64_t* pk_ids = h->ws_misc.as<uint64_t>();
+    for (int64_t p0 = 0; p0 < total; p0 += chunk) {
+        const int64_t n = std::min(chunk, total - p0);
+        const unsigned grid = (unsigned)((n + 255) / 256);
+        if (!EXPORT) {
+            CK(cudaMemcpyAsync(pk_codes, codes + (size_t)p0 * m, (size_t)n * m, cudaMemcpyHostToDevice, h->stream));
+            CK(cudaMemcpyAsync(pk_ids, ids + p0, sizeof(uint64_t) * n, cudaMemcpyHostToDevice, h->stream));
+        }
+        if (h->id_dev_bytes == 4)
+            pack_lists_kernel<uint32_t, EXPORT><<<grid, 256, 0, h->stream>>>(
+                h->d_codes, static_cast<uint32_t*>(h->d_ids), h->d_off, d_pref, kc, m, p0, n, pk_codes, pk_ids);
+        else
+            pack_lists_kernel<uint64_t, EXPORT><<<grid, 256, 0, h->stream>>>(
+                h->d_codes, static_cast<uint64_t*>(h->d_ids), h->d_off, d_pref, kc, m, p0, n, pk_codes, pk_ids);
+        CK(cudaGetLastError());
+        if (launches) *launches += 1;
+        if (EXPORT) {
+            CK(cudaMemcpyAsync(codes + (size_t)p0 * m, pk_codes, (size_t)n * m, cudaMemcpyDeviceToHost, h->stream));
+            CK(cudaMemcpyAsync(ids + p0, pk_ids, sizeof(uint64_t) * n, cudaMemcpyDeviceToHost, h->stream));
+        }
+        CK(cudaStreamSynchronize(h->stream));  // the staging buffers are reused by the next chunk
+    }
+    return cudaSuccess;
+}
+}  // namespace
+
+// every list, cell-ascending, packed: ids uint64[sum len], codes uint8[sum len][m] (src/persistency.jl:68-78)
+cudaError_t lists_export_all(ivfadc_index* h, uint64_t* ids_out, uint8_t* codes_out, int* launches) {
+    return pack_all<true>(h, ids_out, codes_out, launches);
+}
+
+// replace ALL lists by sizes[kc] + packed entries (src/persistency.jl:119-131)
+cudaError_t lists_import_all(ivfadc_index* h, const int64_t* sizes, const uint64_t* ids, const uint8_t* codes,
+                             int* launches) {
+    const int kc = h->cfg.kc;
+    std::vector<int64_t> need(sizes, sizes + kc);
+    int64_t total = 0;
+    for (int c = 0; c < kc; ++c) total += need[c];
+    // the old contents are dropped: lengths to zero first so that a regrow copies nothing
+    const int64_t old_local = h->n_local;
+    std::fill(h->h_len.begin(), h->h_len.end(), 0);
+    h->n_local = 0;
+    CK(cudaMemsetAsync(h->d_len, 0, sizeof(int64_t) * kc, h->stream));
+    CK(reserve_lists(h, need, launches));
+    h->h_len = need;
+    CK(pack_all<false>(h, const_cast<uint64_t*>(ids), const_cast<uint8_t*>(codes), launches));
+    h->n_local = total;
+    h->n_total += total - old_local;
     CK(cudaMemcpyAsync(h->d_len, h->h_len.data(), sizeof(int64_t) * kc, cudaMemcpyHostToDevice, h->stream));
     return cudaStreamSynchronize(h->stream);
 }

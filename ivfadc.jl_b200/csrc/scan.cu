@@ -505,7 +505,6 @@ cudaError_t launch_scan_m(const ivfadc_index* h, const ScanArgs<T>& a, int grid,
 }
 
 constexpr size_t kSmemPreferred = 74 * 1024;   // 3 CTAs per SM
-constexpr size_t kSmemMax = 227 * 1024;
 
 template <typename T> int choose_qn(int m, int dsub, int k) {
     if (scan_smem_bytes<T, 4>(m, dsub, k) <= kSmemPreferred) return 4;

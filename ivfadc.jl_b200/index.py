@@ -212,6 +212,32 @@ class IVFADCIndex:
         _capi.check(self._h, self._lib.ivfadc_import_list(self._h, cell, _capi.ptr(ids), _capi.ptr(codes),
                                                           len(ids)))
 
+    def export_all(self):
+        """Every list in one call (bulk persistency): (sizes int64 [kc], idxs [sum] in the index type, codes uint8
+        [sum, m]); the entries of the lists follow each other in ascending cell order."""
+        sizes = self.list_sizes()
+        n = int(sizes.sum())
+        ids = np.empty(n, dtype=np.uint64)
+        codes = np.empty((n, self.m), dtype=np.uint8)
+        _capi.check(self._h, self._lib.ivfadc_export_all(self._h, _capi.ptr(ids), _capi.ptr(codes)))
+        return sizes, ids.astype(self.I), codes
+
+    def import_all(self, sizes, ids, codes):
+        """Replace ALL lists: sizes int64 [kc], packed ids / codes as export_all returns them."""
+        sizes = np.ascontiguousarray(sizes, dtype=np.int64)
+        assert sizes.shape == (self.kc,)
+        ids = np.ascontiguousarray(ids, dtype=np.uint64)
+        codes = np.ascontiguousarray(codes, dtype=np.uint8).reshape(len(ids), self.m)
+        assert int(sizes.sum()) == len(ids)
+        _capi.check(self._h, self._lib.ivfadc_import_all(self._h, _capi.ptr(sizes), _capi.ptr(ids), _capi.ptr(codes)))
+
+    def add_device(self, dX_ptr: int, n: int, position=_capi.LAST, d_assign_ptr: int = 0, assign_base: int = 0,
+                   d_cells_out_ptr: int = 0):
+        """ivfadc_add_device: the batch (and optional int64 assignments / int32 cells out) are device pointers."""
+        _capi.check(self._h, self._lib.ivfadc_add_device(self._h, ctypes.c_void_p(dX_ptr), n, position,
+                                                         ctypes.c_void_p(d_assign_ptr or None), assign_base,
+                                                         ctypes.c_void_p(d_cells_out_ptr or None)))
+
     def quantizers(self):
         c = np.empty((self.kc, self.nrows), dtype=self.T)
         v = np.empty((self.m, self.k, self.dsub), dtype=self.T)

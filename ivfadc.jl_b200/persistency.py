@@ -48,11 +48,16 @@ def save_ivfadc_index(filename, ivfadc: IVFADCIndex):
             # vectors[j, :] for j in 1:d -- the d x k matrix row by row; ours is stored [k, d]
             f.write(np.ascontiguousarray(cb_vectors[i].T).astype(T.newbyteorder("<")).tobytes())
         f.write(np.eye(nrows, dtype=T).tobytes())  # rot = I for :pq
+        # one bulk device -> host transfer of all lists (ivfadc_export_all), then the per-list records of :68-78
+        sizes, ids, codes = ivfadc.export_all()
+        ids = ids.astype(I.newbyteorder("<"), copy=False)
+        o = 0
         for c in range(nclusters):
-            ids, codes = ivfadc.export_list(c)
-            f.write(np.int64(len(ids)).tobytes())
-            f.write(ids.astype(I.newbyteorder("<")).tobytes())
-            f.write(codes.tobytes())
+            e = o + int(sizes[c])
+            f.write(np.int64(sizes[c]).tobytes())
+            f.write(ids[o:e].tobytes())
+            f.write(codes[o:e].tobytes())
+            o = e
 
 
 def load_ivfadc_index(filename, device=0):
@@ -81,11 +86,23 @@ def load_ivfadc_index(filename, device=0):
             raise NotImplementedError("non-identity rotation (OPQ) is outside the hot-path scope")
         ivfadc = IVFADCIndex.from_quantizers(centroids, cb_vectors, cb_codes, index_type=I,
                                              coarse_distance=dc, quantization_distance=dr, device=device)
+        # the list records of :119-131 are parsed on the host, the lists go to the device in one bulk call
         isz = np.dtype(I).itemsize
+        raw = np.frombuffer(f.read(), dtype=np.uint8)
+        sizes = np.zeros(nclusters, dtype=np.int64)
+        ids = np.empty(n, dtype=np.uint64)
+        codes = np.empty((n, m), dtype=np.uint8)
+        p = o = 0
         for c in range(nclusters):
-            clsize = int(np.frombuffer(f.read(8), dtype=np.int64)[0])
-            ids = np.frombuffer(f.read(isz * clsize), dtype=I)
-            codes = np.frombuffer(f.read(m * clsize), dtype=np.uint8).reshape(clsize, m)
-            if clsize:
-                ivfadc.import_list(c, ids, codes)
+            clsize = int(raw[p:p + 8].view(np.int64)[0])
+            p += 8
+            if o + clsize > n:
+                raise ValueError("list lengths exceed the vector count of the header")
+            ids[o:o + clsize] = raw[p:p + isz * clsize].view(I)
+            p += isz * clsize
+            codes[o:o + clsize] = raw[p:p + m * clsize].reshape(clsize, m)
+            p += m * clsize
+            sizes[c] = clsize
+            o += clsize
+        ivfadc.import_all(sizes, ids[:o], codes[:o])
         return ivfadc

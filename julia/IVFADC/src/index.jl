@@ -8,7 +8,8 @@ mutable struct IVFADCIndex{U<:Unsigned, I<:Unsigned, Dc<:Distances.PreMetric, Dr
     centroids::Matrix{T}                                         # D x kc   (cq.vectors)
     residual_quantizer::QuantizedArrays.OrthogonalQuantizer{U,Dr,T,2}
     coarse_kind::Symbol                                          # :naive | :hnsw (-> exact GPU search)
-    handle::Handle
+    handle::Handle                                               # one GPU (C_NULL when `group` is used)
+    group::Group                                                 # several GPUs, lists sharded by cell (or C_NULL)
 end
 
 const _ID_BITS = Dict(UInt8 => 8, UInt16 => 16, UInt32 => 32, UInt64 => 64)
@@ -16,6 +17,8 @@ const _ID_BITS = Dict(UInt8 => 8, UInt16 => 16, UInt32 => 32, UInt64 => 64)
 _metric_code(::Distances.SqEuclidean) = IVFADC_SQEUCLIDEAN
 _metric_code(d) = throw(ArgumentError("only SqEuclidean is on the GPU hot path, got $(typeof(d))"))
 
+# Returns (handle, group): ENV["IVFADC_DEVICES"] with more than one device id creates a group
+# (ivfadc_group_create: one handle per device, NCCL communicator inside the library).
 function _upload(centroids::Matrix{T}, rq, ::Type{I}, dc, dr, kind::Symbol; device::Int=0) where {T,I}
     m = length(rq.codebooks)
     dsub, ksub = size(rq.codebooks[1].vectors)
@@ -25,15 +28,31 @@ function _upload(centroids::Matrix{T}, rq, ::Type{I}, dc, dr, kind::Symbol; devi
         cbv[:, :, i] .= rq.codebooks[i].vectors
         cbc[:, i] .= UInt8.(rq.codebooks[i].codes)
     end
+    devs = _devices()
     cfg = CConfig(size(centroids, 1), size(centroids, 2), m, ksub, _dtype(T), sizeof(I),
-                  _metric_code(dc), _metric_code(dr), device, 0, 1, 0)
-    capi_create(cfg, centroids, cbv, cbc)
+                  _metric_code(dc), _metric_code(dr), length(devs) == 1 ? devs[1] : device, 0, 1, 0)
+    length(devs) > 1 && return (C_NULL, capi_group_create(cfg, devs, centroids, cbv, cbc))
+    (capi_create(cfg, centroids, cbv, cbc), C_NULL)
+end
+
+# cell -> device by greedy bin-packing on the list lengths (longest list onto the lightest device): every GPU
+# scans about the same number of code bytes per batch
+function _balanced_owners(sizes::Vector{Int}, world::Int)
+    owners = Vector{Cint}(undef, length(sizes)); load = zeros(Int, world); cnt = zeros(Int, world)
+    for c in sortperm(sizes, rev=true, alg=MergeSort)
+        r = argmin(collect(zip(load, cnt)))
+        owners[c] = r - 1; load[r] += sizes[c]; cnt[r] += 1
+    end
+    owners
 end
 
 function _wrap(centroids::Matrix{T}, rq::QuantizedArrays.OrthogonalQuantizer{U,Dr,T,2}, ::Type{I},
-               dc::Dc, kind::Symbol, h::Handle) where {U,I,Dc,Dr,T}
-    idx = IVFADCIndex{U,I,Dc,Dr,T}(centroids, rq, kind, h)
-    finalizer(x -> (x.handle != C_NULL && (capi_destroy(x.handle); x.handle = C_NULL)), idx)
+               dc::Dc, kind::Symbol, hg::Tuple{Handle,Group}) where {U,I,Dc,Dr,T}
+    idx = IVFADCIndex{U,I,Dc,Dr,T}(centroids, rq, kind, hg[1], hg[2])
+    finalizer(idx) do x
+        x.handle != C_NULL && (capi_destroy(x.handle); x.handle = C_NULL)
+        x.group != C_NULL && (capi_group_destroy(x.group); x.group = C_NULL)
+    end
     idx
 end
 
@@ -63,15 +82,22 @@ function IVFADCIndex(data::Matrix{T};
     rq = build_quantizer(residuals, k=k, m=m, method=quantization_method,
                          distance=quantization_distance, maxiter=quantization_maxiter)
 
-    h = _upload(cmodel.centers, rq, I, coarse_distance, quantization_distance, coarse_quantizer)
+    h, g = _upload(cmodel.centers, rq, I, coarse_distance, quantization_distance, coarse_quantizer)
     # index build = ONE call: residuals w.r.t. the k-means assignments, PQ encoding, CSR fill,
     # ids ascending per list (reference _build_residuals + _build_inverted_index, src/index.jl:168-194)
-    rc = capi_add(h, data, IVFADC_LAST, assign=Int64.(cmodel.assignments))
-    _check(h, rc)
-    _wrap(cmodel.centers, rq, I, coarse_distance, coarse_quantizer, h)
+    if g != C_NULL
+        capi_group_set_cell_owners(g, _balanced_owners(counts(cmodel), capi_group_size(g)))
+        _gcheck(g, capi_group_add(g, data, IVFADC_LAST, assign=Int64.(cmodel.assignments)))
+    else
+        _check(h, capi_add(h, data, IVFADC_LAST, assign=Int64.(cmodel.assignments)))
+    end
+    _wrap(cmodel.centers, rq, I, coarse_distance, coarse_quantizer, (h, g))
 end
 
-Base.length(ivfadc::IVFADCIndex) = capi_length(ivfadc.handle)
+_search(ivfadc::IVFADCIndex, Q, k, w) = ivfadc.group != C_NULL ? capi_group_search(ivfadc.group, Q, k, w) :
+                                                                  capi_search(ivfadc.handle, Q, k, w)
+
+Base.length(ivfadc::IVFADCIndex) = ivfadc.group != C_NULL ? capi_group_length(ivfadc.group) : capi_length(ivfadc.handle)
 Base.size(ivfadc::IVFADCIndex) = (size(ivfadc.centroids, 1), length(ivfadc))
 Base.size(ivfadc::IVFADCIndex, i::Int) = size(ivfadc)[i]
 
@@ -89,7 +115,7 @@ function knn_search(ivfadc::IVFADCIndex{U,I,Dc,Dr,T}, point::Vector{T}, k::Int; 
     @assert k >= 1 "Number of neighbors must be k >= 1"
     @assert w >= 1 "Number of clusters to search in must be w >= 1"
     w = min(w, size(ivfadc.centroids, 2))
-    ids, dists, counts = capi_search(ivfadc.handle, reshape(point, :, 1), k, w)
+    ids, dists, counts = _search(ivfadc, reshape(point, :, 1), k, w)
     n = counts[1]
     return I.(ids[1:n, 1]), dists[1:n, 1]
 end
@@ -99,7 +125,7 @@ function knn_search(ivfadc::IVFADCIndex{U,I,Dc,Dr,T}, points::Vector{Vector{T}},
     @assert w >= 1 "Number of clusters to search in must be w >= 1"
     w = min(w, size(ivfadc.centroids, 2))
     Q = reduce(hcat, points)
-    ids, dists, counts = capi_search(ivfadc.handle, Q, k, w)
+    ids, dists, counts = _search(ivfadc, Q, k, w)
     idxs = [I.(ids[1:counts[j], j]) for j in eachindex(points)]
     ds = [dists[1:counts[j], j] for j in eachindex(points)]
     return idxs, ds

@@ -313,3 +313,29 @@ def compare_search(gi, gd, gc, oi, od, oc, rtol: float = 1e-5):
                      np.array_equal(gd[valid].view(np.uint8), od[valid].view(np.uint8)))
     return {"near_tie_id_mismatches": near_ties, "results": int(valid.sum()), "max_rel_err": max_rel,
             "bit_identical": bit_equal}
+
+
+# ---- synthetic inputs: CPU twin of ivfadc.jl_b200/csrc/synth.cu (counter-based, bit-identical) ------------------
+def philox4x32_10(ctr, key):
+    c = np.ascontiguousarray(ctr, dtype=np.uint32)
+    k = np.ascontiguousarray(key, dtype=np.uint32)
+    out = np.empty(4, dtype=np.uint32)
+    lib().oracle_philox4x32_10(_p(c), _p(k), _p(out))
+    return out
+
+
+def synth_uniform(first: int, n: int, D: int, seed: int):
+    X = np.empty((n, D), dtype=np.float32)
+    lib().oracle_synth_uniform_f32(_p(X), _c_i64(first), _c_i64(n), _c_int(D), ctypes.c_uint64(seed))
+    return X
+
+
+def synth_blobs(first: int, n: int, D: int, n_blobs: int, seed: int, scale, centres, want_x: bool = True):
+    """(X [n, D] or None, blob ids int32 [n]) of vectors first .. first + n - 1; scale = sigma sqrt(3) / 2^22 (float32)."""
+    centres = np.ascontiguousarray(centres, dtype=np.float32)
+    assert centres.shape == (n_blobs, D)
+    X = np.empty((n, D), dtype=np.float32) if want_x else None
+    b = np.empty(n, dtype=np.int32)
+    lib().oracle_synth_blobs_f32(_p(X), _p(b), _c_i64(first), _c_i64(n), _c_int(D), _c_int(n_blobs),
+                                 ctypes.c_uint64(seed), ctypes.c_float(float(scale)), _p(centres))
+    return X, b

@@ -68,3 +68,32 @@ def test_cuda_reproduces_golden(name, flags):
         else:
             orc.compare_search(gi, gd, gc, oi, od, oc, rtol=1e-5)
     e.close()
+
+
+# ---- synthetic generator (bench / scale tests): Philox4x32-10 known answers and the statistics of the streams ----
+def test_philox_known_answers():
+    """Random123 known-answer vectors of Philox4x32-10 (kat_vectors: zero, all-ones and the pi digits)."""
+    kat = [([0, 0, 0, 0], [0, 0], [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]),
+           ([0xffffffff] * 4, [0xffffffff] * 2, [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]),
+           ([0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344], [0xa4093822, 0x299f31d0],
+            [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1])]
+    for ctr, key, want in kat:
+        assert [int(x) for x in orc.philox4x32_10(ctr, key)] == want
+
+
+def test_synth_streams_are_counter_based():
+    from ivfadc_jl_b200 import synth
+    D, kb = 24, 13
+    c = orc.synth_uniform(0, kb, D, 1001)
+    assert c.min() >= 0.0 and c.max() < 1.0 and abs(c.mean() - 0.5) < 0.05
+    scale = synth.blob_scale(0.05)
+    X, b = orc.synth_blobs(0, 50000, D, kb, 1002, scale, c)
+    r = X - c[b]
+    assert abs(r.std() - 0.05) < 1e-3 and abs(r.mean()) < 1e-3
+    assert b.min() == 0 and b.max() == kb - 1
+    assert np.bincount(b, minlength=kb).min() > 50000 / kb * 0.9
+    # any slice equals the same rows of the whole stream; other seeds give other data
+    X2, b2 = orc.synth_blobs(1234, 100, D, kb, 1002, scale, c)
+    assert np.array_equal(X2, X[1234:1334]) and np.array_equal(b2, b[1234:1334])
+    X3, _ = orc.synth_blobs(0, 100, D, kb, 1003, scale, c)
+    assert not np.array_equal(X3, X[:100])

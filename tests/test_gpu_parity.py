@@ -720,3 +720,185 @@ def test_device_trainer():
     hits = sum(int(q in ids[i, :counts[i]]) for i, q in enumerate(qs))
     assert hits >= 150, hits   # a database point finds itself among its 10 nearest (PQ-approximate) neighbours
     idx.close()
+
+
+# ------------------------------------------------------------------------------------------------
+# round 2: wide vectors in K4, device-resident build, bulk persistency, the synthetic generator
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype,D,m,ksub,kc", [(np.float32, 960, 8, 256, 20), (np.float64, 512, 8, 256, 12),
+                                               (np.float32, 1024, 16, 256, 9), (np.float64, 430, 10, 64, 7)])
+def test_encode_wide_vectors(dtype, D, m, ksub, kc):
+    """Shapes whose 64 full residual rows exceed a CTA's shared memory (GIST-960 ...): the encode kernel stages one
+    subspace slice per codebook instead; same bits as the oracle."""
+    rng = np.random.default_rng(D)
+    n = 300
+    X = rng.random((n, D)).astype(dtype)
+    cent = X[rng.choice(n, kc, replace=False)].copy()
+    cb = (0.3 * rng.standard_normal((m, ksub, D // m))).astype(dtype)
+    qz = orc.Quantizers(cent, cb, None)
+    e = engine_from(qz, flags=LEGACY | LUT_EXACT)
+    gcell, gcode = e.encode(X)
+    ocell, ocode = orc.encode(qz, X, nthreads=4)
+    np.testing.assert_array_equal(gcell, ocell)
+    np.testing.assert_array_equal(gcode, ocode)
+    e.close()
+
+
+def test_assignments_out_of_range_are_rejected():
+    oidx, qz, assign, X, data = helpers.reference_fixture(np.float32, seed=2)
+    e = engine_from(qz)
+    bad = assign.copy()
+    bad[17] = qz.centroids.shape[0]          # one past the last cell
+    with pytest.raises(iv._capi.IvfadcError):
+        e._add(X, 0, assign=bad, assign_base=0)
+    with pytest.raises(iv._capi.IvfadcError):
+        e.encode(X, assign=bad - 5, assign_base=0)   # negative cells
+    assert len(e) == 0 and int(e.list_sizes().sum()) == 0   # nothing was added
+    e._add(X, 0, assign=assign, assign_base=0)
+    assert_lists_equal(e, oidx)
+    e.close()
+
+
+def test_add_device_equals_add():
+    """ivfadc_add_device (batch, assignments and cells in device memory) builds the same lists as ivfadc_add."""
+    import torch
+    rng = np.random.default_rng(5)
+    D, m, kc, n = 64, 8, 37, 5000
+    X = rng.random((n, D)).astype(np.float32)
+    cent = X[rng.choice(n, kc, replace=False)].copy()
+    cb = (0.2 * rng.standard_normal((m, 256, D // m))).astype(np.float32)
+    qz = orc.Quantizers(cent, cb, None)
+    a, b, c = engine_from(qz), engine_from(qz), engine_from(qz)
+    cells = a._add(X, 0, want_cells=True)
+    dX = torch.from_numpy(X).cuda()
+    dcells = torch.empty(n, dtype=torch.int32, device="cuda")
+    torch.cuda.synchronize()
+    b.add_device(dX.data_ptr(), n, 0, 0, 0, dcells.data_ptr())
+    np.testing.assert_array_equal(dcells.cpu().numpy(), cells)
+    dassign = torch.from_numpy(cells.astype(np.int64) + 1).cuda()
+    torch.cuda.synchronize()
+    c.add_device(dX.data_ptr(), n, 0, dassign.data_ptr(), 1)
+    for e in (b, c):
+        assert len(e) == n
+        np.testing.assert_array_equal(e.list_sizes(), a.list_sizes())
+        for cell in range(kc):
+            ia, ca = a.export_list(cell)
+            ie, ce = e.export_list(cell)
+            np.testing.assert_array_equal(ia, ie)
+            np.testing.assert_array_equal(ca, ce)
+    dassign[3] = kc + 1
+    torch.cuda.synchronize()
+    with pytest.raises(iv._capi.IvfadcError):
+        c.add_device(dX.data_ptr(), n, 0, dassign.data_ptr(), 1)
+    for e in (a, b, c):
+        e.close()
+
+
+@pytest.mark.parametrize("id_type,kc", [(np.uint32, 16384), (np.uint64, 300)])
+def test_bulk_export_import(tmp_path, id_type, kc):
+    """ivfadc_export_all / ivfadc_import_all against the per-list calls at kc = 16 384 (many empty and ragged
+    lists), and the saved file byte-identical to the per-list writer's (src/persistency.jl:68-78)."""
+    rng = np.random.default_rng(kc)
+    D, m, n = 32, 8, 60000
+    X = rng.random((n, D)).astype(np.float32)
+    cent = rng.random((kc, D)).astype(np.float32)
+    cb = (0.2 * rng.standard_normal((m, 256, D // m))).astype(np.float32)
+    qz = orc.Quantizers(cent, cb, None)
+    e = engine_from(qz, id_type, X)
+    sizes, ids, codes = e.export_all()
+    assert int(sizes.sum()) == n and ids.dtype == id_type
+    o = 0
+    for c in range(kc):
+        i1, c1 = e.export_list(c)
+        assert len(i1) == sizes[c]
+        np.testing.assert_array_equal(ids[o:o + len(i1)], i1)
+        np.testing.assert_array_equal(codes[o:o + len(i1)], c1)
+        o += len(i1)
+    # the file: bulk writer == a per-list writer written here after src/persistency.jl:68-78
+    fn = str(tmp_path / "bulk.ivfadc")
+    iv.save_ivfadc_index(fn, e)
+    raw = open(fn, "rb").read()
+    per_list = bytearray()
+    o = 0
+    for c in range(kc):
+        per_list += np.int64(sizes[c]).tobytes() + ids[o:o + sizes[c]].tobytes() + codes[o:o + sizes[c]].tobytes()
+        o += int(sizes[c])
+    assert raw.endswith(bytes(per_list))
+    # import into a fresh engine and into one that already holds other lists (everything is replaced)
+    e2 = iv.load_ivfadc_index(fn)
+    e3 = engine_from(qz, id_type, X[:1000])
+    e3.import_all(sizes, ids, codes)
+    for t in (e2, e3):
+        assert len(t) == n
+        s2, i2, c2 = t.export_all()
+        np.testing.assert_array_equal(s2, sizes)
+        np.testing.assert_array_equal(i2, ids)
+        np.testing.assert_array_equal(c2, codes)
+    Q = rng.random((50, D)).astype(np.float32)
+    r1, r2 = e.search_packed(Q, 5, 8), e3.search_packed(Q, 5, 8)
+    for x, y in zip(r1, r2):
+        np.testing.assert_array_equal(x, y)
+    # mutation after a bulk import keeps working (capacities were rebuilt)
+    iv.push_batch(e3, X[:77])
+    assert len(e3) == n + 77
+    for t in (e, e2, e3):
+        t.close()
+
+
+def test_synth_device_equals_cpu_twin():
+    """csrc/synth.cu against oracle_synth_*: the same floats bit for bit, any slice of the stream."""
+    import torch
+    from ivfadc_jl_b200 import synth
+    for D, kb in ((128, 1024), (96, 50), (10, 7)):
+        c_cpu = orc.synth_uniform(0, kb, D, 1001)
+        c_dev = synth.uniform_device(0, kb, D, 1001)
+        assert np.array_equal(c_dev.cpu().numpy().view(np.uint32), c_cpu.view(np.uint32))
+        for first, n in ((0, 1000), (123_456_789_012, 777), (99_999_000, 1000)):
+            x_cpu, b_cpu = orc.synth_blobs(first, n, D, kb, 1002, synth.blob_scale(0.05), c_cpu)
+            x_dev, b_dev = synth.blobs_device(first, n, c_dev, 1002, 0.05, want_blobs=True)
+            torch.cuda.synchronize()
+            assert np.array_equal(b_dev.cpu().numpy(), b_cpu)
+            assert np.array_equal(x_dev.cpu().numpy().view(np.uint32), x_cpu.view(np.uint32))
+
+
+def test_config_c_full_size_parity():
+    """Deep10M-shaped configuration at FULL size (96-d, 10 M vectors, kc = 4096, m = 12) built in HBM from the
+    device generator; the default engine against the oracle on 256 queries at the north_star tolerance, the PQ codes
+    of a sample bit-identical to the oracle's encoder."""
+    import torch
+    from ivfadc_jl_b200 import synth
+    D, N, kc, m, nq, nchk, k, w = 96, 10_000_000, 4096, 12, 10_000, 256, 10, 16
+    centres = synth.uniform_device(0, kc, D, 1001)
+    cent = centres.cpu().numpy()
+    xs = synth.blobs_device(0, 200_000, centres, 1002)
+    tc, tb = synth.train_on_device_tensor(xs, kc, m, 256, iters=2, init=centres)
+    cent, cb = tc.cpu().numpy(), tb.cpu().numpy()
+    qz = orc.Quantizers(cent, cb, None)
+    e = iv.IVFADCIndex.from_quantizers(cent, cb, None)
+    buf = torch.empty((1 << 20, D), dtype=torch.float32, device="cuda")
+    for s in range(0, N, 1 << 20):
+        n = min(1 << 20, N - s)
+        x = synth.blobs_device(s, n, centres, 1002, out=buf)
+        torch.cuda.synchronize()
+        e.add_device(x.data_ptr(), n)
+    assert len(e) == N
+    # encoding of a slice of the stream: regenerate it on the CPU (counter-based) and compare with the stored codes
+    first, ns = 7_654_321, 4096
+    xc, _ = orc.synth_blobs(first, ns, D, kc, 1002, synth.blob_scale(0.05), centres.cpu().numpy())
+    ocell, ocode = orc.encode(qz, xc, nthreads=8)
+    gcell, gcode = e.encode(xc)
+    np.testing.assert_array_equal(gcell, ocell)
+    np.testing.assert_array_equal(gcode, ocode)
+    Q = synth.blobs_device(0, nq, centres, 2001).cpu().numpy()
+    sizes, ids, codes = e.export_all()
+    off = np.zeros(kc + 1, dtype=np.int64)
+    np.cumsum(sizes, out=off[1:])
+    # the stored entry of vector `first + j` carries exactly the oracle's code
+    pos = {int(v): i for i, v in enumerate(ids[off[ocell[0]]:off[ocell[0] + 1]])}
+    assert np.array_equal(codes[off[ocell[0]] + pos[first]], ocode[0])
+    oi, od, oc, _ = orc.search_csr(qz, off, codes, ids.astype(np.uint64), Q[:nchk], k, w, nthreads=16)
+    gi, gd, gc = e.search_packed(Q, k, w)     # the full batch: ~39 queries per list, the tensor-memory scan
+    rep = orc.compare_search(gi[:nchk], gd[:nchk], gc[:nchk], oi, od, oc, rtol=RTOL)
+    assert rep["near_tie_id_mismatches"] <= 8, rep
+    assert int(e.stats()["last_scan_kernel"]) in (4, 5)
+    e.close()
