@@ -14,7 +14,8 @@ over the SIFT1M-shaped synthetic index (128-d, 1M vectors, kc = 1024, m = 16, 25
   cpu_baseline  the C restatement of the reference's CPU path (oracle/, Julia is not available in
          this image) on the box's host cores over the same index and queries;
   extra  the other named shapes of BASELINE.json measured in the same run: C (Deep10M-shaped) at every N,
-         D (100 M vectors) at N = 1 (code array beyond the L2: the HBM-streaming scan) and at N = 8.
+         D (100 M vectors) at N = 1 (code array beyond the L2: the HBM-streaming scan) and at N = 8,
+         E (build: push! of 10 M vectors + delete_from_index!) at N = 1.
 Data: counter-based generator (Philox4x32-10 keyed (seed, vector, dim); csrc/synth.cu on the device, the same
 function bit for bit in oracle/ for the CPU arm), so the 10 M / 100 M-vector sets are produced in HBM chunk by chunk.
 N > 1 (torchrun, one rank per GPU): inverted lists sharded by cell (owners balanced by list length), the whole
@@ -399,7 +400,7 @@ def run_workload(cx, args, name, steps, headline):
     if breakdown is not None:
         st = dict(st)
         for key_ in ("coarse_ms", "plan_ms", "scan_ms", "merge_ms", "comm_ms", "scan_launches", "scan_code_bytes",
-                     "scanned_vectors", "last_scan_kernel"):
+                     "scanned_vectors", "last_scan_kernel", "last_coarse_redo"):
             st[key_] = breakdown[key_]
         launches = int(breakdown["gpu_launches"] / nbreak * steps)
     else:
@@ -515,6 +516,7 @@ def run_workload(cx, args, name, steps, headline):
                               "vectors": r[2]} for r in ranks]
         bd = {"coarse": st["coarse_ms"] / nbreak, "plan": st["plan_ms"] / nbreak, "scan": st["scan_ms"] / nbreak,
               "merge": st["merge_ms"] / nbreak}
+        bd["coarse_redo_queries_last_step"] = int(st.get("last_coarse_redo", 0))
         if world > 1:
             bd["comm"] = st.get("comm_ms", 0.0) / nbreak
             bd["note"] = "eager steps (per-kernel CUDA events); the timed steps replay the same work from a CUDA graph"
@@ -538,6 +540,88 @@ def run_workload(cx, args, name, steps, headline):
     del dQ, out, result
     torch.cuda.empty_cache()
     return rec
+
+
+def run_build_extra(cx, args):
+    """BASELINE.json configs[4] inside the bench line (N = 1): push! of 10 M 128-d vectors (coarse assign w = 1 + PQ
+    residual encode, m = 16, + append) device-resident and through the host API, then delete_from_index! of 1 M ids;
+    the cells / codes of a sample against the oracle's _encode_point, bit for bit."""
+    import torch
+    import ivfadc_jl_b200 as iv
+    from ivfadc_jl_b200 import synth
+    from oracle import oracle as orc
+    D, N, kc, m, ksub = 128, int(os.environ.get("IVFADC_BENCH_E_N", 10_000_000)), 1024, 16, 256
+    dev = cx.dev
+    centres = synth.uniform_device(0, kc, D, SEED_CENTRES, device=dev)
+    xs = synth.blobs_device(0, 262144, centres, SEED_DATA, SIGMA)
+    tc, tb = synth.train_on_device_tensor(xs, kc, m, ksub, iters=TRAIN_ITERS, init=centres)
+    cent, cb = tc.cpu().numpy(), tb.cpu().numpy()
+    del xs, tc, tb
+    stream = torch.cuda.current_stream(dev)
+    buf = torch.empty((CHUNK, D), dtype=torch.float32, device=dev)
+    # (1) device-resident: the batch is already in HBM
+    e = iv.IVFADCIndex.from_quantizers(cent, cb, None, index_type=np.uint32, device=cx.local_rank)
+    x = synth.blobs_device(0, 4096, centres, SEED_DATA, SIGMA, out=buf)
+    stream.synchronize()
+    e.add_device(x.data_ptr(), 4096)                      # warm-up: kernels loaded, workspaces sized
+    iv.delete_from_index(e, np.arange(1, 4097))
+    dev_s = 0.0
+    for s0 in range(0, N, CHUNK):
+        n = min(CHUNK, N - s0)
+        x = synth.blobs_device(s0, n, centres, SEED_DATA, SIGMA, out=buf)
+        stream.synchronize()
+        t = time.perf_counter()
+        e.add_device(x.data_ptr(), n)                     # synchronous: coarse (w = 1) + encode + append
+        dev_s += time.perf_counter() - t
+    assert len(e) == N
+    rng = np.random.default_rng(7)
+    del_ids = rng.choice(N, size=min(1_000_000, N // 2), replace=False).astype(np.int64) + 1   # 1-based (src/utils.jl:93)
+    t = time.perf_counter()
+    iv.delete_from_index(e, del_ids)
+    del_s = time.perf_counter() - t
+    assert len(e) == N - len(del_ids)
+    e.close()
+    # (2) through the host API: two pinned host chunks pushed alternately, H2D inside the timed region
+    e = iv.IVFADCIndex.from_quantizers(cent, cb, None, index_type=np.uint32, device=cx.local_rank)
+    pinned = [synth.blobs_device(i * CHUNK, CHUNK, centres, SEED_DATA, SIGMA).cpu().pin_memory() for i in range(2)]
+    iv.push_batch(e, pinned[0].numpy()[:4096])
+    iv.delete_from_index(e, np.arange(1, 4097))
+    host_s, nhost = 0.0, 0
+    for i in range(max(1, N // CHUNK)):
+        xh = pinned[i & 1].numpy()
+        t = time.perf_counter()
+        iv.push_batch(e, xh)
+        host_s += time.perf_counter() - t
+        nhost += CHUNK
+    # (3) parity of a sample: regenerate the vectors on the CPU (counter-based) and encode them with the oracle
+    ns = 50_000
+    xc, _ = orc.synth_blobs(0, ns, D, kc, SEED_DATA, synth.blob_scale(SIGMA), centres.cpu().numpy())
+    qz = orc.Quantizers(cent, cb, None)
+    nth = os.cpu_count() or 1
+    t = time.perf_counter()
+    ocells, ocodes = orc.encode(qz, xc, nthreads=nth)
+    cpu_s = time.perf_counter() - t
+    gcells, gcodes = e.encode(xc)
+    same_input = bool(np.array_equal(xc, pinned[0].numpy()[:ns]))
+    parity = bool(np.array_equal(np.asarray(gcells).astype(np.int64), np.asarray(ocells).astype(np.int64))
+                  and np.array_equal(gcodes, ocodes))
+    e.close()
+    del buf, pinned
+    torch.cuda.empty_cache()
+    flop = (2.0 * kc * D + 3.0 * D * ksub) * N     # SURVEY 8d: direct-form work of K1 (w = 1) + K4 per vector
+    return {"config": {"workload": "Build/encode throughput: push! of 10M 128-d vectors (coarse assign + PQ residual encode, "
+                                   "m=16) plus delete_from_index! compaction", "n": N, "chunk": CHUNK, "D": D, "kc": kc,
+                       "m": m, "ksub": ksub, "ids": "UInt32"},
+            "device_resident": {"value": N / dev_s, "unit": "vectors/s", "seconds": dev_s,
+                                "algorithmic_tflops": flop / dev_s / 1e12,
+                                "note": "ivfadc_add_device on batches already in HBM (coarse w=1 on the tensor cores + exact "
+                                        "re-rank, PQ encode, sort by cell + append)"},
+            "host_api": {"value": nhost / host_s, "unit": "vectors/s", "seconds": host_s, "h2d_bytes": int(nhost) * D * 4,
+                         "note": "ivfadc_add on pinned host buffers (the host->device copy inside the timed region)"},
+            "delete": {"ids": int(len(del_ids)), "seconds": del_s, "vectors_compacted_per_s": N / del_s},
+            "cpu_baseline": {"value": ns / cpu_s, "unit": "vectors/s", "cores": nth, "kind": "port",
+                             "sample": f"oracle encode of {ns} vectors ({cpu_s:.2f} s)"},
+            "parity": {"vectors": ns, "cells_and_codes_bit_exact": parity, "cpu_generator_equals_device": same_input}}
 
 
 def main():
@@ -584,14 +668,15 @@ def main():
     if args.extras == "auto":
         names = []
         if args.workload == "B":
-            names = ["C"] + (["D"] if cx.world in (1, 8) else [])
+            names = ["C"] + (["D"] if cx.world in (1, 8) else []) + (["E"] if cx.world == 1 else [])
     elif args.extras == "none":
         names = []
     else:
         names = [x for x in args.extras.split(",") if x]
     for name in names:
         try:
-            rec = run_workload(cx, args, name, min(args.steps, 10), headline=False)
+            rec = (run_build_extra(cx, args) if name == "E" else
+                   run_workload(cx, args, name, min(args.steps, 10), headline=False))
             if cx.rank == 0:
                 extras[name] = rec
         except Exception as ex:   # an extra must never take the headline down

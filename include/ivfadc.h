@@ -139,7 +139,8 @@ typedef struct ivfadc_stats {
     uint64_t scan_launches;
     uint64_t last_scan_kernel;  /* kernel of the last search: 1 vector-per-lane, 2 scanq, 4 scanu (v1), 5 scanw */
     double   comm_ms;           /* sharded search: device time of the two grouped all-gathers (eager steps)  */
-    uint64_t reserved[2];
+    uint64_t last_coarse_redo;  /* queries of the last tensor-core coarse step that the exact FFMA pass had to redo */
+    uint64_t reserved[1];
 } ivfadc_stats;
 
 int ivfadc_abi_version(void);

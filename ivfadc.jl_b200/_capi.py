@@ -52,7 +52,8 @@ class Stats(ctypes.Structure):
         ("searches", c_uint64), ("queries", c_uint64), ("scanned_vectors", c_uint64),
         ("scan_code_bytes", c_uint64), ("gpu_launches", c_uint64), ("coarse_ms", c_double),
         ("plan_ms", c_double), ("scan_ms", c_double), ("merge_ms", c_double), ("encode_ms", c_double),
-        ("scan_launches", c_uint64), ("last_scan_kernel", c_uint64), ("comm_ms", c_double), ("reserved", c_uint64 * 2),
+        ("scan_launches", c_uint64), ("last_scan_kernel", c_uint64), ("comm_ms", c_double), ("last_coarse_redo", c_uint64),
+        ("reserved", c_uint64 * 1),
     ]
 
     def as_dict(self):

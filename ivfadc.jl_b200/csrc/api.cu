@@ -221,6 +221,7 @@ int ivfadc_device_count(void) {
 
 int ivfadc_create(ivfadc_index** out, const ivfadc_config* cfg, const void* centroids,
                   const void* codebook_vectors, const uint8_t* codebook_codes) {
+    IVF_NVTX();
     if (!out || !cfg || !centroids || !codebook_vectors || !codebook_codes) return IVFADC_ERR_BAD_ARG;
     *out = nullptr;
     if (cfg->dim < 1 || cfg->kc < 1 || cfg->m < 1 || cfg->m > cfg->dim || cfg->ksub < 1) return IVFADC_ERR_BAD_ARG;
@@ -372,6 +373,7 @@ const char* ivfadc_last_error(const ivfadc_index* h) { return h ? h->err.c_str()
 
 int ivfadc_add(ivfadc_index* h, const void* X, int64_t n, int32_t position, const int64_t* assign,
                int32_t assign_base, int32_t* cells_out) {
+    IVF_NVTX();
     if (check_handle(h)) return IVFADC_ERR_BAD_ARG;
     if (n < 0 || (n > 0 && !X)) return fail(h, IVFADC_ERR_BAD_ARG, "null data");
     if (position != IVFADC_LAST && position != IVFADC_FIRST) return fail(h, IVFADC_ERR_BAD_ARG, "bad position");
@@ -422,6 +424,7 @@ int ivfadc_add(ivfadc_index* h, const void* X, int64_t n, int32_t position, cons
 
 int ivfadc_add_device(ivfadc_index* h, const void* dX, int64_t n, int32_t position, const int64_t* d_assign,
                       int32_t assign_base, int32_t* d_cells_out) {
+    IVF_NVTX();
     if (check_handle(h)) return IVFADC_ERR_BAD_ARG;
     if (n < 0 || (n > 0 && !dX)) return fail(h, IVFADC_ERR_BAD_ARG, "null data");
     if (position != IVFADC_LAST && position != IVFADC_FIRST) return fail(h, IVFADC_ERR_BAD_ARG, "bad position");
@@ -469,6 +472,7 @@ int ivfadc_add_device(ivfadc_index* h, const void* dX, int64_t n, int32_t positi
 
 int ivfadc_encode(ivfadc_index* h, const void* X, int64_t n, const int64_t* assign, int32_t assign_base,
                   int32_t* cells_out, uint8_t* codes_out) {
+    IVF_NVTX();
     if (check_handle(h)) return IVFADC_ERR_BAD_ARG;
     if (n < 0 || (n > 0 && (!X || !cells_out || !codes_out))) return fail(h, IVFADC_ERR_BAD_ARG, "null pointer");
     if (assign && !assign_in_range(assign, n, assign_base, h->cfg.kc))
@@ -505,6 +509,7 @@ int ivfadc_encode(ivfadc_index* h, const void* X, int64_t n, const int64_t* assi
 
 int ivfadc_coarse_search(ivfadc_index* h, const void* Q, int64_t nq, int32_t w, int32_t* cells_out,
                          void* dc_out) {
+    IVF_NVTX();
     if (check_handle(h)) return IVFADC_ERR_BAD_ARG;
     if (nq < 0 || (nq > 0 && (!Q || !cells_out || !dc_out))) return fail(h, IVFADC_ERR_BAD_ARG, "null pointer");
     if (w < 1) return fail(h, IVFADC_ERR_BAD_ARG, "w < 1");
@@ -531,6 +536,7 @@ int ivfadc_coarse_search(ivfadc_index* h, const void* Q, int64_t nq, int32_t w, 
 
 int ivfadc_search(ivfadc_index* h, const void* Q, int64_t nq, int32_t k, int32_t w, uint64_t* ids_out,
                   void* dists_out, int32_t* counts_out) {
+    IVF_NVTX();
     if (check_handle(h)) return IVFADC_ERR_BAD_ARG;
     if (nq > 0 && (!Q || !ids_out || !dists_out || !counts_out)) return fail(h, IVFADC_ERR_BAD_ARG, "null pointer");
     if (k < 1) return fail(h, IVFADC_ERR_BAD_ARG, "Number of neighbors must be k >= 1");
@@ -570,6 +576,7 @@ int ivfadc_search(ivfadc_index* h, const void* Q, int64_t nq, int32_t k, int32_t
 
 int ivfadc_search_device(ivfadc_index* h, const void* dQ, int64_t nq, int32_t k, int32_t w, uint64_t* d_ids,
                          void* d_dists, int32_t* d_counts, void* stream) {
+    IVF_NVTX();
     if (check_handle(h)) return IVFADC_ERR_BAD_ARG;
     cudaSetDevice(h->cfg.device);
     return search_core(h, dQ, nq, k, w, d_ids, d_dists, nullptr, d_counts, static_cast<cudaStream_t>(stream));
@@ -578,6 +585,7 @@ int ivfadc_search_device(ivfadc_index* h, const void* dQ, int64_t nq, int32_t k,
 int ivfadc_search_local_device(ivfadc_index* h, const void* dQ, int64_t nq, int32_t k, int32_t w,
                                uint64_t* d_ids, void* d_dists, uint64_t* d_keys, int32_t* d_counts,
                                void* stream) {
+    IVF_NVTX();
     if (check_handle(h)) return IVFADC_ERR_BAD_ARG;
     if (!d_keys) return fail(h, IVFADC_ERR_BAD_ARG, "null keys");
     cudaSetDevice(h->cfg.device);
@@ -586,6 +594,7 @@ int ivfadc_search_local_device(ivfadc_index* h, const void* dQ, int64_t nq, int3
 
 int ivfadc_coarse_search_device(ivfadc_index* h, const void* dQ, int64_t nq, int32_t w, int32_t* d_cells,
                                 void* d_dc, void* stream) {
+    IVF_NVTX();
     if (check_handle(h)) return IVFADC_ERR_BAD_ARG;
     if (nq < 0 || (nq > 0 && (!dQ || !d_cells || !d_dc))) return fail(h, IVFADC_ERR_BAD_ARG, "null pointer");
     if (w < 1 || w > h->cfg.kc) return fail(h, IVFADC_ERR_BAD_ARG, "w outside 1..kc (clamp before calling)");
@@ -602,6 +611,7 @@ int ivfadc_coarse_search_device(ivfadc_index* h, const void* dQ, int64_t nq, int
 int ivfadc_search_probes_local_device(ivfadc_index* h, const void* dQ, int64_t nq, int32_t k, int32_t w,
                                       const int32_t* d_cells, const void* d_dc, uint64_t* d_ids, void* d_dists,
                                       uint64_t* d_keys, int32_t* d_counts, void* stream) {
+    IVF_NVTX();
     if (check_handle(h)) return IVFADC_ERR_BAD_ARG;
     if (!d_keys || !d_cells || !d_dc) return fail(h, IVFADC_ERR_BAD_ARG, "null pointer");
     cudaSetDevice(h->cfg.device);
@@ -612,6 +622,7 @@ int ivfadc_search_probes_local_device(ivfadc_index* h, const void* dQ, int64_t n
 int ivfadc_merge_device(ivfadc_index* h, int32_t parts, int64_t nq, int32_t k, const uint64_t* d_ids_in,
                         const void* d_dists_in, const uint64_t* d_keys_in, uint64_t* d_ids, void* d_dists,
                         int32_t* d_counts, void* stream) {
+    IVF_NVTX();
     if (check_handle(h)) return IVFADC_ERR_BAD_ARG;
     if (parts < 1 || parts > 128 || k < 1 || nq < 0) return fail(h, IVFADC_ERR_BAD_ARG, "bad merge shape");
     if (!d_ids_in || !d_dists_in || !d_keys_in || !d_ids || !d_dists || !d_counts)
@@ -626,6 +637,7 @@ int ivfadc_merge_device(ivfadc_index* h, int32_t parts, int64_t nq, int32_t k, c
 }
 
 int ivfadc_delete(ivfadc_index* h, const uint64_t* ids, int64_t n) {
+    IVF_NVTX();
     if (check_handle(h)) return IVFADC_ERR_BAD_ARG;
     if (n < 0 || (n > 0 && !ids)) return fail(h, IVFADC_ERR_BAD_ARG, "null ids");
     if (n == 0) return IVFADC_OK;
@@ -651,6 +663,7 @@ int ivfadc_delete(ivfadc_index* h, const uint64_t* ids, int64_t n) {
 }
 
 int ivfadc_pop(ivfadc_index* h, int32_t position, void* vec_out, int32_t* found_out) {
+    IVF_NVTX();
     if (check_handle(h)) return IVFADC_ERR_BAD_ARG;
     if (!vec_out) return fail(h, IVFADC_ERR_BAD_ARG, "null output");
     if (position != IVFADC_LAST && position != IVFADC_FIRST) return fail(h, IVFADC_ERR_BAD_ARG, "bad position");
@@ -688,6 +701,7 @@ int ivfadc_list_sizes(ivfadc_index* h, int64_t* sizes_out) {
 }
 
 int ivfadc_export_list(ivfadc_index* h, int32_t cell, uint64_t* ids_out, uint8_t* codes_out) {
+    IVF_NVTX();
     if (check_handle(h)) return IVFADC_ERR_BAD_ARG;
     if (cell < 0 || cell >= h->cfg.kc) return fail(h, IVFADC_ERR_BAD_ARG, "bad cell");
     if (h->h_len[cell] > 0 && (!ids_out || !codes_out)) return fail(h, IVFADC_ERR_BAD_ARG, "null pointer");
@@ -697,6 +711,7 @@ int ivfadc_export_list(ivfadc_index* h, int32_t cell, uint64_t* ids_out, uint8_t
 }
 
 int ivfadc_import_list(ivfadc_index* h, int32_t cell, const uint64_t* ids, const uint8_t* codes, int64_t len) {
+    IVF_NVTX();
     if (check_handle(h)) return IVFADC_ERR_BAD_ARG;
     if (cell < 0 || cell >= h->cfg.kc || len < 0) return fail(h, IVFADC_ERR_BAD_ARG, "bad cell / length");
     if (len > 0 && (!ids || !codes)) return fail(h, IVFADC_ERR_BAD_ARG, "null pointer");
@@ -708,6 +723,7 @@ int ivfadc_import_list(ivfadc_index* h, int32_t cell, const uint64_t* ids, const
 }
 
 int ivfadc_export_all(ivfadc_index* h, uint64_t* ids_out, uint8_t* codes_out) {
+    IVF_NVTX();
     if (check_handle(h)) return IVFADC_ERR_BAD_ARG;
     if (h->n_local > 0 && (!ids_out || !codes_out)) return fail(h, IVFADC_ERR_BAD_ARG, "null pointer");
     cudaSetDevice(h->cfg.device);
@@ -718,6 +734,7 @@ int ivfadc_export_all(ivfadc_index* h, uint64_t* ids_out, uint8_t* codes_out) {
 }
 
 int ivfadc_import_all(ivfadc_index* h, const int64_t* sizes, const uint64_t* ids, const uint8_t* codes) {
+    IVF_NVTX();
     if (check_handle(h) || !sizes) return IVFADC_ERR_BAD_ARG;
     int64_t total = 0;
     for (int c = 0; c < h->cfg.kc; ++c) {
@@ -810,6 +827,12 @@ int ivfadc_get_stats(ivfadc_index* h, ivfadc_stats* out) {
     if (cudaMemcpy(&scanned, x->d_scanned, sizeof(uint64_t), cudaMemcpyDeviceToHost) == cudaSuccess) {
         h->stats.scanned_vectors = scanned;
         h->stats.scan_code_bytes = scanned * (uint64_t)h->cfg.m;
+    }
+    h->stats.last_coarse_redo = 0;
+    if (h->last_redo_nq > 0 && h->ws_coarse_redo.p) {   // redo flags of the last coarse step (one byte per query)
+        std::vector<uint8_t> flags((size_t)h->last_redo_nq);
+        if (cudaMemcpy(flags.data(), h->ws_coarse_redo.p, flags.size(), cudaMemcpyDeviceToHost) == cudaSuccess)
+            for (uint8_t f : flags) h->stats.last_coarse_redo += f ? 1 : 0;
     }
     *out = h->stats;
     return IVFADC_OK;

@@ -198,7 +198,8 @@ constexpr int PDK = 64;              // dims per centroid chunk (double-buffered
 template <int NTY, int R>
 __global__ void __launch_bounds__(16 * NTY)
 coarse2_kernel(const float* __restrict__ Q, const float* __restrict__ Ct, int64_t nq, int kc, int kcp, int D, int w,
-               int32_t* __restrict__ cells_out, float* __restrict__ dc_out, const uint8_t* __restrict__ redo) {
+               int32_t* __restrict__ cells_out, float* __restrict__ dc_out, const int32_t* __restrict__ redo_list,
+               const int* __restrict__ redo_count, int list_skip) {
     constexpr int TQ2 = 4 * NTY, NT = 16 * NTY, NW = NT / 32, QPW = TQ2 / NW;  // 8 queries per warp
     constexpr int LDQ = 2 * TQ2 + 4;  // floats per dim row of the duplicated queries (16-byte aligned rows)
     constexpr int LDD = PC + 1;
@@ -211,10 +212,12 @@ coarse2_kernel(const float* __restrict__ Q, const float* __restrict__ Ct, int64_
     const int tx = tid & 15;   // centroids 4 tx .. 4 tx + 3 of the tile
     const int ty = tid >> 4;   // queries 4 ty .. 4 ty + 3 of the block
     const int64_t q0 = (int64_t)blockIdx.x * TQ2;
-    if (redo) {  // second pass behind the tensor-core kernel: only the queries it flagged (normally none)
-        bool any = false;
-        for (int i = tid; i < TQ2; i += NT) any = any || (q0 + i < nq && redo[q0 + i]);
-        if (!__syncthreads_or(any)) return;
+    // second pass behind the tensor-core kernel: only the queries it flagged (normally none), as a compacted list
+    // -- the cost is proportional to their number, blocks beyond the list exit at once
+    if (redo_list) {   // the first list_skip flagged queries belong to coarse_redo_small_kernel
+        nq = max(0, *redo_count - list_skip);
+        if (q0 >= nq) return;
+        redo_list += list_skip;
     }
     const int nck = (D + PDK - 1) / PDK;                 // chunks per tile
     const int ntile = (kc + PC - 1) / PC;
@@ -237,8 +240,9 @@ coarse2_kernel(const float* __restrict__ Q, const float* __restrict__ Ct, int64_
     // queries: coalesced along d, stored transposed, negated and duplicated
     for (int idx = tid; idx < TQ2 * D; idx += NT) {
         const int row = idx / D, d = idx - row * D;
-        const int64_t q = q0 + row;
-        const float v = q < nq ? -Q[q * D + d] : 0.f;
+        int64_t q = q0 + row;
+        if (q < nq && redo_list) q = redo_list[q];
+        const float v = q0 + row < nq ? -Q[q * D + d] : 0.f;
         *reinterpret_cast<float2*>(&sQ[d * LDQ + 2 * row]) = make_float2(v, v);
     }
 
@@ -314,9 +318,9 @@ coarse2_kernel(const float* __restrict__ Q, const float* __restrict__ Ct, int64_
     }
 #pragma unroll
     for (int a = 0; a < QPW; ++a) {
-        const int64_t q = q0 + wid * QPW + a;
+        int64_t q = q0 + wid * QPW + a;
         if (q >= nq) continue;
-        if (redo && !redo[q]) continue;
+        if (redo_list) q = redo_list[q];
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             const int e = lane * R + r;
@@ -325,6 +329,74 @@ coarse2_kernel(const float* __restrict__ Q, const float* __restrict__ Ct, int64_
                 dc_out[q * w + e] = lst[a].v[r];
             }
         }
+    }
+}
+
+// A handful of queries flagged by the tensor-core kernel (candidate overflow: about one in 10^4 on the benchmark
+// data): one block per (query, 256 centroids) evaluates the reference's direct-form chain, the last block of a
+// query to finish selects its w nearest by (distance, cell) -- the latency of a flagged query is a few
+// microseconds instead of one CTA streaming all centroids (150 us at kc = 1024).  Queries beyond RS_MAXQ go to
+// coarse2_kernel with the compacted list.
+__global__ void __launch_bounds__(256)
+coarse_redo_small_kernel(const float* __restrict__ Q, const float* __restrict__ C, int kc, int kcp, int D, int w,
+                         int32_t* __restrict__ cells_out, float* __restrict__ dc_out,
+                         const int32_t* __restrict__ redo_list, const int* __restrict__ redo_count,
+                         float* __restrict__ scratch, unsigned* __restrict__ done) {
+    const int slot = blockIdx.y;
+    if (slot >= min(*redo_count, ctc::RS_MAXQ)) return;
+    const int64_t q = redo_list[slot];
+    __shared__ float sq[PMAXD];
+    __shared__ unsigned long long red[8];
+    __shared__ int s_last;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    for (int d = tid; d < D; d += 256) sq[d] = Q[q * D + d];
+    __syncthreads();
+    const int c = blockIdx.x * 256 + tid;
+    float* row = scratch + (size_t)slot * kcp;
+    if (c < kcp) {
+        float acc = Limits<float>::inf();
+        if (c < kc) {
+            acc = 0.f;
+            const float* cr = C + (size_t)c * D;
+            for (int d = 0; d < D; ++d) {
+                const float diff = sub_rn(cr[d], sq[d]);  // oracle A1: c - q, one sequential fma chain
+                acc = fma_rn(diff, diff, acc);
+            }
+        }
+        __stcg(row + c, acc);
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_last = atomicAdd(done + slot, 1u) == gridDim.x - 1 ? 1 : 0;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    // w rounds of a block-wide minimum of (distance bits, cell) above the previous winner: ascending (distance, cell)
+    unsigned long long prev = 0ull;
+    bool first = true;
+    for (int r = 0; r < w; ++r) {
+        unsigned long long best = ~0ull;
+        for (int i = tid; i < kcp; i += 256) {
+            const unsigned long long key = ((unsigned long long)__float_as_uint(__ldcg(row + i)) << 32) | (unsigned)i;
+            if ((first || key > prev) && key < best) best = key;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
+            best = other < best ? other : best;
+        }
+        if (lane == 0) red[wid] = best;
+        __syncthreads();
+        best = red[0];
+#pragma unroll
+        for (int i = 1; i < 8; ++i) best = red[i] < best ? red[i] : best;
+        __syncthreads();
+        if (tid == 0) {
+            cells_out[q * w + r] = (int32_t)(unsigned)best;
+            dc_out[q * w + r] = __uint_as_float((unsigned)(best >> 32));
+        }
+        prev = best;
+        first = false;
     }
 }
 
@@ -337,20 +409,22 @@ __global__ void transpose_centroids_kernel(const float* __restrict__ C, int kc, 
 
 template <int NTY, int R>
 cudaError_t launch_coarse2_inst(const ivfadc_index* h, const float* Q, const float* Ct, int64_t nq, int kc, int kcp, int D, int w,
-                                int32_t* cells, float* dc, cudaStream_t s, const uint8_t* redo) {
+                                int32_t* cells, float* dc, cudaStream_t s, const int32_t* redo_list, const int* redo_count) {
     constexpr int TQ2 = 4 * NTY;
     const size_t smem = ((size_t)D * (2 * TQ2 + 4) + 2 * (size_t)PDK * PLDC + (size_t)TQ2 * (PC + 1)) * sizeof(float);
     cudaError_t e = ensure_smem(h, reinterpret_cast<const void*>(&coarse2_kernel<NTY, R>), smem);
     if (e != cudaSuccess) return e;
-    coarse2_kernel<NTY, R><<<(unsigned)((nq + TQ2 - 1) / TQ2), 16 * NTY, smem, s>>>(Q, Ct, nq, kc, kcp, D, w, cells, dc, redo);
+    coarse2_kernel<NTY, R><<<(unsigned)((nq + TQ2 - 1) / TQ2), 16 * NTY, smem, s>>>(Q, Ct, nq, kc, kcp, D, w, cells, dc, redo_list,
+                                                                                  redo_count, redo_list ? ctc::RS_MAXQ : 0);
     return cudaGetLastError();
 }
 template <int R>
 cudaError_t launch_coarse2_r(const ivfadc_index* h, int nty, const float* Q, const float* Ct, int64_t nq, int kc, int kcp, int D, int w,
-                             int32_t* cells, float* dc, cudaStream_t s, const uint8_t* redo = nullptr) {
-    if (nty == 4) return launch_coarse2_inst<4, R>(h, Q, Ct, nq, kc, kcp, D, w, cells, dc, s, redo);
-    if (nty == 6) return launch_coarse2_inst<6, R>(h, Q, Ct, nq, kc, kcp, D, w, cells, dc, s, redo);
-    return launch_coarse2_inst<8, R>(h, Q, Ct, nq, kc, kcp, D, w, cells, dc, s, redo);
+                             int32_t* cells, float* dc, cudaStream_t s, const int32_t* redo_list = nullptr,
+                             const int* redo_count = nullptr) {
+    if (nty == 4) return launch_coarse2_inst<4, R>(h, Q, Ct, nq, kc, kcp, D, w, cells, dc, s, redo_list, redo_count);
+    if (nty == 6) return launch_coarse2_inst<6, R>(h, Q, Ct, nq, kc, kcp, D, w, cells, dc, s, redo_list, redo_count);
+    return launch_coarse2_inst<8, R>(h, Q, Ct, nq, kc, kcp, D, w, cells, dc, s, redo_list, redo_count);
 }
 
 template <typename T>
@@ -426,6 +500,7 @@ cudaError_t launch_coarse(const ivfadc_index* h, const void* dQ, int64_t nq, int
                           void* d_dc, cudaStream_t s, int* launches) {
     if (nq <= 0) return cudaSuccess;
     if (launches) *launches += 1;
+    h->last_redo_nq = 0;
     if (h->cfg.dtype == IVFADC_F32 && h->d_centroids_t && h->cfg.dim <= PMAXD && (h->cfg.dim & 3) == 0 &&
         !(h->cfg.flags & IVFADC_FLAG_COARSE_SCALAR)) {
         // queries per CTA: the block count that fills the resident-CTA slots of the SMs most evenly
@@ -454,7 +529,9 @@ cudaError_t launch_coarse(const ivfadc_index* h, const void* dQ, int64_t nq, int
             ctc::smem_layout(D / 8).total <= (size_t)(227 * 1024)) {
             // redo flags [nq] | candidate counts [nq] | candidate rows [nq][CAP]
             const size_t off_cnt = ((size_t)nq + 255) / 256 * 256, off_cand = off_cnt + (size_t)nq * 4;
-            cudaError_t e = h->ws_coarse_redo.reserve(off_cand + (size_t)nq * ctc::CAP * 4);
+            const size_t off_list = off_cand + (size_t)nq * ctc::CAP * 4;   // flagged queries, compacted | their number
+            const size_t off_done = off_list + (size_t)nq * 4 + 16, off_scr = off_done + ctc::RS_MAXQ * 4;
+            cudaError_t e = h->ws_coarse_redo.reserve(off_scr + (size_t)ctc::RS_MAXQ * h->kc_pad256 * 4);
             if (e != cudaSuccess) return e;
             ctc::Args ca;
             ca.Q = Q; ca.C = static_cast<const float*>(h->d_centroids);
@@ -463,6 +540,9 @@ cudaError_t launch_coarse(const ivfadc_index* h, const void* dQ, int64_t nq, int
             ca.cells_out = d_cells; ca.dc_out = dc; ca.redo = h->ws_coarse_redo.as<uint8_t>(); ca.err = h->d_err;
             ca.cnt_out = reinterpret_cast<int32_t*>(ca.redo + off_cnt);
             ca.cand_out = reinterpret_cast<int32_t*>(ca.redo + off_cand);
+            ca.redo_list = reinterpret_cast<int32_t*>(ca.redo + off_list);
+            ca.redo_count = reinterpret_cast<int*>(ca.redo + off_list + (size_t)nq * 4);
+            ca.redo_done = reinterpret_cast<unsigned*>(ca.redo + off_done);
             ca.force_redo = (h->cfg.flags & IVFADC_FLAG_TEST_COARSE_REDO) ? 1 : 0;
             const unsigned grid = (unsigned)((nq + ctc::MQ - 1) / ctc::MQ);
             const size_t smem = ctc::smem_layout(D / 8).total;
@@ -478,7 +558,14 @@ cudaError_t launch_coarse(const ivfadc_index* h, const void* dQ, int64_t nq, int
             ctc::coarse3_rerank_kernel<<<std::min(rr_need, rr_slots), ctc::RR_WARPS * 32, rsmem, s>>>(ca);
             if ((e = cudaGetLastError()) != cudaSuccess) return e;
             if (launches) *launches += 2;
-            return launch_coarse2_r<1>(h, best, Q, Ct, nq, h->cfg.kc, h->kc_pad, D, w, d_cells, dc, s, ca.redo);
+            h->last_redo_nq = nq;
+            // flagged queries: the first RS_MAXQ in parallel over the centroids, any further ones in 16-query blocks
+            coarse_redo_small_kernel<<<dim3((unsigned)(h->kc_pad256 / 256), ctc::RS_MAXQ), 256, 0, s>>>(
+                Q, ca.C, h->cfg.kc, h->kc_pad256, D, w, d_cells, dc, ca.redo_list, ca.redo_count,
+                reinterpret_cast<float*>(ca.redo + off_scr), ca.redo_done);
+            if ((e = cudaGetLastError()) != cudaSuccess) return e;
+            if (launches) *launches += 1;
+            return launch_coarse2_r<1>(h, 4, Q, Ct, nq, h->cfg.kc, h->kc_pad, D, w, d_cells, dc, s, ca.redo_list, ca.redo_count);
         }
         if (w <= 32) return launch_coarse2_r<1>(h, best, Q, Ct, nq, h->cfg.kc, h->kc_pad, D, w, d_cells, dc, s);
         if (w <= 64) return launch_coarse2_r<2>(h, best, Q, Ct, nq, h->cfg.kc, h->kc_pad, D, w, d_cells, dc, s);

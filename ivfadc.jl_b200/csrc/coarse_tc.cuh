@@ -42,6 +42,7 @@ constexpr int ABLK = 4096;              // A block: 128 rows x 8 k (tf32 words),
 constexpr int BBLK = 8192;              // B block: 256 rows x 8 k
 constexpr int NSLOT = 8;                // B ring depth (k-steps in flight)
 constexpr int CAP = 64;                 // candidate slots per query
+constexpr int RS_MAXQ = 32;             // flagged queries served by the wide redo kernel (one block per 256 centroids)
 constexpr int GRP = 8;                  // columns per group of the bound in the first GRP_FINE_TILES tiles (16 afterwards)
 constexpr int GRP_FINE_TILES = 2;
 constexpr int CSTR = MQ + 1;            // slot stride (words) of the candidate arrays: conflict-free by row and by slot
@@ -162,6 +163,9 @@ struct Args {
     int32_t* cand_out;     // [nq][CAP] cells that survive the pruning
     int32_t* cnt_out;      // [nq] their number, -1 = overflow
     int* err;
+    int32_t* redo_list;    // [nq] flagged queries, compacted (filled by the re-rank kernel)
+    int* redo_count;       // their number (zeroed by coarse3_kernel)
+    unsigned* redo_done;   // [RS_MAXQ] block counters of coarse_redo_small_kernel (zeroed by coarse3_kernel)
     int force_redo;        // test switch: flag every query
 };
 
@@ -209,6 +213,8 @@ __global__ void __launch_bounds__(THREADS, 1) coarse3_kernel(const Args a) {
     const int KS = a.ksteps;
     const int KB = KS + 1;  // k-steps per tile: the dims, then the squared norms (ones block x split norms)
     bool dead = false;
+    if (blockIdx.x == 0 && tid == 0) *a.redo_count = 0;  // the re-rank kernel (next in the stream) appends the flagged queries
+    if (blockIdx.x == 0 && tid < RS_MAXQ) a.redo_done[tid] = 0u;
 #ifdef C3_STAMP
     long long stamps[40];
     int nst = 0;
@@ -481,7 +487,10 @@ __global__ void __launch_bounds__(RR_WARPS * 32) coarse3_rerank_kernel(const Arg
         total_n = __ldg(a.cnt_out + q + qstep);
     }
     if (total < w) {  // overflow (-1); fewer than w cannot happen (the candidates contain the top w), never return garbage
-        if (lane == 0) a.redo[q] = 1;
+        if (lane == 0) {
+            a.redo[q] = 1;
+            a.redo_list[atomicAdd(a.redo_count, 1)] = (int32_t)q;
+        }
         continue;
     }
     if (lane == 0) a.redo[q] = 0;

@@ -8,6 +8,8 @@
 #include <unordered_map>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "ivfadc.h"
 
 namespace ivf {
@@ -158,11 +160,22 @@ struct ivfadc_index {
     bool stats_timing = true;
     ivfadc_stats stats{};
     std::string err;
+    mutable int64_t last_redo_nq = 0;  // coarse.cu: queries of the last tensor-core coarse step (redo flags in ws_coarse_redo)
     void* extra = nullptr;      // api.cu: event ring, scanned-vector counter
     void* shard_ctx = nullptr;  // shard.cu: NCCL communicator, gathered buffers, CUDA graphs
 };
 
 namespace ivf {
+
+// NVTX range around a C-ABI call (header-only NVTX 3: a no-op unless a profiler injects itself), so that an
+// nsys / ncu timeline of a Julia or Python host shows which call owns which kernels.
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+    NvtxRange(const NvtxRange&) = delete;
+    NvtxRange& operator=(const NvtxRange&) = delete;
+};
+#define IVF_NVTX() ::ivf::NvtxRange nvtx_range_(__func__)
 
 constexpr size_t kSmemMax = 227 * 1024;   // dynamic shared memory a CTA can opt in to on sm_100a
 

@@ -348,6 +348,7 @@ int ivfadc_nccl_unique_id(void* id_out) {
 }
 
 int ivfadc_comm_init_rank(ivfadc_index* h, const void* id, int32_t world, int32_t rank) {
+    IVF_NVTX();
     if (!h || !id) return IVFADC_ERR_BAD_ARG;
     if (world != h->cfg.shard_world || rank != h->cfg.shard_rank)
         return api_fail(h, IVFADC_ERR_BAD_ARG, "communicator shape differs from the handle's shard_rank / shard_world");
@@ -378,6 +379,7 @@ int ivfadc_set_graph_replay(ivfadc_index* h, int32_t enable) {
 
 int ivfadc_search_sharded_device(ivfadc_index* h, const void* dQ, int64_t nq, int32_t k, int32_t w, uint64_t* d_ids,
                                  void* d_dists, int32_t* d_counts, void* stream) {
+    IVF_NVTX();
     if (!h) return IVFADC_ERR_BAD_ARG;
     ShardCtx* c = ctx(h);
     if (!c) return api_fail(h, IVFADC_ERR_BAD_ARG, "no communicator: call ivfadc_comm_init_rank first");
@@ -391,6 +393,7 @@ int ivfadc_search_sharded_device(ivfadc_index* h, const void* dQ, int64_t nq, in
 
 int ivfadc_search_sharded(ivfadc_index* h, const void* Q, int64_t nq, int32_t k, int32_t w, uint64_t* ids_out,
                           void* dists_out, int32_t* counts_out) {
+    IVF_NVTX();
     if (!h) return IVFADC_ERR_BAD_ARG;
     ShardCtx* c = ctx(h);
     if (!c) return api_fail(h, IVFADC_ERR_BAD_ARG, "no communicator: call ivfadc_comm_init_rank first");
@@ -436,6 +439,7 @@ int ivfadc_sharded_step_bytes(ivfadc_index* h, int64_t nq, int32_t k, int32_t w,
 // ---- single process, several GPUs ------------------------------------------------------------------------
 int ivfadc_group_create(ivfadc_group** out, const ivfadc_config* cfg, int32_t n_devices, const int32_t* device_ids,
                         const void* centroids, const void* codebook_vectors, const uint8_t* codebook_codes) {
+    IVF_NVTX();
     if (!out || !cfg || n_devices < 1 || n_devices > 64) return IVFADC_ERR_BAD_ARG;
     *out = nullptr;
     ivfadc_group* g = new (std::nothrow) ivfadc_group();
@@ -504,6 +508,7 @@ int ivfadc_group_set_cell_owners(ivfadc_group* g, const int32_t* owners) {
 
 int ivfadc_group_add(ivfadc_group* g, const void* X, int64_t n, int32_t position, const int64_t* assign,
                      int32_t assign_base, int32_t* cells_out) {
+    IVF_NVTX();
     if (!g) return IVFADC_ERR_BAD_ARG;
     // every shard sees the whole batch and keeps the cells it owns (ids stay global); a rejected batch
     // (capacity) is rejected by the first shard before any shard has changed
@@ -515,6 +520,7 @@ int ivfadc_group_add(ivfadc_group* g, const void* X, int64_t n, int32_t position
 }
 
 int ivfadc_group_delete(ivfadc_group* g, const uint64_t* ids, int64_t n) {
+    IVF_NVTX();
     if (!g) return IVFADC_ERR_BAD_ARG;
     for (ivfadc_index* h : g->hs) {
         int rc = ivfadc_delete(h, ids, n);
@@ -524,6 +530,7 @@ int ivfadc_group_delete(ivfadc_group* g, const uint64_t* ids, int64_t n) {
 }
 
 int ivfadc_group_pop(ivfadc_group* g, int32_t position, void* vec_out) {
+    IVF_NVTX();
     if (!g || !vec_out) return IVFADC_ERR_BAD_ARG;
     // every shard renumbers; the one that owned the vector returns it
     std::vector<char> tmp(g->hs[0]->cfg.dim * g->hs[0]->tsize);
@@ -547,6 +554,7 @@ int ivfadc_group_length(const ivfadc_group* g, int64_t* n_out) {
 
 int ivfadc_group_search(ivfadc_group* g, const void* Q, int64_t nq, int32_t k, int32_t w, uint64_t* ids_out,
                         void* dists_out, int32_t* counts_out) {
+    IVF_NVTX();
     if (!g) return IVFADC_ERR_BAD_ARG;
     ivfadc_index* h0 = g->hs[0];
     if (nq > 0 && (!Q || !ids_out || !dists_out || !counts_out)) return api_fail(h0, IVFADC_ERR_BAD_ARG, "null pointer");
