@@ -271,6 +271,7 @@ def build_index(cx, wl, flags):
         engine.check_async(stream.cuda_stream)
         owners = sharded.balanced_owners(counts.cpu().numpy(), cx.world)
         engine.set_cell_owners(owners)
+        engine.reserve(N, np.where(owners == cx.rank, counts.cpu().numpy(), 0))   # exact list lengths: one allocation
         assign_s = time.perf_counter() - t0
         for s in range(0, N, CHUNK):
             n = min(CHUNK, N - s)
@@ -281,6 +282,7 @@ def build_index(cx, wl, flags):
         del cells_all
         sharded.init_comm(engine)
     else:
+        engine.reserve(N)
         for s in range(0, N, CHUNK):
             n = min(CHUNK, N - s)
             x = synth.blobs_device(s, n, centres, SEED_DATA, SIGMA, out=buf)
@@ -565,6 +567,7 @@ def run_build_extra(cx, args):
     stream.synchronize()
     e.add_device(x.data_ptr(), 4096)                      # warm-up: kernels loaded, workspaces sized
     iv.delete_from_index(e, np.arange(1, 4097))
+    e.reserve(N)                                          # sizehint!: one arena allocation for the bulk build
     dev_s = 0.0
     for s0 in range(0, N, CHUNK):
         n = min(CHUNK, N - s0)
@@ -586,6 +589,7 @@ def run_build_extra(cx, args):
     pinned = [synth.blobs_device(i * CHUNK, CHUNK, centres, SEED_DATA, SIGMA).cpu().pin_memory() for i in range(2)]
     iv.push_batch(e, pinned[0].numpy()[:4096])
     iv.delete_from_index(e, np.arange(1, 4097))
+    e.reserve(N)
     host_s, nhost = 0.0, 0
     for i in range(max(1, N // CHUNK)):
         xh = pinned[i & 1].numpy()

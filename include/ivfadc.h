@@ -186,6 +186,14 @@ int ivfadc_add_device(ivfadc_index* h, const void* dX, int64_t n, int32_t positi
                       const int64_t* d_assign, int32_t assign_base, int32_t* d_cells_out);
 
 /*
+ * Capacity hint before a bulk build (Julia's sizehint!; the reference grows its lists by push!, src/utils.jl:142-143):
+ * room for n_total vectors over all shards -- an even share per list plus 12% -- or, with sizes != NULL (int64[kc],
+ * e.g. the k-means cluster counts), exactly sizes[c] entries in list c.  One arena allocation instead of geometric
+ * regrowth (each regrowth is a device allocation + a copy of everything stored so far).  Never shrinks.
+ */
+int ivfadc_reserve(ivfadc_index* h, int64_t n_total, const int64_t* sizes);
+
+/*
  * Encode without mutating: cells int32[n] (0-based), codes uint8[n][m].  If assign != NULL
  * the cells are taken from it as in ivfadc_add.  Parity hook for _encode_point
  * (src/utils.jl:148-161) and QuantizedArrays.quantize_data (src/index.jl:187).

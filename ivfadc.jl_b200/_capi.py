@@ -36,7 +36,7 @@ SYMBOLS = [
     "ivfadc_group_last_error", "ivfadc_group_set_cell_owners", "ivfadc_group_add", "ivfadc_group_search",
     "ivfadc_group_delete", "ivfadc_group_pop", "ivfadc_group_length",
     "ivfadc_add_device", "ivfadc_export_all", "ivfadc_import_all", "ivfadc_synth_uniform_device",
-    "ivfadc_synth_blobs_device",
+    "ivfadc_synth_blobs_device", "ivfadc_reserve",
 ]
 NCCL_ID_BYTES = 128
 
@@ -107,6 +107,7 @@ def load(build_if_missing: bool = True):
     lib.ivfadc_export_list.argtypes = [H, c_int32, c_void_p, c_void_p]
     lib.ivfadc_import_list.argtypes = [H, c_int32, c_void_p, c_void_p, c_int64]
     lib.ivfadc_add_device.argtypes = [H, c_void_p, c_int64, c_int32, c_void_p, c_int32, c_void_p]
+    lib.ivfadc_reserve.argtypes = [H, c_int64, c_void_p]
     lib.ivfadc_export_all.argtypes = [H, c_void_p, c_void_p]
     lib.ivfadc_import_all.argtypes = [H, c_void_p, c_void_p, c_void_p]
     lib.ivfadc_synth_uniform_device.argtypes = [c_void_p, c_int64, c_int64, c_int32, c_uint64, c_void_p]

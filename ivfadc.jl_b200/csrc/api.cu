@@ -722,6 +722,25 @@ int ivfadc_import_list(ivfadc_index* h, int32_t cell, const uint64_t* ids, const
     return IVFADC_OK;
 }
 
+int ivfadc_reserve(ivfadc_index* h, int64_t n_total, const int64_t* sizes) {
+    IVF_NVTX();
+    if (check_handle(h)) return IVFADC_ERR_BAD_ARG;
+    if (n_total < 0) return fail(h, IVFADC_ERR_BAD_ARG, "negative size");
+    cudaSetDevice(h->cfg.device);
+    const int kc = h->cfg.kc;
+    std::vector<int64_t> need(h->h_len);
+    // without per-list sizes: an even share of this shard's part of n_total plus 12% (k-means cells are not balanced)
+    const int64_t even = (n_total / std::max(1, h->cfg.shard_world) / kc) * 9 / 8 + 1;
+    for (int c = 0; c < kc; ++c) {
+        if (sizes && sizes[c] < 0) return fail(h, IVFADC_ERR_BAD_ARG, "negative list length");
+        need[c] = std::max(need[c], sizes ? sizes[c] : even);
+    }
+    int launches = 0;
+    CUDA_OR_FAIL(h, lists_reserve(h, need, &launches), "reserve");
+    h->stats.gpu_launches += launches;
+    return IVFADC_OK;
+}
+
 int ivfadc_export_all(ivfadc_index* h, uint64_t* ids_out, uint8_t* codes_out) {
     IVF_NVTX();
     if (check_handle(h)) return IVFADC_ERR_BAD_ARG;

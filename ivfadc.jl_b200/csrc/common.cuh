@@ -256,6 +256,7 @@ cudaError_t lists_delete(ivfadc_index* h, const uint64_t* d_sorted_ids, int64_t 
 cudaError_t lists_find(ivfadc_index* h, uint64_t id, int32_t* cell, int64_t* pos, int* launches);
 cudaError_t lists_decode(ivfadc_index* h, int32_t cell, int64_t pos, void* d_vec_out, int* launches);
 cudaError_t lists_export(ivfadc_index* h, int32_t cell, uint64_t* ids_out, uint8_t* codes_out);
+cudaError_t lists_reserve(ivfadc_index* h, const std::vector<int64_t>& need, int* launches);
 cudaError_t lists_export_all(ivfadc_index* h, uint64_t* ids_out, uint8_t* codes_out, int* launches);
 cudaError_t lists_import_all(ivfadc_index* h, const int64_t* sizes, const uint64_t* ids, const uint8_t* codes,
                              int* launches);

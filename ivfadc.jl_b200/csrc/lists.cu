@@ -534,6 +534,11 @@ cudaError_t pack_all(ivfadc_index* h, uint64_t* ids, uint8_t* codes, int* launch
 }
 }  // namespace
 
+// capacity for need[c] entries in every list (sizehint!): one arena allocation instead of geometric regrowth
+cudaError_t lists_reserve(ivfadc_index* h, const std::vector<int64_t>& need, int* launches) {
+    return reserve_lists(h, need, launches);
+}
+
 // every list, cell-ascending, packed: ids uint64[sum len], codes uint8[sum len][m] (src/persistency.jl:68-78)
 cudaError_t lists_export_all(ivfadc_index* h, uint64_t* ids_out, uint8_t* codes_out, int* launches) {
     return pack_all<true>(h, ids_out, codes_out, launches);

@@ -547,17 +547,25 @@ bool use_scanq(const ivfadc_index* h, int64_t npairs, int k) {
     if (!scanq_shape_ok(h, k)) return false;
     if (h->cfg.flags & IVFADC_FLAG_SCAN_QLANE) return true;
     if (npairs < (int64_t)8 * h->cfg.kc) return false;
-    // Cost model from the measured runs ("which scan kernel"): a query-per-lane work item costs the
-    // same whether 5 or 32 queries share it -- kc (n/32 + 1/2) items of ceil(L / 1024) passes of `tables` table
-    // builds + scans at ~0.0099 us of GPU time each -- while the vector-per-lane kernel streams the pairs' code
-    // bytes at ~1.3 TB/s.  Few queries per (long) list, as in config D (10 per list of 6100), favour the latter.
+    // Cost model fitted to the round-2 runs ("which scan kernel"; microseconds of GPU time):
+    //  * query per lane: kc (n/32 + 1/2) work items, the same cost whether 5 or 32 queries share one.  A pass of
+    //    `tables` table rounds costs tables x (0.0022 + 0.0040 fill) + 0.016 (fill = vectors of the pass / 1152: the
+    //    lookups are bound by the tensor-memory pipe, the rest is the fixed cost of a round and of the selection);
+    //    an item never takes less than the loaders need to stage it (~0.085);
+    //  * vector per lane: 0.0081 per pair for its exact lookup tables (twice that at dsub = 16) + the pairs' code
+    //    bytes at ~3.2 TB/s.  Few queries per (long) list, as in config D (10 per list of 6100), favour it; short
+    //    lists with many queries (64 vectors, 150 queries) do not: 1.35 ms against ~0.5 ms on the 1 M / 1024 shape.
     // (a shard owns every world-th cell: its share of the cells and of the pairs, its own vectors)
     const int world = std::max(1, h->cfg.shard_world);
     const double kc = std::max(1.0, (double)h->cfg.kc / world), np_loc = (double)npairs / world, nbar = np_loc / kc;
     const double lbar = std::max(1.0, (double)h->n_local / kc);
     const int tables = h->cfg.m * ((h->dsub <= 8 || h->dsub == 16) ? scanu_dup(h) : 1);
-    const double est_q = kc * (nbar / 32.0 + 0.5) * std::ceil(lbar / 1024.0) * tables * 0.0099;
-    const double est_v = np_loc * lbar * h->cfg.m / 1.3e6;
+    const double vp = (double)W_VP, nfull = std::floor(lbar / vp), frem = (lbar - nfull * vp) / vp;
+    double item = nfull * (tables * 0.0062 + 0.016);
+    if (frem > 0.0) item += tables * (0.0022 + 0.0040 * frem) + 0.016;
+    item = std::max(item, 0.085);
+    const double est_q = kc * (nbar / 32.0 + 0.5) * item;
+    const double est_v = np_loc * 0.0081 * std::max(1.0, h->dsub / 8.0) + np_loc * lbar * h->cfg.m / 3.2e6;
     return est_q < est_v;
 }
 

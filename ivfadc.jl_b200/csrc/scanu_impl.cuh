@@ -149,6 +149,11 @@ __device__ __forceinline__ float f_unflip(uint32_t u) {
 // the 16 code bytes of the chunk.  Everything here is warp-uniform except acc / base.
 // acc[0..1] += t[0..1] as ONE packed add (add.rn.f32x2: each half is an ordinary IEEE fp32 add of its own chain)
 __device__ __forceinline__ void add_pair(float& a0, float& a1, float t0, float t1) {
+#if defined(IVF_X_SCALAR_ADD) && IVF_X_SCALAR_ADD
+    a0 = __fadd_rn(a0, t0);
+    a1 = __fadd_rn(a1, t1);
+    return;
+#endif
     unsigned long long a, t;
     asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "f"(a0), "f"(a1));
     asm("mov.b64 %0, {%1, %2};" : "=l"(t) : "f"(t0), "f"(t1));

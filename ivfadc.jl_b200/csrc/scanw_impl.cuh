@@ -37,11 +37,41 @@
 
 namespace ivf {
 
-constexpr int W_SCAN = 12;                   // scanning warps
-constexpr int W_THREADS = 512;               // + producer, two loaders, finalizer
-constexpr int W_ISSUE = 12, W_LOAD = 13, W_OPER = 15;
+// Two shapes of the CTA (-DIVF_W16=1 selects the second one; A/B runs through IVFADC_NVCC_EXTRA):
+//   12 scanners x 96 partial distances (152 registers), 1152 vectors per pass, 512 threads
+//   16 scanners x 64 partial distances (112 registers), 1024 vectors per pass, 640 threads -- four scanning warps
+//      per scheduler instead of three: a warp's table round is a chain of lookup batches (32 in flight, then
+//      tcgen05.wait::ld), so the issue slots fill with the number of warps that interleave their round trips.
+//      Register budget: setmaxnreg.inc is served from what the CTA's own warps released with setmaxnreg.dec (not
+//      from unallocated registers of the SM): 640 threads launch with 96; the four service warps drop to 32 and
+//      free 4 x 32 x 64 = 8192 = 16 x 32 x (112 - 96).  (120 / 32 and 112 / 56 wait forever in setmaxnreg.inc.)
+#ifndef IVF_W16
+#define IVF_W16 0
+#endif
+// bring-up timing experiments (wrong results): IVF_X_NOLOOKUP skips the lookups, IVF_X_NOEXTRACT the end-of-pass selection
+#ifndef IVF_X_NOLOOKUP
+#define IVF_X_NOLOOKUP 0
+#endif
+#ifndef IVF_X_NOEXTRACT
+#define IVF_X_NOEXTRACT 0
+#endif
+#ifndef IVF_W_PIPE
+#define IVF_W_PIPE 1   // table switch inside a lookup batch (full warps); -DIVF_W_PIPE=0 keeps one drain per table
+#endif
+#if IVF_W16
+constexpr int W_SCAN = 16;                   // scanning warps
+constexpr int W_NV = 64;                     // partial distances per lane
+#define IVF_W_SCAN_REGS "112"
+#define IVF_W_SERVICE_REGS "32"
+#else
+constexpr int W_SCAN = 12;
+constexpr int W_NV = 96;
+#define IVF_W_SCAN_REGS "152"
+#define IVF_W_SERVICE_REGS "40"
+#endif
+constexpr int W_THREADS = (W_SCAN + 4) * 32; // + issuer, two loaders, operand writer
+constexpr int W_ISSUE = W_SCAN, W_LOAD = W_SCAN + 1, W_OPER = W_SCAN + 3;
 constexpr int W_NLOAD = 64;                  // loader threads
-constexpr int W_NV = 96;                     // partial distances per lane
 constexpr int W_NCH = W_NV / 16;             // chunks of 16 vectors per scanner and pass
 constexpr int W_VP = W_SCAN * W_NV;          // 1152 vectors per pass
 constexpr int W_CSTEP = 16 * W_SCAN;         // byte distance of a scanner's consecutive chunks in a plane
@@ -273,7 +303,8 @@ scanw_kernel(const ScanUArgs ua) {
     // DBG: clocks of a window of four consecutive table builds in the middle of the launch (CTA 0), 8 events per warp
     // and table, as 32-bit words behind the 128 profile counters
     constexpr uint32_t W_TR0 = 20 * m + 6;
-    uint32_t* const trace = stamps ? reinterpret_cast<uint32_t*>(stamps + 128) + wid * 32 : nullptr;
+    const int drow = wid < 12 ? wid : wid >= W_SCAN ? wid - W_SCAN + 12 : -1;  // 12 scanners + the 4 service warps
+    uint32_t* const trace = (stamps && drow >= 0) ? reinterpret_cast<uint32_t*>(stamps + 128) + drow * 32 : nullptr;
     auto tr = [&](uint32_t t, int ev) {
         if constexpr (DBG) {
             if (trace && lane == 0 && t - W_TR0 < 4u) trace[(t - W_TR0) * 8 + ev] = (uint32_t)clock();
@@ -282,7 +313,7 @@ scanw_kernel(const ScanUArgs ua) {
 
     if (wid < W_SCAN) {
         // =========================================== SCANNERS ===========================================
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 152;");
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 " IVF_W_SCAN_REGS ";");
         const uint32_t tq = tmem_base + ((uint32_t)((wid & 3) * 32) << 16);
         const uint32_t plane_w0 = planes_u + 16 * wid;
         WProf<DBG> pf;  // 0 wait staged, 1 wait table, 2 lookups, 3 release, 4 minima + barrier, 5 rank + barrier, 6 candidates
@@ -309,6 +340,83 @@ scanw_kernel(const ScanUArgs ua) {
             // tg is a multiple of m (even), so table t = tg + s lives in buffer s & 1 and its phase flips every two tables.
             const uint32_t plane_seg = plane_w0 + spar * PLANES_BYTES;
             uint32_t par = (tg >> 1) & 1;
+#if IVF_W_PIPE
+            if (nch == W_NCH) {
+                // Full warp (all its chunks inside the list): the table switch happens INSIDE a lookup batch.  The
+                // last chunk of table s stays in flight while the warp releases nothing yet, acquires table s + 1
+                // and issues its first chunk; one tcgen05.wait::ld covers both, then table s is released.  The
+                // fixed cost of a switch (arrive, mbarrier wait, fences, address shuffles, code-byte loads) runs
+                // under 16 lookups per warp instead of an idle tensor-memory pipe.
+                float tp[16];
+#pragma unroll 1
+                for (int s = 0; s < m; ++s) {
+                    const uint32_t b = (uint32_t)s & 1u;
+                    pf.tick(3);
+                    tr(tg + s, 0);
+                    if (!mbar_try_wait_hint(bar_mma + 8 * b, par, 100000u)) warp_wait(bar_mma + 8 * b, par, 2);
+                    tc_fence_after();
+                    pf.tick(1);
+                    tr(tg + s, 1);
+                    const uint32_t tb = __shfl_sync(0xffffffffu, tq + b * 256, 0);
+                    const uint32_t plane_w = __shfl_sync(0xffffffffu, plane_seg + (uint32_t)(s / DUP) * W_VP, 0);
+                    if (DBG && g == 0 && blockIdx.x == 0 && ua.dbg != nullptr) {  // bring-up: dump the tables of the first segment
+                        if (wid < 4) {
+                            for (int c = wid; c < 256; c += 4) {
+                                const float v = tc_ld1(tb + c);
+                                tc_wait_ld();
+                                ua.dbg[((size_t)s * 256 + c) * 32 + lane] = v * lds_f(stt + 7 * QG * 4 + lane * 4);
+                            }
+                        }
+                        if (s == 0 && wid == 0) {
+                            reinterpret_cast<int*>(ua.dbg + (size_t)m * 256 * 32)[lane] = (int)lds_u(stt + lane * 4);
+                            if (lane == 0) reinterpret_cast<int*>(ua.dbg + (size_t)m * 256 * 32)[QG] = (int)lds_u(sg + 24);
+                        }
+                    }
+                    {
+                        float t0[16];
+                        const uint4 x0 = lds_v4(plane_w);
+                        scanu_issue<0>(tb, x0, t0);
+                        tc_wait_ld();
+                        if (s > 0) {  // the last chunk of table s - 1 (other buffer) has landed with it
+#pragma unroll
+                            for (int i = 0; i < 16; i += 2)
+                                add_pair(acc[16 * (W_NCH - 1) + i], acc[16 * (W_NCH - 1) + i + 1], tp[i], tp[i + 1]);
+                            tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(bar_free + 8 * (b ^ 1u));
+                            tr(tg + s - 1, 3);
+                        }
+#pragma unroll
+                        for (int i = 0; i < 16; i += 2) add_pair(acc[i], acc[i + 1], t0[i], t0[i + 1]);
+                    }
+#pragma unroll
+                    for (int jp = 0; jp < (W_NCH - 2) / 2; ++jp) {
+                        const int j0 = 1 + 2 * jp, j1 = 2 + 2 * jp;
+                        const uint4 xa = lds_v4(plane_w + j0 * W_CSTEP), xb = lds_v4(plane_w + j1 * W_CSTEP);
+                        float t[32];
+                        scanu_issue<0>(tb, xa, t);
+                        scanu_issue<0>(tb, xb, t + 16);
+                        tc_wait_ld();
+#pragma unroll
+                        for (int i = 0; i < 32; i += 2) add_pair(acc[16 * j0 + i], acc[16 * j0 + i + 1], t[i], t[i + 1]);
+                    }
+                    {
+                        const uint4 xl = lds_v4(plane_w + (W_NCH - 1) * W_CSTEP);
+                        scanu_issue<0>(tb, xl, tp);  // stays in flight across the switch
+                    }
+                    pf.tick(2);
+                    tr(tg + s, 2);
+                    par ^= b;
+                }
+                tc_wait_ld();
+#pragma unroll
+                for (int i = 0; i < 16; i += 2)
+                    add_pair(acc[16 * (W_NCH - 1) + i], acc[16 * (W_NCH - 1) + i + 1], tp[i], tp[i + 1]);
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_free + 8 * ((uint32_t)(m - 1) & 1u));
+            } else
+#endif
 #pragma unroll 1
             for (int s = 0; s < m; ++s) {
                 const uint32_t b = (uint32_t)s & 1u;
@@ -321,8 +429,12 @@ scanw_kernel(const ScanUArgs ua) {
                 tr(tg + s, 1);
                 const uint32_t tb = __shfl_sync(0xffffffffu, tq + b * 256, 0);
                 const uint32_t plane_w = __shfl_sync(0xffffffffu, plane_seg + (uint32_t)(s / DUP) * W_VP, 0);
+#if IVF_X_NOLOOKUP
+                acc[s & 15] += 1.0f + (float)wid;
+#else
                 if (nch == W_NCH) scanw_sub<true>(tb, plane_w, nch, acc);
                 else scanw_sub<false>(tb, plane_w, nch, acc);
+#endif
                 pf.tick(2);
                 tr(tg + s, 2);
                 if (DBG && g == 0 && blockIdx.x == 0 && ua.dbg != nullptr) {  // bring-up: dump the tables of the first segment
@@ -359,9 +471,13 @@ scanw_kernel(const ScanUArgs ua) {
                     }
                 }
             }
+#if IVF_X_NOEXTRACT == 5
+#pragma unroll
+            for (int j = 0; j < W_NV; ++j) asm volatile("" ::"f"(acc[j]));   // keep the partial distances alive, nothing else
+#endif
             float mn0 = Limits<float>::inf(), mn1 = Limits<float>::inf();
 #pragma unroll
-            for (int j = 0; j < W_NV / 2; ++j) {
+            for (int j = 0; j < ((IVF_X_NOEXTRACT == 1 || IVF_X_NOEXTRACT == 5) ? 2 : W_NV / 2); ++j) {
                 mn0 = fminf(mn0, acc[j]);
                 mn1 = fminf(mn1, acc[W_NV / 2 + j]);
             }
@@ -396,13 +512,14 @@ scanw_kernel(const ScanUArgs ua) {
                 const float unscale = lds_f(stt + 7 * QG * 4 + lane * 4);   // 2^-(ew + sr): exact
                 int c = 0;
 #pragma unroll
-                for (int j = 0; j < W_NV; ++j) c += acc[j] <= cut ? 1 : 0;
+                for (int j = 0; j < ((IVF_X_NOEXTRACT == 1 || IVF_X_NOEXTRACT == 2 || IVF_X_NOEXTRACT == 5) ? 1 : W_NV); ++j) c += acc[j] <= cut ? 1 : 0;
+                if (IVF_X_NOEXTRACT == 1 || IVF_X_NOEXTRACT == 2 || IVF_X_NOEXTRACT == 5) c = 0;
                 if (pair < 0 || lds_u(stt + 4 * QG * 4 + lane * 4) != 0u) c = 0;
                 // the staging area is single-buffered: the loaders have copied out the previous segment long ago
                 if (g > 0) warp_wait(bar_candfree, (g - 1) & 1, 27);
                 int old = 0;
                 if (c > 0) old = atoms_add(segcnt_u + spar * (QG * 4) + lane * 4, c);
-                const bool ok = c > 0 && old + c <= U_CAP;
+                const bool ok = c > 0 && old + c <= U_CAP && IVF_X_NOEXTRACT != 3;
                 // more than a row can hold (the counter keeps the total): the loaders queue the pair for the redo kernel
                 if (ok) {
                     uint32_t pd = cand_u + (uint32_t)(lane * U_CAP + old) * 4;
@@ -421,9 +538,9 @@ scanw_kernel(const ScanUArgs ua) {
             if (lane == 0) mbar_arrive(bar_extract + 8 * spar);
             pf.tick(6);
         }
-        pf.store(stamps && lane == 0 ? stamps + 8 * wid : nullptr);
+        pf.store(stamps && lane == 0 && drow >= 0 ? stamps + 8 * drow : nullptr);
     } else {
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 " IVF_W_SERVICE_REGS ";");
         if (wid == W_ISSUE) {
             // =========================================== ISSUER ===========================================
             const uint64_t descA0 = tc_smem_desc(aring_u), descB0 = tc_smem_desc(bring_u);
@@ -477,7 +594,7 @@ scanw_kernel(const ScanUArgs ua) {
                     pf.tick(4);
                 }
             }
-            pf.store(stamps && lane == 0 ? stamps + 8 * wid : nullptr);
+            pf.store(stamps && lane == 0 && drow >= 0 ? stamps + 8 * drow : nullptr);
             // drain: codebook operands fetched for builds that never ran
             if (lane == 0) {
                 for (uint32_t f = t; f < nfill; ++f) mbar_wait_w(bar_full + 8 * (f % W_NB), (f / W_NB) & 1, dead_u, ua.err, 5);
@@ -535,7 +652,7 @@ scanw_kernel(const ScanUArgs ua) {
                     tr(t, 3);
                 }
             }
-            pf.store(stamps && lane == 0 ? stamps + 8 * wid : nullptr);
+            pf.store(stamps && lane == 0 && drow >= 0 ? stamps + 8 * drow : nullptr);
         } else {
             // =========================================== LOADERS ===========================================
             const int lt = tid - W_LOAD * 32;  // 0..63
@@ -569,7 +686,7 @@ scanw_kernel(const ScanUArgs ua) {
                 if (pair >= 0 && !bad) {
                     uint32_t* row = reinterpret_cast<uint32_t*>(a.pair_d) + (size_t)pair * (2 * U_CAP) + base;
                     const uint32_t src = cand_u + (uint32_t)(q * U_CAP) * 4;
-                    for (int i = half; i < n; i += 2) {
+                    for (int i = half; i < (IVF_X_NOEXTRACT == 4 ? 0 : n); i += 2) {
                         row[i] = lds_u(src + i * 4);
                         row[U_CAP + i] = lds_u(src + W_CAND + i * 4);
                     }
@@ -785,7 +902,7 @@ scanw_kernel(const ScanUArgs ua) {
                     new_item = true;
                 }
             }
-            pf.store(stamps && lane == 0 ? stamps + 8 * wid : nullptr);
+            pf.store(stamps && lane == 0 && drow >= 0 ? stamps + 8 * drow : nullptr);
         }
     }
 

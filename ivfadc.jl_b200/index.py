@@ -212,6 +212,11 @@ class IVFADCIndex:
         _capi.check(self._h, self._lib.ivfadc_import_list(self._h, cell, _capi.ptr(ids), _capi.ptr(codes),
                                                           len(ids)))
 
+    def reserve(self, n_total, sizes=None):
+        """Capacity hint before a bulk build (sizehint!): n_total vectors, or exact per-list sizes int64 [kc]."""
+        s = None if sizes is None else np.ascontiguousarray(sizes, dtype=np.int64)
+        _capi.check(self._h, self._lib.ivfadc_reserve(self._h, int(n_total), _capi.ptr(s)))
+
     def export_all(self):
         """Every list in one call (bulk persistency): (sizes int64 [kc], idxs [sum] in the index type, codes uint8
         [sum, m]); the entries of the lists follow each other in ascending cell order."""

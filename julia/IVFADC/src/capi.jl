@@ -188,3 +188,7 @@ function capi_group_length(g::Group)
     ccall((:ivfadc_group_length, LIBIVFADC[]), Cint, (Group, Ref{Int64}), g, n)
     Int(n[])
 end
+
+# capacity hint before a bulk build (ivfadc_reserve): exact per-list sizes, e.g. counts(kmeans result)
+capi_reserve(h::Handle, n::Int, sizes::Vector{Int64}) =
+    _check(h, ccall((:ivfadc_reserve, LIBIVFADC[]), Cint, (Handle, Int64, Ptr{Int64}), h, n, sizes))

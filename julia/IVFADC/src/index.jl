@@ -89,6 +89,7 @@ function IVFADCIndex(data::Matrix{T};
         capi_group_set_cell_owners(g, _balanced_owners(counts(cmodel), capi_group_size(g)))
         _gcheck(g, capi_group_add(g, data, IVFADC_LAST, assign=Int64.(cmodel.assignments)))
     else
+        capi_reserve(h, nvectors, Int64.(counts(cmodel)))   # the cluster sizes are known: one allocation
         _check(h, capi_add(h, data, IVFADC_LAST, assign=Int64.(cmodel.assignments)))
     end
     _wrap(cmodel.centers, rq, I, coarse_distance, coarse_quantizer, (h, g))

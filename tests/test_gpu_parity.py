@@ -320,7 +320,7 @@ def test_scan_kernel_choice():
     the tensor-memory query-per-lane kernel (4), few queries per long list (config-D-like) -> vector per lane (1).
     Both answers stay within the tolerance bar of the oracle."""
     from ivfadc_jl_b200 import synth
-    for (D, m, kc, n, nq, w, want) in ((128, 16, 16, 16000, 600, 8, 5), (128, 8, 64, 64000, 100, 8, 1)):
+    for (D, m, kc, n, nq, w, want) in ((128, 16, 16, 16000, 600, 8, 5), (128, 8, 64, 384000, 100, 8, 1)):
         X = synth.blobs(n, D, kc, seed=31)
         cent, cb, codes = synth.random_quantizers(kc, D, m, 256, seed=7, data=X)
         cent = synth.blob_centres(D, kc)   # balanced lists of n / kc vectors
@@ -773,6 +773,8 @@ def test_add_device_equals_add():
     dX = torch.from_numpy(X).cuda()
     dcells = torch.empty(n, dtype=torch.int32, device="cuda")
     torch.cuda.synchronize()
+    b.reserve(n)                                   # capacity hints (sizehint!): even share, then exact list sizes
+    c.reserve(n, np.bincount(cells, minlength=kc))
     b.add_device(dX.data_ptr(), n, 0, 0, 0, dcells.data_ptr())
     np.testing.assert_array_equal(dcells.cpu().numpy(), cells)
     dassign = torch.from_numpy(cells.astype(np.int64) + 1).cuda()
