@@ -346,9 +346,8 @@ coarse_redo_small_kernel(const float* __restrict__ Q, const float* __restrict__ 
     if (slot >= min(*redo_count, ctc::RS_MAXQ)) return;
     const int64_t q = redo_list[slot];
     __shared__ float sq[PMAXD];
-    __shared__ unsigned long long red[8];
     __shared__ int s_last;
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int tid = threadIdx.x;
     for (int d = tid; d < D; d += 256) sq[d] = Q[q * D + d];
     __syncthreads();
     const int c = blockIdx.x * 256 + tid;
@@ -371,32 +370,39 @@ coarse_redo_small_kernel(const float* __restrict__ Q, const float* __restrict__ 
     __syncthreads();
     if (!s_last) return;
     __threadfence();
-    // w rounds of a block-wide minimum of (distance bits, cell) above the previous winner: ascending (distance, cell)
-    unsigned long long prev = 0ull;
-    bool first = true;
-    for (int r = 0; r < w; ++r) {
-        unsigned long long best = ~0ull;
-        for (int i = tid; i < kcp; i += 256) {
-            const unsigned long long key = ((unsigned long long)__float_as_uint(__ldcg(row + i)) << 32) | (unsigned)i;
-            if ((first || key > prev) && key < best) best = key;
+    // Selection without a round per result: keys = (distance bits, cell) are distinct, so the w-th smallest of the
+    // 256 per-thread minima bounds the w-th smallest key; the few keys within the bound are ranked by counting.
+    __shared__ unsigned long long tmin[256];
+    __shared__ unsigned long long cand[ctc::RS_MAXC];
+    __shared__ unsigned long long s_bound;
+    __shared__ int s_nc;
+    unsigned long long best = ~0ull;
+    for (int i = tid; i < kcp; i += 256) {
+        const unsigned long long key = ((unsigned long long)__float_as_uint(__ldcg(row + i)) << 32) | (unsigned)i;
+        best = key < best ? key : best;
+    }
+    tmin[tid] = best;
+    if (tid == 0) s_nc = 0;
+    __syncthreads();
+    int rk = 0;
+    for (int i = 0; i < 256; ++i) rk += tmin[i] < best ? 1 : 0;
+    if (rk == w - 1) s_bound = best;   // w <= 32 <= 256 distinct finite minima (kc >= 256 on this path)
+    __syncthreads();
+    const unsigned long long bound = s_bound;
+    for (int i = tid; i < kcp; i += 256) {
+        const unsigned long long key = ((unsigned long long)__float_as_uint(__ldcg(row + i)) << 32) | (unsigned)i;
+        if (key <= bound) cand[atomicAdd(&s_nc, 1)] = key;   // at most w keys per thread: <= RS_MAXC
+    }
+    __syncthreads();
+    const int nc = s_nc;
+    for (int i = tid; i < nc; i += 256) {
+        const unsigned long long key = cand[i];
+        int r = 0;
+        for (int x = 0; x < nc; ++x) r += cand[x] < key ? 1 : 0;
+        if (r < w) {
+            cells_out[q * w + r] = (int32_t)(unsigned)key;
+            dc_out[q * w + r] = __uint_as_float((unsigned)(key >> 32));
         }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
-            best = other < best ? other : best;
-        }
-        if (lane == 0) red[wid] = best;
-        __syncthreads();
-        best = red[0];
-#pragma unroll
-        for (int i = 1; i < 8; ++i) best = red[i] < best ? red[i] : best;
-        __syncthreads();
-        if (tid == 0) {
-            cells_out[q * w + r] = (int32_t)(unsigned)best;
-            dc_out[q * w + r] = __uint_as_float((unsigned)(best >> 32));
-        }
-        prev = best;
-        first = false;
     }
 }
 
@@ -409,22 +415,23 @@ __global__ void transpose_centroids_kernel(const float* __restrict__ C, int kc, 
 
 template <int NTY, int R>
 cudaError_t launch_coarse2_inst(const ivfadc_index* h, const float* Q, const float* Ct, int64_t nq, int kc, int kcp, int D, int w,
-                                int32_t* cells, float* dc, cudaStream_t s, const int32_t* redo_list, const int* redo_count) {
+                                int32_t* cells, float* dc, cudaStream_t s, const int32_t* redo_list, const int* redo_count,
+                                int list_skip) {
     constexpr int TQ2 = 4 * NTY;
     const size_t smem = ((size_t)D * (2 * TQ2 + 4) + 2 * (size_t)PDK * PLDC + (size_t)TQ2 * (PC + 1)) * sizeof(float);
     cudaError_t e = ensure_smem(h, reinterpret_cast<const void*>(&coarse2_kernel<NTY, R>), smem);
     if (e != cudaSuccess) return e;
     coarse2_kernel<NTY, R><<<(unsigned)((nq + TQ2 - 1) / TQ2), 16 * NTY, smem, s>>>(Q, Ct, nq, kc, kcp, D, w, cells, dc, redo_list,
-                                                                                  redo_count, redo_list ? ctc::RS_MAXQ : 0);
+                                                                                  redo_count, list_skip);
     return cudaGetLastError();
 }
 template <int R>
 cudaError_t launch_coarse2_r(const ivfadc_index* h, int nty, const float* Q, const float* Ct, int64_t nq, int kc, int kcp, int D, int w,
                              int32_t* cells, float* dc, cudaStream_t s, const int32_t* redo_list = nullptr,
-                             const int* redo_count = nullptr) {
-    if (nty == 4) return launch_coarse2_inst<4, R>(h, Q, Ct, nq, kc, kcp, D, w, cells, dc, s, redo_list, redo_count);
-    if (nty == 6) return launch_coarse2_inst<6, R>(h, Q, Ct, nq, kc, kcp, D, w, cells, dc, s, redo_list, redo_count);
-    return launch_coarse2_inst<8, R>(h, Q, Ct, nq, kc, kcp, D, w, cells, dc, s, redo_list, redo_count);
+                             const int* redo_count = nullptr, int list_skip = 0) {
+    if (nty == 4) return launch_coarse2_inst<4, R>(h, Q, Ct, nq, kc, kcp, D, w, cells, dc, s, redo_list, redo_count, list_skip);
+    if (nty == 6) return launch_coarse2_inst<6, R>(h, Q, Ct, nq, kc, kcp, D, w, cells, dc, s, redo_list, redo_count, list_skip);
+    return launch_coarse2_inst<8, R>(h, Q, Ct, nq, kc, kcp, D, w, cells, dc, s, redo_list, redo_count, list_skip);
 }
 
 template <typename T>
@@ -559,13 +566,18 @@ cudaError_t launch_coarse(const ivfadc_index* h, const void* dQ, int64_t nq, int
             if ((e = cudaGetLastError()) != cudaSuccess) return e;
             if (launches) *launches += 2;
             h->last_redo_nq = nq;
-            // flagged queries: the first RS_MAXQ in parallel over the centroids, any further ones in 16-query blocks
-            coarse_redo_small_kernel<<<dim3((unsigned)(h->kc_pad256 / 256), ctc::RS_MAXQ), 256, 0, s>>>(
-                Q, ca.C, h->cfg.kc, h->kc_pad256, D, w, d_cells, dc, ca.redo_list, ca.redo_count,
-                reinterpret_cast<float*>(ca.redo + off_scr), ca.redo_done);
-            if ((e = cudaGetLastError()) != cudaSuccess) return e;
-            if (launches) *launches += 1;
-            return launch_coarse2_r<1>(h, 4, Q, Ct, nq, h->cfg.kc, h->kc_pad, D, w, d_cells, dc, s, ca.redo_list, ca.redo_count);
+            // flagged queries: the first RS_MAXQ in parallel over the centroids (when the selection's candidate
+            // buffer covers the worst case), any further ones in 16-query blocks
+            const bool wide = (size_t)w * (size_t)(h->kc_pad256 / 256) <= (size_t)ctc::RS_MAXC;
+            if (wide) {
+                coarse_redo_small_kernel<<<dim3((unsigned)(h->kc_pad256 / 256), ctc::RS_MAXQ), 256, 0, s>>>(
+                    Q, ca.C, h->cfg.kc, h->kc_pad256, D, w, d_cells, dc, ca.redo_list, ca.redo_count,
+                    reinterpret_cast<float*>(ca.redo + off_scr), ca.redo_done);
+                if ((e = cudaGetLastError()) != cudaSuccess) return e;
+                if (launches) *launches += 1;
+            }
+            return launch_coarse2_r<1>(h, 4, Q, Ct, nq, h->cfg.kc, h->kc_pad, D, w, d_cells, dc, s, ca.redo_list, ca.redo_count,
+                                       wide ? ctc::RS_MAXQ : 0);
         }
         if (w <= 32) return launch_coarse2_r<1>(h, best, Q, Ct, nq, h->cfg.kc, h->kc_pad, D, w, d_cells, dc, s);
         if (w <= 64) return launch_coarse2_r<2>(h, best, Q, Ct, nq, h->cfg.kc, h->kc_pad, D, w, d_cells, dc, s);

@@ -42,6 +42,7 @@ constexpr int ABLK = 4096;              // A block: 128 rows x 8 k (tf32 words),
 constexpr int BBLK = 8192;              // B block: 256 rows x 8 k
 constexpr int NSLOT = 8;                // B ring depth (k-steps in flight)
 constexpr int CAP = 64;                 // candidate slots per query
+constexpr int RS_MAXC = 2048;           // keys within the selection bound of the wide redo kernel (<= w x kc / 256)
 constexpr int RS_MAXQ = 32;             // flagged queries served by the wide redo kernel (one block per 256 centroids)
 constexpr int GRP = 8;                  // columns per group of the bound in the first GRP_FINE_TILES tiles (16 afterwards)
 constexpr int GRP_FINE_TILES = 2;

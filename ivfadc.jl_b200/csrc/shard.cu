@@ -8,6 +8,8 @@
 //   plan + list scan + per-query selection over the cells this rank owns   (api_search_core, scan.cu)
 //   ONE grouped in-place all-gather: candidate ids, distances, merge keys  [world][nq][k]
 //   merge by (distance, probe rank << 32 | position) -- the reference's order, src/index.jl:247-257
+//   (from four ranks on: an all-to-all of candidate slices, every rank merges its slice of the queries, and a small
+//    all-gather distributes the finished rows -- see slice_merge)
 //
 // enqueued on one stream with no host synchronisation in between, and replayed from a CUDA graph from the second
 // call with the same shape on (the step is ~15 launches of 3..150 us: launch latency would otherwise set the pace).
@@ -39,6 +41,8 @@ struct NcclApi {
     ncclResult_t (*CommInitAll)(ncclComm_t*, int, const int*) = nullptr;
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*GroupStart)() = nullptr;
     ncclResult_t (*GroupEnd)() = nullptr;
     const char* (*GetErrorString)(ncclResult_t) = nullptr;
@@ -62,6 +66,8 @@ NcclApi* nccl_api() {
     IVF_SYM(CommInitAll, "ncclCommInitAll");
     IVF_SYM(CommDestroy, "ncclCommDestroy");
     IVF_SYM(AllGather, "ncclAllGather");
+    IVF_SYM(Send, "ncclSend");
+    IVF_SYM(Recv, "ncclRecv");
     IVF_SYM(GroupStart, "ncclGroupStart");
     IVF_SYM(GroupEnd, "ncclGroupEnd");
     IVF_SYM(GetErrorString, "ncclGetErrorString");
@@ -89,14 +95,16 @@ struct ShardCtx {
     bool use_graph = true;
     // gathered buffers: queries [nqp][D], probes [nqp][w], candidates [world][nq][k]
     DevBuf g_q, g_cells, g_dc, g_ids, g_d, g_keys, loc_cnt, out_ids, out_d, out_cnt;
+    // slice merge (world >= 4): candidates of this rank's query slice from every rank [world][ns][k], results [nqp][k]
+    DevBuf a_ids, a_d, a_keys, r_ids, r_d, r_cnt;
     // CUDA graph of the last shape (one entry: a serving loop repeats one shape)
     GraphKey key;
     int seen = 0;                 // eager runs with this key so far
     cudaGraphExec_t exec = nullptr;
     uint64_t graph_launches = 0;  // kernels of this library inside one replay
     // timing of the eager path: coarse slice, the two collectives
-    cudaEvent_t ev[6] = {};
-    bool ev_ok = false, ev_pending = false;
+    cudaEvent_t ev[7] = {};
+    bool ev_ok = false, ev_pending = false, ev_slices = false;
     double coarse_ms = 0, comm_ms = 0;
 };
 
@@ -136,6 +144,15 @@ Step make_step(const ivfadc_index* h, const ShardCtx* c, int64_t nq, int k, int 
     return st;
 }
 
+// From four ranks on, every rank merges only ITS slice of the queries: the candidates travel in an all-to-all of
+// [slice][k] blocks (each rank receives world x nq / world x k entries instead of world x nq x k), the merge kernel
+// runs on nq / world queries, and one small all-gather distributes the finished rows.  Same kernels, same order of
+// the parts (rank-major), so the result is bit-identical to the all-gather path (and to one GPU).
+bool slice_merge(const ShardCtx* c) {
+    NcclApi* n = nccl_api();
+    return c->world >= 4 && n && n->Send && n->Recv;
+}
+
 int reserve_step(ivfadc_index* h, ShardCtx* c, const Step& st, bool gather_q) {
     const size_t T = h->tsize;
     if (gather_q) CUDA_OR_FAIL(h, c->g_q.reserve((size_t)st.nqp * h->cfg.dim * T), "workspace");
@@ -146,6 +163,15 @@ int reserve_step(ivfadc_index* h, ShardCtx* c, const Step& st, bool gather_q) {
     CUDA_OR_FAIL(h, c->g_keys.reserve(sizeof(uint64_t) * nk * c->world), "workspace");
     CUDA_OR_FAIL(h, c->g_d.reserve(T * nk * c->world), "workspace");
     CUDA_OR_FAIL(h, c->loc_cnt.reserve(sizeof(int32_t) * (size_t)st.nq), "workspace");
+    if (slice_merge(c)) {
+        const size_t sk = (size_t)st.qs * st.k;
+        CUDA_OR_FAIL(h, c->a_ids.reserve(sizeof(uint64_t) * sk * c->world), "workspace");
+        CUDA_OR_FAIL(h, c->a_keys.reserve(sizeof(uint64_t) * sk * c->world), "workspace");
+        CUDA_OR_FAIL(h, c->a_d.reserve(T * sk * c->world), "workspace");
+        CUDA_OR_FAIL(h, c->r_ids.reserve(sizeof(uint64_t) * sk * c->world), "workspace");
+        CUDA_OR_FAIL(h, c->r_d.reserve(T * sk * c->world), "workspace");
+        CUDA_OR_FAIL(h, c->r_cnt.reserve(sizeof(int32_t) * (size_t)st.nqp), "workspace");
+    }
     return IVFADC_OK;
 }
 
@@ -195,6 +221,62 @@ int phase_merge(ivfadc_index* h, ShardCtx* c, const Step& st, uint64_t* d_ids, v
     return IVFADC_OK;
 }
 
+// slice merge: all-to-all of the candidate slices, merge of this rank's slice, all-gather of the finished rows
+int coll_cands_slices(ivfadc_index* h, ShardCtx* c, const Step& st, cudaStream_t s) {
+    NcclApi* n = nccl_api();
+    const size_t nk = (size_t)st.nq * st.k, T = h->tsize, k = (size_t)st.k;
+    const char* l_ids = c->g_ids.as<char>() + nk * c->rank * 8;      // this rank's candidates for all queries
+    const char* l_d = c->g_d.as<char>() + nk * c->rank * T;
+    const char* l_keys = c->g_keys.as<char>() + nk * c->rank * 8;
+    const size_t ns = (size_t)(st.hi - st.lo);
+    for (int r = 0; r < c->world; ++r) {
+        const int64_t lo_r = std::min(st.nq, (int64_t)r * st.qs), hi_r = std::min(st.nq, lo_r + st.qs);
+        const size_t ns_r = (size_t)(hi_r - lo_r);
+        if (r == c->rank) continue;
+        if (ns_r > 0) {
+            NCCL_OR_FAIL(h, n->Send(l_ids + (size_t)lo_r * k * 8, ns_r * k * 8, ncclChar, r, c->comm, s), "send (ids)");
+            NCCL_OR_FAIL(h, n->Send(l_d + (size_t)lo_r * k * T, ns_r * k * T, ncclChar, r, c->comm, s), "send (distances)");
+            NCCL_OR_FAIL(h, n->Send(l_keys + (size_t)lo_r * k * 8, ns_r * k * 8, ncclChar, r, c->comm, s), "send (keys)");
+        }
+        if (ns > 0) {
+            NCCL_OR_FAIL(h, n->Recv(c->a_ids.as<char>() + (size_t)r * ns * k * 8, ns * k * 8, ncclChar, r, c->comm, s), "recv (ids)");
+            NCCL_OR_FAIL(h, n->Recv(c->a_d.as<char>() + (size_t)r * ns * k * T, ns * k * T, ncclChar, r, c->comm, s), "recv (distances)");
+            NCCL_OR_FAIL(h, n->Recv(c->a_keys.as<char>() + (size_t)r * ns * k * 8, ns * k * 8, ncclChar, r, c->comm, s), "recv (keys)");
+        }
+    }
+    return IVFADC_OK;
+}
+int phase_merge_slice(ivfadc_index* h, ShardCtx* c, const Step& st, cudaStream_t s) {
+    const size_t T = h->tsize, k = (size_t)st.k, ns = (size_t)(st.hi - st.lo);
+    if (ns == 0) return IVFADC_OK;
+    const size_t nk = (size_t)st.nq * st.k;
+    // own block of the slice: a device copy instead of a send to self
+    CUDA_OR_FAIL(h, cudaMemcpyAsync(c->a_ids.as<char>() + (size_t)c->rank * ns * k * 8,
+                                    c->g_ids.as<char>() + nk * c->rank * 8 + (size_t)st.lo * k * 8, ns * k * 8,
+                                    cudaMemcpyDeviceToDevice, s), "D2D");
+    CUDA_OR_FAIL(h, cudaMemcpyAsync(c->a_d.as<char>() + (size_t)c->rank * ns * k * T,
+                                    c->g_d.as<char>() + nk * c->rank * T + (size_t)st.lo * k * T, ns * k * T,
+                                    cudaMemcpyDeviceToDevice, s), "D2D");
+    CUDA_OR_FAIL(h, cudaMemcpyAsync(c->a_keys.as<char>() + (size_t)c->rank * ns * k * 8,
+                                    c->g_keys.as<char>() + nk * c->rank * 8 + (size_t)st.lo * k * 8, ns * k * 8,
+                                    cudaMemcpyDeviceToDevice, s), "D2D");
+    int launches = 0;
+    CUDA_OR_FAIL(h, launch_merge_parts(h, c->world, (int64_t)ns, st.k, c->a_ids.as<uint64_t>(), c->a_d.p,
+                                       c->a_keys.as<uint64_t>(), c->r_ids.as<uint64_t>() + (size_t)st.lo * k,
+                                       c->r_d.as<char>() + (size_t)st.lo * k * T, c->r_cnt.as<int32_t>() + st.lo, s,
+                                       &launches), "merge kernel");
+    h->stats.gpu_launches += launches;
+    return IVFADC_OK;
+}
+int coll_results(ivfadc_index* h, ShardCtx* c, const Step& st, cudaStream_t s) {
+    NcclApi* n = nccl_api();
+    const size_t T = h->tsize, row = (size_t)c->rank * st.qs, k = (size_t)st.k;
+    NCCL_OR_FAIL(h, n->AllGather(c->r_ids.as<char>() + row * k * 8, c->r_ids.p, (size_t)st.qs * k * 8, ncclChar, c->comm, s), "all-gather (result ids)");
+    NCCL_OR_FAIL(h, n->AllGather(c->r_d.as<char>() + row * k * T, c->r_d.p, (size_t)st.qs * k * T, ncclChar, c->comm, s), "all-gather (result distances)");
+    NCCL_OR_FAIL(h, n->AllGather(c->r_cnt.as<char>() + row * 4, c->r_cnt.p, (size_t)st.qs * 4, ncclChar, c->comm, s), "all-gather (result counts)");
+    return IVFADC_OK;
+}
+
 // one step of one rank (one process per GPU), asynchronous on `s`
 int enqueue_step(ivfadc_index* h, ShardCtx* c, const Step& st, const void* dQ, bool gather_q, uint64_t* d_ids,
                  void* d_dists, int32_t* d_counts, cudaStream_t s, bool timed) {
@@ -210,6 +292,29 @@ int enqueue_step(ivfadc_index* h, ShardCtx* c, const Step& st, const void* dQ, b
     if (timed) cudaEventRecord(c->ev[2], s);
     if ((rc = phase_scan(h, c, st, dQ, s)) != IVFADC_OK) return rc;
     if (timed) cudaEventRecord(c->ev[3], s);
+    if (slice_merge(c)) {
+        NCCL_OR_FAIL(h, n->GroupStart(), "ncclGroupStart");
+        rc = coll_cands_slices(h, c, st, s);
+        NCCL_OR_FAIL(h, n->GroupEnd(), "ncclGroupEnd");
+        if (rc != IVFADC_OK) return rc;
+        if (timed) cudaEventRecord(c->ev[4], s);
+        if ((rc = phase_merge_slice(h, c, st, s)) != IVFADC_OK) return rc;
+        if (timed) cudaEventRecord(c->ev[5], s);
+        NCCL_OR_FAIL(h, n->GroupStart(), "ncclGroupStart");
+        rc = coll_results(h, c, st, s);
+        NCCL_OR_FAIL(h, n->GroupEnd(), "ncclGroupEnd");
+        if (rc != IVFADC_OK) return rc;
+        const size_t nk = (size_t)st.nq * st.k;
+        CUDA_OR_FAIL(h, cudaMemcpyAsync(d_ids, c->r_ids.p, sizeof(uint64_t) * nk, cudaMemcpyDeviceToDevice, s), "D2D");
+        CUDA_OR_FAIL(h, cudaMemcpyAsync(d_dists, c->r_d.p, h->tsize * nk, cudaMemcpyDeviceToDevice, s), "D2D");
+        CUDA_OR_FAIL(h, cudaMemcpyAsync(d_counts, c->r_cnt.p, sizeof(int32_t) * (size_t)st.nq, cudaMemcpyDeviceToDevice, s), "D2D");
+        if (timed) {
+            cudaEventRecord(c->ev[6], s);
+            c->ev_pending = true;
+            c->ev_slices = true;
+        }
+        return IVFADC_OK;
+    }
     NCCL_OR_FAIL(h, n->GroupStart(), "ncclGroupStart");
     rc = coll_cands(h, c, st, s);
     NCCL_OR_FAIL(h, n->GroupEnd(), "ncclGroupEnd");
@@ -219,6 +324,7 @@ int enqueue_step(ivfadc_index* h, ShardCtx* c, const Step& st, const void* dQ, b
     if (timed) {
         cudaEventRecord(c->ev[5], s);
         c->ev_pending = true;
+        c->ev_slices = false;
     }
     return rc;
 }
@@ -300,7 +406,7 @@ void shard_flush_timing(ivfadc_index* h) {
     ShardCtx* c = ctx(h);
     if (!c || !c->ev_pending) return;
     c->ev_pending = false;
-    if (cudaEventSynchronize(c->ev[5]) != cudaSuccess) {
+    if (cudaEventSynchronize(c->ev[c->ev_slices ? 6 : 5]) != cudaSuccess) {
         cudaGetLastError();
         return;
     }
@@ -309,6 +415,7 @@ void shard_flush_timing(ivfadc_index* h) {
     if (cudaEventElapsedTime(&ms, c->ev[1], c->ev[2]) == cudaSuccess) h->stats.comm_ms += ms;
     if (cudaEventElapsedTime(&ms, c->ev[3], c->ev[4]) == cudaSuccess) h->stats.comm_ms += ms;
     if (cudaEventElapsedTime(&ms, c->ev[4], c->ev[5]) == cudaSuccess) h->stats.merge_ms += ms;
+    if (c->ev_slices && cudaEventElapsedTime(&ms, c->ev[5], c->ev[6]) == cudaSuccess) h->stats.comm_ms += ms;
     cudaGetLastError();
 }
 
@@ -318,7 +425,8 @@ void shard_destroy_ctx(ivfadc_index* h) {
     if (c->exec) cudaGraphExecDestroy(c->exec);
     for (auto& ev : c->ev)
         if (ev) cudaEventDestroy(ev);
-    DevBuf* bufs[] = {&c->g_q, &c->g_cells, &c->g_dc, &c->g_ids, &c->g_d, &c->g_keys, &c->loc_cnt, &c->out_ids, &c->out_d, &c->out_cnt};
+    DevBuf* bufs[] = {&c->g_q, &c->g_cells, &c->g_dc, &c->g_ids, &c->g_d, &c->g_keys, &c->loc_cnt, &c->out_ids, &c->out_d, &c->out_cnt,
+                      &c->a_ids, &c->a_d, &c->a_keys, &c->r_ids, &c->r_d, &c->r_cnt};
     for (DevBuf* b : bufs) b->release();
     if (c->comm && nccl_api()) nccl_api()->CommDestroy(c->comm);
     delete c;
@@ -431,8 +539,13 @@ int ivfadc_sharded_step_bytes(ivfadc_index* h, int64_t nq, int32_t k, int32_t w,
     if (h2d_out) *h2d_out = (st.hi - st.lo) * h->cfg.dim * T;
     if (d2h_out) *d2h_out = nq * k * (8 + T) + nq * 4;
     // bytes this rank RECEIVES over NVLink per step: the other ranks' query slices, probes and candidates
-    if (nvlink_out)
-        *nvlink_out = (int64_t)(c->world - 1) * (st.qs * (h->cfg.dim * T + st.w * (4 + T)) + nq * k * (16 + T));
+    if (nvlink_out) {
+        const int64_t probes = (int64_t)(c->world - 1) * st.qs * (h->cfg.dim * T + st.w * (4 + T));
+        const int64_t ns = st.hi - st.lo;
+        *nvlink_out = probes + (slice_merge(c)
+                                    ? (int64_t)(c->world - 1) * (ns * k * (16 + T) + st.qs * (k * (8 + T) + 4))   // candidate slices + finished rows
+                                    : (int64_t)(c->world - 1) * nq * k * (16 + T));                                // all candidates
+    }
     return IVFADC_OK;
 }
 
