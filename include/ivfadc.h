@@ -391,6 +391,25 @@ int ivfadc_get_stats(ivfadc_index* h, ivfadc_stats* out);
 int ivfadc_reset_stats(ivfadc_index* h);
 
 /*
+ * ---- quantizer training on the device (not parity-graded) ------------------------------
+ * The constructor's cost at 10^6+ vectors is Clustering.kmeans (src/index.jl:129-134) and build_quantizer
+ * (src/index.jl:142-147).  Lloyd on the GPU with ONE handle for all iterations: assignment = the engine's own coarse
+ * kernel (ivfadc_coarse_search_device, w = 1), centre update = accumulate (fp64 atomics) + finish, then
+ * ivfadc_set_centroids_device installs the new centres (index must be empty).  k-means++ seeding (D^2 sampling,
+ * Philox4x32-10 keyed by `seed`: deterministic; `trials` > 1 = the greedy variant of scikit-learn: that many
+ * candidates per round, the one that lowers the potential most wins) picks k rows of a device-resident sample.
+ * dtype: IVFADC_F32 / IVFADC_F64 of the data; d_scratch: double[ns]; d_sums: double[kc][D] and d_counts: uint64[kc],
+ * zeroed by the caller before the first accumulate of an iteration; d_empty_out (optional): int32[kc], 1 = no point.
+ */
+int ivfadc_set_centroids_device(ivfadc_index* h, const void* d_centroids);
+int ivfadc_kmeanspp_device(const void* dS, int64_t ns, int32_t D, int32_t k, int32_t dtype, uint64_t seed, int32_t trials,
+                           void* d_scratch, void* d_centres_out, int64_t* d_picked_out, void* stream);
+int ivfadc_kmeans_accumulate_device(const void* dX, int64_t n, int32_t D, int32_t dtype, const int32_t* d_cells,
+                                    double* d_sums, uint64_t* d_counts, void* stream);
+int ivfadc_kmeans_finish_device(const double* d_sums, const uint64_t* d_counts, int32_t kc, int32_t D, int32_t dtype,
+                                void* d_centroids_inout, int32_t* d_empty_out, void* stream);
+
+/*
  * ---- synthetic inputs (harness utility) -------------------------------------------------
  * Counter-based generator, Philox4x32-10 keyed by `seed`, counter = (vector lo, vector hi, dim, stream): every
  * value depends only on (seed, vector index, dim), so a slice [first, first + n) of a data set of any size is

@@ -36,7 +36,8 @@ SYMBOLS = [
     "ivfadc_group_last_error", "ivfadc_group_set_cell_owners", "ivfadc_group_add", "ivfadc_group_search",
     "ivfadc_group_delete", "ivfadc_group_pop", "ivfadc_group_length",
     "ivfadc_add_device", "ivfadc_export_all", "ivfadc_import_all", "ivfadc_synth_uniform_device",
-    "ivfadc_synth_blobs_device", "ivfadc_reserve",
+    "ivfadc_synth_blobs_device", "ivfadc_reserve", "ivfadc_set_centroids_device", "ivfadc_kmeanspp_device",
+    "ivfadc_kmeans_accumulate_device", "ivfadc_kmeans_finish_device",
 ]
 NCCL_ID_BYTES = 128
 
@@ -108,6 +109,11 @@ def load(build_if_missing: bool = True):
     lib.ivfadc_import_list.argtypes = [H, c_int32, c_void_p, c_void_p, c_int64]
     lib.ivfadc_add_device.argtypes = [H, c_void_p, c_int64, c_int32, c_void_p, c_int32, c_void_p]
     lib.ivfadc_reserve.argtypes = [H, c_int64, c_void_p]
+    lib.ivfadc_set_centroids_device.argtypes = [H, c_void_p]
+    lib.ivfadc_kmeanspp_device.argtypes = [c_void_p, c_int64, c_int32, c_int32, c_int32, c_uint64, c_int32, c_void_p, c_void_p,
+                                           c_void_p, c_void_p]
+    lib.ivfadc_kmeans_accumulate_device.argtypes = [c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p]
+    lib.ivfadc_kmeans_finish_device.argtypes = [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p]
     lib.ivfadc_export_all.argtypes = [H, c_void_p, c_void_p]
     lib.ivfadc_import_all.argtypes = [H, c_void_p, c_void_p, c_void_p]
     lib.ivfadc_synth_uniform_device.argtypes = [c_void_p, c_int64, c_int64, c_int32, c_uint64, c_void_p]

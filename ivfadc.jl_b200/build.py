@@ -10,7 +10,7 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 OBJDIR = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libivfadc_cuda.so")
-SOURCES = ["api.cu", "coarse.cu", "scan.cu", "encode.cu", "lists.cu", "shard.cu", "synth.cu"]
+SOURCES = ["api.cu", "coarse.cu", "scan.cu", "encode.cu", "lists.cu", "shard.cu", "synth.cu", "train.cu"]
 HEADERS = ["common.cuh", "warp_topk.cuh", "scan_impl.cuh", "scanq_impl.cuh", "tc_common.cuh", "scanu_impl.cuh", "scanw_impl.cuh", "coarse_tc.cuh"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",

@@ -722,6 +722,20 @@ int ivfadc_import_list(ivfadc_index* h, int32_t cell, const uint64_t* ids, const
     return IVFADC_OK;
 }
 
+int ivfadc_set_centroids_device(ivfadc_index* h, const void* d_centroids) {
+    IVF_NVTX();
+    if (check_handle(h) || !d_centroids) return IVFADC_ERR_BAD_ARG;
+    if (h->n_total != 0) return fail(h, IVFADC_ERR_BAD_ARG, "centroids can only be replaced while the index is empty");
+    cudaSetDevice(h->cfg.device);
+    int launches = 0;
+    CUDA_OR_FAIL(h, cudaMemcpyAsync(h->d_centroids, d_centroids, (size_t)h->cfg.kc * h->cfg.dim * h->tsize,
+                                    cudaMemcpyDeviceToDevice, h->stream), "D2D");
+    CUDA_OR_FAIL(h, coarse_prepare(h, h->stream, &launches), "coarse operands");
+    CUDA_OR_FAIL(h, cudaStreamSynchronize(h->stream), "sync");
+    h->stats.gpu_launches += launches;
+    return IVFADC_OK;
+}
+
 int ivfadc_reserve(ivfadc_index* h, int64_t n_total, const int64_t* sizes) {
     IVF_NVTX();
     if (check_handle(h)) return IVFADC_ERR_BAD_ARG;

@@ -460,8 +460,8 @@ cudaError_t coarse_prepare(ivfadc_index* h, cudaStream_t s, int* launches) {
     if (h->cfg.dtype != IVFADC_F32) return cudaSuccess;
     h->kc_pad = (h->cfg.kc + PC - 1) / PC * PC;
     const size_t n = (size_t)h->kc_pad * h->cfg.dim;
-    cudaError_t e = cudaMalloc(&h->d_centroids_t, n * sizeof(float));
-    if (e != cudaSuccess) return e;
+    cudaError_t e = cudaSuccess;   // re-entrant: ivfadc_set_centroids_device refreshes the derived operands
+    if (!h->d_centroids_t && (e = cudaMalloc(&h->d_centroids_t, n * sizeof(float))) != cudaSuccess) return e;
     transpose_centroids_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(static_cast<const float*>(h->d_centroids), h->cfg.kc,
                                                                         h->kc_pad, h->cfg.dim,
                                                                         static_cast<float*>(h->d_centroids_t));
@@ -473,8 +473,8 @@ cudaError_t coarse_prepare(ivfadc_index* h, cudaStream_t s, int* launches) {
         h->kc_pad256 = (kc + ctc::NC - 1) / ctc::NC * ctc::NC;
         const int ksteps = D / 8;
         const size_t words = (size_t)h->kc_pad256 * (ksteps + 1) * 8;
-        if ((e = cudaMalloc(&h->d_tcC, words * sizeof(float))) != cudaSuccess) return e;
-        if ((e = cudaMalloc(&h->d_ccn, ((size_t)h->kc_pad256 + 4) * sizeof(float))) != cudaSuccess) return e;
+        if (!h->d_tcC && (e = cudaMalloc(&h->d_tcC, words * sizeof(float))) != cudaSuccess) return e;
+        if (!h->d_ccn && (e = cudaMalloc(&h->d_ccn, ((size_t)h->kc_pad256 + 4) * sizeof(float))) != cudaSuccess) return e;
         if ((e = cudaMemsetAsync(h->d_ccn, 0, ((size_t)h->kc_pad256 + 4) * sizeof(float), s)) != cudaSuccess) return e;
         if (!h->d_err) {
             if ((e = cudaMalloc(&h->d_err, sizeof(int))) != cudaSuccess) return e;

@@ -112,8 +112,8 @@ def kmeans_torch(X, k: int, iters: int = 10, seed: int = 0, chunk: int = 1 << 18
 # Device trainer: Lloyd iterations whose assignment step is the engine's own coarse
 # kernel (K1: exact nearest centre in the reference's direct form, tensor-core pruned where the
 # shape allows) -- what makes IVFADCIndex(data; ...) practical at 10^6+ vectors, where the host
-# trainer above would need an n x kc float64 distance matrix.  torch carries the device buffers and
-# the centre update (index_add); seeding is k-means++ on a sample.  Not parity-graded (the
+# trainer above would need an n x kc float64 distance matrix.  Seeding (k-means++ on a sample) and the
+# centre update are kernels of the library too (csrc/train.cu); torch carries the device buffers.  Not parity-graded (the
 # reference's training is unseeded); graded by quantisation error against the host trainer
 # (tests/test_gpu_parity.py::test_device_trainer).
 # ---------------------------------------------------------------------------------------------
@@ -125,56 +125,81 @@ def _dummy_codebook(d: int, dtype):
 
 def kmeans_device(X, k: int, maxiter: int = 25, seed: int = 0, device: int = 0, chunk: int = 1 << 20):
     """Lloyd on the GPU.  X [n, d] (numpy, float32 / float64) -> (centers [k, d] in X.dtype, assignments
-    int64[n] 0-based, consistent with the returned centers)."""
+    int64[n] 0-based, consistent with the returned centers).
+
+    Everything that touches the data is a kernel of the library: k-means++ seeding (ivfadc_kmeanspp_device, D^2
+    sampling on a sample, Philox keyed by `seed`), the assignment step (the engine's coarse kernel through ONE handle
+    whose centroids are replaced in place every iteration, ivfadc_set_centroids_device), the centre update
+    (ivfadc_kmeans_accumulate_device / ivfadc_kmeans_finish_device).  torch only owns the device buffers."""
+    import ctypes
+
     import torch
 
-    from . import sharded
+    from . import _capi, sharded
     from .index import IVFADCIndex
 
     X = np.ascontiguousarray(X)
     n, d = X.shape
     assert 1 <= k <= n
+    lib = _capi.load()
     dev = torch.device("cuda", device)
     dX = torch.from_numpy(X).to(dev)
+    dt = _capi.F32 if X.dtype == np.float32 else _capi.F64
     rng = np.random.default_rng(seed)
-    gen = torch.Generator(device=dev).manual_seed(seed)
-    # k-means++ on a sample
+    stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    vp = lambda t: ctypes.c_void_p(t.data_ptr())  # noqa: E731
+
+    def ok(rc, what):
+        if rc != 0:
+            raise _capi.IvfadcError(rc, what)
+
+    # k-means++ seeding on a sample
     ns = min(n, max(32768, 8 * k))
-    S = dX[torch.from_numpy(rng.choice(n, ns, replace=False)).to(dev)].double()
-    centers = torch.empty((k, d), dtype=torch.float64, device=dev)
-    centers[0] = S[int(rng.integers(ns))]
-    d2 = ((S - centers[0]) ** 2).sum(1)
-    for j in range(1, k):
-        tot = float(d2.sum())
-        idx = int(torch.multinomial(d2 / tot, 1, generator=gen)) if tot > 0 else int(rng.integers(ns))
-        centers[j] = S[idx]
-        d2 = torch.minimum(d2, ((S - centers[j]) ** 2).sum(1))
-    cb = _dummy_codebook(d, X.dtype)
-    assign = torch.zeros(n, dtype=torch.long, device=dev)
+    S = dX[torch.from_numpy(rng.choice(n, ns, replace=False)).to(dev)].contiguous()
+    centers = torch.empty((k, d), dtype=dX.dtype, device=dev)
+    scratch = torch.empty(ns, dtype=torch.float64, device=dev)
+    picked = torch.empty(k, dtype=torch.int64, device=dev)
+    # greedy k-means++ like scikit-learn (2 + ln k candidates per round) while the seeding stays affordable on one CTA
+    trials = 2 + int(np.log(k)) if float(ns) * k * d <= 4e10 else 1
+    ok(lib.ivfadc_kmeanspp_device(vp(S), ns, d, k, dt, seed, trials, vp(scratch), vp(centers), vp(picked), stream),
+       "ivfadc_kmeanspp_device")
+    torch.cuda.synchronize(dev)
+
+    eng = IVFADCIndex.from_quantizers(centers.cpu().numpy(), _dummy_codebook(d, X.dtype), None, device=device)
+    assign = torch.zeros(n, dtype=torch.int32, device=dev)
+    new_assign = torch.empty_like(assign)
     dist = torch.empty(n, dtype=dX.dtype, device=dev)
-    for it in range(maxiter + 1):
-        cnp = centers.to(dX.dtype).cpu().numpy()
-        eng = IVFADCIndex.from_quantizers(cnp, cb, None, device=device)
-        new_assign = torch.empty_like(assign)
-        for s in range(0, n, chunk):  # K1: nearest centre of every point (w = 1), the engine's coarse kernel
-            c, dc = sharded.coarse_device(eng, dX[s:s + chunk], 1)
-            new_assign[s:s + chunk] = c[:, 0].long()
-            dist[s:s + chunk] = dc[:, 0]
+    sums = torch.empty((k, d), dtype=torch.float64, device=dev)
+    counts = torch.empty(k, dtype=torch.int64, device=dev)
+    empty = torch.empty(k, dtype=torch.int32, device=dev)
+    try:
+        for it in range(maxiter + 1):
+            sums.zero_()
+            counts.zero_()
+            for s in range(0, n, chunk):  # K1: nearest centre of every point (w = 1), then the sums of the chunk
+                xb = dX[s:s + chunk]
+                c, dc = sharded.coarse_device(eng, xb, 1)
+                new_assign[s:s + chunk] = c[:, 0]
+                dist[s:s + chunk] = dc[:, 0]
+                ok(lib.ivfadc_kmeans_accumulate_device(vp(xb), xb.shape[0], d, dt, vp(new_assign[s:s + chunk]), vp(sums),
+                                                       vp(counts), stream), "ivfadc_kmeans_accumulate_device")
+            same = it > 0 and bool(torch.equal(new_assign, assign))
+            assign, new_assign = new_assign, assign
+            if it == maxiter or same:
+                break
+            ok(lib.ivfadc_kmeans_finish_device(vp(sums), vp(counts), k, d, dt, vp(centers), vp(empty), stream),
+               "ivfadc_kmeans_finish_device")
+            nempty = int(empty.sum())
+            if nempty:  # re-seed empty clusters on the points farthest from their centre
+                far = torch.topk(dist.double(), nempty).indices
+                centers[empty.bool()] = dX[far]
+            torch.cuda.synchronize(dev)
+            eng.check_async(stream.value)
+            _capi.check(eng._h, lib.ivfadc_set_centroids_device(eng._h, vp(centers)))
         torch.cuda.synchronize(dev)
+    finally:
         eng.close()
-        same = it > 0 and bool(torch.equal(new_assign, assign))
-        assign = new_assign
-        if it == maxiter or same:
-            break
-        counts = torch.bincount(assign, minlength=k)
-        sums = torch.zeros((k, d), dtype=torch.float64, device=dev).index_add_(0, assign, dX.double())
-        nz = counts > 0
-        centers[nz] = sums[nz] / counts[nz, None].double()
-        nempty = int((~nz).sum())
-        if nempty:  # re-seed empty clusters on the points farthest from their centre
-            far = torch.topk(dist.double(), nempty).indices
-            centers[~nz] = dX[far].double()
-    return centers.to(dX.dtype).cpu().numpy(), assign.cpu().numpy().astype(np.int64)
+    return centers.cpu().numpy(), assign.cpu().numpy().astype(np.int64)
 
 
 def train_quantizers_device(data, kc: int, k: int, m: int, coarse_maxiter: int = 25,

@@ -97,3 +97,45 @@ def test_synth_streams_are_counter_based():
     assert np.array_equal(X2, X[1234:1334]) and np.array_equal(b2, b[1234:1334])
     X3, _ = orc.synth_blobs(0, 100, D, kb, 1003, scale, c)
     assert not np.array_equal(X3, X[:100])
+
+
+def test_validation_bundle_against_oracle():
+    """tests/golden/validation/ (written on a B200 by make_validation_bundle.py for julia/validate_against_reference.jl):
+    the index file this engine saved in the reference's format, parsed here independently after src/persistency.jl,
+    searched by the oracle -- the engine's recorded exact-mode results must be the oracle's, bit for bit."""
+    d = os.path.join(HERE, "golden", "validation")
+    raw = open(os.path.join(d, "index.ivfadc"), "rb").read()
+    lines = raw.split(b"\n", 9)
+    nrows, kc = (int(x) for x in lines[0].split())
+    n, m, k, dsub = (int(x) for x in lines[1].split())
+    assert lines[2] == b"NaiveQuantizer" and lines[4] == b"UInt8" and lines[5] == b"UInt16" and lines[8] == b"Float32"
+    body = np.frombuffer(lines[9], dtype=np.uint8)
+    p = 4 * nrows * kc
+    cent = body[:p].view(np.float32).reshape(kc, nrows)
+    cbv = np.empty((m, k, dsub), dtype=np.float32)
+    cbc = np.empty((m, k), dtype=np.uint8)
+    for i in range(m):
+        cbc[i] = body[p:p + k]; p += k
+        cbv[i] = body[p:p + 4 * k * dsub].view(np.float32).reshape(dsub, k).T; p += 4 * k * dsub
+    assert np.array_equal(body[p:p + 4 * nrows * nrows].view(np.float32).reshape(nrows, nrows), np.eye(nrows, dtype=np.float32))
+    p += 4 * nrows * nrows
+    offsets = np.zeros(kc + 1, dtype=np.int64)
+    ids, codes = [], []
+    for c in range(kc):
+        ln = int(body[p:p + 8].view(np.int64)[0]); p += 8
+        ids.append(body[p:p + 2 * ln].view(np.uint16).astype(np.uint64)); p += 2 * ln
+        codes.append(body[p:p + m * ln].reshape(ln, m)); p += m * ln
+        offsets[c + 1] = offsets[c] + ln
+    assert p == len(body) and offsets[-1] == n
+    with open(os.path.join(d, "queries.bin"), "rb") as f:
+        nq, D, kk, w = (int(x) for x in f.readline().split())
+        Q = np.frombuffer(f.read(4 * nq * D), dtype="<f4").reshape(nq, D)
+        gc = np.frombuffer(f.read(4 * nq), dtype="<i4")
+        gi = np.frombuffer(f.read(8 * nq * kk), dtype="<u8").reshape(nq, kk)
+        gd = np.frombuffer(f.read(4 * nq * kk), dtype="<f4").reshape(nq, kk)
+    qz = orc.Quantizers(np.ascontiguousarray(cent), cbv, cbc)
+    oi, od, oc, _ = orc.search_csr(qz, offsets, np.concatenate(codes), np.concatenate(ids), np.ascontiguousarray(Q), kk, w, nthreads=2)
+    assert np.array_equal(gc, oc)
+    for j in range(nq):
+        assert np.array_equal(gi[j, :gc[j]], oi[j, :oc[j]])
+        assert np.array_equal(gd[j, :gc[j]].view(np.uint32), od[j, :oc[j]].view(np.uint32))
