@@ -50,7 +50,10 @@ extern "C" {
 #define IVFADC_F64 1
 
 /* Distances.PreMetric of the coarse / residual quantizer (src/defaults.jl:6,8) */
-#define IVFADC_SQEUCLIDEAN 0
+#define IVFADC_SQEUCLIDEAN 0   /* Distances.SqEuclidean: the tensor-core paths                                  */
+#define IVFADC_EUCLIDEAN   1   /* Distances.Euclidean, Cityblock, CosineDist: exact generic kernels (correct,    */
+#define IVFADC_CITYBLOCK   2   /* untuned); Dc applies to coarse_search and the lookup tables                    */
+#define IVFADC_COSINEDIST  3   /* (src/coarsequantizers.jl:34, src/index.jl:234), Dr to quantize_data            */
 
 /* position argument of push!/pushfirst! and pop!/popfirst! (src/utils.jl:29,37,114,123) */
 #define IVFADC_LAST  0
@@ -117,8 +120,8 @@ typedef struct ivfadc_config {
     int32_t ksub;           /* codewords per codebook (<= 256, codes are uint8)                   */
     int32_t dtype;          /* IVFADC_F32 | IVFADC_F64                                            */
     int32_t id_bytes;       /* sizeof(I) of the Julia index type: 1, 2, 4 or 8                    */
-    int32_t metric_coarse;  /* IVFADC_SQEUCLIDEAN                                                 */
-    int32_t metric_resid;   /* IVFADC_SQEUCLIDEAN                                                 */
+    int32_t metric_coarse;  /* Dc: IVFADC_SQEUCLIDEAN | _EUCLIDEAN | _CITYBLOCK | _COSINEDIST      */
+    int32_t metric_resid;   /* Dr: same codes                                                     */
     int32_t device;         /* CUDA device ordinal                                                */
     int32_t shard_rank;     /* this handle keeps only cells with cell % shard_world == shard_rank */
     int32_t shard_world;    /* 1 = unsharded                                                      */

@@ -16,7 +16,8 @@ LIB_PATH = os.path.join(HERE, "libivfadc_cuda.so")
 OK = 0
 ERR_BAD_ARG, ERR_CAPACITY, ERR_CUDA, ERR_OOM, ERR_UNSUPPORTED, ERR_EMPTY = -1, -2, -3, -4, -5, -6
 F32, F64 = 0, 1
-SQEUCLIDEAN = 0
+SQEUCLIDEAN, EUCLIDEAN, CITYBLOCK, COSINEDIST = 0, 1, 2, 3
+METRICS = {"SqEuclidean": 0, "Euclidean": 1, "Cityblock": 2, "CosineDist": 3}
 LAST, FIRST = 0, 1
 FLAG_SCAN_LEGACY, FLAG_SCAN_QLANE, FLAG_LUT_EXACT, FLAG_LUT_MMASYNC, FLAG_SCAN_TMEM_V1, FLAG_COARSE_SCALAR = 1, 2, 4, 8, 16, 32
 FLAG_TEST_MERGE_SWEEP = 64

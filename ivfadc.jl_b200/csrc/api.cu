@@ -228,7 +228,8 @@ int ivfadc_create(ivfadc_index** out, const ivfadc_config* cfg, const void* cent
     if (cfg->dtype != IVFADC_F32 && cfg->dtype != IVFADC_F64) return IVFADC_ERR_BAD_ARG;
     if (cfg->id_bytes != 1 && cfg->id_bytes != 2 && cfg->id_bytes != 4 && cfg->id_bytes != 8)
         return IVFADC_ERR_UNSUPPORTED;
-    if (cfg->metric_coarse != IVFADC_SQEUCLIDEAN || cfg->metric_resid != IVFADC_SQEUCLIDEAN)
+    if (cfg->metric_coarse < IVFADC_SQEUCLIDEAN || cfg->metric_coarse > IVFADC_COSINEDIST ||
+        cfg->metric_resid < IVFADC_SQEUCLIDEAN || cfg->metric_resid > IVFADC_COSINEDIST)
         return IVFADC_ERR_UNSUPPORTED;
     if (cfg->ksub > 256) return IVFADC_ERR_UNSUPPORTED;
     if (cfg->shard_world < 1 || cfg->shard_rank < 0 || cfg->shard_rank >= cfg->shard_world)

@@ -406,6 +406,60 @@ coarse_redo_small_kernel(const float* __restrict__ Q, const float* __restrict__ 
     }
 }
 
+// coarse_search for the metrics beyond SqEuclidean (Euclidean, Cityblock, CosineDist; reference
+// src/coarsequantizers.jl:33-37 with D = Dc): one block per query at a time -- thread per centroid evaluates the
+// metric's chain (common.cuh metric_dist, the oracle's dist_colwise), the distances go to the block's scratch row,
+// then w rounds of a block-wide minimum of (distance, cell) above the previous winner = sortperm order, ties to the
+// lower cell.  A compatibility path: exact, not tuned.
+template <typename T>
+__global__ void __launch_bounds__(256)
+coarse_metric_kernel(const T* __restrict__ Q, const T* __restrict__ C, int64_t nq, int kc, int D, int w, int metric,
+                     int32_t* __restrict__ cells_out, T* __restrict__ dc_out, T* __restrict__ scratch) {
+    extern __shared__ __align__(16) unsigned char cm_smem[];
+    T* sq = reinterpret_cast<T*>(cm_smem);
+    __shared__ T red_d[8];
+    __shared__ int red_c[8];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    T* row = scratch + (size_t)blockIdx.x * kc;
+    for (int64_t q = blockIdx.x; q < nq; q += gridDim.x) {
+        __syncthreads();
+        for (int d = tid; d < D; d += 256) sq[d] = Q[q * D + d];
+        __syncthreads();
+        for (int c = tid; c < kc; c += 256) row[c] = metric_dist<T>(metric, C + (size_t)c * D, sq, D);
+        __syncthreads();
+        T pd = (T)0;
+        int pc = -1;
+        for (int r = 0; r < w; ++r) {
+            T bd = Limits<T>::inf();
+            int bc = 0x7fffffff;
+            for (int c = tid; c < kc; c += 256) {
+                const T v = row[c];
+                const bool above = pc < 0 || v > pd || (v == pd && c > pc);
+                if (above && (v < bd || (v == bd && c < bc))) { bd = v; bc = c; }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const T od = __shfl_xor_sync(0xffffffffu, bd, o);
+                const int oc = __shfl_xor_sync(0xffffffffu, bc, o);
+                if (od < bd || (od == bd && oc < bc)) { bd = od; bc = oc; }
+            }
+            if (lane == 0) { red_d[wid] = bd; red_c[wid] = bc; }
+            __syncthreads();
+            bd = red_d[0]; bc = red_c[0];
+#pragma unroll
+            for (int i = 1; i < 8; ++i)
+                if (red_d[i] < bd || (red_d[i] == bd && red_c[i] < bc)) { bd = red_d[i]; bc = red_c[i]; }
+            __syncthreads();
+            if (tid == 0) {
+                cells_out[q * w + r] = bc;
+                dc_out[q * w + r] = bd;
+            }
+            pd = bd;
+            pc = bc;
+        }
+    }
+}
+
 __global__ void transpose_centroids_kernel(const float* __restrict__ C, int kc, int kcp, int D, float* __restrict__ Ct) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= kcp * D) return;
@@ -508,6 +562,21 @@ cudaError_t launch_coarse(const ivfadc_index* h, const void* dQ, int64_t nq, int
     if (nq <= 0) return cudaSuccess;
     if (launches) *launches += 1;
     h->last_redo_nq = 0;
+    if (h->cfg.metric_coarse != IVFADC_SQEUCLIDEAN) {   // Euclidean / Cityblock / CosineDist: the generic exact kernel
+        const int kc = h->cfg.kc, D = h->cfg.dim;
+        const unsigned grid = (unsigned)std::min<int64_t>(nq, 4 * (h->num_sms > 0 ? h->num_sms : 148));
+        cudaError_t e = h->ws_coarse_redo.reserve((size_t)grid * kc * h->tsize);
+        if (e != cudaSuccess) return e;
+        if (h->cfg.dtype == IVFADC_F32)
+            coarse_metric_kernel<float><<<grid, 256, (size_t)D * 4, s>>>(static_cast<const float*>(dQ), static_cast<const float*>(h->d_centroids),
+                                                                       nq, kc, D, w, h->cfg.metric_coarse, d_cells,
+                                                                       static_cast<float*>(d_dc), h->ws_coarse_redo.as<float>());
+        else
+            coarse_metric_kernel<double><<<grid, 256, (size_t)D * 8, s>>>(static_cast<const double*>(dQ), static_cast<const double*>(h->d_centroids),
+                                                                        nq, kc, D, w, h->cfg.metric_coarse, d_cells,
+                                                                        static_cast<double*>(d_dc), h->ws_coarse_redo.as<double>());
+        return cudaGetLastError();
+    }
     if (h->cfg.dtype == IVFADC_F32 && h->d_centroids_t && h->cfg.dim <= PMAXD && (h->cfg.dim & 3) == 0 &&
         !(h->cfg.flags & IVFADC_FLAG_COARSE_SCALAR)) {
         // queries per CTA: the block count that fills the resident-CTA slots of the SMs most evenly

@@ -28,6 +28,42 @@ __device__ __forceinline__ double sub_rn(double a, double b) { return __dsub_rn(
 __device__ __forceinline__ float mul_rn(float a, float b) { return __fmul_rn(a, b); }
 __device__ __forceinline__ double mul_rn(double a, double b) { return __dmul_rn(a, b); }
 
+__device__ __forceinline__ float sqrt_rn(float a) { return __fsqrt_rn(a); }
+__device__ __forceinline__ double sqrt_rn(double a) { return __dsqrt_rn(a); }
+__device__ __forceinline__ float div_rn(float a, float b) { return __fdiv_rn(a, b); }
+__device__ __forceinline__ double div_rn(double a, double b) { return __ddiv_rn(a, b); }
+
+// colwise(Dc, a, b) for the metrics beyond SqEuclidean (oracle dist_colwise, same chains): 1 Euclidean = sqrt of
+// the SqEuclidean chain, 2 Cityblock = sequential sum of |a - b|, 3 CosineDist = max(1 - dot / (|a| |b|), 0) from
+// three sequential fma chains.  `a` = the centroid / codeword, `b` = the query / residual.
+template <typename T>
+__device__ __forceinline__ T metric_dist(int metric, const T* __restrict__ a, const T* __restrict__ b, int n) {
+    if (metric == 2) {
+        T s = (T)0;
+        for (int i = 0; i < n; ++i) {
+            const T d = sub_rn(a[i], b[i]);
+            s = add_rn(s, d < (T)0 ? -d : d);
+        }
+        return s;
+    }
+    if (metric == 3) {
+        T ab = (T)0, a2 = (T)0, b2 = (T)0;
+        for (int i = 0; i < n; ++i) {
+            ab = fma_rn(a[i], b[i], ab);
+            a2 = fma_rn(a[i], a[i], a2);
+            b2 = fma_rn(b[i], b[i], b2);
+        }
+        const T v = sub_rn((T)1, div_rn(ab, mul_rn(sqrt_rn(a2), sqrt_rn(b2))));
+        return v > (T)0 ? v : (T)0;
+    }
+    T s = (T)0;
+    for (int i = 0; i < n; ++i) {
+        const T d = sub_rn(a[i], b[i]);
+        s = fma_rn(d, d, s);
+    }
+    return metric == 1 ? sqrt_rn(s) : s;
+}
+
 template <typename T> struct Limits;
 template <> struct Limits<float> {
     typedef uint32_t bits_t;

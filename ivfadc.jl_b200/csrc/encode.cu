@@ -48,7 +48,7 @@ __global__ void __launch_bounds__(ETHREADS)
 encode_kernel(const T* __restrict__ X, int64_t n, const int32_t* __restrict__ cells,
               const T* __restrict__ C, const T* __restrict__ cb, const uint8_t* __restrict__ cb_codes,
               const T* __restrict__ cb_norms, int D, int m, int dsub_rt, int ksub,
-              uint8_t* __restrict__ codes_out, int tiled) {
+              uint8_t* __restrict__ codes_out, int tiled, int metric) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int dsub = DSUB > 0 ? DSUB : dsub_rt;
     const int Dp = m * dsub;
@@ -97,7 +97,33 @@ encode_kernel(const T* __restrict__ X, int64_t n, const int32_t* __restrict__ ce
         const T* xr = s_res + v * LDR + (tiled ? 0 : i * dsub);
         T best = Limits<T>::inf();
         int besti = -1;
-        if constexpr (DSUB > 0) {
+        if (metric != 0) {
+            // quantization_distance beyond SqEuclidean (oracle encode_residual): pairwise(Euclidean) = sqrt of the GEMM
+            // form, pairwise(Cityblock) = the direct sum per pair, pairwise(CosineDist) = 1 - dot / (|w| |x|), clamped at 0
+            T sb = (T)0;
+            for (int d = 0; d < dsub; ++d) sb = fma_rn(xr[d], xr[d], sb);
+            for (int c = clo; c < chi; ++c) {
+                const T* wv = s_cw + c * dsub;
+                T val;
+                if (metric == 2) {
+                    val = metric_dist<T>(2, wv, xr, dsub);
+                } else {
+                    T dot = (T)0;
+                    for (int d = 0; d < dsub; ++d) dot = fma_rn(wv[d], xr[d], dot);
+                    if (metric == 1) {
+                        val = sub_rn(add_rn(s_nrm[c], sb), mul_rn((T)2, dot));
+                        val = sqrt_rn(val > (T)0 ? val : (T)0);
+                    } else {
+                        val = sub_rn((T)1, div_rn(dot, mul_rn(sqrt_rn(s_nrm[c]), sqrt_rn(sb))));
+                        val = val > (T)0 ? val : (T)0;
+                    }
+                }
+                if (besti < 0 || val < best) {
+                    best = val;
+                    besti = c;
+                }
+            }
+        } else if constexpr (DSUB > 0) {
             T x[DSUB > 0 ? DSUB : 1];
             T sb = (T)0;
 #pragma unroll
@@ -185,7 +211,7 @@ cudaError_t launch_encode_t(const ivfadc_index* h, const void* dX, int64_t n, co
         cudaError_t e = ensure_smem(h, reinterpret_cast<const void*>(kern), smem);                 \
         if (e != cudaSuccess) return e;                                                             \
         kern<<<grid, ETHREADS, smem, s>>>(X, n, d_cells, C, cb, h->d_cb_codes, nrm, D, m, dsub,     \
-                                          ksub, d_codes_out, tiled);                                \
+                                          ksub, d_codes_out, tiled, h->cfg.metric_resid);           \
     } while (0)
     switch (dsub) {
         case 4: IVF_LAUNCH_ENC(4); break;

@@ -544,6 +544,7 @@ bool scanq_shape_ok(const ivfadc_index* h, int k) {
 int scanu_dup(const ivfadc_index* h);
 bool use_scanq(const ivfadc_index* h, int64_t npairs, int k) {
     if (h->cfg.flags & IVFADC_FLAG_SCAN_LEGACY) return false;
+    if (h->cfg.metric_coarse != IVFADC_SQEUCLIDEAN) return false;   // other metrics: exact tables on the general kernel
     if (!scanq_shape_ok(h, k)) return false;
     if (h->cfg.flags & IVFADC_FLAG_SCAN_QLANE) return true;
     if (npairs < (int64_t)8 * h->cfg.kc) return false;
@@ -679,6 +680,7 @@ cudaError_t search_t(ivfadc_index* h, const void* dQ, int64_t nq, int k, int w, 
     a.cb = static_cast<const T*>(h->d_cb);
     a.cb_codes = h->d_cb_codes;
     a.cb_identity = h->cb_identity;
+    a.metric = h->cfg.metric_coarse;
     a.D = h->cfg.dim; a.m = h->cfg.m; a.dsub = h->dsub; a.ksub = h->cfg.ksub; a.kc = kc; a.w = w; a.k = k;
     a.list_off = h->d_off; a.list_len = h->d_len; a.codes = h->d_codes;
     a.cells = d_cells; a.dc = static_cast<const T*>(d_dc);

@@ -30,6 +30,7 @@ template <typename T> struct ScanArgs {
     const T* cb;         // [m][ksub][dsub]
     const uint8_t* cb_codes;
     int cb_identity;
+    int metric;          // Dc of the lookup tables: 0 SqEuclidean (fast paths), 1 Euclidean, 2 Cityblock, 3 CosineDist
     int D, m, dsub, ksub, kc, w, k;
     // lists
     const int64_t* list_off;
@@ -114,7 +115,10 @@ __device__ __forceinline__ void build_lut(const ScanArgs<T>& a, T* lut, const T*
         T s[QN];
 #pragma unroll
         for (int j = 0; j < QN; ++j) s[j] = (T)0;
-        if constexpr (DSUB > 0) {
+        if (a.metric != 0) {  // other metrics of Distances.jl: colwise(Dc, codeword, residual slice), generic chains
+#pragma unroll
+            for (int j = 0; j < QN; ++j) s[j] = metric_dist<T>(a.metric, wv, resid + j * Dp + i * dsub, dsub);
+        } else if constexpr (DSUB > 0) {
             T wreg[DSUB > 0 ? DSUB : 1];
             constexpr int VEC = 16 / sizeof(T);
             if constexpr (DSUB % VEC == 0) {

@@ -114,8 +114,12 @@ class IVFADCIndex:
 
     def _init_from_quantizers(self, centroids, cb_vectors, cb_codes, index_type, coarse_quantizer,
                               coarse_distance, quantization_distance, device, shard, flags=0):
-        if str(coarse_distance) != "SqEuclidean" or str(quantization_distance) != "SqEuclidean":
-            raise NotImplementedError("only SqEuclidean is on the hot path (SURVEY 8f-3)")
+        # Dc / Dr (src/index.jl:41-42,108-109): SqEuclidean runs on the tensor-core paths, Euclidean / Cityblock /
+        # CosineDist on the exact generic kernels; any other Distances.jl metric is outside the engine
+        for name in (str(coarse_distance), str(quantization_distance)):
+            if name not in _capi.METRICS:
+                raise NotImplementedError(f"distance {name}: supported are {sorted(_capi.METRICS)} (SURVEY 8f-3)")
+        self.coarse_distance, self.quantization_distance = str(coarse_distance), str(quantization_distance)
         self.T = centroids.dtype
         self.I = np.dtype(index_type)
         self.coarse_quantizer = coarse_quantizer
@@ -126,7 +130,8 @@ class IVFADCIndex:
         self._lib = _capi.load()
         cfg = _capi.Config(dim=self.nrows, kc=self.kc, m=self.m, ksub=self.k,
                            dtype=_dtype_code(self.T), id_bytes=self.I.itemsize,
-                           metric_coarse=_capi.SQEUCLIDEAN, metric_resid=_capi.SQEUCLIDEAN,
+                           metric_coarse=_capi.METRICS[self.coarse_distance],
+                           metric_resid=_capi.METRICS[self.quantization_distance],
                            device=device, shard_rank=shard[0], shard_world=shard[1], flags=int(flags))
         h = ctypes.c_void_p()
         rc = self._lib.ivfadc_create(ctypes.byref(h), ctypes.byref(cfg), _capi.ptr(centroids),

@@ -40,7 +40,7 @@ def save_ivfadc_index(filename, ivfadc: IVFADCIndex):
     with open(filename, "wb") as f:
         header = [f"{nrows} {nclusters}", f"{n} {m} {k} {d}", "NaiveQuantizer",
                   "QuantizedArrays.OrthogonalQuantization", "UInt8", _NP_TO_JULIA[I],
-                  "Distances.SqEuclidean", "Distances.SqEuclidean", _NP_TO_JULIA[T]]
+                  "Distances." + ivfadc.coarse_distance, "Distances." + ivfadc.quantization_distance, _NP_TO_JULIA[T]]
         f.write(("\n".join(header) + "\n").encode("ascii"))
         f.write(centroids.astype(T.newbyteorder("<")).tobytes())
         for i in range(m):

@@ -14,8 +14,12 @@ end
 
 const _ID_BITS = Dict(UInt8 => 8, UInt16 => 16, UInt32 => 32, UInt64 => 64)
 
+# SqEuclidean runs on the tensor-core paths; Euclidean / Cityblock / CosineDist on the exact generic kernels
 _metric_code(::Distances.SqEuclidean) = IVFADC_SQEUCLIDEAN
-_metric_code(d) = throw(ArgumentError("only SqEuclidean is on the GPU hot path, got $(typeof(d))"))
+_metric_code(::Distances.Euclidean) = Cint(1)
+_metric_code(::Distances.Cityblock) = Cint(2)
+_metric_code(::Distances.CosineDist) = Cint(3)
+_metric_code(d) = throw(ArgumentError("libivfadc_cuda supports SqEuclidean, Euclidean, Cityblock and CosineDist, got $(typeof(d))"))
 
 # Returns (handle, group): ENV["IVFADC_DEVICES"] with more than one device id creates a group
 # (ivfadc_group_create: one handle per device, NCCL communicator inside the library).

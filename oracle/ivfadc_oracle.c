@@ -21,6 +21,11 @@
 #include <stdlib.h>
 #include <string.h>
 
+/* metrics of the next calls (0 SqEuclidean, 1 Euclidean, 2 Cityblock, 3 CosineDist): Dc for coarse_search and the
+ * lookup tables (src/coarsequantizers.jl:34, src/index.jl:234), Dr for quantize_data (src/index.jl:187, src/utils.jl:158) */
+static int g_metric_coarse = 0, g_metric_resid = 0;
+void oracle_set_metrics(int coarse, int resid) { g_metric_coarse = coarse; g_metric_resid = resid; }
+
 #define T float
 #define FN(name) name##_f32
 #define FMA fmaf

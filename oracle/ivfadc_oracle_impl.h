@@ -25,6 +25,38 @@ static inline T FN(sqdist_direct)(const T* a, const T* b, int n) {
     return s;
 }
 
+/*
+ * Other metrics of Distances.jl (the type parameters Dc / Dr admit any PreMetric, src/index.jl:41-42,108-109).
+ * Dependency semantics restated from the published definitions of Distances ^0.10 -- UNVERIFIABLE here, one
+ * swappable function each:
+ *   Euclidean   colwise: sqrt(sum (a - b)^2)                                 (the SqEuclidean chain, then one sqrt)
+ *   Cityblock   colwise: sum |a - b|, sequential
+ *   CosineDist  colwise: max(1 - dot / (sqrt(sum a^2) sqrt(sum b^2)), 0), three sequential fma chains
+ * metric codes: 0 SqEuclidean, 1 Euclidean, 2 Cityblock, 3 CosineDist (oracle_set_metrics).
+ */
+static inline T FN(dist_colwise)(int metric, const T* a, const T* b, int n) {
+    if (metric == 0) return FN(sqdist_direct)(a, b, n);
+    if (metric == 1) return (sizeof(T) == 4) ? (T)sqrtf((float)FN(sqdist_direct)(a, b, n)) : (T)sqrt((double)FN(sqdist_direct)(a, b, n));
+    if (metric == 2) {
+        T s = (T)0;
+        for (int i = 0; i < n; ++i) {
+            T d = a[i] - b[i];
+            s = s + (d < (T)0 ? -d : d);
+        }
+        return s;
+    }
+    T ab = (T)0, a2 = (T)0, b2 = (T)0;
+    for (int i = 0; i < n; ++i) {
+        ab = FMA(a[i], b[i], ab);
+        a2 = FMA(a[i], a[i], a2);
+        b2 = FMA(b[i], b[i], b2);
+    }
+    const T na = (sizeof(T) == 4) ? (T)sqrtf((float)a2) : (T)sqrt((double)a2);
+    const T nb = (sizeof(T) == 4) ? (T)sqrtf((float)b2) : (T)sqrt((double)b2);
+    const T v = (T)1 - ab / (na * nb);
+    return v > (T)0 ? v : (T)0;   /* a zero vector gives NaN in Julia (max(NaN, 0)); here 0 -- degenerate input, not pinned */
+}
+
 static inline T FN(sumsq)(const T* a, int n) {
     T s = (T)0;
     for (int i = 0; i < n; ++i) s = FMA(a[i], a[i], s);
@@ -39,7 +71,7 @@ static inline T FN(sumsq)(const T* a, int n) {
  */
 static void FN(coarse_one)(const T* centroids, int kc, int D, const T* q, int w, int32_t* cells,
                            T* dc, T* scratch) {
-    for (int c = 0; c < kc; ++c) scratch[c] = FN(sqdist_direct)(centroids + (size_t)c * D, q, D);
+    for (int c = 0; c < kc; ++c) scratch[c] = FN(dist_colwise)(g_metric_coarse, centroids + (size_t)c * D, q, D);
     /* partial stable selection of the w smallest (distance, cell): insertion into a sorted
        prefix; equivalent to sortperm(...)[1:w]. */
     int cnt = 0;
@@ -89,10 +121,25 @@ static void FN(encode_residual)(const T* resid, int D, int m, int ksub, const T*
         int besti = -1;
         for (int c = 0; c < ksub; ++c) {
             const T* wv = cb_vectors + ((size_t)i * ksub + c) * dsub;
-            T dot = (T)0;
-            for (int d = 0; d < dsub; ++d) dot = FMA(wv[d], x[d], dot);
-            T v = (cb_norms[(size_t)i * ksub + c] + sb) - (T)2 * dot;
-            v = v > (T)0 ? v : (T)0;
+            T v;
+            if (g_metric_resid == 0 || g_metric_resid == 1) {
+                /* pairwise(SqEuclidean): GEMM form (A2); pairwise(Euclidean): its square root */
+                T dot = (T)0;
+                for (int d = 0; d < dsub; ++d) dot = FMA(wv[d], x[d], dot);
+                v = (cb_norms[(size_t)i * ksub + c] + sb) - (T)2 * dot;
+                v = v > (T)0 ? v : (T)0;
+                if (g_metric_resid == 1) v = (sizeof(T) == 4) ? (T)sqrtf((float)v) : (T)sqrt((double)v);
+            } else if (g_metric_resid == 2) {
+                v = FN(dist_colwise)(2, wv, x, dsub);   /* pairwise(Cityblock): the generic loop, evaluate per pair */
+            } else {
+                /* pairwise(CosineDist): dot products by GEMM, norms = sqrt of the column sums of squares */
+                T dot = (T)0;
+                for (int d = 0; d < dsub; ++d) dot = FMA(wv[d], x[d], dot);
+                const T na = (sizeof(T) == 4) ? (T)sqrtf((float)cb_norms[(size_t)i * ksub + c]) : (T)sqrt((double)cb_norms[(size_t)i * ksub + c]);
+                const T nb = (sizeof(T) == 4) ? (T)sqrtf((float)sb) : (T)sqrt((double)sb);
+                v = (T)1 - dot / (na * nb);
+                v = v > (T)0 ? v : (T)0;
+            }
             if (besti < 0 || v < best) {
                 best = v;
                 besti = c;
@@ -169,8 +216,8 @@ static int FN(search_one)(const T* centroids, int kc, int D, int m, int ksub, co
            -- keyed by code VALUE. */
         for (int i = 0; i < m; ++i)
             for (int cw = 0; cw < ksub; ++cw)
-                lut[i * 256 + cb_codes[(size_t)i * ksub + cw]] = FN(sqdist_direct)(
-                    cb_vectors + ((size_t)i * ksub + cw) * dsub, resid + (size_t)i * dsub, dsub);
+                lut[i * 256 + cb_codes[(size_t)i * ksub + cw]] = FN(dist_colwise)(
+                    g_metric_coarse, cb_vectors + ((size_t)i * ksub + cw) * dsub, resid + (size_t)i * dsub, dsub);
         /* :240-255  scan the list */
         for (int64_t p = offsets[cell]; p < offsets[cell + 1]; ++p) {
             const uint8_t* cd = codes + (size_t)p * m;

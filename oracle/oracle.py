@@ -66,7 +66,9 @@ class Quantizers:
     cb_codes   uint8[m][ksub]     (Julia codebooks[i].codes)
     """
 
-    def __init__(self, centroids, cb_vectors, cb_codes=None):
+    def __init__(self, centroids, cb_vectors, cb_codes=None, coarse_distance="SqEuclidean",
+                 quantization_distance="SqEuclidean"):
+        self.coarse_distance, self.quantization_distance = coarse_distance, quantization_distance
         self.centroids = np.ascontiguousarray(centroids)
         self.cb_vectors = np.ascontiguousarray(cb_vectors, dtype=self.centroids.dtype)
         self.kc, self.D = self.centroids.shape
@@ -78,6 +80,15 @@ class Quantizers:
         self.dtype = self.centroids.dtype
 
 
+METRICS = {"SqEuclidean": 0, "Euclidean": 1, "Cityblock": 2, "CosineDist": 3}
+
+
+def _set_metrics(qz):
+    """Dc / Dr of the next oracle call (the reference's type parameters, src/index.jl:41-42)."""
+    lib().oracle_set_metrics(_c_int(METRICS[getattr(qz, "coarse_distance", "SqEuclidean")]),
+                             _c_int(METRICS[getattr(qz, "quantization_distance", "SqEuclidean")]))
+
+
 def coarse_search(qz: Quantizers, Q, w: int, nthreads: int = 1):
     """coarse_search, src/coarsequantizers.jl:33-37.  Returns 0-based cells [nq, w] and dc [nq, w]."""
     Q = np.ascontiguousarray(Q, dtype=qz.dtype).reshape(-1, qz.D)
@@ -85,6 +96,7 @@ def coarse_search(qz: Quantizers, Q, w: int, nthreads: int = 1):
     w = min(w, qz.kc)
     cells = np.empty((nq, w), dtype=np.int32)
     dc = np.empty((nq, w), dtype=qz.dtype)
+    _set_metrics(qz)
     fn = getattr(lib(), "oracle_coarse_search_" + _sfx(qz.dtype))
     fn.restype = None
     fn(_p(qz.centroids), _c_int(qz.kc), _c_int(qz.D), _p(Q), _c_i64(nq), _c_int(w), _p(cells),
@@ -100,6 +112,7 @@ def encode(qz: Quantizers, X, assign=None, assign_base: int = 0, nthreads: int =
     cells = np.empty(n, dtype=np.int32)
     codes = np.empty((n, qz.m), dtype=np.uint8)
     a = None if assign is None else np.ascontiguousarray(assign, dtype=np.int64)
+    _set_metrics(qz)
     fn = getattr(lib(), "oracle_encode_" + _sfx(qz.dtype))
     fn.restype = None
     fn(_p(qz.centroids), _c_int(qz.kc), _c_int(qz.D), _c_int(qz.m), _c_int(qz.ksub),
@@ -119,6 +132,7 @@ def search_csr(qz: Quantizers, offsets, codes, ids, Q, k: int, w: int, nthreads:
     ids_out = np.empty((nq, k), dtype=np.uint64)
     dists_out = np.empty((nq, k), dtype=qz.dtype)
     counts = np.empty(nq, dtype=np.int32)
+    _set_metrics(qz)
     fn = getattr(lib(), "oracle_search_" + _sfx(qz.dtype))
     fn.restype = _c_i64
     scanned = fn(_p(qz.centroids), _c_int(qz.kc), _c_int(qz.D), _c_int(qz.m), _c_int(qz.ksub),

@@ -918,3 +918,51 @@ def test_config_c_full_size_parity():
     assert rep["near_tie_id_mismatches"] <= 8, rep
     assert int(e.stats()["last_scan_kernel"]) in (4, 5)
     e.close()
+
+
+# ------------------------------------------------------------------------------------------------
+# f3: the other metrics of Distances.jl for Dc (coarse_search + lookup tables) and Dr (quantize_data)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("dc,dr", [("Euclidean", "SqEuclidean"), ("Cityblock", "Cityblock"), ("CosineDist", "Euclidean"),
+                                   ("SqEuclidean", "CosineDist")])
+def test_other_metrics_bit_exact(dtype, dc, dr, tmp_path):
+    """Euclidean / Cityblock / CosineDist (src/index.jl:108-109): coarse cells and distances, PQ codes, and every
+    returned distance bit-identical to the oracle's restatement of the Distances.jl definitions; the saved file
+    carries the metric names and reloads to the same results."""
+    rng = np.random.default_rng(11)
+    D, m, ksub, kc, n, nq, k, w = 24, 6, 64, 40, 3000, 60, 7, 5
+    X = (rng.random((n, D)) + 0.1).astype(dtype)
+    cent = X[rng.choice(n, kc, replace=False)].copy()
+    cb = (0.3 * rng.standard_normal((m, ksub, D // m))).astype(dtype)
+    cb[:, -1] = cb[:, 0]   # an exact tie between two codewords: the first one wins
+    codes = np.stack([rng.permutation(256)[:ksub].astype(np.uint8) for _ in range(m)])
+    qz = orc.Quantizers(cent, cb, codes, coarse_distance=dc, quantization_distance=dr)
+    Q = (rng.random((nq, D)) + 0.1).astype(dtype)
+    e = iv.IVFADCIndex.from_quantizers(cent, cb, codes, coarse_distance=dc, quantization_distance=dr)
+    gcell, gdc = e.coarse_search(Q, w)
+    ocell, odc = orc.coarse_search(qz, Q, w, nthreads=2)
+    np.testing.assert_array_equal(gcell, ocell)
+    assert np.array_equal(gdc.view(np.uint8), odc.view(np.uint8))
+    gc, gcode = e.encode(X)
+    oc, ocode = orc.encode(qz, X, nthreads=4)
+    np.testing.assert_array_equal(gc, oc)
+    np.testing.assert_array_equal(gcode, ocode)
+    iv.push_batch(e, X)
+    order = np.argsort(oc, kind="stable")
+    off = np.zeros(kc + 1, dtype=np.int64)
+    np.cumsum(np.bincount(oc, minlength=kc), out=off[1:])
+    oi, od, ocnt, _ = orc.search_csr(qz, off, ocode[order], order.astype(np.uint64), Q, k, w, nthreads=4)
+    for eng in (e,):
+        gi, gd, gcnt = eng.search_packed(Q, k, w)
+        np.testing.assert_array_equal(gcnt, ocnt)
+        assert np.array_equal(gd.view(np.uint8), od.view(np.uint8))
+        np.testing.assert_array_equal(gi, oi)
+    fn = str(tmp_path / "metric.ivfadc")
+    iv.save_ivfadc_index(fn, e)
+    lines = open(fn, "rb").read().split(b"\n", 9)
+    assert lines[6] == ("Distances." + dc).encode() and lines[7] == ("Distances." + dr).encode()
+    e2 = iv.load_ivfadc_index(fn)
+    gi2, gd2, gcnt2 = e2.search_packed(Q, k, w)
+    assert np.array_equal(gi2, gi) and np.array_equal(gd2.view(np.uint8), gd.view(np.uint8))
+    e.close(); e2.close()
