@@ -506,7 +506,7 @@ def run_workload(cx, args, name, steps, headline):
         if os.path.exists(tp) and world == 1:
             tj = json.load(open(tp))
             traffic = tj.get(name)
-            traffic_src = tj.get("source", "ncu capture kept in profiles/ (not re-measured in this run)")
+            traffic_src = tj.get(name + "_source", tj.get("source", "ncu capture kept in profiles/ (not re-measured in this run)")) if traffic else None
         kern = SCAN_KERNELS.get(int(st.get("last_scan_kernel", 0)), "?")
         roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "traffic_source": traffic_src,

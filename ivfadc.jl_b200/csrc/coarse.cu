@@ -356,10 +356,23 @@ coarse_redo_small_kernel(const float* __restrict__ Q, const float* __restrict__ 
         float acc = Limits<float>::inf();
         if (c < kc) {
             acc = 0.f;
-            const float* cr = C + (size_t)c * D;
-            for (int d = 0; d < D; ++d) {
-                const float diff = sub_rn(cr[d], sq[d]);  // oracle A1: c - q, one sequential fma chain
-                acc = fma_rn(diff, diff, acc);
+            // the row as 128-bit loads, eight in flight (a scalar loop pays one L2 round trip per element: 26 us per
+            // flagged query); the chain itself stays sequential -- oracle A1: c - q, one fma chain
+            const float4* cr = reinterpret_cast<const float4*>(C + (size_t)c * D);   // D % 16 == 0 on this path
+            for (int d4 = 0; d4 < (D >> 2); d4 += 8) {
+                float4 v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) v[u] = d4 + u < (D >> 2) ? __ldg(cr + d4 + u) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    if (d4 + u < (D >> 2)) {
+                        const float* qd = sq + 4 * (d4 + u);
+                        float diff = sub_rn(v[u].x, qd[0]); acc = fma_rn(diff, diff, acc);
+                        diff = sub_rn(v[u].y, qd[1]); acc = fma_rn(diff, diff, acc);
+                        diff = sub_rn(v[u].z, qd[2]); acc = fma_rn(diff, diff, acc);
+                        diff = sub_rn(v[u].w, qd[3]); acc = fma_rn(diff, diff, acc);
+                    }
+                }
             }
         }
         __stcg(row + c, acc);
