@@ -55,6 +55,9 @@ namespace ivf {
 #ifndef IVF_X_NOEXTRACT
 #define IVF_X_NOEXTRACT 0
 #endif
+#ifndef IVF_W_HINT_NS
+#define IVF_W_HINT_NS 100000u   // suspend-time hint of mbarrier.try_wait (ns)
+#endif
 #ifndef IVF_W_PIPE
 #define IVF_W_PIPE 1   // table switch inside a lookup batch (full warps); -DIVF_W_PIPE=0 keeps one drain per table
 #endif
@@ -150,7 +153,7 @@ __device__ __forceinline__ void mbar_wait_w(uint32_t bar, uint32_t parity, uint3
     for (uint32_t o = 0; o < (W_SPIN >> 8); ++o) {
 #pragma unroll 1
         for (uint32_t i = 0; i < 256u; ++i)
-            if (mbar_try_wait_hint(bar, parity, 100000u)) return;
+            if (mbar_try_wait_hint(bar, parity, IVF_W_HINT_NS)) return;
         if (lds_u(dead_u) != 0u) return;
     }
     sts_u(dead_u, 1u);
@@ -353,7 +356,7 @@ scanw_kernel(const ScanUArgs ua) {
                     const uint32_t b = (uint32_t)s & 1u;
                     pf.tick(3);
                     tr(tg + s, 0);
-                    if (!mbar_try_wait_hint(bar_mma + 8 * b, par, 100000u)) warp_wait(bar_mma + 8 * b, par, 2);
+                    if (!mbar_try_wait_hint(bar_mma + 8 * b, par, IVF_W_HINT_NS)) warp_wait(bar_mma + 8 * b, par, 2);
                     tc_fence_after();
                     pf.tick(1);
                     tr(tg + s, 1);
@@ -423,7 +426,7 @@ scanw_kernel(const ScanUArgs ua) {
                 pf.tick(3);
                 tr(tg + s, 0);
                 // every lane polls (no divergence on the common path); the bounded loop only when the build is late
-                if (!mbar_try_wait_hint(bar_mma + 8 * b, par, 100000u)) warp_wait(bar_mma + 8 * b, par, 2);
+                if (!mbar_try_wait_hint(bar_mma + 8 * b, par, IVF_W_HINT_NS)) warp_wait(bar_mma + 8 * b, par, 2);
                 tc_fence_after();
                 pf.tick(1);
                 tr(tg + s, 1);
