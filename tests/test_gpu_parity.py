@@ -966,3 +966,56 @@ def test_other_metrics_bit_exact(dtype, dc, dr, tmp_path):
     gi2, gd2, gcnt2 = e2.search_packed(Q, k, w)
     assert np.array_equal(gi2, gi) and np.array_equal(gd2.view(np.uint8), gd.view(np.uint8))
     e.close(); e2.close()
+
+
+def test_config_d_full_size_parity():
+    """The 100 M-vector configuration at FULL size on one GPU (128-d, kc = 16384, m = 8, UInt32 ids; codes 800 MB):
+    built in HBM from the device generator, 64 queries of a full 10 000-query batch against the oracle over the lists
+    they probe (the cost model sends this shape -- 10 queries per list of 6 100 vectors -- to the exact vector-per-lane
+    kernel, so ids and distance bits are the oracle's), and the stored codes of a slice of the stream."""
+    import torch
+    from ivfadc_jl_b200 import synth
+    D, N, kc, m, nq, nchk, k, w = 128, 100_000_000, 16384, 8, 10_000, 64, 10, 16
+    centres = synth.uniform_device(0, kc, D, 1001)
+    xs = synth.blobs_device(0, 1 << 20, centres, 1002)
+    tc, tb = synth.train_on_device_tensor(xs, kc, m, 256, iters=1, init=centres)
+    del xs
+    cent, cb = tc.cpu().numpy(), tb.cpu().numpy()
+    qz = orc.Quantizers(cent, cb, None)
+    e = iv.IVFADCIndex.from_quantizers(cent, cb, None)
+    e.reserve(N)
+    buf = torch.empty((1 << 20, D), dtype=torch.float32, device="cuda")
+    for s in range(0, N, 1 << 20):
+        n = min(1 << 20, N - s)
+        x = synth.blobs_device(s, n, centres, 1002, out=buf)
+        torch.cuda.synchronize()
+        e.add_device(x.data_ptr(), n)
+    assert len(e) == N
+    Q = synth.blobs_device(0, nq, centres, 2001).cpu().numpy()
+    gi, gd, gc = e.search_packed(Q, k, w)
+    assert int(e.stats()["last_scan_kernel"]) == 1
+    # oracle over exactly the probed lists
+    ocell, _ = orc.coarse_search(qz, Q[:nchk], w, nthreads=8)
+    sizes = e.list_sizes()
+    off = np.zeros(kc + 1, dtype=np.int64)
+    need = np.unique(ocell)
+    lens = np.zeros(kc, dtype=np.int64)
+    lens[need] = sizes[need]
+    np.cumsum(lens, out=off[1:])
+    ids = np.empty(int(off[-1]), dtype=np.uint64)
+    codes = np.empty((int(off[-1]), m), dtype=np.uint8)
+    for c in need:
+        i, cd = e.export_list(int(c))
+        ids[off[c]:off[c + 1]] = i
+        codes[off[c]:off[c + 1]] = cd
+    oi, od, oc, _ = orc.search_csr(qz, off, codes, ids, Q[:nchk], k, w, nthreads=16)
+    np.testing.assert_array_equal(gc[:nchk], oc)
+    assert np.array_equal(gd[:nchk].view(np.uint8), od.view(np.uint8))
+    np.testing.assert_array_equal(gi[:nchk], oi)
+    first, ns = 87_654_321, 2048
+    xc, _ = orc.synth_blobs(first, ns, D, kc, 1002, synth.blob_scale(0.05), centres.cpu().numpy())
+    ocells, ocodes = orc.encode(qz, xc, nthreads=8)
+    gcells, gcodes = e.encode(xc)
+    np.testing.assert_array_equal(gcells, ocells)
+    np.testing.assert_array_equal(gcodes, ocodes)
+    e.close()
