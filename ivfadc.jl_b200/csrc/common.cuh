@@ -196,6 +196,8 @@ struct ivfadc_index {
     bool stats_timing = true;
     ivfadc_stats stats{};
     std::string err;
+    mutable int64_t scanw_ws_n = -1;   // scan.cu: list population the CTA shape of the scan kernel was chosen for
+    mutable int scanw_ws = 0;          // 12 or 16 scanning warps (0 = not chosen yet)
     mutable int64_t last_redo_nq = 0;  // coarse.cu: queries of the last tensor-core coarse step (redo flags in ws_coarse_redo)
     void* extra = nullptr;      // api.cu: event ring, scanned-vector counter
     void* shard_ctx = nullptr;  // shard.cu: NCCL communicator, gathered buffers, CUDA graphs

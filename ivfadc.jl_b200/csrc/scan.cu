@@ -620,7 +620,7 @@ bool use_scanq(const ivfadc_index* h, int64_t npairs, int k) {
     const double kc = std::max(1.0, (double)h->cfg.kc / world), np_loc = (double)npairs / world, nbar = np_loc / kc;
     const double lbar = std::max(1.0, (double)h->n_local / kc);
     const int tables = h->cfg.m * ((h->dsub <= 8 || h->dsub == 16) ? scanu_dup(h) : 1);
-    const double vp = (double)W_VP, nfull = std::floor(lbar / vp), frem = (lbar - nfull * vp) / vp;
+    const double vp = (double)WShape<12>::VP, nfull = std::floor(lbar / vp), frem = (lbar - nfull * vp) / vp;
     double item = nfull * (tables * 0.0062 + 0.016);
     if (frem > 0.0) item += tables * (0.0022 + 0.0040 * frem) + 0.016;
     item = std::max(item, 0.085);
@@ -643,7 +643,29 @@ bool use_scanu(const ivfadc_index* h) {
 // warp-specialised version (scanw_impl.cuh), the default; IVFADC_FLAG_SCAN_TMEM_V1 keeps the round-1 kernel
 bool use_scanw(const ivfadc_index* h) {
     if (h->cfg.flags & IVFADC_FLAG_SCAN_TMEM_V1) return false;
-    return scanw_smem_layout(h->cfg.m * scanu_dup(h), h->cfg.m).total + 1024 <= kSmemMax;
+    return scanw_smem_layout(h->cfg.m * scanu_dup(h), h->cfg.m, 12).total + 1024 <= kSmemMax;
+}
+// Shape of the warp-specialised CTA: 12 scanners x 96 distances (1152 vectors per pass) or 16 x 64 (1024 per pass,
+// four scanning warps per scheduler: ~6 % faster per pass).  The wider shape wins unless lists of 1025..1152 vectors
+// make it pay a second pass: count the passes of both shapes over the lists this handle holds (recounted when the
+// index changed) and take 16 when 0.97 x passes16 < passes12.  IVFADC_SCANW_SHAPE=12|16 pins one (A/B runs).
+int scanw_shape(const ivfadc_index* h) {
+    static const int pinned = [] {
+        const char* e = getenv("IVFADC_SCANW_SHAPE");
+        return e ? atoi(e) : 0;
+    }();
+    if (pinned == 12 || pinned == 16) return pinned;
+    if (h->scanw_ws_n != h->n_local || h->scanw_ws == 0) {
+        double p12 = 0.0, p16 = 0.0;
+        for (int64_t len : h->h_len) {
+            if (len <= 0) continue;
+            p12 += (double)((len + WShape<12>::VP - 1) / WShape<12>::VP);
+            p16 += (double)((len + WShape<16>::VP - 1) / WShape<16>::VP);
+        }
+        h->scanw_ws = 0.97 * p16 < p12 ? 16 : 12;
+        h->scanw_ws_n = h->n_local;
+    }
+    return h->scanw_ws;
 }
 
 template <int NP, bool DBG, int DUP>
@@ -656,9 +678,15 @@ cudaError_t launch_scanu_inst(const ivfadc_index* h, bool v1, const ScanUArgs& u
         if ((e = ensure_smem(h, reinterpret_cast<const void*>(&scanu_kernel<NP, DBG, DUP>), smem)) != cudaSuccess) return e;
         scanu_kernel<NP, DBG, DUP><<<grid, QTHREADS, smem, s>>>(ua);
     } else {
-        const size_t smem = scanw_smem_layout(4 * NP * DUP, 4 * NP).total;
-        if ((e = ensure_smem(h, reinterpret_cast<const void*>(&scanw_kernel<NP, DBG, DUP>), smem)) != cudaSuccess) return e;
-        scanw_kernel<NP, DBG, DUP><<<grid, W_THREADS, smem, s>>>(ua);
+        if (!DBG && scanw_shape(h) == 16) {   // (the phase profile / table dump of the DBG instantiation knows the 12 x 96 shape)
+            const size_t smem = scanw_smem_layout(4 * NP * DUP, 4 * NP, 16).total;
+            if ((e = ensure_smem(h, reinterpret_cast<const void*>(&scanw_kernel<NP, false, DUP, 16>), smem)) != cudaSuccess) return e;
+            scanw_kernel<NP, false, DUP, 16><<<grid, WShape<16>::THREADS, smem, s>>>(ua);
+        } else {
+            const size_t smem = scanw_smem_layout(4 * NP * DUP, 4 * NP, 12).total;
+            if ((e = ensure_smem(h, reinterpret_cast<const void*>(&scanw_kernel<NP, DBG, DUP, 12>), smem)) != cudaSuccess) return e;
+            scanw_kernel<NP, DBG, DUP, 12><<<grid, WShape<12>::THREADS, smem, s>>>(ua);
+        }
     }
     return cudaGetLastError();
 }

@@ -37,7 +37,7 @@
 
 namespace ivf {
 
-// Two shapes of the CTA (-DIVF_W16=1 selects the second one; A/B runs through IVFADC_NVCC_EXTRA):
+// Two shapes of the CTA (scan.cu chooses per index; IVFADC_SCANW_SHAPE=12|16 in the environment pins one for A/B runs):
 //   12 scanners x 96 partial distances (152 registers), 1152 vectors per pass, 512 threads
 //   16 scanners x 64 partial distances (112 registers), 1024 vectors per pass, 640 threads -- four scanning warps
 //      per scheduler instead of three: a warp's table round is a chain of lookup batches (32 in flight, then
@@ -45,9 +45,6 @@ namespace ivf {
 //      Register budget: setmaxnreg.inc is served from what the CTA's own warps released with setmaxnreg.dec (not
 //      from unallocated registers of the SM): 640 threads launch with 96; the four service warps drop to 32 and
 //      free 4 x 32 x 64 = 8192 = 16 x 32 x (112 - 96).  (120 / 32 and 112 / 56 wait forever in setmaxnreg.inc.)
-#ifndef IVF_W16
-#define IVF_W16 0
-#endif
 // bring-up timing experiments (wrong results): IVF_X_NOLOOKUP skips the lookups, IVF_X_NOEXTRACT the end-of-pass selection
 #ifndef IVF_X_NOLOOKUP
 #define IVF_X_NOLOOKUP 0
@@ -61,24 +58,25 @@ namespace ivf {
 #ifndef IVF_W_PIPE
 #define IVF_W_PIPE 1   // table switch inside a lookup batch (full warps); -DIVF_W_PIPE=0 keeps one drain per table
 #endif
-#if IVF_W16
-constexpr int W_SCAN = 16;                   // scanning warps
-constexpr int W_NV = 64;                     // partial distances per lane
-#define IVF_W_SCAN_REGS "112"
-#define IVF_W_SERVICE_REGS "32"
-#else
-constexpr int W_SCAN = 12;
-constexpr int W_NV = 96;
-#define IVF_W_SCAN_REGS "152"
-#define IVF_W_SERVICE_REGS "40"
-#endif
-constexpr int W_THREADS = (W_SCAN + 4) * 32; // + issuer, two loaders, operand writer
-constexpr int W_ISSUE = W_SCAN, W_LOAD = W_SCAN + 1, W_OPER = W_SCAN + 3;
+// Both shapes are compiled (template parameter WS = scanning warps); scan.cu picks one per index from the list lengths.
+template <int WS> struct WShape {
+    static_assert(WS == 12 || WS == 16, "12 x 96 or 16 x 64");
+    static constexpr int SCAN = WS;                      // scanning warps
+    static constexpr int NV = WS == 16 ? 64 : 96;        // partial distances per lane
+    static constexpr int THREADS = (WS + 4) * 32;        // + issuer, two loaders, operand writer
+    static constexpr int ISSUE = WS, LOAD = WS + 1, OPER = WS + 3;
+    static constexpr int NCH = NV / 16;                  // chunks of 16 vectors per scanner and pass
+    static constexpr int VP = SCAN * NV;                 // vectors per pass: 1152 / 1024
+    static constexpr int CSTEP = 16 * SCAN;              // byte distance of a scanner's consecutive chunks in a plane
+    static constexpr int NMIN = 2 * SCAN;                // group minima per query and pass
+};
+// the names the kernel body uses, bound to the shape of the instantiation
+#define IVF_W_SHAPE_ALIASES(WS)                                                                           \
+    constexpr int W_SCAN = WShape<WS>::SCAN, W_NV = WShape<WS>::NV, W_ISSUE = WShape<WS>::ISSUE,          \
+                  W_LOAD = WShape<WS>::LOAD, W_OPER = WShape<WS>::OPER, W_NCH = WShape<WS>::NCH,          \
+                  W_VP = WShape<WS>::VP, W_CSTEP = WShape<WS>::CSTEP, W_NMIN = WShape<WS>::NMIN;          \
+    (void)W_SCAN; (void)W_NV; (void)W_ISSUE; (void)W_LOAD; (void)W_OPER; (void)W_NCH; (void)W_VP; (void)W_CSTEP; (void)W_NMIN
 constexpr int W_NLOAD = 64;                  // loader threads
-constexpr int W_NCH = W_NV / 16;             // chunks of 16 vectors per scanner and pass
-constexpr int W_VP = W_SCAN * W_NV;          // 1152 vectors per pass
-constexpr int W_CSTEP = 16 * W_SCAN;         // byte distance of a scanner's consecutive chunks in a plane
-constexpr int W_NMIN = 2 * W_SCAN;           // group minima per query and pass
 constexpr int W_STATE = 8 * QG * 4;          // per item: pair | dc -> base 2^s | run | cnt | flag | 2^sr | a | 2^-s
 constexpr int W_SEG = 32;                    // per segment: valid, nv, pass, ipar, nj, last
 constexpr int W_CAND = QG * U_CAP * 4;       // one plane (distances or positions) of the staged candidates of a pass
@@ -96,7 +94,8 @@ struct ScanWSmem {
 };
 
 // m = tables per item (8 dims each), mc = code bytes per vector
-__host__ __device__ inline ScanWSmem scanw_smem_layout(int m, int mc) {
+__host__ __device__ inline ScanWSmem scanw_smem_layout(int m, int mc, int ws) {
+    const int W_VP = ws == 16 ? WShape<16>::VP : WShape<12>::VP, W_NMIN = 2 * ws;
     ScanWSmem s;
     uint32_t o = 0;
     s.aring = o;   o += 2 * W_ASUB;
@@ -165,8 +164,9 @@ __device__ __forceinline__ void mbar_wait_w(uint32_t bar, uint32_t parity, uint3
 // instantiation + ncu): a lookup comes back after ~300 clocks under load, and with 16 in flight per warp the twelve
 // scanners keep only ~190 lookups in the tensor-memory pipe -- 0.5 per clock of the 1.0 it sustains.  Two chunks
 // (32 lookups) per wait.
-template <bool FULL>
-__device__ __forceinline__ void scanw_sub(uint32_t tb, uint32_t plane_w, int nch, float (&acc)[W_NV]) {
+template <bool FULL, int WS>
+__device__ __forceinline__ void scanw_sub(uint32_t tb, uint32_t plane_w, int nch, float (&acc)[WShape<WS>::NV]) {
+    IVF_W_SHAPE_ALIASES(WS);
 #pragma unroll
     for (int jp = 0; jp < W_NCH / 2; ++jp) {
         const int j0 = 2 * jp, j1 = 2 * jp + 1;
@@ -232,9 +232,10 @@ struct WProf {
     }
 };
 
-template <int NP, bool DBG, int DUP = 1>
-__global__ void __launch_bounds__(W_THREADS, 1)
+template <int NP, bool DBG, int DUP, int WS>
+__global__ void __launch_bounds__(WShape<WS>::THREADS, 1)
 scanw_kernel(const ScanUArgs ua) {
+    IVF_W_SHAPE_ALIASES(WS);
     const ScanQArgs& a = ua.q;
     extern __shared__ __align__(1024) unsigned char smem_w[];
     constexpr int mc = 4 * NP;      // code bytes per vector
@@ -252,7 +253,7 @@ scanw_kernel(const ScanUArgs ua) {
 
     uint32_t sb;
     asm volatile("mov.u32 %0, %1;" : "=r"(sb) : "r"(smem_u32(smem_w)));
-    const ScanWSmem L = scanw_smem_layout(m, mc);
+    const ScanWSmem L = scanw_smem_layout(m, mc, WS);
     const uint32_t aring_u = sb + L.aring, bring_u = sb + L.bring, planes_u = sb + L.planes,
                    raw_u = sb + L.raw, resid_u = sb + L.resid, rawq_u = sb + L.rawq, smin_u = sb + L.smin,
                    thr_u = sb + L.thr, rnorm_u = sb + L.rnorm, rmax_u = sb + L.rmax, state_u = sb + L.state, seg_u = sb + L.seg,
@@ -316,7 +317,8 @@ scanw_kernel(const ScanUArgs ua) {
 
     if (wid < W_SCAN) {
         // =========================================== SCANNERS ===========================================
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 " IVF_W_SCAN_REGS ";");
+        if constexpr (WS == 16) asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
+        else asm volatile("setmaxnreg.inc.sync.aligned.u32 152;");
         const uint32_t tq = tmem_base + ((uint32_t)((wid & 3) * 32) << 16);
         const uint32_t plane_w0 = planes_u + 16 * wid;
         WProf<DBG> pf;  // 0 wait staged, 1 wait table, 2 lookups, 3 release, 4 minima + barrier, 5 rank + barrier, 6 candidates
@@ -344,7 +346,7 @@ scanw_kernel(const ScanUArgs ua) {
             const uint32_t plane_seg = plane_w0 + spar * PLANES_BYTES;
             uint32_t par = (tg >> 1) & 1;
 #if IVF_W_PIPE
-            if (nch == W_NCH) {
+            if (WS == 12 && nch == W_NCH) {   // (measured: the 16-scanner shape is faster with one drain per table)
                 // Full warp (all its chunks inside the list): the table switch happens INSIDE a lookup batch.  The
                 // last chunk of table s stays in flight while the warp releases nothing yet, acquires table s + 1
                 // and issues its first chunk; one tcgen05.wait::ld covers both, then table s is released.  The
@@ -435,8 +437,8 @@ scanw_kernel(const ScanUArgs ua) {
 #if IVF_X_NOLOOKUP
                 acc[s & 15] += 1.0f + (float)wid;
 #else
-                if (nch == W_NCH) scanw_sub<true>(tb, plane_w, nch, acc);
-                else scanw_sub<false>(tb, plane_w, nch, acc);
+                if (nch == W_NCH) scanw_sub<true, WS>(tb, plane_w, nch, acc);
+                else scanw_sub<false, WS>(tb, plane_w, nch, acc);
 #endif
                 pf.tick(2);
                 tr(tg + s, 2);
@@ -543,7 +545,8 @@ scanw_kernel(const ScanUArgs ua) {
         }
         pf.store(stamps && lane == 0 && drow >= 0 ? stamps + 8 * drow : nullptr);
     } else {
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 " IVF_W_SERVICE_REGS ";");
+        if constexpr (WS == 16) asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
+        else asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
         if (wid == W_ISSUE) {
             // =========================================== ISSUER ===========================================
             const uint64_t descA0 = tc_smem_desc(aring_u), descB0 = tc_smem_desc(bring_u);
