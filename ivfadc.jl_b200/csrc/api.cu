@@ -124,9 +124,125 @@ int search_chunk(ivfadc_index* h, const void* dQ, int64_t nq, int k, int w, uint
     return IVFADC_OK;
 }
 
+// ---- Float64 indexes: the Float32 search twin ---------------------------------------------------------------
+// The reference's own tests are Float64 (test/index.jl:7).  With default flags a LARGE Float64 batch -- one the
+// cost model would give to the tensor-memory kernel -- is searched by a Float32 engine that shares this handle's
+// lists (the CSR arenas hold bytes and ids, no floats) and holds the quantizers rounded to fp32: distances come
+// back within the north_star tolerance (1e-5 relative; measured ~5e-7) widened to Float64.  Small batches, any
+// tuning flag, IVFADC_FLAG_LUT_EXACT, sharded handles and caller-supplied probes keep the exact fp64 chain.
+__global__ void narrow_kernel(const double* __restrict__ in, float* __restrict__ out, int64_t n, int* __restrict__ bad) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float v = (float)in[i];
+    out[i] = v;
+    if (!(fabsf(v) <= 1e18f)) *bad = 40;   // outside what the fp32 pipeline can square: reported as a pipeline fault
+}
+__global__ void widen_kernel(const float* __restrict__ in, double* __restrict__ out, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (double)in[i];
+}
+
+struct ListsView {
+    uint8_t* d_codes; void* d_ids; int64_t arena_cap, arena_used; int64_t *d_off, *d_len; int64_t n_total, n_local;
+};
+ListsView lists_view(const ivfadc_index* h) {
+    return {h->d_codes, h->d_ids, h->arena_cap, h->arena_used, h->d_off, h->d_len, h->n_total, h->n_local};
+}
+void lists_set(ivfadc_index* h, const ListsView& v) {
+    h->d_codes = v.d_codes; h->d_ids = v.d_ids; h->arena_cap = v.arena_cap; h->arena_used = v.arena_used;
+    h->d_off = v.d_off; h->d_len = v.d_len; h->n_total = v.n_total; h->n_local = v.n_local;
+}
+
+// pipeline flag of the twin after a synchronised search (the twin's kernels report into its own flag word)
+int twin_check(ivfadc_index* h) {
+    if (!h->twin || !h->twin_used || !h->twin->d_err) return IVFADC_OK;
+    h->twin_used = false;
+    int flag = 0;
+    if (cudaMemcpy(&flag, h->twin->d_err, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) {
+        cudaGetLastError();
+        return fail(h, IVFADC_ERR_CUDA, "D2H");
+    }
+    if (!flag) return IVFADC_OK;
+    cudaMemset(h->twin->d_err, 0, sizeof(int));
+    if (flag == 40) return fail(h, IVFADC_ERR_UNSUPPORTED, "Float64 query outside the Float32 range of the default search path: use IVFADC_FLAG_LUT_EXACT");
+    return api_check_pipeline_flag(h, flag);
+}
+
+bool twin_ensure(ivfadc_index* h) {
+    if (h->twin) return true;
+    if (h->twin_failed) return false;
+    h->twin_failed = true;   // until everything below has worked
+    const ivfadc_config& c = h->cfg;
+    const size_t nc = (size_t)c.kc * c.dim, nb = (size_t)c.m * c.ksub * h->dsub, ncode = (size_t)c.m * c.ksub;
+    std::vector<double> cd(nc), bd(nb);
+    std::vector<uint8_t> codes(ncode);
+    if (cudaMemcpy(cd.data(), h->d_centroids, nc * 8, cudaMemcpyDeviceToHost) != cudaSuccess ||
+        cudaMemcpy(bd.data(), h->d_cb, nb * 8, cudaMemcpyDeviceToHost) != cudaSuccess ||
+        cudaMemcpy(codes.data(), h->d_cb_codes, ncode, cudaMemcpyDeviceToHost) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    std::vector<float> cf(nc), bf(nb);
+    for (size_t i = 0; i < nc; ++i) { cf[i] = (float)cd[i]; if (!(std::fabs(cf[i]) <= 1e18f)) return false; }
+    for (size_t i = 0; i < nb; ++i) { bf[i] = (float)bd[i]; if (!(std::fabs(bf[i]) <= 1e18f)) return false; }
+    ivfadc_config c32 = c;
+    c32.dtype = IVFADC_F32;
+    ivfadc_index* t = nullptr;
+    if (ivfadc_create(&t, &c32, cf.data(), bf.data(), codes.data()) != IVFADC_OK) return false;
+    if (!t->d_err && (cudaMalloc(&t->d_err, sizeof(int)) != cudaSuccess || cudaMemset(t->d_err, 0, sizeof(int)) != cudaSuccess)) {
+        cudaGetLastError();
+        ivfadc_destroy(t);
+        return false;
+    }
+    h->twin = t;
+    h->twin_failed = false;
+    return true;
+}
+
 int search_core(ivfadc_index* h, const void* dQ, int64_t nq, int k, int w, uint64_t* d_ids, void* d_dists,
                 uint64_t* d_keys, int32_t* d_counts, cudaStream_t s, const int32_t* ext_cells = nullptr,
-                const void* ext_dc = nullptr) {
+                const void* ext_dc = nullptr);
+
+// returns 1 when the twin declined (the caller continues on the exact path), else a status code
+int search_via_twin(ivfadc_index* h, const void* dQ, int64_t nq, int k, int w, uint64_t* d_ids, void* d_dists,
+                    uint64_t* d_keys, int32_t* d_counts, cudaStream_t s) {
+    if (!twin_ensure(h)) return 1;
+    ivfadc_index* t = h->twin;
+    const ListsView own = lists_view(t);
+    lists_set(t, lists_view(h));
+    t->h_off = h->h_off; t->h_len = h->h_len; t->h_cap = h->h_cap;
+    const int wc = std::min(w, h->cfg.kc);
+    int rc = 1;
+    if (k <= scan_max_k() && wc <= coarse_max_w() && scan_takes_tensor_path(t, nq * (int64_t)wc, k)) {
+        const size_t nqd = (size_t)nq * h->cfg.dim, nk = (size_t)nq * k;
+        rc = IVFADC_OK;
+        if (t->ws_q.reserve(nqd * 4) != cudaSuccess || t->ws_out_d.reserve(nk * 4) != cudaSuccess) rc = fail(h, IVFADC_ERR_OOM, "workspace");
+        if (rc == IVFADC_OK) {
+            narrow_kernel<<<(unsigned)((nqd + 255) / 256), 256, 0, s>>>(static_cast<const double*>(dQ), t->ws_q.as<float>(),
+                                                                        (int64_t)nqd, t->d_err);
+            t->stats_timing = h->stats_timing;
+            rc = search_core(t, t->ws_q.p, nq, k, w, d_ids, t->ws_out_d.p, d_keys, d_counts, s, nullptr, nullptr);
+            if (rc != IVFADC_OK) h->err = t->err;
+        }
+        if (rc == IVFADC_OK) {
+            widen_kernel<<<(unsigned)((nk + 255) / 256), 256, 0, s>>>(t->ws_out_d.as<float>(), static_cast<double*>(d_dists), (int64_t)nk);
+            if (cudaGetLastError() != cudaSuccess) rc = fail(h, IVFADC_ERR_CUDA, "widen kernel");
+            h->stats.searches += 1;
+            h->stats.queries += nq;
+            h->stats.gpu_launches += 2;
+            h->stats.last_scan_kernel = t->stats.last_scan_kernel;
+            h->twin_used = true;
+        }
+    }
+    lists_set(t, own);   // the kernels took the device pointers by value; the twin owns nothing of the parent's
+    t->h_off.assign(h->cfg.kc, 0); t->h_len.assign(h->cfg.kc, 0); t->h_cap.assign(h->cfg.kc, 0);
+    t->scanw_ws_n = -1;
+    return rc;
+}
+
+int search_core(ivfadc_index* h, const void* dQ, int64_t nq, int k, int w, uint64_t* d_ids, void* d_dists,
+                uint64_t* d_keys, int32_t* d_counts, cudaStream_t s, const int32_t* ext_cells,
+                const void* ext_dc) {
     if (!dQ || !d_ids || !d_dists || !d_counts) return fail(h, IVFADC_ERR_BAD_ARG, "null pointer");
     if (nq < 0) return fail(h, IVFADC_ERR_BAD_ARG, "nq < 0");
     if (k < 1) return fail(h, IVFADC_ERR_BAD_ARG, "Number of neighbors must be k >= 1");
@@ -136,6 +252,11 @@ int search_core(ivfadc_index* h, const void* dQ, int64_t nq, int k, int w, uint6
     if (k > scan_max_k()) return fail(h, IVFADC_ERR_UNSUPPORTED, "k > 128 is not supported by the scan kernel yet");
     if (w > coarse_max_w()) return fail(h, IVFADC_ERR_UNSUPPORTED, "w > 128 is not supported by the coarse kernel yet");
     if (nq == 0) return IVFADC_OK;
+    if (h->cfg.dtype == IVFADC_F64 && h->cfg.flags == 0 && h->cfg.shard_world == 1 && !ext_cells &&
+        h->cfg.metric_coarse == IVFADC_SQEUCLIDEAN && !h->d_dbg_lut) {
+        const int rc = search_via_twin(h, dQ, nq, k, w, d_ids, d_dists, d_keys, d_counts, s);
+        if (rc != 1) return rc;
+    }
     h->stats.searches += 1;
     // bound the per-pair candidate workspace (~512 MB): a pair's row holds k sorted entries, or 64 candidates
     // (distance + position) when the tensor-memory kernels serve the batch (pair_stride in scan.cu)
@@ -333,6 +454,10 @@ int ivfadc_destroy(ivfadc_index* h) {
     if (!h) return IVFADC_OK;
     cudaSetDevice(h->cfg.device);
     cudaDeviceSynchronize();
+    if (h->twin) {
+        ivfadc_destroy(h->twin);
+        h->twin = nullptr;
+    }
     shard_destroy_ctx(h);
     if (h->d_owner) cudaFree(h->d_owner);
     Extra* x = extra(h);
@@ -572,7 +697,7 @@ int ivfadc_search(ivfadc_index* h, const void* Q, int64_t nq, int32_t k, int32_t
         else CUDA_OR_FAIL(h, cudaMemcpy(&flag, h->d_err, sizeof(int), cudaMemcpyDeviceToHost), "D2H");
         if (flag) return api_check_pipeline_flag(h, flag);
     }
-    return IVFADC_OK;
+    return twin_check(h);
 }
 
 int ivfadc_search_device(ivfadc_index* h, const void* dQ, int64_t nq, int32_t k, int32_t w, uint64_t* d_ids,
@@ -823,10 +948,12 @@ int ivfadc_check_async(ivfadc_index* h, void* stream) {
     if (check_handle(h)) return IVFADC_ERR_BAD_ARG;
     cudaSetDevice(h->cfg.device);
     CUDA_OR_FAIL(h, cudaStreamSynchronize(static_cast<cudaStream_t>(stream)), "sync");
-    if (!h->d_err) return IVFADC_OK;
-    int flag = 0;
-    CUDA_OR_FAIL(h, cudaMemcpy(&flag, h->d_err, sizeof(int), cudaMemcpyDeviceToHost), "D2H");
-    return api_check_pipeline_flag(h, flag);
+    if (h->d_err) {
+        int flag = 0;
+        CUDA_OR_FAIL(h, cudaMemcpy(&flag, h->d_err, sizeof(int), cudaMemcpyDeviceToHost), "D2H");
+        if (flag) return api_check_pipeline_flag(h, flag);
+    }
+    return twin_check(h);
 }
 
 int ivfadc_debug_tables(ivfadc_index* h, void* out) {
@@ -869,6 +996,15 @@ int ivfadc_get_stats(ivfadc_index* h, ivfadc_stats* out) {
             for (uint8_t f : flags) h->stats.last_coarse_redo += f ? 1 : 0;
     }
     *out = h->stats;
+    if (h->twin) {   // Float64 handle: the large batches ran on the Float32 twin
+        ivfadc_stats ts;
+        if (ivfadc_get_stats(h->twin, &ts) == IVFADC_OK) {
+            out->coarse_ms += ts.coarse_ms; out->plan_ms += ts.plan_ms; out->scan_ms += ts.scan_ms; out->merge_ms += ts.merge_ms;
+            out->scan_launches += ts.scan_launches; out->gpu_launches += ts.gpu_launches;
+            out->scanned_vectors += ts.scanned_vectors; out->scan_code_bytes += ts.scan_code_bytes;
+            if (ts.last_coarse_redo) out->last_coarse_redo = ts.last_coarse_redo;
+        }
+    }
     return IVFADC_OK;
 }
 
@@ -878,6 +1014,7 @@ int ivfadc_reset_stats(ivfadc_index* h) {
     flush_all(h);
     h->stats = ivfadc_stats{};
     cudaMemset(extra(h)->d_scanned, 0, sizeof(uint64_t));
+    if (h->twin) ivfadc_reset_stats(h->twin);
     return IVFADC_OK;
 }
 

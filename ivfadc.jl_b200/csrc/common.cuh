@@ -199,6 +199,10 @@ struct ivfadc_index {
     mutable int64_t scanw_ws_n = -1;   // scan.cu: list population the CTA shape of the scan kernel was chosen for
     mutable int scanw_ws = 0;          // 12 or 16 scanning warps (0 = not chosen yet)
     mutable int64_t last_redo_nq = 0;  // coarse.cu: queries of the last tensor-core coarse step (redo flags in ws_coarse_redo)
+    // Float64 index, default flags, large batch: the search runs on a Float32 twin (same lists, quantizers rounded
+    // to fp32) -- the tensor-core path within the north_star tolerance instead of the exact fp64 chain (api.cu)
+    ivfadc_index* twin = nullptr;
+    bool twin_failed = false, twin_used = false;
     void* extra = nullptr;      // api.cu: event ring, scanned-vector counter
     void* shard_ctx = nullptr;  // shard.cu: NCCL communicator, gathered buffers, CUDA graphs
 };
@@ -241,6 +245,7 @@ struct ScanPlanSizes {
 int scan_max_k();
 cudaError_t scanq_prepare(ivfadc_index* h, cudaStream_t s, int* launches);
 bool scan_supported(const ivfadc_index* h, std::string* why);
+bool scan_takes_tensor_path(const ivfadc_index* h, int64_t npairs, int k);   // the cost model picks the tensor-memory kernel
 bool encode_supported(const ivfadc_index* h);   // encode.cu: one codeword block + one residual slice fit a CTA
 ScanPlanSizes scan_plan_sizes(const ivfadc_index* h, int64_t nq, int w, int k);
 // K2+K3: plan, fused LUT build + list scan + per-pair top-k, then per-query merge.

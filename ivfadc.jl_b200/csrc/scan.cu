@@ -937,6 +937,8 @@ cudaError_t scanq_prepare(ivfadc_index* h, cudaStream_t s, int* launches) {
     return cudaGetLastError();
 }
 
+bool scan_takes_tensor_path(const ivfadc_index* h, int64_t npairs, int k) { return use_scanq(h, npairs, k) && use_scanu(h); }
+
 bool scan_supported(const ivfadc_index* h, std::string* why) {
     if (h->cfg.ksub > 256 || h->cfg.ksub < 1) {
         if (why) *why = "codebooks with more than 256 codewords (UInt16 codes) are outside the hot-path scope";

@@ -1019,3 +1019,47 @@ def test_config_d_full_size_parity():
     np.testing.assert_array_equal(gcells, ocells)
     np.testing.assert_array_equal(gcodes, ocodes)
     e.close()
+
+
+def test_float64_large_batch_takes_the_float32_twin():
+    """Float64 index (the reference's own tests are Float64), default flags: a large batch is searched by the Float32
+    twin (tensor-memory kernel; distances within the north_star tolerance, widened to Float64); a small batch and
+    IVFADC_FLAG_LUT_EXACT keep the exact fp64 chain (bit-identical); the twin follows mutations of the lists."""
+    from ivfadc_jl_b200 import synth
+    D, m, kc, n, nq, k, w = 128, 16, 64, 60000, 1500, 10, 8
+    X = synth.blobs(n, D, kc, seed=51, dtype=np.float64)
+    Q = synth.blobs(nq, D, kc, seed=52, dtype=np.float64)
+    _, cb, codes = synth.random_quantizers(kc, D, m, 256, seed=9, dtype=np.float64, data=X)
+    cent = synth.blob_centres(D, kc, dtype=np.float64)
+    qz = orc.Quantizers(cent, cb, codes)
+    e = iv.IVFADCIndex.from_quantizers(cent, cb, codes)          # default flags
+    iv.push_batch(e, X)
+
+    def oracle_of(engine, queries):
+        sizes, ids, codes_all = engine.export_all()
+        off = np.zeros(kc + 1, dtype=np.int64)
+        np.cumsum(sizes, out=off[1:])
+        return orc.search_csr(qz, off, codes_all, ids.astype(np.uint64), queries, k, w, nthreads=8)[:3]
+
+    oi, od, oc = oracle_of(e, Q)
+    gi, gd, gc = e.search_packed(Q, k, w)
+    assert gd.dtype == np.float64 and int(e.stats()["last_scan_kernel"]) in (4, 5)
+    rep = orc.compare_search(gi, gd, gc, oi, od, oc, rtol=RTOL)
+    assert rep["max_rel_err"] > 0 and rep["near_tie_id_mismatches"] <= 4, rep
+    # a small batch stays on the exact chain
+    si, sd, sc = e.search_packed(Q[:20], k, w)
+    assert int(e.stats()["last_scan_kernel"]) == 1
+    assert np.array_equal(sd.view(np.uint8), od[:20].view(np.uint8)) and np.array_equal(si, oi[:20])
+    # the twin sees the lists as they are now
+    iv.delete_from_index(e, np.arange(1, 5001))
+    iv.push_batch(e, X[:777])
+    oi2, od2, oc2 = oracle_of(e, Q)
+    gi2, gd2, gc2 = e.search_packed(Q, k, w)
+    orc.compare_search(gi2, gd2, gc2, oi2, od2, oc2, rtol=RTOL)
+    assert not np.array_equal(gi2, gi)
+    e.close()
+    ex = iv.IVFADCIndex.from_quantizers(cent, cb, codes, flags=LUT_EXACT)
+    iv.push_batch(ex, X)
+    xi, xd, xc = ex.search_packed(Q, k, w)
+    assert np.array_equal(xd.view(np.uint8), od.view(np.uint8)) and np.array_equal(xi, oi)
+    ex.close()
