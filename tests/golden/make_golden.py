@@ -40,7 +40,39 @@ def make(name, data, kc, k, m, id_bytes, nq, searches, seed):
     print(path, os.path.getsize(path), "bytes")
 
 
+METRIC_PAIRS = [("Euclidean", "SqEuclidean"), ("Cityblock", "Cityblock"), ("CosineDist", "Euclidean"), ("SqEuclidean", "CosineDist")]
+
+
+def make_metrics(name, dtype, seed):
+    """The other metrics of Distances.jl (Dc for coarse_search + lookup tables, Dr for quantize_data): one small data set,
+    per (Dc, Dr) pair the oracle's cells, codes, coarse distances and search results."""
+    rng = np.random.default_rng(seed)
+    D, m, ksub, kc, n, nq, k, w = 12, 3, 32, 20, 600, 24, 5, 4
+    X = (rng.random((n, D)) + 0.1).astype(dtype)
+    cent = X[rng.choice(n, kc, replace=False)].copy()
+    cb = (0.3 * rng.standard_normal((m, ksub, D // m))).astype(dtype)
+    codes = np.stack([rng.permutation(256)[:ksub].astype(np.uint8) for _ in range(m)])
+    Q = (rng.random((nq, D)) + 0.1).astype(dtype)
+    out = dict(centroids=cent, cb_vectors=cb, cb_codes=codes, X=X, Q=Q, k=np.int64(k), w=np.int64(w))
+    for dc, dr in METRIC_PAIRS:
+        qz = orc.Quantizers(cent, cb, codes, coarse_distance=dc, quantization_distance=dr)
+        cells, pq = orc.encode(qz, X, nthreads=2)
+        ccells, cdc = orc.coarse_search(qz, Q, w, nthreads=2)
+        order = np.argsort(cells, kind="stable")
+        off = np.zeros(kc + 1, dtype=np.int64)
+        np.cumsum(np.bincount(cells, minlength=kc), out=off[1:])
+        oi, od, oc, _ = orc.search_csr(qz, off, pq[order], order.astype(np.uint64), Q, k, w, nthreads=2)
+        t = f"{dc}_{dr}"
+        out.update({f"cells_{t}": cells, f"codes_{t}": pq, f"ccells_{t}": ccells, f"cdc_{t}": cdc,
+                    f"ids_{t}": oi, f"dists_{t}": od, f"counts_{t}": oc})
+    path = os.path.join(HERE, name + ".npz")
+    np.savez_compressed(path, **out)
+    print(path, os.path.getsize(path), "bytes")
+
+
 if __name__ == "__main__":
+    make_metrics("metrics_f32", np.float32, 5)
+    make_metrics("metrics_f64", np.float64, 6)
     # config A, README.md:31-46 (shrunk database: 400 vectors, kc = 40, k = 64 keeps the file small)
     rng = np.random.default_rng(0)
     make("readme_f32", rng.random((50, 400)).astype(np.float32), kc=40, k=64, m=10, id_bytes=2, nq=48,

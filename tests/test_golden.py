@@ -139,3 +139,62 @@ def test_validation_bundle_against_oracle():
     for j in range(nq):
         assert np.array_equal(gi[j, :gc[j]], oi[j, :oc[j]])
         assert np.array_equal(gd[j, :gc[j]].view(np.uint32), od[j, :oc[j]].view(np.uint32))
+
+
+# ---- the other metrics (Euclidean / Cityblock / CosineDist): fixtures of the oracle's restatement -----------------
+METRIC_PAIRS = [("Euclidean", "SqEuclidean"), ("Cityblock", "Cityblock"), ("CosineDist", "Euclidean"), ("SqEuclidean", "CosineDist")]
+
+
+def _metric_case(z, dc, dr):
+    qz = orc.Quantizers(z["centroids"], z["cb_vectors"], z["cb_codes"], coarse_distance=dc, quantization_distance=dr)
+    t = f"{dc}_{dr}"
+    return qz, t
+
+
+@pytest.mark.parametrize("name", ["metrics_f32", "metrics_f64"])
+@pytest.mark.parametrize("dc,dr", METRIC_PAIRS)
+def test_oracle_reproduces_metric_golden(name, dc, dr):
+    z = np.load(os.path.join(HERE, "golden", name + ".npz"))
+    qz, t = _metric_case(z, dc, dr)
+    X, Q, k, w = z["X"], z["Q"], int(z["k"]), int(z["w"])
+    cells, pq = orc.encode(qz, X, nthreads=2)
+    np.testing.assert_array_equal(cells, z[f"cells_{t}"])
+    np.testing.assert_array_equal(pq, z[f"codes_{t}"])
+    ccells, cdc = orc.coarse_search(qz, Q, w, nthreads=2)
+    np.testing.assert_array_equal(ccells, z[f"ccells_{t}"])
+    assert np.array_equal(cdc.view(np.uint8), z[f"cdc_{t}"].view(np.uint8))
+    order = np.argsort(cells, kind="stable")
+    off = np.zeros(qz.kc + 1, dtype=np.int64)
+    np.cumsum(np.bincount(cells, minlength=qz.kc), out=off[1:])
+    oi, od, oc, _ = orc.search_csr(qz, off, pq[order], order.astype(np.uint64), Q, k, w, nthreads=2)
+    np.testing.assert_array_equal(oc, z[f"counts_{t}"])
+    np.testing.assert_array_equal(oi, z[f"ids_{t}"])
+    assert np.array_equal(od.view(np.uint8), z[f"dists_{t}"].view(np.uint8))
+    # and against the plain numpy float64 definition of the metric (loose: different summation order / precision)
+    c, q = z["centroids"].astype(np.float64), Q[0].astype(np.float64)
+    ref = {"SqEuclidean": ((c - q) ** 2).sum(1), "Euclidean": np.sqrt(((c - q) ** 2).sum(1)), "Cityblock": np.abs(c - q).sum(1),
+           "CosineDist": 1 - (c @ q) / np.sqrt((c * c).sum(1) * (q @ q))}[dc]
+    np.testing.assert_allclose(cdc[0], np.sort(ref)[:w], rtol=1e-4 if z["X"].dtype == np.float32 else 1e-11, atol=1e-6)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["metrics_f32", "metrics_f64"])
+@pytest.mark.parametrize("dc,dr", METRIC_PAIRS)
+def test_cuda_reproduces_metric_golden(name, dc, dr):
+    import ivfadc_jl_b200 as iv
+    z = np.load(os.path.join(HERE, "golden", name + ".npz"))
+    qz, t = _metric_case(z, dc, dr)
+    X, Q, k, w = z["X"], z["Q"], int(z["k"]), int(z["w"])
+    e = iv.IVFADCIndex.from_quantizers(qz.centroids, qz.cb_vectors, qz.cb_codes, coarse_distance=dc, quantization_distance=dr)
+    gcell, gcode = e.encode(X)
+    np.testing.assert_array_equal(gcell, z[f"cells_{t}"])
+    np.testing.assert_array_equal(gcode, z[f"codes_{t}"])
+    ccells, cdc = e.coarse_search(Q, w)
+    np.testing.assert_array_equal(ccells, z[f"ccells_{t}"])
+    assert np.array_equal(cdc.view(np.uint8), z[f"cdc_{t}"].view(np.uint8))
+    iv.push_batch(e, X)
+    gi, gd, gc = e.search_packed(Q, k, w)
+    np.testing.assert_array_equal(gc, z[f"counts_{t}"])
+    np.testing.assert_array_equal(gi, z[f"ids_{t}"])
+    assert np.array_equal(gd.view(np.uint8), z[f"dists_{t}"].view(np.uint8))
+    e.close()
