@@ -299,3 +299,86 @@ class ShardedSearcher:
             wk.wait()
         shape = (self.world, nq, k)
         return self.engine.merge(ids_all.view(shape), dists_all.view(shape), keys_all.view(shape), k)
+
+
+class DeviceGroup:
+    """One process, several GPUs (ivfadc_group_*): what the Julia glue binds when IVFADC_DEVICES names more than one
+    device.  Same calls as a single index; the lists are sharded by cell inside the library."""
+
+    def __init__(self, centroids, cb_vectors, cb_codes=None, *, devices=None, n_devices=None, index_type=np.uint32, flags=0):
+        centroids = np.ascontiguousarray(centroids)
+        cb_vectors = np.ascontiguousarray(cb_vectors, dtype=centroids.dtype)
+        if cb_codes is None:
+            cb_codes = np.tile(np.arange(cb_vectors.shape[1], dtype=np.uint8), (cb_vectors.shape[0], 1))
+        cb_codes = np.ascontiguousarray(cb_codes, dtype=np.uint8)
+        self.T, self.I = centroids.dtype, np.dtype(index_type)
+        self.kc, self.nrows = centroids.shape
+        self.m, self.k, self.dsub = cb_vectors.shape
+        self._lib = _capi.load()
+        devs = None if devices is None else np.ascontiguousarray(devices, dtype=np.int32)
+        n = len(devs) if devs is not None else int(n_devices)
+        cfg = _capi.Config(dim=self.nrows, kc=self.kc, m=self.m, ksub=self.k,
+                           dtype=_capi.F32 if self.T == np.float32 else _capi.F64, id_bytes=self.I.itemsize,
+                           metric_coarse=_capi.SQEUCLIDEAN, metric_resid=_capi.SQEUCLIDEAN, device=0, shard_rank=0,
+                           shard_world=1, flags=int(flags))
+        g = ctypes.c_void_p()
+        rc = self._lib.ivfadc_group_create(ctypes.byref(g), ctypes.byref(cfg), n, _capi.ptr(devs), _capi.ptr(centroids),
+                                           _capi.ptr(cb_vectors), _capi.ptr(cb_codes))
+        if rc != 0:
+            raise _capi.IvfadcError(rc, "ivfadc_group_create failed (fewer devices than asked for, or NCCL not loadable)")
+        self._g = g
+
+    def _check(self, rc):
+        if rc != 0:
+            msg = self._lib.ivfadc_group_last_error(self._g)
+            raise _capi.IvfadcError(rc, (msg or b"").decode("utf-8", "replace"))
+
+    def close(self):
+        if getattr(self, "_g", None):
+            self._lib.ivfadc_group_destroy(self._g)
+            self._g = None
+
+    def __len__(self):
+        n = ctypes.c_int64()
+        self._check(self._lib.ivfadc_group_length(self._g, ctypes.byref(n)))
+        return int(n.value)
+
+    def size(self):
+        return int(self._lib.ivfadc_group_size(self._g))
+
+    def set_cell_owners(self, owners):
+        owners = np.ascontiguousarray(owners, dtype=np.int32)
+        self._check(self._lib.ivfadc_group_set_cell_owners(self._g, _capi.ptr(owners)))
+
+    def add(self, X, position=_capi.LAST, assign=None, assign_base=0):
+        X = np.ascontiguousarray(X, dtype=self.T)
+        a = None if assign is None else np.ascontiguousarray(assign, dtype=np.int64)
+        self._check(self._lib.ivfadc_group_add(self._g, _capi.ptr(X), X.shape[0], position, _capi.ptr(a), assign_base, None))
+
+    def search(self, Q, k, w=1):
+        Q = np.ascontiguousarray(Q, dtype=self.T).reshape(-1, self.nrows)
+        nq = Q.shape[0]
+        ids = np.empty((nq, k), dtype=np.uint64)
+        dists = np.empty((nq, k), dtype=self.T)
+        counts = np.empty(nq, dtype=np.int32)
+        self._check(self._lib.ivfadc_group_search(self._g, _capi.ptr(Q), nq, k, w, _capi.ptr(ids), _capi.ptr(dists),
+                                                  _capi.ptr(counts)))
+        return ids, dists, counts
+
+    def delete(self, ids0):
+        ids0 = np.ascontiguousarray(ids0, dtype=np.uint64)
+        self._check(self._lib.ivfadc_group_delete(self._g, _capi.ptr(ids0), len(ids0)))
+
+    def pop(self, position=_capi.LAST):
+        out = np.empty(self.nrows, dtype=self.T)
+        self._check(self._lib.ivfadc_group_pop(self._g, position, _capi.ptr(out)))
+        return out
+
+    def shard_sizes(self):
+        """list lengths per shard: int64 [n_devices, kc]"""
+        out = np.zeros((self.size(), self.kc), dtype=np.int64)
+        for i in range(self.size()):
+            h = ctypes.c_void_p()
+            self._check(self._lib.ivfadc_group_handle(self._g, i, ctypes.byref(h)))
+            self._check(self._lib.ivfadc_list_sizes(h, _capi.ptr(out[i])))
+        return out

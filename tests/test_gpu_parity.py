@@ -1063,3 +1063,45 @@ def test_float64_large_batch_takes_the_float32_twin():
     xi, xd, xc = ex.search_packed(Q, k, w)
     assert np.array_equal(xd.view(np.uint8), od.view(np.uint8)) and np.array_equal(xi, oi)
     ex.close()
+
+
+def test_device_group_equals_one_gpu():
+    """ivfadc_group_* (one process, several GPUs: what the Julia glue binds with IVFADC_DEVICES): build, search, delete,
+    pop and length against the single-GPU engine, bit for bit.  Needs two devices (skipped on a one-GPU box)."""
+    from ivfadc_jl_b200 import sharded, synth
+    if iv._capi.load().ivfadc_device_count() < 2:
+        pytest.skip("needs two GPUs")
+    D, m, kc, n, nq, k, w = 64, 8, 48, 40000, 700, 10, 8
+    X = synth.blobs(n, D, kc, seed=61)
+    Q = synth.blobs(nq, D, kc, seed=62)
+    cent, cb, codes = synth.random_quantizers(kc, D, m, 256, seed=10, data=X)
+    one = iv.IVFADCIndex.from_quantizers(cent, cb, codes)
+    cells = one._add(X, iv._capi.LAST, want_cells=True)
+    g = sharded.DeviceGroup(cent, cb, codes, n_devices=2)
+    g.set_cell_owners(sharded.balanced_owners(np.bincount(cells, minlength=kc), 2))
+    g.add(X, assign=cells.astype(np.int64), assign_base=0)
+    assert len(g) == len(one) == n
+    ss = g.shard_sizes()
+    np.testing.assert_array_equal(ss.sum(0), one.list_sizes())
+    assert abs(int(ss[0].sum()) - int(ss[1].sum())) < 0.05 * n      # balanced by list length
+    for kk, ww in ((k, w), (3, 1), (16, 48)):
+        ui, ud, uc = one.search_packed(Q, kk, ww)
+        gi, gd, gc = g.search(Q, kk, ww)
+        np.testing.assert_array_equal(gc, uc)
+        np.testing.assert_array_equal(gi, ui)
+        assert np.array_equal(gd.view(np.uint8), ud.view(np.uint8))
+    dele = np.random.default_rng(3).choice(n, 3000, replace=False)
+    iv.delete_from_index(one, dele + 1)
+    g.delete(np.sort(dele).astype(np.uint64))
+    assert len(g) == len(one) == n - 3000
+    v1, v2 = iv.pop(one), g.pop()
+    np.testing.assert_array_equal(v1, v2)
+    v1, v2 = iv.popfirst(one), g.pop(iv._capi.FIRST)
+    np.testing.assert_array_equal(v1, v2)
+    g.add(X[:500])
+    iv.push_batch(one, X[:500])
+    ui, ud, uc = one.search_packed(Q, k, w)
+    gi, gd, gc = g.search(Q, k, w)
+    np.testing.assert_array_equal(gi, ui)
+    assert np.array_equal(gd.view(np.uint8), ud.view(np.uint8))
+    g.close(); one.close()
