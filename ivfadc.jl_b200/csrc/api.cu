@@ -210,7 +210,7 @@ int search_via_twin(ivfadc_index* h, const void* dQ, int64_t nq, int k, int w, u
     ivfadc_index* t = h->twin;
     const ListsView own = lists_view(t);
     lists_set(t, lists_view(h));
-    t->h_off = h->h_off; t->h_len = h->h_len; t->h_cap = h->h_cap;
+    t->h_off.swap(h->h_off); t->h_len.swap(h->h_len); t->h_cap.swap(h->h_cap);   // O(1): handed back below
     const int wc = std::min(w, h->cfg.kc);
     int rc = 1;
     if (k <= scan_max_k() && wc <= coarse_max_w() && scan_takes_tensor_path(t, nq * (int64_t)wc, k)) {
@@ -235,7 +235,7 @@ int search_via_twin(ivfadc_index* h, const void* dQ, int64_t nq, int k, int w, u
         }
     }
     lists_set(t, own);   // the kernels took the device pointers by value; the twin owns nothing of the parent's
-    t->h_off.assign(h->cfg.kc, 0); t->h_len.assign(h->cfg.kc, 0); t->h_cap.assign(h->cfg.kc, 0);
+    t->h_off.swap(h->h_off); t->h_len.swap(h->h_len); t->h_cap.swap(h->h_cap);
     t->scanw_ws_n = -1;
     return rc;
 }
